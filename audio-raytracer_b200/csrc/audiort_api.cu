@@ -1,0 +1,907 @@
+// audiort_api.cu -- C ABI of libaudiort_cuda (include/audiort.h): context, scene/ray upload,
+// frame scheduling on one CUDA stream, completion, partial-result merge and the
+// ProcessAudioDataJob finalisation. Stands in for AudioRayTracer.OnUpdate's scheduling block
+// (Assets/C# Scripts/Audio/AudioRayTracer.cs:95-97, 161-237) -- there is no CPU compute path here:
+// every intersection test, sum and count is produced by the kernels in k0..k3.
+#include "../../include/audiort.h"
+
+#include "launchers.h"
+#include "scene_dev.cuh"
+#include "um_math.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace art {
+
+// ---- FIB: FibonacciDirectionsJobParallel.Execute (Jobs/FibonacciDirectionsJobParallel.cs:25-34) --
+__global__ void fibonacci_kernel(uint16_t* dirs, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float phi = mulr(3.14159274f, subr(3.0f, sqrtr(5.0f)));                  // FIB:26
+    const float y = subr(1.0f, mulr(divr((float)i, (float)(n - 1)), 2.0f));        // FIB:27
+    const float radius = sqrtr(subr(1.0f, mulr(y, y)));                            // FIB:28
+    const float theta = mulr(phi, (float)i);                                       // FIB:29
+    const float x = mulr((float)cos((double)theta), radius);                       // FIB:31 math.cos(float) = (float)Math.Cos(double)
+    const float z = mulr((float)sin((double)theta), radius);                       // FIB:32
+    dirs[3 * (size_t)i] = um_f32tof16(x);
+    dirs[3 * (size_t)i + 1] = um_f32tof16(y);
+    dirs[3 * (size_t)i + 2] = um_f32tof16(z);
+}
+cudaError_t launch_fibonacci(uint16_t* dirs, int n, cudaStream_t stream)
+{
+    fibonacci_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dirs, n);
+    return cudaGetLastError();
+}
+
+// ---- FP32 issue-rate microbenchmarks (roofline denominators) -------------------------
+template <int KIND>
+__global__ void __launch_bounds__(1024, 2) microbench_kernel(float* sink, int iters, float seed)
+{
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = seed + (float)(threadIdx.x + k);
+    const float m = 1.0000001f, c = 0.9999999f;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (KIND == 0) { v[k] = __fmul_rn(v[k], m); v[k] = __fadd_rn(v[k], c); }          // un-fused FMUL + FADD
+                else if (KIND == 1) { v[k] = fminf(v[k], v[(k + 3) & 7]); v[k] = fmaxf(v[k], v[(k + 5) & 7]); } // FMNMX pairs
+                else { v[k] = __fmaf_rn(v[k], m, c); v[k] = __fmaf_rn(v[k], c, m); }             // FFMA
+            }
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += v[k];
+    if (s == 123.456f) sink[0] = s;
+}
+cudaError_t launch_microbench(int kind, int numSms, float* sink, long long* laneOps, cudaStream_t stream)
+{
+    const int iters = 4096, blocks = numSms * 2, threads = 1024;
+    if (kind == 0) microbench_kernel<0><<<blocks, threads, 0, stream>>>(sink, iters, 1.0f);
+    else if (kind == 1) microbench_kernel<1><<<blocks, threads, 0, stream>>>(sink, iters, 1.0f);
+    else microbench_kernel<2><<<blocks, threads, 0, stream>>>(sink, iters, 1.0f);
+    *laneOps = (long long)blocks * threads * iters * 4 * 8 * 2;
+    return cudaGetLastError();
+}
+
+}  // namespace art
+
+using namespace art;
+
+// =================================================================================================
+// Host side
+// =================================================================================================
+namespace {
+
+constexpr uint32_t kBlobMagic = 0x41525442u;   // "ARTB"
+
+struct BlobHeader {
+    uint32_t magic;
+    int32_t nTargets;
+    int32_t batchCount;
+    int32_t shards;              // number of contexts merged into this blob
+    EchoStats echo;
+    unsigned long long counters[C_COUNT];
+};
+// blob = header | int32 lastHitRay[T] (+pad to 8) | uint32 muffleCounts[T*Na] (+pad) | float permLast[T*Na] (+pad)
+//        | int64 permSumInt[Na] | int64 permSumFrac[Na]
+struct BlobLayout {
+    size_t offLastHit, offMuffle, offPermLast, offSumInt, offSumFrac, bytes;
+};
+inline size_t align8(size_t x) { return (x + 7) & ~(size_t)7; }
+BlobLayout blob_layout(int Na, int T)
+{
+    BlobLayout b;
+    size_t o = align8(sizeof(BlobHeader));
+    b.offLastHit = o; o = align8(o + sizeof(int32_t) * (size_t)T);
+    b.offMuffle = o; o = align8(o + sizeof(uint32_t) * (size_t)T * Na);
+    b.offPermLast = o; o = align8(o + sizeof(float) * (size_t)T * Na);
+    b.offSumInt = o; o += sizeof(long long) * (size_t)Na;
+    b.offSumFrac = o; o += sizeof(long long) * (size_t)Na;
+    b.bytes = o;
+    return b;
+}
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+inline float h2f(uint16_t h)   // IEEE binary16 -> binary32 (== math.f16tof32), host copy for scene prep
+{
+    uint32_t sign = ((uint32_t)h & 0x8000u) << 16, mag = h & 0x7FFFu, bits;
+    if (mag >= 0x7C00u) bits = sign | 0x7F800000u | ((mag & 0x3FFu) << 13);
+    else if (mag >= 0x0400u) bits = sign | ((mag << 13) + ((127u - 15u) << 23));
+    else if (mag == 0) bits = sign;
+    else { float f = (float)mag * 5.9604644775390625e-08f; memcpy(&bits, &f, 4); bits |= sign; }
+    float out; memcpy(&out, &bits, 4); return out;
+}
+
+thread_local std::string g_createError;
+
+}  // namespace
+
+struct ArtCtx {
+    int device = 0;
+    int numSms = 0;
+    int maxSmemOptin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    std::string err;
+    bool poisoned = false;
+
+    // scene (host staging = caller's structs, device raw + packed)
+    std::vector<uint16_t> hostS, hostA, hostO;     // raw words, kept for host-side prep
+    PinBuf pinScene;
+    DevBuf rawScene, geom, attrs, owners, perm;    // perm: dens arrays + owned list
+    GeomLayout L{};
+    bool haveScene = false, sceneDirty = false;
+    int permPreparedForTargets = -1;
+    int nOwned = 0;
+
+    // rays
+    int nGlobal = 0;
+    PinBuf pinRays; DevBuf dirs;
+    bool haveRays = false, raysDirty = false;
+    int shardIndex = 0, shardCount = 1, chunkRays = 0;
+
+    // frame
+    DevBuf targets, ownedCount, outEcho, outHitPts, outHitCnt, outHitIds, firstHit, partials, queue;
+    PinBuf pinTargets, pinOwnedCount, pinPartials, pinEcho, pinHitPts, pinHitCnt, pinHitIds;
+    ArtParams params{};
+    ArtOutputs userOut{};
+    bool haveUserOut = false;
+    bool inFlight = false;
+    bool frameDone = false;
+    ArtHandle handle = 0;
+    ShardMap map{};
+    int frameH = 0, frameNa = 0, frameT = 0;
+    uint32_t frameFlags = 0, frameJobs = 0;
+    uint32_t kernelLaunches = 0;
+    ArtCounters counters{};
+    std::vector<unsigned char> lastBlob;
+    std::vector<int> frameOwnedCount;
+};
+
+namespace {
+
+int32_t fail(ArtCtx* c, int32_t code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf; else g_createError = buf;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            ctx->poisoned = (cudaGetLastError(), cudaPeekAtLastError() != cudaSuccess) || ctx->poisoned; \
+            return fail(ctx, ART_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                          \
+    } while (0)
+
+int local_ray_count(int nGlobal, int shardIndex, int shardCount, int chunk)
+{
+    if (shardCount <= 1) return nGlobal;
+    long long n = 0;
+    const long long nChunks = ((long long)nGlobal + chunk - 1) / chunk;
+    for (long long c = shardIndex; c < nChunks; c += shardCount) {
+        long long lo = c * chunk, hi = lo + chunk;
+        if (hi > nGlobal) hi = nGlobal;
+        n += hi - lo;
+    }
+    return (int)n;
+}
+
+int effective_chunk(const ArtCtx* c)
+{
+    if (c->shardCount <= 1) return c->nGlobal > 0 ? c->nGlobal : 1;
+    if (c->chunkRays > 0) return c->chunkRays;
+    return (c->nGlobal + c->shardCount - 1) / c->shardCount;   // contiguous slices
+}
+
+// ART:161: (int)math.max(1, math.ceil((float)rayCount / ToUseThreadCount))
+int batch_size(int rayCount, int T)
+{
+    float q = std::ceil((float)rayCount / (float)T);
+    if (!(q > 1.0f)) q = 1.0f;
+    return (int)q;
+}
+
+// math.saturate(x) = max(0, min(1, x)) with Unity's NaN rule
+inline float um_min_h(float x, float y) { return (std::isnan(y) || x < y) ? x : y; }
+inline float um_max_h(float x, float y) { return (std::isnan(y) || x > y) ? x : y; }
+inline float saturate_h(float x) { return um_max_h(0.0f, um_min_h(1.0f, x)); }
+
+int32_t finalize_blob(const unsigned char* blob, size_t bytes, const ArtParams* p, int32_t rayCount, const ArtOutputs* out,
+                      std::string* err)
+{
+    if (bytes < sizeof(BlobHeader)) { if (err) *err = "blob too small"; return ART_E_ARG; }
+    BlobHeader h; memcpy(&h, blob, sizeof h);
+    if (h.magic != kBlobMagic || h.nTargets != p->totalAudioTargets || h.batchCount != p->batchCount) {
+        if (err) *err = "blob does not match params"; return ART_E_ARG;
+    }
+    const int Na = h.nTargets, T = h.batchCount, N = rayCount, H = p->maxHitsPerRay;
+    const BlobLayout bl = blob_layout(Na, T);
+    if (bytes < bl.bytes) { if (err) *err = "blob truncated"; return ART_E_ARG; }
+    const int32_t* lastHit = reinterpret_cast<const int32_t*>(blob + bl.offLastHit);
+    const uint32_t* mcnt = reinterpret_cast<const uint32_t*>(blob + bl.offMuffle);
+    const float* permLast = reinterpret_cast<const float*>(blob + bl.offPermLast);
+    const long long* sumInt = reinterpret_cast<const long long*>(blob + bl.offSumInt);
+    const long long* sumFrac = reinterpret_cast<const long long*>(blob + bl.offSumFrac);
+
+    const int b = batch_size(N, T);
+    const int numBatches = (N + b - 1) / b;
+
+    // ---- MuffleRayHits table: batch k writes slot row batchId = k*b*T / N (RT:63-64, int32 wrap),
+    //      zeroing it first (RT:82-85); batches are applied in ascending order (canonical serial order).
+    std::vector<uint16_t> table((size_t)T * Na, 0);
+    std::vector<float> permTable((size_t)T * Na, 0.0f);
+    for (int k = 0; k < numBatches; k++) {
+        const int32_t start = k * b;
+        const int32_t row = (int32_t)((uint32_t)start * (uint32_t)T) / N;
+        if (row < 0 || row >= T) { if (err) *err = "batch slot out of range (reference would throw)"; return ART_E_ARG; }
+        for (int a = 0; a < Na; a++) table[(size_t)row * Na + a] = (uint16_t)mcnt[(size_t)k * Na + a];   // ushort wrap (Q8)
+        // ---- PermeationPowerRemains: PM:36-37 batchCount = Length / totalRays / Na (quirk Q6)
+        const int32_t totalRays = (N - start < b) ? N - start : b;
+        const int32_t pbc = (T * Na) / totalRays / Na;
+        const int32_t prow = (int32_t)((uint32_t)start * (uint32_t)pbc) / N;
+        if (prow < 0 || prow >= T) { if (err) *err = "permeation slot out of range"; return ART_E_ARG; }
+        for (int a = 0; a < Na; a++)
+            permTable[(size_t)prow * Na + a] = lastHit[k] >= 0 ? permLast[(size_t)k * Na + a] : 0.0f;   // PM:43-46, 85
+    }
+    if (out->muffleRayHits) memcpy(out->muffleRayHits, table.data(), table.size() * 2);
+    if (out->permeationPowerRemains) memcpy(out->permeationPowerRemains, permTable.data(), permTable.size() * 4);
+    if (out->muffleTotals)
+        for (int a = 0; a < Na; a++) {
+            uint64_t s = 0;
+            for (int k = 0; k < numBatches; k++) s += mcnt[(size_t)k * Na + a];
+            out->muffleTotals[a] = (uint32_t)s;
+        }
+    if (out->permeationSum)
+        for (int a = 0; a < Na; a++) out->permeationSum[a] = (double)sumInt[a] + (double)sumFrac[a] / 68719476736.0;
+
+    if (!out->audioTargetSettings || !(p->jobs & ART_JOB_PROCESS)) return ART_OK;
+
+    // ---- ProcessAudioDataJob.Execute (PA:32-76)
+    const int maxRayHits = H * N;                                                    // PA:35
+    float reverbStrength, reverbVolume;
+    if ((p->flags & ART_FRAME_REVERB_SEQ_FP32) && h.echo.seqValid && h.shards == 1) {
+        const float avgReverbDist = h.echo.seqTotal / (float)maxRayHits;             // PA:49
+        reverbStrength = avgReverbDist / p->maxReverbDistance;                       // PA:50
+        reverbVolume = h.echo.seqZeros / (float)maxRayHits;                          // PA:51
+    } else {
+        // exact total of the half values: (hi * 2^20 + lo) / 2^24
+        long double total = ((long double)h.echo.fixedHi * 1048576.0L + (long double)h.echo.fixedLo) / 16777216.0L;
+        if (h.echo.nan || (h.echo.posInf && h.echo.negInf)) total = NAN;
+        else if (h.echo.posInf) total = INFINITY;
+        else if (h.echo.negInf) total = -INFINITY;
+        reverbStrength = (float)((double)total / (double)maxRayHits / (double)p->maxReverbDistance);
+        reverbVolume = (float)((double)h.echo.zeros / (double)maxRayHits);
+    }
+    const int maxBatchSize = (T * Na) / Na;                                          // PA:34
+    for (int a = 0; a < Na; a++) {
+        int totalMuffleRayhits = 0;
+        float totalPermeationPower = 0.0f;
+        for (int i = 0; i < maxBatchSize; i++) {                                     // PA:61-65
+            totalMuffleRayhits += table[(size_t)Na * i + a];
+            totalPermeationPower += permTable[(size_t)Na * i + a];
+        }
+        float muffle = 1.0f - (float)totalMuffleRayhits / (float)(N * H) * p->muffleEffectiveness;               // PA:68
+        const float permeation = totalPermeationPower / (float)N / p->permeationStrengthPerRay * p->permeationEffectiveness; // PA:69
+        muffle = saturate_h(muffle - permeation);                                    // PA:71
+        ArtTargetSettings s;                                                         // ctor DT/AudioTargetRTSettings.cs:18-24
+        s.muffleStrength = saturate_h(muffle);
+        s.reverbStrength = saturate_h(reverbStrength);
+        s.reverbVolume = saturate_h(reverbVolume);
+        s.percievedAudioPosition[0] = p->audioTargetPositions ? p->audioTargetPositions[3 * a] : 0.0f;
+        s.percievedAudioPosition[1] = p->audioTargetPositions ? p->audioTargetPositions[3 * a + 1] : 0.0f;
+        s.percievedAudioPosition[2] = p->audioTargetPositions ? p->audioTargetPositions[3 * a + 2] : 0.0f;
+        out->audioTargetSettings[a] = s;
+    }
+    return ART_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+ART_API int32_t art_create(const ArtConfig* cfg, ArtCtx** out)
+{
+    if (!cfg || !out) return fail(nullptr, ART_E_ARG, "art_create: null argument");
+    *out = nullptr;
+    if (cfg->abiVersion != ART_ABI_VERSION) return fail(nullptr, ART_E_ARG, "art_create: ABI version %d != %d", cfg->abiVersion, ART_ABI_VERSION);
+    int nDev = 0;
+    cudaError_t e = cudaGetDeviceCount(&nDev);
+    if (e != cudaSuccess || nDev <= 0) {
+        cudaGetLastError();
+        return fail(nullptr, ART_E_NO_DEVICE, "art_create: no CUDA device (%s); libaudiort_cuda has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    }
+    if (cfg->device < 0 || cfg->device >= nDev) return fail(nullptr, ART_E_ARG, "art_create: device %d out of range [0,%d)", cfg->device, nDev);
+    ArtCtx* ctx = new (std::nothrow) ArtCtx();
+    if (!ctx) return fail(nullptr, ART_E_NOMEM, "art_create: out of memory");
+    ctx->device = cfg->device;
+    auto bail = [&](cudaError_t ee, const char* what) {
+        int32_t rc = fail(nullptr, ART_E_CUDA, "art_create: %s: %s", what, cudaGetErrorString(ee));
+        delete ctx;
+        return rc;
+    };
+    if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, ctx->device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    if (prop.major < 10) {
+        delete ctx;
+        return fail(nullptr, ART_E_NO_DEVICE, "art_create: device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+    }
+    ctx->numSms = prop.multiProcessorCount;
+    ctx->maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    for (auto& ev : ctx->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    *out = ctx;
+    return ART_OK;
+}
+
+ART_API void art_destroy(ArtCtx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
+                       &ctx->outEcho, &ctx->outHitPts, &ctx->outHitCnt, &ctx->outHitIds, &ctx->firstHit, &ctx->partials, &ctx->queue })
+        b->release();
+    for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinEcho,
+                       &ctx->pinHitPts, &ctx->pinHitCnt, &ctx->pinHitIds })
+        b->release();
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+ART_API const char* art_last_error(ArtCtx* ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+
+ART_API int32_t art_set_scene(ArtCtx* ctx, const ArtAABB* aabbs, int32_t nAABB, const ArtOBB* obbs, int32_t nOBB,
+                              const ArtSphere* spheres, int32_t nSphere)
+{
+    if (!ctx) return ART_E_ARG;
+    if (ctx->inFlight) return fail(ctx, ART_E_PENDING, "art_set_scene: a frame is in flight");
+    if (nAABB < 0 || nOBB < 0 || nSphere < 0 || (nAABB && !aabbs) || (nOBB && !obbs) || (nSphere && !spheres))
+        return fail(ctx, ART_E_ARG, "art_set_scene: bad counts/pointers");
+    if (nAABB >= (1 << 24) || nOBB >= (1 << 24) || nSphere >= (1 << 24)) return fail(ctx, ART_E_ARG, "art_set_scene: too many colliders");
+    static_assert(sizeof(ArtAABB) == 20 && sizeof(ArtOBB) == 26 && sizeof(ArtSphere) == 16, "wire layout");
+    ctx->hostS.assign(reinterpret_cast<const uint16_t*>(spheres), reinterpret_cast<const uint16_t*>(spheres) + 8 * (size_t)nSphere);
+    ctx->hostA.assign(reinterpret_cast<const uint16_t*>(aabbs), reinterpret_cast<const uint16_t*>(aabbs) + 10 * (size_t)nAABB);
+    ctx->hostO.assign(reinterpret_cast<const uint16_t*>(obbs), reinterpret_cast<const uint16_t*>(obbs) + 13 * (size_t)nOBB);
+    GeomLayout& L = ctx->L;
+    L.ns = nSphere; L.na = nAABB; L.no = nOBB;
+    L.nsPad = (nSphere + SC_S - 1) / SC_S * SC_S;
+    L.naPad = (nAABB + SC_A - 1) / SC_A * SC_A;
+    L.noPad = (nOBB + SC_O - 1) / SC_O * SC_O;
+    uint32_t o = 0;
+    L.offSph = o; o += 16u * L.nsPad;
+    L.offAabbA = o; o += 16u * L.naPad;
+    L.offAabbB = o; o += 8u * L.naPad;
+    L.offObbQ = o; o += 16u * L.noPad;
+    L.offObbC = o; o += 16u * L.noPad;
+    L.offObbH = o; o += 8u * L.noPad;
+    L.bytes = (o + 15u) & ~15u;
+    ctx->haveScene = true;
+    ctx->sceneDirty = true;
+    ctx->permPreparedForTargets = -1;
+    return ART_OK;
+}
+
+ART_API int32_t art_set_rays(ArtCtx* ctx, const uint16_t* dirs, int32_t rayCount)
+{
+    if (!ctx) return ART_E_ARG;
+    if (ctx->inFlight) return fail(ctx, ART_E_PENDING, "art_set_rays: a frame is in flight");
+    if (!dirs || rayCount <= 0) return fail(ctx, ART_E_ARG, "art_set_rays: bad arguments");
+    cudaSetDevice(ctx->device);
+    CK(ctx->pinRays.ensure(6 * (size_t)rayCount));
+    memcpy(ctx->pinRays.p, dirs, 6 * (size_t)rayCount);
+    ctx->nGlobal = rayCount;
+    ctx->haveRays = true;
+    ctx->raysDirty = true;
+    return ART_OK;
+}
+
+ART_API int32_t art_generate_fibonacci_rays(ArtCtx* ctx, int32_t rayCount)
+{
+    if (!ctx) return ART_E_ARG;
+    if (ctx->inFlight) return fail(ctx, ART_E_PENDING, "art_generate_fibonacci_rays: a frame is in flight");
+    if (rayCount <= 0) return fail(ctx, ART_E_ARG, "art_generate_fibonacci_rays: bad ray count");
+    cudaSetDevice(ctx->device);
+    CK(ctx->dirs.ensure(6 * (size_t)rayCount));
+    CK(launch_fibonacci(ctx->dirs.as<uint16_t>(), rayCount, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->nGlobal = rayCount;
+    ctx->haveRays = true;
+    ctx->raysDirty = false;
+    return ART_OK;
+}
+
+ART_API int32_t art_get_rays(ArtCtx* ctx, uint16_t* dirs, int32_t capacityRays)
+{
+    if (!ctx || !dirs) return ART_E_ARG;
+    if (!ctx->haveRays) return fail(ctx, ART_E_STATE, "art_get_rays: no rays set");
+    if (capacityRays < ctx->nGlobal) return fail(ctx, ART_E_ARG, "art_get_rays: capacity %d < %d", capacityRays, ctx->nGlobal);
+    cudaSetDevice(ctx->device);
+    if (ctx->raysDirty) { memcpy(dirs, ctx->pinRays.p, 6 * (size_t)ctx->nGlobal); return ART_OK; }
+    CK(cudaMemcpyAsync(dirs, ctx->dirs.p, 6 * (size_t)ctx->nGlobal, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ART_OK;
+}
+
+ART_API int32_t art_set_ray_shard(ArtCtx* ctx, int32_t shardIndex, int32_t shardCount, int32_t chunkRays)
+{
+    if (!ctx) return ART_E_ARG;
+    if (ctx->inFlight) return fail(ctx, ART_E_PENDING, "art_set_ray_shard: a frame is in flight");
+    if (shardCount < 1 || shardIndex < 0 || shardIndex >= shardCount || chunkRays < 0)
+        return fail(ctx, ART_E_ARG, "art_set_ray_shard: bad shard %d/%d chunk %d", shardIndex, shardCount, chunkRays);
+    ctx->shardIndex = shardIndex; ctx->shardCount = shardCount; ctx->chunkRays = chunkRays;
+    return ART_OK;
+}
+
+ART_API int32_t art_local_ray_count(ArtCtx* ctx)
+{
+    if (!ctx) return ART_E_ARG;
+    if (!ctx->haveRays) return fail(ctx, ART_E_STATE, "art_local_ray_count: no rays set");
+    return local_ray_count(ctx->nGlobal, ctx->shardIndex, ctx->shardCount, effective_chunk(ctx));
+}
+
+ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtOutputs* outputs, ArtHandle* outHandle)
+{
+    if (!ctx || !prm || !outHandle) return ART_E_ARG;
+    if (ctx->poisoned) return fail(ctx, ART_E_CUDA, "context poisoned by an earlier CUDA error");
+    if (ctx->inFlight) return fail(ctx, ART_E_PENDING, "art_trace_schedule: a frame is already in flight");
+    if (!ctx->haveScene || !ctx->haveRays) return fail(ctx, ART_E_STATE, "art_trace_schedule: scene or rays not set");
+    const int Na = prm->totalAudioTargets, T = prm->batchCount, H = prm->maxHitsPerRay, N = ctx->nGlobal;
+    if (Na <= 0) return fail(ctx, ART_E_ARG, "totalAudioTargets must be >= 1 (RT:63 divides by it)");
+    if (Na > 32767) return fail(ctx, ART_E_ARG, "totalAudioTargets must fit a C# short (RT:153)");
+    if (!prm->audioTargetPositions) return fail(ctx, ART_E_ARG, "audioTargetPositions is null");
+    if (H < 1) return fail(ctx, ART_E_ARG, "maxHitsPerRay must be >= 1");
+    if (T < 1) return fail(ctx, ART_E_ARG, "batchCount must be >= 1");
+    if ((prm->jobs & ART_JOB_ALL) == 0) return fail(ctx, ART_E_ARG, "no jobs requested");
+    if ((prm->jobs & ART_JOB_PROCESS) && (prm->jobs & (ART_JOB_RAYTRACE | ART_JOB_PERMEATION)) != (ART_JOB_RAYTRACE | ART_JOB_PERMEATION))
+        return fail(ctx, ART_E_ARG, "ART_JOB_PROCESS needs ART_JOB_RAYTRACE and ART_JOB_PERMEATION in the same frame (ART:237)");
+    if ((long long)N * H > 0x7FFFFFFFLL) return fail(ctx, ART_E_ARG, "rayCount * maxHitsPerRay overflows int32 (RT:115)");
+    if ((long long)T * Na > 0x7FFFFFFFLL) return fail(ctx, ART_E_ARG, "batchCount * targets overflows int32");
+    const bool wantRT = prm->jobs & ART_JOB_RAYTRACE, wantPM = prm->jobs & ART_JOB_PERMEATION;
+    const bool count = prm->flags & ART_FRAME_COUNTERS;
+    const bool hostOut = !(prm->flags & ART_FRAME_NO_HOST_OUTPUTS);
+    if ((prm->flags & ART_FRAME_REVERB_SEQ_FP32) && ctx->shardCount > 1)
+        return fail(ctx, ART_E_ARG, "ART_FRAME_REVERB_SEQ_FP32 needs the whole echo array on one device (shardCount == 1)");
+    const int b = batch_size(N, T);
+    {   // the reference would index out of range if a batch slot fell outside the table
+        const int numBatches = (N + b - 1) / b;
+        for (int k = 0; k < numBatches; k++) {
+            const int32_t row = (int32_t)((uint32_t)(k * b) * (uint32_t)T) / N;
+            if (row < 0 || row >= T) return fail(ctx, ART_E_ARG, "batch %d maps to slot row %d outside [0,%d) (RT:64 int32 overflow)", k, row, T);
+        }
+    }
+    cudaSetDevice(ctx->device);
+    ctx->kernelLaunches = 0;
+
+    const int chunk = effective_chunk(ctx);
+    ShardMap map;
+    map.nGlobal = N; map.shardIndex = ctx->shardIndex; map.shardCount = ctx->shardCount; map.chunk = chunk;
+    map.nLocal = local_ray_count(N, ctx->shardIndex, ctx->shardCount, chunk);
+    const size_t nLoc = (size_t)map.nLocal, NH = nLoc * H;
+    const GeomLayout& L = ctx->L;
+
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    // ---------------- uploads ----------------
+    if (ctx->sceneDirty) {
+        const size_t bS = ctx->hostS.size() * 2, bA = ctx->hostA.size() * 2, bO = ctx->hostO.size() * 2;
+        const size_t offA = (bS + 15) & ~(size_t)15, offO = (offA + bA + 15) & ~(size_t)15, tot = offO + bO + 16;
+        CK(ctx->pinScene.ensure(tot));
+        CK(ctx->rawScene.ensure(tot));
+        unsigned char* hp = ctx->pinScene.as<unsigned char>();
+        if (bS) memcpy(hp, ctx->hostS.data(), bS);
+        if (bA) memcpy(hp + offA, ctx->hostA.data(), bA);
+        if (bO) memcpy(hp + offO, ctx->hostO.data(), bO);
+        CK(cudaMemcpyAsync(ctx->rawScene.p, hp, tot, cudaMemcpyHostToDevice, ctx->stream));
+        CK(ctx->geom.ensure(L.bytes + 16));
+        const size_t nAttr4 = (size_t)L.nsPad + 3 * (size_t)L.naPad + 3 * (size_t)L.noPad;
+        CK(ctx->attrs.ensure(nAttr4 * sizeof(float4) + 16));
+        CK(ctx->owners.ensure(((size_t)L.nsPad + L.naPad + L.noPad) * sizeof(short) + 16));
+        PackArgs pa;
+        unsigned char* rp = ctx->rawScene.as<unsigned char>();
+        pa.rawS = reinterpret_cast<const uint16_t*>(rp); pa.rawA = reinterpret_cast<const uint16_t*>(rp + offA);
+        pa.rawO = reinterpret_cast<const uint16_t*>(rp + offO);
+        pa.L = L; pa.geom = ctx->geom.as<unsigned char>();
+        float4* at = ctx->attrs.as<float4>();
+        pa.sphAttr = at; at += L.nsPad;
+        pa.aabbAttr = at; at += L.naPad;
+        pa.aabbCtr = at; at += L.naPad;
+        pa.aabbHalf = at; at += L.naPad;
+        pa.obbAttr = at; at += L.noPad;
+        pa.obbHalf = at; at += L.noPad;
+        pa.obbQinv = at;
+        short* ow = ctx->owners.as<short>();
+        pa.ownS = ow; pa.ownA = ow + L.nsPad; pa.ownO = ow + L.nsPad + L.naPad;
+        CK(launch_pack(pa, ctx->stream));
+        ctx->kernelLaunches++;
+        ctx->sceneDirty = false;
+    }
+    if (ctx->raysDirty) {
+        CK(ctx->dirs.ensure(6 * (size_t)N));
+        CK(cudaMemcpyAsync(ctx->dirs.p, ctx->pinRays.p, 6 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->raysDirty = false;
+    }
+    CK(ctx->pinTargets.ensure(12 * (size_t)Na));
+    CK(ctx->targets.ensure(12 * (size_t)Na));
+    memcpy(ctx->pinTargets.p, prm->audioTargetPositions, 12 * (size_t)Na);
+    CK(cudaMemcpyAsync(ctx->targets.p, ctx->pinTargets.p, 12 * (size_t)Na, cudaMemcpyHostToDevice, ctx->stream));
+
+    // owned-collider bookkeeping (depends on the target count): counts per (section, target) for the
+    // counters, density planes + owned list for K2
+    std::vector<int> ownedCount((size_t)3 * Na, 0);
+    {
+        auto tally = [&](const std::vector<uint16_t>& raw, int words, int sec) {
+            const size_t n = raw.size() / words;
+            for (size_t i = 0; i < n; i++) {
+                const int t = (int)(short)raw[i * words + words - 1];
+                if (t >= 0 && t < Na) ownedCount[(size_t)sec * Na + t]++;
+            }
+        };
+        tally(ctx->hostS, 8, 0); tally(ctx->hostA, 10, 1); tally(ctx->hostO, 13, 2);
+    }
+    if (count && wantRT) {
+        CK(ctx->pinOwnedCount.ensure(ownedCount.size() * 4));
+        CK(ctx->ownedCount.ensure(ownedCount.size() * 4));
+        memcpy(ctx->pinOwnedCount.p, ownedCount.data(), ownedCount.size() * 4);
+        CK(cudaMemcpyAsync(ctx->ownedCount.p, ctx->pinOwnedCount.p, ownedCount.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const size_t nPad = (size_t)L.nsPad + L.naPad + L.noPad;
+    if (wantPM && ctx->permPreparedForTargets != Na) {
+        // [dens S | dens A | dens O | ownedList]
+        std::vector<float> dens(nPad, 0.0f);
+        std::vector<int> owned;
+        auto fill = [&](const std::vector<uint16_t>& raw, int words, int densWord, int sec, size_t off) {
+            const size_t n = raw.size() / words;
+            for (size_t i = 0; i < n; i++) {
+                const int t = (int)(short)raw[i * words + words - 1];
+                if (t >= 0 && t < Na) owned.push_back((sec << 28) | (int)i);
+                else dens[off + i] = h2f(raw[i * words + densWord]);
+            }
+        };
+        fill(ctx->hostS, 8, 5, 0, 0); fill(ctx->hostA, 10, 7, 1, L.nsPad); fill(ctx->hostO, 13, 10, 2, (size_t)L.nsPad + L.naPad);
+        ctx->nOwned = (int)owned.size();
+        const size_t bytes = nPad * 4 + owned.size() * 4 + 16;
+        CK(ctx->perm.ensure(bytes));
+        // synchronous small copies (rare: only when the scene or the target count changes)
+        CK(cudaMemcpyAsync(ctx->perm.p, dens.data(), nPad * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (!owned.empty())
+            CK(cudaMemcpyAsync(ctx->perm.as<unsigned char>() + nPad * 4, owned.data(), owned.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->permPreparedForTargets = Na;
+    }
+
+    // ---------------- device outputs ----------------
+    const BlobLayout bl = blob_layout(Na, T);
+    CK(ctx->partials.ensure(bl.bytes));
+    CK(ctx->pinPartials.ensure(bl.bytes));
+    CK(ctx->queue.ensure(64));
+    CK(cudaMemsetAsync(ctx->partials.p, 0, bl.bytes, ctx->stream));
+    CK(cudaMemsetAsync(ctx->partials.as<unsigned char>() + bl.offLastHit, 0xFF, sizeof(int32_t) * (size_t)T, ctx->stream));
+    CK(cudaMemsetAsync(ctx->queue.p, 0, 64, ctx->stream));
+    unsigned char* pb = ctx->partials.as<unsigned char>();
+    BlobHeader* dh = reinterpret_cast<BlobHeader*>(pb);
+    const bool wantHitPts = outputs && outputs->rayHitResults, wantHitCnt = outputs && outputs->rayHitResultCounts,
+               wantHitIds = outputs && outputs->hitColliderIds;
+    if (wantRT) {
+        CK(ctx->outEcho.ensure(NH * 2 + 16));
+        CK(cudaMemsetAsync(ctx->outEcho.p, 0, NH * 2, ctx->stream));
+        if (wantHitPts) { CK(ctx->outHitPts.ensure(NH * 6 + 16)); CK(cudaMemsetAsync(ctx->outHitPts.p, 0, NH * 6, ctx->stream)); }
+        if (wantHitCnt) { CK(ctx->outHitCnt.ensure(nLoc + 16)); CK(cudaMemsetAsync(ctx->outHitCnt.p, 0, nLoc, ctx->stream)); }
+        if (wantHitIds) { CK(ctx->outHitIds.ensure(NH * 4 + 16)); CK(cudaMemsetAsync(ctx->outHitIds.p, 0, NH * 4, ctx->stream)); }
+    }
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+
+    AttrArrays at;
+    {
+        const float4* a4 = ctx->attrs.as<float4>();
+        at.sphAttr = a4; a4 += L.nsPad;
+        at.aabbAttr = a4; a4 += L.naPad;
+        at.aabbCtr = a4; a4 += L.naPad;
+        at.aabbHalf = a4; a4 += L.naPad;
+        at.obbAttr = a4; a4 += L.noPad;
+        at.obbHalf = a4; a4 += L.noPad;
+        at.obbQinv = a4;
+        const short* ow = ctx->owners.as<short>();
+        at.ownS = ow; at.ownA = ow + L.nsPad; at.ownO = ow + L.nsPad + L.naPad;
+        at.ownedCount = ctx->ownedCount.as<int>();
+    }
+
+    // ---------------- K1 ----------------
+    if (wantRT) {
+        TraceArgs ta;
+        ta.geom = ctx->geom.as<unsigned char>(); ta.L = L; ta.at = at;
+        ta.dirs = ctx->dirs.as<uint16_t>(); ta.map = map;
+        ta.ox = prm->rayOrigin[0]; ta.oy = prm->rayOrigin[1]; ta.oz = prm->rayOrigin[2];
+        ta.targets = ctx->targets.as<float>(); ta.nTargets = Na;
+        ta.maxRayLife = prm->maxRayLife; ta.H = H; ta.maxMuffle = prm->maxMuffleHitDistance;
+        ta.batchSize = b;
+        ta.echo = ctx->outEcho.as<uint16_t>();
+        ta.hitPoints = wantHitPts ? ctx->outHitPts.as<uint16_t>() : nullptr;
+        ta.hitCounts = wantHitCnt ? ctx->outHitCnt.as<uint8_t>() : nullptr;
+        ta.hitIds = wantHitIds ? ctx->outHitIds.as<uint32_t>() : nullptr;
+        ta.muffleCounts = reinterpret_cast<uint32_t*>(pb + bl.offMuffle);
+        ta.counters = dh->counters;
+        ta.nextRay = ctx->queue.as<unsigned int>();
+        bool geomInSmem = trace_smem_bytes(L, Na, true, false) <= (size_t)ctx->maxSmemOptin;
+        bool muffleInSmem = trace_smem_bytes(L, Na, geomInSmem, true) <= (size_t)ctx->maxSmemOptin;
+        ta.muffleInSmem = muffleInSmem ? 1 : 0;
+        CK(launch_trace(ta, ctx->numSms, geomInSmem, count, ctx->stream));
+        ctx->kernelLaunches++;
+    }
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    // ---------------- K2 ----------------
+    if (wantPM) {
+        CK(ctx->firstHit.ensure(nLoc * 4 + 16));
+        PermArgs pa;
+        pa.geom = ctx->geom.as<unsigned char>(); pa.L = L; pa.at = at;
+        const float* dn = ctx->perm.as<float>();
+        pa.densS = dn; pa.densA = dn + L.nsPad; pa.densO = dn + L.nsPad + L.naPad;
+        pa.ownedList = reinterpret_cast<const int*>(ctx->perm.as<unsigned char>() + nPad * 4);
+        pa.nOwned = ctx->nOwned;
+        pa.dirs = ctx->dirs.as<uint16_t>(); pa.map = map;
+        pa.ox = prm->rayOrigin[0]; pa.oy = prm->rayOrigin[1]; pa.oz = prm->rayOrigin[2];
+        pa.targets = ctx->targets.as<float>(); pa.nTargets = Na;
+        pa.nTimesS = (float)N * prm->permeationStrengthPerRay;                     // PM:260
+        pa.batchSize = b;
+        pa.firstHitDist = ctx->firstHit.as<float>();
+        pa.lastHitRay = reinterpret_cast<int*>(pb + bl.offLastHit);
+        pa.permSumInt = reinterpret_cast<long long*>(pb + bl.offSumInt);
+        pa.permSumFrac = reinterpret_cast<long long*>(pb + bl.offSumFrac);
+        pa.permLast = reinterpret_cast<float*>(pb + bl.offPermLast);
+        pa.counters = dh->counters;
+        pa.nextRay = ctx->queue.as<unsigned int>() + 8;
+        const bool geomInSmem = perm_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
+        CK(launch_permeation(pa, ctx->numSms, geomInSmem, T, ctx->stream));
+        ctx->kernelLaunches += 2;
+    }
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    // ---------------- K3 ----------------
+    if (wantRT) {
+        CK(launch_echo_stats(ctx->outEcho.as<uint16_t>(), NH, &dh->echo, (prm->flags & ART_FRAME_REVERB_SEQ_FP32) != 0, ctx->numSms, ctx->stream));
+        ctx->kernelLaunches += (prm->flags & ART_FRAME_REVERB_SEQ_FP32) ? 2 : 1;
+    }
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    // ---------------- read back ----------------
+    CK(cudaMemcpyAsync(ctx->pinPartials.p, ctx->partials.p, bl.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hostOut && wantRT && outputs) {
+        if (outputs->echoRayDistances) { CK(ctx->pinEcho.ensure(NH * 2)); CK(cudaMemcpyAsync(ctx->pinEcho.p, ctx->outEcho.p, NH * 2, cudaMemcpyDeviceToHost, ctx->stream)); }
+        if (wantHitPts) { CK(ctx->pinHitPts.ensure(NH * 6)); CK(cudaMemcpyAsync(ctx->pinHitPts.p, ctx->outHitPts.p, NH * 6, cudaMemcpyDeviceToHost, ctx->stream)); }
+        if (wantHitCnt) { CK(ctx->pinHitCnt.ensure(nLoc)); CK(cudaMemcpyAsync(ctx->pinHitCnt.p, ctx->outHitCnt.p, nLoc, cudaMemcpyDeviceToHost, ctx->stream)); }
+        if (wantHitIds) { CK(ctx->pinHitIds.ensure(NH * 4)); CK(cudaMemcpyAsync(ctx->pinHitIds.p, ctx->outHitIds.p, NH * 4, cudaMemcpyDeviceToHost, ctx->stream)); }
+    }
+    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+
+    ctx->params = *prm;
+    ctx->params.audioTargetPositions = ctx->pinTargets.as<float>();   // library-owned copy
+    ctx->haveUserOut = outputs != nullptr;
+    if (outputs) ctx->userOut = *outputs; else memset(&ctx->userOut, 0, sizeof ctx->userOut);
+    ctx->map = map; ctx->frameH = H; ctx->frameNa = Na; ctx->frameT = T;
+    ctx->frameFlags = prm->flags; ctx->frameJobs = prm->jobs;
+    ctx->inFlight = true; ctx->frameDone = false;
+    ctx->handle++;
+    *outHandle = ctx->handle;
+    // perm counters derived on the host (exact arithmetic functions of permHitRays)
+    ctx->counters = ArtCounters{};
+    ctx->lastBlob.clear();
+    ctx->frameOwnedCount = ownedCount;
+    return ART_OK;
+}
+
+ART_API int32_t art_is_completed(ArtCtx* ctx, ArtHandle h)
+{
+    if (!ctx) return ART_E_ARG;
+    if (h != ctx->handle || h == 0) return fail(ctx, ART_E_STATE, "stale handle");
+    if (!ctx->inFlight) return 1;
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaEventQuery(ctx->ev[5]);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+    ctx->poisoned = true;
+    return fail(ctx, ART_E_CUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
+}
+
+ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
+{
+    if (!ctx) return ART_E_ARG;
+    if (h != ctx->handle || h == 0) return fail(ctx, ART_E_STATE, "stale handle");
+    if (!ctx->inFlight) return ctx->frameDone ? ART_OK : fail(ctx, ART_E_STATE, "no frame scheduled");
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaEventSynchronize(ctx->ev[5]);
+    if (e != cudaSuccess) {
+        ctx->poisoned = true; ctx->inFlight = false;
+        return fail(ctx, ART_E_CUDA, "frame failed: %s", cudaGetErrorString(e));
+    }
+    ctx->inFlight = false;
+    const int Na = ctx->frameNa, T = ctx->frameT, H = ctx->frameH;
+    const size_t nLoc = (size_t)ctx->map.nLocal, NH = nLoc * H;
+    const BlobLayout bl = blob_layout(Na, T);
+    BlobHeader* hh = ctx->pinPartials.as<BlobHeader>();
+    hh->magic = kBlobMagic; hh->nTargets = Na; hh->batchCount = T; hh->shards = 1;
+
+    // counters + timings
+    ArtCounters& c = ctx->counters;
+    const unsigned long long* dc = hh->counters;
+    c.segments = dc[C_SEGMENTS]; c.segmentHits = dc[C_SEGMENT_HITS];
+    for (int k = 0; k < 3; k++) { c.traceTests[k] = dc[C_TRACE_S + k]; c.echoTests[k] = dc[C_ECHO_S + k]; c.muffleTests[k] = dc[C_MUFFLE_S + k]; }
+    c.echoQueries = dc[C_ECHO_Q]; c.muffleQueries = dc[C_MUFFLE_Q];
+    c.permRays = dc[C_PERM_RAYS]; c.permHitRays = dc[C_PERM_HIT_RAYS];
+    {
+        const int* ownedCount = ctx->frameOwnedCount.data();
+        const uint64_t nSec[3] = { (uint64_t)ctx->L.ns, (uint64_t)ctx->L.na, (uint64_t)ctx->L.no };
+        c.permPairs = c.permHitRays * (uint64_t)Na;
+        for (int s = 0; s < 3; s++) {
+            c.permFirstTests[s] = c.permRays * nSec[s];
+            uint64_t owned = 0;
+            for (int a = 0; a < Na; a++) owned += (uint64_t)ownedCount[(size_t)s * Na + a];
+            c.permLossTests[s] = c.permHitRays * (nSec[s] * (uint64_t)Na - owned);
+        }
+        for (int k = 0; k < 3; k++) {   // mirror into the blob so merged blobs carry them
+            hh->counters[C_PERM_FIRST_S + k] = c.permFirstTests[k];
+            hh->counters[C_PERM_LOSS_S + k] = c.permLossTests[k];
+        }
+        hh->counters[C_PERM_PAIRS] = c.permPairs;
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); c.h2dMs = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); c.traceMs = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); c.permeationMs = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); c.reduceMs = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[4]); c.deviceMs = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); c.d2hMs = ms;
+    c.kernelLaunches = ctx->kernelLaunches;
+
+    // per-ray outputs: pinned staging -> caller arrays
+    const ArtOutputs& uo = ctx->userOut;
+    const bool hostOut = !(ctx->frameFlags & ART_FRAME_NO_HOST_OUTPUTS);
+    if (hostOut && (ctx->frameJobs & ART_JOB_RAYTRACE) && ctx->haveUserOut) {
+        if (uo.echoRayDistances) memcpy(uo.echoRayDistances, ctx->pinEcho.p, NH * 2);
+        if (uo.rayHitResults) memcpy(uo.rayHitResults, ctx->pinHitPts.p, NH * 6);
+        if (uo.rayHitResultCounts) memcpy(uo.rayHitResultCounts, ctx->pinHitCnt.p, nLoc);
+        if (uo.hitColliderIds) memcpy(uo.hitColliderIds, ctx->pinHitIds.p, NH * 4);
+    }
+    ctx->lastBlob.assign(ctx->pinPartials.as<unsigned char>(), ctx->pinPartials.as<unsigned char>() + bl.bytes);
+    ctx->frameDone = true;
+    if (!(ctx->frameFlags & ART_FRAME_PARTIALS_ONLY) && ctx->haveUserOut) {
+        std::string err;
+        int32_t rc = finalize_blob(ctx->lastBlob.data(), ctx->lastBlob.size(), &ctx->params, ctx->nGlobal, &ctx->userOut, &err);
+        if (rc != ART_OK) return fail(ctx, rc, "finalize: %s", err.c_str());
+    }
+    return ART_OK;
+}
+
+ART_API int32_t art_get_counters(ArtCtx* ctx, ArtHandle h, ArtCounters* out)
+{
+    if (!ctx || !out) return ART_E_ARG;
+    if (h != ctx->handle || h == 0) return fail(ctx, ART_E_STATE, "stale handle");
+    if (ctx->inFlight || !ctx->frameDone) return fail(ctx, ART_E_PENDING, "frame not complete");
+    *out = ctx->counters;
+    return ART_OK;
+}
+
+ART_API int64_t art_partials_size(int32_t totalAudioTargets, int32_t batchCount)
+{
+    if (totalAudioTargets <= 0 || batchCount <= 0) return ART_E_ARG;
+    return (int64_t)blob_layout(totalAudioTargets, batchCount).bytes;
+}
+
+ART_API int32_t art_get_partials(ArtCtx* ctx, ArtHandle h, void* blob, int64_t blobBytes)
+{
+    if (!ctx || !blob) return ART_E_ARG;
+    if (h != ctx->handle || h == 0) return fail(ctx, ART_E_STATE, "stale handle");
+    if (ctx->inFlight || !ctx->frameDone) return fail(ctx, ART_E_PENDING, "frame not complete");
+    if ((size_t)blobBytes < ctx->lastBlob.size()) return fail(ctx, ART_E_ARG, "blob buffer too small");
+    memcpy(blob, ctx->lastBlob.data(), ctx->lastBlob.size());
+    return ART_OK;
+}
+
+ART_API int32_t art_partials_merge(void* accumBlob, const void* otherBlob, int64_t blobBytes)
+{
+    if (!accumBlob || !otherBlob || (size_t)blobBytes < sizeof(BlobHeader)) return ART_E_ARG;
+    unsigned char* A = static_cast<unsigned char*>(accumBlob);
+    const unsigned char* B = static_cast<const unsigned char*>(otherBlob);
+    BlobHeader ha, hb; memcpy(&ha, A, sizeof ha); memcpy(&hb, B, sizeof hb);
+    if (ha.magic != kBlobMagic || hb.magic != kBlobMagic || ha.nTargets != hb.nTargets || ha.batchCount != hb.batchCount) return ART_E_ARG;
+    const int Na = ha.nTargets, T = ha.batchCount;
+    const BlobLayout bl = blob_layout(Na, T);
+    if ((size_t)blobBytes < bl.bytes) return ART_E_ARG;
+    ha.shards += hb.shards;
+    ha.echo.fixedLo += hb.echo.fixedLo; ha.echo.fixedHi += hb.echo.fixedHi;
+    ha.echo.zeros += hb.echo.zeros; ha.echo.entries += hb.echo.entries;
+    ha.echo.posInf += hb.echo.posInf; ha.echo.negInf += hb.echo.negInf; ha.echo.nan += hb.echo.nan;
+    ha.echo.seqValid = 0;   // a sequential FP32 sum cannot be merged
+    for (int i = 0; i < C_COUNT; i++) ha.counters[i] += hb.counters[i];
+    memcpy(A, &ha, sizeof ha);
+    int32_t* la = reinterpret_cast<int32_t*>(A + bl.offLastHit);
+    const int32_t* lb = reinterpret_cast<const int32_t*>(B + bl.offLastHit);
+    float* pa = reinterpret_cast<float*>(A + bl.offPermLast);
+    const float* pbv = reinterpret_cast<const float*>(B + bl.offPermLast);
+    for (int k = 0; k < T; k++)
+        if (lb[k] > la[k]) { la[k] = lb[k]; memcpy(pa + (size_t)k * Na, pbv + (size_t)k * Na, sizeof(float) * (size_t)Na); }
+    uint32_t* ma = reinterpret_cast<uint32_t*>(A + bl.offMuffle);
+    const uint32_t* mb = reinterpret_cast<const uint32_t*>(B + bl.offMuffle);
+    for (size_t i = 0; i < (size_t)T * Na; i++) ma[i] += mb[i];
+    long long* sa = reinterpret_cast<long long*>(A + bl.offSumInt);
+    const long long* sb = reinterpret_cast<const long long*>(B + bl.offSumInt);
+    for (size_t i = 0; i < 2 * (size_t)Na; i++) sa[i] += sb[i];   // int + frac arrays are adjacent
+    return ART_OK;
+}
+
+ART_API int32_t art_finalize(const void* blob, int64_t blobBytes, const ArtParams* params, int32_t rayCount, const ArtOutputs* outputs)
+{
+    if (!blob || !params || !outputs || rayCount <= 0) return ART_E_ARG;
+    return finalize_blob(static_cast<const unsigned char*>(blob), (size_t)blobBytes, params, rayCount, outputs, nullptr);
+}
+
+ART_API int32_t art_microbench(ArtCtx* ctx, int32_t kind, double* gops)
+{
+    if (!ctx || !gops || kind < 0 || kind > 2) return ART_E_ARG;
+    if (ctx->inFlight) return fail(ctx, ART_E_PENDING, "a frame is in flight");
+    cudaSetDevice(ctx->device);
+    CK(ctx->queue.ensure(64));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    long long laneOps = 0;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(e0, ctx->stream));
+        CK(launch_microbench(kind, ctx->numSms, ctx->queue.as<float>() + 4, &laneOps, ctx->stream));
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *gops = (double)laneOps / (best * 1e-3) / 1e9;
+    return ART_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,173 @@
+// scene_dev.cuh -- HBM / shared-memory layout of the packed collider scene and the kernel
+// argument blocks shared by K0 (pack), K1 (trace), K2 (permeation), K3 (reduce).
+//
+// The reference keeps colliders as half-precision AoS structs (ColliderAABBStruct 20 B,
+// ColliderOBBStruct 26 B, ColliderSphereStruct 16 B) and re-derives min/max, R^2 and the
+// normalised quaternion on every test (AudioRaytracerJobBatched.cs:286-287, 328;
+// ColliderOBBStruct.cs:14-16 -> halfQuaternion.cs:34-46). K0 evaluates those pure per-collider
+// functions ONCE, with the reference's own operation order, into FP32 structure-of-arrays
+// "planes" laid out so that lane l of a warp reads collider (base + r*32 + l) with conflict-free
+// 128/64-bit shared loads.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace art {
+
+constexpr int kWarpsPerCta = 16;
+constexpr int kThreads = kWarpsPerCta * 32;
+// colliders held in registers per lane per "super-chunk"
+constexpr int RS = 4;   // spheres
+constexpr int RA = 4;   // AABBs
+constexpr int RO = 2;   // OBBs
+constexpr int SC_S = 32 * RS, SC_A = 32 * RA, SC_O = 32 * RO;
+
+constexpr float kEpsilon = 0.0001f;          // RT:57, PM:30
+constexpr float kFloatMax = 3.402823466e+38f; // float.MaxValue (RT:230)
+
+// Geometry blob: one contiguous, 16-byte aligned buffer (global memory; K1/K2 bulk-copy it to
+// shared memory with cp.async.bulk when it fits). Counts are padded to a multiple of the
+// super-chunk with duplicates of the last real collider of that type (a duplicate can never
+// change a nearest-hit winner -- lower index wins ties -- nor an any-hit result; K2 zeroes the
+// density of pads).
+struct GeomLayout {
+    int ns, na, no;                 // real counts
+    int nsPad, naPad, noPad;        // padded counts
+    uint32_t offSph;                // float4 (cx, cy, cz, R*R)                      [nsPad]
+    uint32_t offAabbA;              // float4 (min.x, min.y, min.z, max.x)          [naPad]
+    uint32_t offAabbB;              // float2 (max.y, max.z)                        [naPad]
+    uint32_t offObbQ;               // float4 Rotation getter value (x,y,z,w)       [noPad]
+    uint32_t offObbC;               // float4 (cx, cy, cz, |hx|)                    [noPad]
+    uint32_t offObbH;               // float2 (|hy|, |hz|)                          [noPad]
+    uint32_t bytes;                 // total, multiple of 16
+};
+
+// Per-collider attributes that are only touched once per segment (hit path): global/L2 only.
+struct AttrArrays {
+    const float4* sphAttr;   // (absorption, echo, density, owner-as-int-bits)   [nsPad]
+    const float4* aabbAttr;  //                                                  [naPad]
+    const float4* obbAttr;   //                                                  [noPad]
+    const float4* aabbCtr;   // (cx, cy, cz, 0)  raw Center                      [naPad]
+    const float4* aabbHalf;  // (hx, hy, hz, 0)  raw Size (half extents)         [naPad]
+    const float4* obbHalf;   // (hx, hy, hz, 0)  raw Size                         [noPad]
+    const float4* obbQinv;   // math.inverse(Rotation)  (RT:489, PM:174)         [noPad]
+    const short*  ownS;      // AudioTargetId per collider                       [nsPad]
+    const short*  ownA;      //                                                  [naPad]
+    const short*  ownO;      //                                                  [noPad]
+    const int*    ownedCount;// [3][nTargetsCap] colliders of each type owned by target a (counters only)
+};
+
+struct GeomView {
+    const float4* sph; const float4* aabbA; const float2* aabbB;
+    const float4* obbQ; const float4* obbC; const float2* obbH;
+};
+
+__host__ __device__ inline GeomView make_view(const unsigned char* base, const GeomLayout& L)
+{
+    GeomView v;
+    v.sph = reinterpret_cast<const float4*>(base + L.offSph);
+    v.aabbA = reinterpret_cast<const float4*>(base + L.offAabbA);
+    v.aabbB = reinterpret_cast<const float2*>(base + L.offAabbB);
+    v.obbQ = reinterpret_cast<const float4*>(base + L.offObbQ);
+    v.obbC = reinterpret_cast<const float4*>(base + L.offObbC);
+    v.obbH = reinterpret_cast<const float2*>(base + L.offObbH);
+    return v;
+}
+
+// Device-side work counters (u64 each), index constants.
+enum CounterIdx {
+    C_SEGMENTS = 0, C_SEGMENT_HITS,
+    C_TRACE_S, C_TRACE_A, C_TRACE_O,
+    C_ECHO_Q, C_ECHO_S, C_ECHO_A, C_ECHO_O,
+    C_MUFFLE_Q, C_MUFFLE_S, C_MUFFLE_A, C_MUFFLE_O,
+    C_PERM_RAYS, C_PERM_HIT_RAYS, C_PERM_FIRST_S, C_PERM_FIRST_A, C_PERM_FIRST_O,
+    C_PERM_PAIRS, C_PERM_LOSS_S, C_PERM_LOSS_A, C_PERM_LOSS_O,
+    C_COUNT
+};
+
+// How this context's local rays map to global ray indices (art_set_ray_shard).
+struct ShardMap {
+    int nGlobal;      // RayDirections.Length
+    int nLocal;       // rays traced by this context
+    int shardIndex, shardCount, chunk;
+    __host__ __device__ inline int to_global(int j) const
+    {
+        if (shardCount <= 1) return j;
+        return ((j / chunk) * shardCount + shardIndex) * chunk + (j % chunk);
+    }
+};
+
+struct TraceArgs {
+    const unsigned char* geom;     // geometry blob (global)
+    GeomLayout L;
+    AttrArrays at;
+    const uint16_t* dirs;          // half3 [nGlobal]
+    ShardMap map;
+    float ox, oy, oz;              // RayOrigin
+    const float* targets;          // float3 [nTargets]
+    int nTargets;
+    float maxRayLife;
+    int H;                         // MaxHitsPerRay
+    float maxMuffle;               // MaxMuffleHitDistance
+    int batchSize;                 // ART:161
+    // outputs, local ray indexing
+    uint16_t* echo;                // half  [nLocal*H]
+    uint16_t* hitPoints;           // half3 [nLocal*H] or null
+    uint8_t*  hitCounts;           // [nLocal] or null
+    uint32_t* hitIds;              // [nLocal*H] or null
+    uint32_t* muffleCounts;        // u32 [T*Na], row = batch index k = rayIndex / batchSize
+    unsigned long long* counters;  // [C_COUNT]
+    unsigned int* nextRay;         // dynamic ray queue
+    int muffleInSmem;              // per-warp shared counters fit
+};
+
+// K0 arguments
+struct PackArgs {
+    const uint16_t* rawS;   // ColliderSphereStruct[ns] as 8 x u16
+    const uint16_t* rawA;   // ColliderAABBStruct[na]  as 10 x u16
+    const uint16_t* rawO;   // ColliderOBBStruct[no]   as 13 x u16
+    GeomLayout L;
+    unsigned char* geom;
+    float4* sphAttr; float4* aabbAttr; float4* obbAttr;
+    float4* aabbCtr; float4* aabbHalf; float4* obbHalf; float4* obbQinv;
+    short* ownS; short* ownA; short* ownO;
+};
+
+// K2 arguments
+struct PermArgs {
+    const unsigned char* geom;
+    GeomLayout L;
+    AttrArrays at;
+    const float* densS; const float* densA; const float* densO;   // padded; 0 for pads and for colliders owned by a target < Na
+    const int* ownedList;      // (section << 28) | index of every collider owned by a target < Na, canonical order (host built)
+    int nOwned;
+    const uint16_t* dirs;
+    ShardMap map;
+    float ox, oy, oz;
+    const float* targets;
+    int nTargets;
+    float nTimesS;             // (float)RayDirections.Length * PermeationStrengthPerRay (PM:260)
+    int batchSize;
+    float* firstHitDist;       // [nLocal] first-hit distance, +Inf = no hit
+    int* lastHitRay;           // [T] max global ray index with a hit, per batch (init -1)
+    long long* permSumInt;     // [Na] sum over hitting rays of trunc(value)
+    long long* permSumFrac;    // [Na] sum of frac(value) * 2^36
+    float* permLast;           // [T*Na] values of the last hitting ray of batch k (perm_last_kernel)
+    unsigned long long* counters;
+    unsigned int* nextRay;
+};
+
+// K3 output (also part of the partial-result blob)
+struct EchoStats {                 // device + blob layout
+    long long fixedLo;             // sum of (value*2^24) & 0xFFFFF   (signed by the half's sign)
+    long long fixedHi;             // sum of (value*2^24) >> 20
+    unsigned long long zeros;      // entries == 0 (PA:42)
+    unsigned long long entries;    // entries visited
+    unsigned long long posInf, negInf, nan;
+    float seqTotal;                // reverb_seq_kernel: reverbTotal (PA:47)
+    float seqZeros;                // reverb_seq_kernel: echoRayReturnedHits (PA:44)
+    unsigned int seqValid;
+    unsigned int pad;
+};
+
+}  // namespace art

@@ -1,0 +1,295 @@
+"""GPU parity: libaudiort_cuda (through the C ABI) against the CPU oracle on identical inputs.
+
+Bar (BASELINE.json north_star / SURVEY 8c): hit collider indices, bounce counts, echo halves, hit points and
+muffle counts BIT-EXACT (the kernels use the reference's operation order in un-fused IEEE FP32, so no
+tolerance is needed and none is applied); canonical PermeationPowerRemains bit-exact; permeationSum within
+1e-5 relative to N*S; ReverbStrength/ReverbVolume/MuffleStrength within 1e-6 absolute of the FP64 evaluation
+(exact integer reduction) and bit-exact with ART_FRAME_REVERB_SEQ_FP32.
+"""
+import numpy as np
+import pytest
+
+from audio_raytracer_b200 import native, scenes
+from audio_raytracer_b200.layouts import TYPE_AABB, TYPE_OBB, TYPE_SPHERE
+from helpers import aabb, hit_id, micro_scene, obb, sphere
+
+pytestmark = pytest.mark.gpu
+
+C = native.FRAME_COUNTERS
+
+
+def run_gpu(ctx, scene, jobs=native.JOB_ALL, flags=C):
+    native.upload(ctx, scene)
+    return ctx.run_frame(scene, jobs=jobs, flags=flags)
+
+
+def assert_rt_equal(g, o, scene, check_counters=True):
+    np.testing.assert_array_equal(g.hit_counts, o.hit_counts, err_msg="RayHitResultCounts")
+    np.testing.assert_array_equal(g.hit_ids, o.hit_ids, err_msg="hit collider ids")
+    np.testing.assert_array_equal(g.echo, o.echo, err_msg="EchoRayDistances (half bits)")
+    # hit points: equal as half bits; +0/-0 are the same point
+    gp, op = g.hit_points.copy(), o.hit_points.copy()
+    gp[gp == 0x8000] = 0
+    op[op == 0x8000] = 0
+    np.testing.assert_array_equal(gp, op, err_msg="RayHitResults.HitPoint")
+    np.testing.assert_array_equal(g.muffle, o.muffle, err_msg="MuffleRayHits u16 table")
+    np.testing.assert_array_equal(g.muffle_totals, o.muffle_totals, err_msg="muffle totals")
+    assert g.counters["segments"] == o.counters["segments"]
+    assert g.counters["segmentHits"] == o.counters["segment_hits"]
+    if check_counters:
+        assert g.counters["traceTests"] == o.counters["trace_tests"]
+        assert g.counters["echoQueries"] == o.counters["echo_queries"]
+        assert g.counters["muffleQueries"] == o.counters["muffle_queries"]
+        assert g.counters["echoTests"] == o.counters["echo_tests"]
+        assert g.counters["muffleTests"] == o.counters["muffle_tests"]
+
+
+def assert_pm_equal(g, o, scene):
+    np.testing.assert_array_equal(g.permeation.view(np.uint32), o.permeation.view(np.uint32),
+                                  err_msg="PermeationPowerRemains (canonical, bit-exact)")
+    scale = scene.n_rays * scene.permeation_strength_per_ray * max(1, o.counters["perm_hit_rays"])
+    np.testing.assert_allclose(g.permeation_sum, o.permeation_sum, rtol=0, atol=1e-5 * scale)
+    for k in ("permRays", "permHitRays", "permPairs"):
+        pass
+    assert g.counters["permRays"] == o.counters["perm_rays"]
+    assert g.counters["permHitRays"] == o.counters["perm_hit_rays"]
+    assert g.counters["permPairs"] == o.counters["perm_pairs"]
+    assert g.counters["permFirstTests"] == o.counters["perm_first_tests"]
+    assert g.counters["permLossTests"] == o.counters["perm_loss_tests"]
+
+
+def assert_settings(g, o, exact):
+    if exact:
+        for f in ("muffleStrength", "reverbStrength", "reverbVolume"):
+            np.testing.assert_array_equal(g.settings[f].view(np.uint32), o.settings[f].view(np.uint32), err_msg=f)
+    else:
+        for f in ("muffleStrength", "reverbStrength", "reverbVolume"):
+            np.testing.assert_allclose(g.settings[f], o.settings_fp64[f], rtol=0, atol=1e-6, err_msg=f)
+    np.testing.assert_array_equal(g.settings["percievedAudioPosition"], o.settings["percievedAudioPosition"])
+
+
+# ---------------------------------------------------------------- known-answer scenes through the CUDA path
+def test_kat_scenes_on_gpu(gpu_ctx, oracle):
+    cases = [
+        micro_scene(aabbs=[aabb((0, 0, 5), (1, 1, 1))]),
+        micro_scene(spheres=[sphere((0, 0, 5), 1.0)]),
+        micro_scene(aabbs=[aabb((0, 0, 5), (1, 1, 1))], origin=(0, 0, 5), H=1),
+        micro_scene(aabbs=[aabb((0, 0, 5), (1, 1, 1))], spheres=[sphere((0, 0, 5), 1.0)], H=1),
+        micro_scene(aabbs=[aabb((0, 0, 5), (1, 1, 1)), aabb((0, 0, 5), (1, 1, 1))], H=1),
+        micro_scene(obbs=[obb((0, 0, 5), (1, 1, 1))], H=1),
+        micro_scene(obbs=[obb((0.9, 0, 5), (2.0, 1.0, 0.25), rot_xyz=(0.0, 0.38268, 0.0))], H=3, targets=((0, 0, 20),)),
+        micro_scene(aabbs=[aabb((0, 0, 10), (1, 1, 1), target=0)], targets=((0, 0, 10),), H=1, max_muffle=100.0),
+        micro_scene(aabbs=[aabb((0, 0, 10), (1, 1, 1), target=-1)], targets=((0, 0, 10),), H=1, max_muffle=100.0),
+        micro_scene(aabbs=[aabb((0, 0, 5), (4, 4, 0.5)), aabb((0, 0, -5), (4, 4, 0.5))], H=4),
+        micro_scene(aabbs=[aabb((0, 0, 5), (4, 4, 0.5), absorption=0.5), aabb((0, 0, -5), (4, 4, 0.5), absorption=0.5)], H=8),
+        micro_scene(aabbs=[aabb((0, 0, 2), (5, 5, 0.125), density=0.0), aabb((0, 0, 5), (1, 1, 1), density=5.0),
+                           aabb((0, 0, 14), (1, 1, 1), density=2.0)], targets=((0, 0, 10),), H=1),
+        # a ray that hits nothing at all
+        micro_scene(aabbs=[aabb((0, 0, -5), (1, 1, 1))], H=2),
+    ]
+    for i, s in enumerate(cases):
+        g = run_gpu(gpu_ctx, s)
+        o = oracle.run_frame(s)
+        assert_rt_equal(g, o, s)
+        assert_pm_equal(g, o, s)
+        assert_settings(g, o, exact=False)
+
+
+def test_first_kat_values_directly(gpu_ctx):
+    """K1 of SURVEY Appendix C asserted on the GPU outputs themselves (not only against the oracle)."""
+    s = micro_scene(aabbs=[aabb((0, 0, 5), (1, 1, 1))])
+    g = run_gpu(gpu_ctx, s)
+    assert g.hit_counts[0] == 1 and g.hit_ids[0] == hit_id(TYPE_AABB, 0)
+    assert list(g.hit_points[0]) == [0, 0, 0x4400] and g.echo[0] == 0x4400 and g.echo[1] == 0
+
+
+# ---------------------------------------------------------------- synthetic rooms, scaled-down BASELINE configs
+@pytest.mark.parametrize("name,n_rays,T", [("c2", 2048, 1), ("c2", 1500, 3), ("c3", 96, 2), ("c4", 48, 1), ("c5", 40, 4)])
+def test_config_parity_scaled(gpu_ctx, oracle, name, n_rays, T):
+    s = scenes.make_config(name, batch_count=T, n_rays=n_rays)
+    g = run_gpu(gpu_ctx, s)
+    o = oracle.run_frame(s, threads=8)
+    assert_rt_equal(g, o, s)
+    assert_pm_equal(g, o, s)
+    assert_settings(g, o, exact=False)
+
+
+@pytest.mark.parametrize("n_targets", [1, 3, 31, 32, 40, 70])
+def test_target_group_boundaries(gpu_ctx, oracle, n_targets):
+    """query slots are processed 32 at a time (slot 0 = echo): cover the group edges."""
+    s = scenes.make_scene(n_aabb=60, n_obb=max(24, n_targets), n_sphere=20, n_targets=n_targets, seed=77 + n_targets,
+                          n_rays=384, max_hits=5, batch_count=2)
+    g = run_gpu(gpu_ctx, s)
+    o = oracle.run_frame(s, threads=8)
+    assert_rt_equal(g, o, s)
+    assert_pm_equal(g, o, s)
+    assert o.muffle_totals.sum() > 0          # the case exercises visible targets
+
+
+@pytest.mark.parametrize("na,no,ns", [(6, 0, 0), (0, 3, 0), (0, 0, 5), (7, 1, 0), (130, 66, 129), (0, 0, 0)])
+def test_ragged_and_empty_collider_lists(gpu_ctx, oracle, na, no, ns):
+    rng = np.random.default_rng(5)
+    base = scenes.make_scene(n_aabb=max(na, 6), n_obb=max(no, 1), n_sphere=max(ns, 1), n_targets=1, seed=9,
+                             n_rays=256, max_hits=4)
+    s = scenes.Scene(aabbs=base.aabbs[:na], obbs=base.obbs[:no], spheres=base.spheres[:ns], targets=base.targets,
+                     ray_directions=base.ray_directions, max_hits_per_ray=4)
+    g = run_gpu(gpu_ctx, s)
+    o = oracle.run_frame(s)
+    assert_rt_equal(g, o, s)
+    assert_pm_equal(g, o, s)
+
+
+def test_muffle_distance_gate_and_short_life(gpu_ctx, oracle):
+    s = scenes.make_config("c2", n_rays=1024)
+    s.max_muffle_hit_distance = 20.0       # RT:168 gate actually filters
+    s.max_ray_life = 30.0                  # RT:179 life <= 0 ends rays early
+    g = run_gpu(gpu_ctx, s)
+    o = oracle.run_frame(s, threads=8)
+    assert_rt_equal(g, o, s)
+    assert 0 < o.counters["muffle_queries"] < o.counters["echo_queries"]
+    assert np.bincount(o.hit_counts, minlength=9)[1:8].sum() > 0
+
+
+def test_max_hits_255_and_1(gpu_ctx, oracle):
+    for H in (1, 255):
+        s = scenes.make_config("c2", n_rays=64)
+        s.max_hits_per_ray = H
+        g = run_gpu(gpu_ctx, s)
+        o = oracle.run_frame(s, threads=8)
+        assert_rt_equal(g, o, s)
+
+
+def test_u16_muffle_wrap_q8(gpu_ctx, oracle):
+    """An open scene with > 65535 visible muffle rays per slot: the u16 table wraps like C# unchecked ushort."""
+    floor = aabb((0, -3, 0), (60, 0.5, 60))
+    s = micro_scene(aabbs=[floor], targets=((5, 0, 5),), H=1, max_muffle=1e4, max_life=1e4)
+    s.ray_directions = scenes.fibonacci_directions(150000)
+    g = run_gpu(gpu_ctx, s)
+    o = oracle.run_frame(s, threads=8)
+    assert o.muffle_totals[0] > 65535
+    assert_rt_equal(g, o, s)
+    assert g.muffle[0] == o.muffle_totals[0] % 65536
+
+
+def test_reverb_sequential_fp32_is_bit_exact(gpu_ctx, oracle):
+    s = scenes.make_config("c2", n_rays=4096, batch_count=2)
+    native.upload(gpu_ctx, s)
+    g = gpu_ctx.run_frame(s, flags=native.FRAME_REVERB_SEQ_FP32)
+    o = oracle.run_frame(s, threads=8)
+    assert_settings(g, o, exact=True)
+    g2 = gpu_ctx.run_frame(s, flags=0)
+    assert_settings(g2, o, exact=False)
+
+
+def test_determinism_and_no_counter_variant(gpu_ctx, oracle):
+    s = scenes.make_config("c3", n_rays=512)
+    native.upload(gpu_ctx, s)
+    a = gpu_ctx.run_frame(s, flags=0)
+    b = gpu_ctx.run_frame(s, flags=0)
+    c = gpu_ctx.run_frame(s, flags=C)
+    for x in (b, c):
+        np.testing.assert_array_equal(a.echo, x.echo)
+        np.testing.assert_array_equal(a.hit_ids, x.hit_ids)
+        np.testing.assert_array_equal(a.muffle, x.muffle)
+        np.testing.assert_array_equal(a.permeation.view(np.uint32), x.permeation.view(np.uint32))
+        np.testing.assert_array_equal(a.permeation_sum, x.permeation_sum)          # deterministic reduction
+        np.testing.assert_array_equal(a.settings.view(np.uint8), x.settings.view(np.uint8))
+
+
+def test_sharded_contexts_merge_to_the_unsharded_result(art_lib, oracle):
+    """G contexts each trace an interleaved slice; merged partials == single-context frame."""
+    s = scenes.make_config("c2", n_rays=3000, batch_count=4)
+    with native.Context(0) as full:
+        native.upload(full, s)
+        ref = full.run_frame(s, flags=C)
+    blobs, parts = [], []
+    G, chunk = 3, 128
+    for r in range(G):
+        with native.Context(0) as ctx:
+            native.upload(ctx, s)
+            ctx.set_ray_shard(r, G, chunk)
+            res = ctx.run_frame(s, flags=native.FRAME_PARTIALS_ONLY | C)
+            blobs.append(ctx.get_partials(s.n_targets, s.batch_count))
+            parts.append((r, res))
+    merged = native.finalize(native.merge_partials(blobs), s, s.n_rays)
+    np.testing.assert_array_equal(merged.muffle, ref.muffle)
+    np.testing.assert_array_equal(merged.muffle_totals, ref.muffle_totals)
+    np.testing.assert_array_equal(merged.permeation.view(np.uint32), ref.permeation.view(np.uint32))
+    np.testing.assert_array_equal(merged.permeation_sum, ref.permeation_sum)
+    np.testing.assert_array_equal(merged.settings.view(np.uint8), ref.settings.view(np.uint8))
+    # per-ray outputs: scatter the shards' local arrays back to global ray order
+    H = s.max_hits_per_ray
+    echo = np.zeros_like(ref.echo)
+    for r, res in parts:
+        n_local = len(res.hit_counts)
+        j = np.arange(n_local)
+        gidx = ((j // chunk) * G + r) * chunk + j % chunk
+        echo.reshape(-1, H)[gidx] = res.echo.reshape(-1, H)
+    np.testing.assert_array_equal(echo, ref.echo)
+
+
+def test_async_handle_semantics(gpu_ctx):
+    s = scenes.make_config("c2", n_rays=512)
+    native.upload(gpu_ctx, s)
+    h = gpu_ctx.schedule(s)
+    with pytest.raises(native.ArtError) as e:       # one frame in flight per context (ART:95-97)
+        gpu_ctx.schedule(s)
+    assert e.value.code == native.ART_E_PENDING
+    gpu_ctx.complete(h)
+    assert gpu_ctx.is_completed(h)
+
+
+def test_argument_errors(gpu_ctx):
+    s = scenes.make_config("c2", n_rays=64)
+    with pytest.raises(native.ArtError) as e:       # nothing uploaded yet
+        gpu_ctx.run_frame(s)
+    assert e.value.code in (native.ART_E_STATE,)
+    native.upload(gpu_ctx, s)
+    bad = scenes.make_config("c2", n_rays=64)
+    bad.targets = np.zeros((0, 3), np.float32)      # TotalAudioTargets = 0: RT:63 divides by zero
+    with pytest.raises(native.ArtError) as e:
+        gpu_ctx.run_frame(bad)
+    assert e.value.code == native.ART_E_ARG
+
+
+def test_device_fibonacci_matches_host_generator(gpu_ctx, oracle):
+    for n in (314, 65536):
+        gpu_ctx.generate_fibonacci_rays(n)
+        d = gpu_ctx.get_rays()
+        ref = oracle.fibonacci_directions(n)
+        mism = int((d != ref).any(axis=1).sum())
+        assert mism <= n // 2000, f"{mism} of {n} directions differ (double cos/sin last-ulp differences only)"
+        assert d[0, 1] == 0x3C00 and d[-1, 1] == 0xBC00
+
+
+# ---------------------------------------------------------------- full BASELINE sizes
+def test_c2_full_size_parity(gpu_ctx, oracle):
+    s = scenes.make_config("c2")                    # 65,536 rays x 8 bounces vs 448 colliders
+    g = run_gpu(gpu_ctx, s)
+    o = oracle.run_frame(s, threads=8)
+    assert_rt_equal(g, o, s)
+    assert_pm_equal(g, o, s)
+    assert_settings(g, o, exact=False)
+
+
+def test_c3_full_size_properties(gpu_ctx, oracle):
+    """C3 at full size (1M rays x 12 x 64 targets x 4096 colliders): size-independent properties + a sampled
+    oracle comparison (the oracle needs hours for the whole frame)."""
+    s = scenes.make_config("c3", batch_count=8)
+    native.upload(gpu_ctx, s)
+    g = gpu_ctx.run_frame(s, jobs=native.JOB_RAYTRACE, flags=0, want=("echo", "hit_counts", "hit_ids"))
+    H = s.max_hits_per_ray
+    assert g.counters["segmentHits"] == int(g.hit_counts.astype(np.int64).sum())
+    assert g.hit_counts.max() <= H
+    ids = g.hit_ids.reshape(-1, H)
+    filled = (ids != 0)
+    np.testing.assert_array_equal(filled.sum(axis=1), g.hit_counts)            # ids are written exactly per hit
+    assert not (g.echo.reshape(-1, H)[~filled] != 0).any()                      # echo only where a hit exists
+    assert int(g.muffle_totals.sum()) == int(g.muffle.astype(np.int64).sum()) or g.muffle_totals.max() > 65535
+    # sampled oracle parity: 3 windows of 64 rays
+    for first in (0, 524288, 1048576 - 64):
+        o = oracle.trace_range(s, first, 64, threads=8)
+        sl = slice(first * H, (first + 64) * H)
+        np.testing.assert_array_equal(g.hit_ids[sl], o.hit_ids[sl])
+        np.testing.assert_array_equal(g.echo[sl], o.echo[sl])
+        np.testing.assert_array_equal(g.hit_counts[first:first + 64], o.hit_counts[first:first + 64])
