@@ -1,9 +1,18 @@
 // intersect.cuh -- ray / collider primitive tests shared by K1 (trace) and K2 (permeation).
 // RT = Assets/C# Scripts/Jobs/AudioRaytracerJobBatched.cs, PM = .../AudioPermeationJobBatched.cs.
+//
+// Every test is split into a FAST part that runs for all lanes (a handful of un-fused FP32 ops
+// that decide "certainly a miss" with exactly the reference's own comparison), and an EXACT part
+// (IEEE sqrt / divisions / quaternion rotations in the reference's operation order) kept out of
+// line (__noinline__) so that the hot loops stay small enough for the instruction caches; the
+// exact part only runs for the few lanes whose ray actually comes near the collider.
 #pragma once
 #include "um_math.cuh"
 
 namespace art {
+
+__device__ __forceinline__ float quiet_nan() { return __int_as_float(0x7FC00000); }
+__device__ __forceinline__ float pos_inf() { return __int_as_float(0x7F800000); }
 
 // ---- slab kernels -------------------------------------------------------------------------------
 // CLS 0..7: bit k set <=> invDir component k is negative (near plane = max). CLS 8: generic form
@@ -39,36 +48,36 @@ __device__ __forceinline__ bool slab_hit(float tNear, float tFar, float& dist)
     return !(tNear > tFar || tFar < 0.0f);
 }
 
-// RT:323-355 with a = dot(d,d) hoisted; cc = dot(oc,oc) - R*R
-__device__ __forceinline__ bool sphere_hit(f3 oc, float cc, f3 d, float fourA, float twoA, float& dist)
+// ---- sphere (RT:323-355 == PM:182-214) ----------------------------------------------------------
+// Reference: b = 2*dot(oc,d); disc = b*b - 4*a*c; miss if disc < 0.
+// Scaling by 2 and 4 is exact, so  disc < 0  <=>  dot*dot < a*c  (both products rounded once, exactly
+// as in the reference up to the exact power-of-two scale): that comparison is the fast reject.
+__device__ __forceinline__ bool sphere_fast_miss(f3 oc, float cc, f3 d, float a)
 {
-    float b = mulr(2.0f, dot3(oc, d));
-    float disc = subr(mulr(b, b), mulr(fourA, cc));
-    dist = 0.0f;
-    if (disc < 0.0f) return false;
-    float sq = sqrtr(disc);
-    float t0 = divr(subr(-b, sq), twoA);
-    if (t0 >= 0.0f) { dist = t0; return true; }
-    float t1 = divr(addr(-b, sq), twoA);
-    if (t1 >= 0.0f) { dist = t1; return true; }
-    return false;
+    const float dt = dot3(oc, d);
+    return mulr(dt, dt) < mulr(a, cc);
+}
+// Exact distance in the reference's operation order, or NaN for a miss (NaN fails every `dist < x`).
+static __device__ __noinline__ float sphere_dist_exact(float ocx, float ocy, float ocz, float cc, float dx, float dy, float dz, float a)
+{
+    const float b = mulr(2.0f, dot3(mk3(ocx, ocy, ocz), mk3(dx, dy, dz)));     // RT:327
+    const float disc = subr(mulr(b, b), mulr(mulr(4.0f, a), cc));              // RT:329
+    if (disc < 0.0f) return quiet_nan();
+    const float sq = sqrtr(disc);
+    const float twoA = mulr(2.0f, a);
+    const float t0 = divr(subr(-b, sq), twoA);                                 // RT:338
+    if (t0 >= 0.0f) return t0;
+    const float t1 = divr(addr(-b, sq), twoA);                                 // RT:339
+    if (t1 >= 0.0f) return t1;
+    return quiet_nan();
 }
 
-// RT:314-320 with the per-origin part (lo = q*(o-C)) supplied by the caller.
-__device__ __forceinline__ bool obb_hit(f4 q, f3 lo, f3 h, f3 d, float& dist)
-{
-    f3 ld = qmul3(q, d);
-    float ix = rcpr(ld.x), iy = rcpr(ld.y), iz = rcpr(ld.z);
-    float tNear, tFar;
-    slab<8>(subr(-h.x, lo.x), subr(-h.y, lo.y), subr(-h.z, lo.z), subr(h.x, lo.x), subr(h.y, lo.y), subr(h.z, lo.z),
-            ix, iy, iz, tNear, tFar);
-    return slab_hit(tNear, tFar, dist);
-}
-
-// Conservative rejection of an OBB by its bounding sphere: true only if the exact test is
-// certain to report a miss. pc = o - C, cB = |pc|^2 - Rb^2 (Rb inflated), dd = dot(d,d).
-// The ray's line misses the sphere when (pc.d)^2 - dd*cB < 0; the tolerance term covers the FP32
-// cancellation error of that difference; a sphere behind an outside origin is missed as well.
+// ---- OBB (RT:314-320) ----------------------------------------------------------------------------
+// Conservative rejection by the bounding sphere: true only if the exact test is certain to report a
+// miss. pc = o - C, cB = |pc|^2 - Rb^2 (Rb inflated), dd = dot(d,d). The ray's line misses the sphere
+// when (pc.d)^2 - dd*cB < 0; the tolerance term covers the FP32 cancellation error of that
+// difference; a sphere behind an outside origin is missed as well. FMAs are fine here: the outcome
+// only decides whether the exact test runs, and it is skipped only when it must fail.
 __device__ __forceinline__ bool obb_sure_miss(f3 pc, float cB, f3 d, float dd)
 {
     float bq = fmaf(pc.z, d.z, fmaf(pc.y, d.y, pc.x * d.x));
@@ -82,6 +91,65 @@ __device__ __forceinline__ float obb_cull_c(f3 pc, f3 h)
     float rb2 = fmaf(h.z, h.z, fmaf(h.y, h.y, h.x * h.x));
     float pp = fmaf(pc.z, pc.z, fmaf(pc.y, pc.y, pc.x * pc.x));
     return pp - (rb2 * 1.05f + 1e-3f) - 1e-4f * pp;
+}
+// Exact OBB distance (or NaN): local = q*(o-C) is computed here so that callers keep only pc live.
+static __device__ __noinline__ float obb_dist_exact(float qx, float qy, float qz, float qw, float pcx, float pcy, float pcz,
+                                             float hx, float hy, float hz, float dx, float dy, float dz)
+{
+    f4 q; q.x = qx; q.y = qy; q.z = qz; q.w = qw;
+    const f3 lo = qmul3(q, mk3(pcx, pcy, pcz));                                // RT:316
+    const f3 ld = qmul3(q, mk3(dx, dy, dz));                                   // RT:317
+    const float ix = rcpr(ld.x), iy = rcpr(ld.y), iz = rcpr(ld.z);             // RT:289
+    float tNear, tFar, dist;
+    slab<8>(subr(-hx, lo.x), subr(-hy, lo.y), subr(-hz, lo.z), subr(hx, lo.x), subr(hy, lo.y), subr(hz, lo.z),
+            ix, iy, iz, tNear, tFar);
+    return slab_hit(tNear, tFar, dist) ? dist : quiet_nan();
+}
+
+// ---- permeation variants (PM:265-328) -------------------------------------------------------------
+__device__ __forceinline__ float slab_loss(float tEnter, float tExit, float dens)
+{
+    if (tEnter > tExit || tExit < 0.0f) return 0.0f;                            // PM:281
+    const float enter = um_max(tEnter, 0.0f);                                   // PM:286
+    return mulr(um_max(0.0f, subr(tExit, enter)), dens);                        // PM:287
+}
+// PM:303-328 (assumes a unit direction): b = dot(oc,d); disc = b*b - c; miss if disc < 0
+__device__ __forceinline__ bool sphere_loss_fast_miss(f3 oc, float cc, f3 d, float& b)
+{
+    b = dot3(oc, d);
+    return mulr(b, b) < cc;      // <=> b*b - c < 0 (the rounded difference keeps the sign of the exact one)
+}
+static __device__ __noinline__ float sphere_loss_exact(float b, float cc, float dens)
+{
+    const float disc = subr(mulr(b, b), cc);
+    if (disc < 0.0f) return 0.0f;
+    const float sqrtD = sqrtr(disc);
+    const float tEnter = subr(-b, sqrtD);
+    const float tExit = addr(-b, sqrtD);
+    if (tExit < 0.0f) return 0.0f;
+    const float enter = um_max(tEnter, 0.0f);
+    return mulr(um_max(0.0f, subr(tExit, enter)), dens);
+}
+// PM:294-300
+static __device__ __noinline__ float obb_loss_exact(float qx, float qy, float qz, float qw, float pcx, float pcy, float pcz,
+                                             float hx, float hy, float hz, float dx, float dy, float dz, float dens)
+{
+    f4 q; q.x = qx; q.y = qy; q.z = qz; q.w = qw;
+    const f3 lo = qmul3(q, mk3(pcx, pcy, pcz));
+    const f3 ld = qmul3(q, mk3(dx, dy, dz));
+    const float ix = rcpr(ld.x), iy = rcpr(ld.y), iz = rcpr(ld.z);
+    float tEnter, tExit;
+    slab<8>(subr(-hx, lo.x), subr(-hy, lo.y), subr(-hz, lo.z), subr(hx, lo.x), subr(hy, lo.y), subr(hz, lo.z),
+            ix, iy, iz, tEnter, tExit);
+    return slab_loss(tEnter, tExit, dens);
+}
+template <int CLS>
+__device__ __forceinline__ float aabb_loss(float4 A, float2 B, f3 P, float ix, float iy, float iz, float dens)
+{
+    float tEnter, tExit;
+    slab<CLS>(subr(A.x, P.x), subr(A.y, P.y), subr(A.z, P.z), subr(A.w, P.x), subr(B.x, P.y), subr(B.y, P.z),
+              ix, iy, iz, tEnter, tExit);
+    return slab_loss(tEnter, tExit, dens);
 }
 
 }  // namespace art

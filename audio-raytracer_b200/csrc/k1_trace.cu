@@ -134,46 +134,37 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a)
             uint32_t bkey = 0xFFFFFFFFu;   // (typeOrder << 28) | index ; typeOrder sphere 0, AABB 1, OBB 2
             {
                 const float dd = dot3(d, d);                 // RT:326
-                const float fourA = mulr(4.0f, dd);          // RT:329  4 * a (* c)
-                const float twoA = mulr(2.0f, dd);           // RT:338  2.0f * a
                 for (int base = 0; base < nsPad; base += SC_S) {
+                    f3 oc[RS]; float cc[RS];
+                    uint32_t need = 0;
 #pragma unroll
                     for (int r = 0; r < RS; r++) {
-                        const int idx = base + r * 32 + lane;
-                        const float4 s = gv.sph[idx];
-                        f3 oc = sub3(o, mk3(s.x, s.y, s.z));                 // RT:325
-                        float cc = subr(dot3(oc, oc), s.w);                  // RT:328
-                        float dist;
-                        if (sphere_hit(oc, cc, d, fourA, twoA, dist) && dist < best) { best = dist; bkey = (uint32_t)idx; }
+                        const float4 s = gv.sph[base + r * 32 + lane];
+                        oc[r] = sub3(o, mk3(s.x, s.y, s.z));                   // RT:325
+                        cc[r] = subr(dot3(oc[r], oc[r]), s.w);                 // RT:328
+                        if (!sphere_fast_miss(oc[r], cc[r], d, dd)) need |= 1u << r;
+                    }
+                    if (need) {
+#pragma unroll
+                        for (int r = 0; r < RS; r++)
+                            if ((need >> r) & 1u) {
+                                const float dist = sphere_dist_exact(oc[r].x, oc[r].y, oc[r].z, cc[r], d.x, d.y, d.z, dd);
+                                if (dist < best) { best = dist; bkey = (uint32_t)(base + r * 32 + lane); }
+                            }
                     }
                 }
                 const float ix = rcpr(d.x), iy = rcpr(d.y), iz = rcpr(d.z);  // RT:289
-                const int cls = slab_class(ix, iy, iz);
-                auto aabb_pass = [&](auto clsTag) {
-                    constexpr int CLS = decltype(clsTag)::value;
-                    for (int base = 0; base < naPad; base += SC_A) {
+                for (int base = 0; base < naPad; base += SC_A) {
 #pragma unroll
-                        for (int r = 0; r < RA; r++) {
-                            const int idx = base + r * 32 + lane;
-                            const float4 A = gv.aabbA[idx];
-                            const float2 B = gv.aabbB[idx];
-                            float tNear, tFar, dist;
-                            slab<CLS>(subr(A.x, o.x), subr(A.y, o.y), subr(A.z, o.z), subr(A.w, o.x), subr(B.x, o.y), subr(B.y, o.z),
-                                      ix, iy, iz, tNear, tFar);              // RT:291-298
-                            if (slab_hit(tNear, tFar, dist) && dist < best) { best = dist; bkey = (1u << 28) | (uint32_t)idx; }
-                        }
+                    for (int r = 0; r < RA; r++) {
+                        const int idx = base + r * 32 + lane;
+                        const float4 A = gv.aabbA[idx];
+                        const float2 B = gv.aabbB[idx];
+                        float tNear, tFar, dist;
+                        slab<8>(subr(A.x, o.x), subr(A.y, o.y), subr(A.z, o.z), subr(A.w, o.x), subr(B.x, o.y), subr(B.y, o.z),
+                                ix, iy, iz, tNear, tFar);                      // RT:291-298
+                        if (slab_hit(tNear, tFar, dist) && dist < best) { best = dist; bkey = (1u << 28) | (uint32_t)idx; }
                     }
-                };
-                switch (cls) {
-                case 0: aabb_pass(std::integral_constant<int, 0>{}); break;
-                case 1: aabb_pass(std::integral_constant<int, 1>{}); break;
-                case 2: aabb_pass(std::integral_constant<int, 2>{}); break;
-                case 3: aabb_pass(std::integral_constant<int, 3>{}); break;
-                case 4: aabb_pass(std::integral_constant<int, 4>{}); break;
-                case 5: aabb_pass(std::integral_constant<int, 5>{}); break;
-                case 6: aabb_pass(std::integral_constant<int, 6>{}); break;
-                case 7: aabb_pass(std::integral_constant<int, 7>{}); break;
-                default: aabb_pass(std::integral_constant<int, 8>{}); break;
                 }
                 for (int base = 0; base < noPad; base += SC_O) {
 #pragma unroll
@@ -185,9 +176,8 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a)
                         const f3 h = mk3(c4.w, h2.x, h2.y);
                         const f3 pc = sub3(o, mk3(c4.x, c4.y, c4.z));        // RT:316 rayOrigin - Center
                         if (!obb_sure_miss(pc, obb_cull_c(pc, h), d, dd)) {
-                            f4 q; q.x = q4.x; q.y = q4.y; q.z = q4.z; q.w = q4.w;
-                            float dist;
-                            if (obb_hit(q, qmul3(q, pc), h, d, dist) && dist < best) { best = dist; bkey = (2u << 28) | (uint32_t)idx; }
+                            const float dist = obb_dist_exact(q4.x, q4.y, q4.z, q4.w, pc.x, pc.y, pc.z, h.x, h.y, h.z, d.x, d.y, d.z);
+                            if (dist < best) { best = dist; bkey = (2u << 28) | (uint32_t)idx; }
                         }
                     }
                 }
@@ -293,12 +283,15 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a)
                         m &= m - 1;
                         const float4 r0 = rec[q], r1 = rec[32 + q];
                         const f3 qd = mk3(r1.x, r1.y, r1.z);
-                        const float fourA = mulr(4.0f, r1.w), twoA = mulr(2.0f, r1.w);
-                        uint32_t hm = 0;
+                        uint32_t need = 0, hm = 0;
 #pragma unroll
-                        for (int r = 0; r < RS; r++) {
-                            float dist;
-                            if (sphere_hit(oc[r], cc[r], qd, fourA, twoA, dist) && dist < r0.w) hm |= 1u << r;
+                        for (int r = 0; r < RS; r++)
+                            if (!sphere_fast_miss(oc[r], cc[r], qd, r1.w)) need |= 1u << r;
+                        if (need) {
+#pragma unroll
+                            for (int r = 0; r < RS; r++)
+                                if ((need >> r) & 1u)
+                                    if (sphere_dist_exact(oc[r].x, oc[r].y, oc[r].z, cc[r], qd.x, qd.y, qd.z, r1.w) < r0.w) hm |= 1u << r;
                         }
                         if (__any_sync(kFull, hm != 0)) {
                             hm = owner_filter<RS>(hm, a.at.ownS, base, lane, __float_as_int(rec[64 + q].x));
@@ -367,16 +360,14 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a)
                 }
                 // ---- OBBs (RT:388-395 / 434-445)
                 for (int base = 0; base < noPad && open; base += SC_O) {
-                    f4 oq[RO]; f3 pc[RO], lo[RO], hh[RO]; float cB[RO];
+                    float4 oq[RO]; f3 pc[RO], hh[RO]; float cB[RO];
 #pragma unroll
                     for (int r = 0; r < RO; r++) {
-                        const float4 q4 = gv.obbQ[base + r * 32 + lane];
+                        oq[r] = gv.obbQ[base + r * 32 + lane];
                         const float4 c4 = gv.obbC[base + r * 32 + lane];
                         const float2 h2 = gv.obbH[base + r * 32 + lane];
-                        oq[r].x = q4.x; oq[r].y = q4.y; oq[r].z = q4.z; oq[r].w = q4.w;
                         hh[r] = mk3(c4.w, h2.x, h2.y);
                         pc[r] = sub3(Pp, mk3(c4.x, c4.y, c4.z));
-                        lo[r] = qmul3(oq[r], pc[r]);
                         cB[r] = obb_cull_c(pc[r], hh[r]);
                     }
                     uint32_t m = open;
@@ -385,13 +376,16 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a)
                         m &= m - 1;
                         const float4 r0 = rec[q], r1 = rec[32 + q];
                         const f3 qd = mk3(r1.x, r1.y, r1.z);
-                        uint32_t hm = 0;
+                        uint32_t need = 0, hm = 0;
 #pragma unroll
-                        for (int r = 0; r < RO; r++) {
-                            if (!obb_sure_miss(pc[r], cB[r], qd, r1.w)) {
-                                float dist;
-                                if (obb_hit(oq[r], lo[r], hh[r], qd, dist) && dist < r0.w) hm |= 1u << r;
-                            }
+                        for (int r = 0; r < RO; r++)
+                            if (!obb_sure_miss(pc[r], cB[r], qd, r1.w)) need |= 1u << r;
+                        if (need) {
+#pragma unroll
+                            for (int r = 0; r < RO; r++)
+                                if ((need >> r) & 1u)
+                                    if (obb_dist_exact(oq[r].x, oq[r].y, oq[r].z, oq[r].w, pc[r].x, pc[r].y, pc[r].z,
+                                                       hh[r].x, hh[r].y, hh[r].z, qd.x, qd.y, qd.z) < r0.w) hm |= 1u << r;
                         }
                         if (__any_sync(kFull, hm != 0)) {
                             hm = owner_filter<RO>(hm, a.at.ownO, base, lane, __float_as_int(rec[64 + q].x));

@@ -7,9 +7,10 @@
 // (PM:225-261, no early exit, no distance clip -- quirk Q7).
 //
 // Mapping: one warp owns one ray, lanes own colliders (same planes and super-chunks as K1).
-// Targets are processed in blocks of TB: the origin-dependent part of each collider test is
-// computed once per super-chunk and reused for the TB targets, each lane keeps TB partial sums,
-// and every target's total is formed by a fixed-order butterfly (deterministic).
+// Targets are processed in blocks of TBK: the origin-dependent part of each collider test is
+// computed once per super-chunk and reused for the TBK targets of the block; every lane keeps one
+// partial sum per target in shared memory (acc[target][lane], conflict free), and each target's total
+// is formed by one lane adding the 32 partials in lane order -- a fixed order, hence deterministic.
 //
 // What the reference finally KEEPS of all this work is, per batch, only the values of the last
 // hitting ray (PM:85 overwrites, quirk Q5/Q6). perm_last_kernel recomputes exactly that ray with
@@ -24,50 +25,10 @@
 
 namespace art {
 
-constexpr int TB = 8;   // targets per register block
-
-
-// PM:265-288 given tEnter/tExit
-__device__ __forceinline__ float slab_loss(float tEnter, float tExit, float dens)
-{
-    if (tEnter > tExit || tExit < 0.0f) return 0.0f;
-    const float enter = um_max(tEnter, 0.0f);
-    return mulr(um_max(0.0f, subr(tExit, enter)), dens);
-}
-// PM:303-328 (assumes a unit direction: b = dot(oc, d), disc = b*b - c)
-__device__ __forceinline__ float sphere_loss(f3 oc, float cc, f3 d, float dens)
-{
-    const float b = dot3(oc, d);
-    const float disc = subr(mulr(b, b), cc);
-    if (disc < 0.0f) return 0.0f;
-    const float sqrtD = sqrtr(disc);
-    const float tEnter = subr(-b, sqrtD);
-    const float tExit = addr(-b, sqrtD);
-    if (tExit < 0.0f) return 0.0f;
-    const float enter = um_max(tEnter, 0.0f);
-    return mulr(um_max(0.0f, subr(tExit, enter)), dens);
-}
-// PM:294-300 with lo = q*(o-C) supplied
-__device__ __forceinline__ float obb_loss(f4 q, f3 lo, f3 h, f3 d, float dens)
-{
-    const f3 ld = qmul3(q, d);
-    const float ix = rcpr(ld.x), iy = rcpr(ld.y), iz = rcpr(ld.z);
-    float tEnter, tExit;
-    slab<8>(subr(-h.x, lo.x), subr(-h.y, lo.y), subr(-h.z, lo.z), subr(h.x, lo.x), subr(h.y, lo.y), subr(h.z, lo.z),
-            ix, iy, iz, tEnter, tExit);
-    return slab_loss(tEnter, tExit, dens);
-}
-
-template <int CLS>
-__device__ __forceinline__ float aabb_loss(float4 A, float2 B, f3 P, float ix, float iy, float iz, float dens)
-{
-    float tEnter, tExit;
-    slab<CLS>(subr(A.x, P.x), subr(A.y, P.y), subr(A.z, P.z), subr(A.w, P.x), subr(B.x, P.y), subr(B.y, P.z),
-              ix, iy, iz, tEnter, tExit);
-    return slab_loss(tEnter, tExit, dens);
-}
-
+constexpr int TBK = 16;          // targets per accumulator block
+constexpr int kAccStride = 33;   // acc[t * 33 + lane]: conflict free per target and in the final per-lane sums
 constexpr int kPermRecFloat4PerWarp = 96;
+constexpr int kPermWarpBytes = kPermRecFloat4PerWarp * 16 + ((TBK * kAccStride * 4 + 15) / 16) * 16;
 
 template <bool SMEM>
 __global__ void __launch_bounds__(kThreads, 1) permeation_kernel(const PermArgs a)
@@ -85,7 +46,8 @@ __global__ void __launch_bounds__(kThreads, 1) permeation_kernel(const PermArgs 
         geomBase = p;
         p += a.L.bytes;
     }
-    float4* rec = reinterpret_cast<float4*>(p) + warp * kPermRecFloat4PerWarp;
+    float4* rec = reinterpret_cast<float4*>(p + (size_t)warp * kPermWarpBytes);
+    float* acc = reinterpret_cast<float*>(p + (size_t)warp * kPermWarpBytes + kPermRecFloat4PerWarp * 16);
     const GeomView gv = make_view(geomBase, a.L);
     const int nsPad = a.L.nsPad, naPad = a.L.naPad, noPad = a.L.noPad;
     const f3 RayOrigin = mk3(a.ox, a.oy, a.oz);
@@ -103,18 +65,26 @@ __global__ void __launch_bounds__(kThreads, 1) permeation_kernel(const PermArgs 
         const f3 o = RayOrigin;
 
         // ================= ShootRayCast, distance only (PM:101-141) =================
-        float best = __int_as_float(0x7F800000);   // math.INFINITY
+        float best = pos_inf();   // math.INFINITY
         {
             const float dd = dot3(d, d);
-            const float fourA = mulr(4.0f, dd), twoA = mulr(2.0f, dd);
             for (int base = 0; base < nsPad; base += SC_S) {
+                f3 oc[RS]; float cc[RS];
+                uint32_t need = 0;
 #pragma unroll
                 for (int r = 0; r < RS; r++) {
                     const float4 s = gv.sph[base + r * 32 + lane];
-                    const f3 oc = sub3(o, mk3(s.x, s.y, s.z));
-                    const float cc = subr(dot3(oc, oc), s.w);
-                    float dist;
-                    if (sphere_hit(oc, cc, d, fourA, twoA, dist) && dist < best) best = dist;
+                    oc[r] = sub3(o, mk3(s.x, s.y, s.z));
+                    cc[r] = subr(dot3(oc[r], oc[r]), s.w);
+                    if (!sphere_fast_miss(oc[r], cc[r], d, dd)) need |= 1u << r;
+                }
+                if (need) {
+#pragma unroll
+                    for (int r = 0; r < RS; r++)
+                        if ((need >> r) & 1u) {
+                            const float dist = sphere_dist_exact(oc[r].x, oc[r].y, oc[r].z, cc[r], d.x, d.y, d.z, dd);
+                            if (dist < best) best = dist;
+                        }
                 }
             }
             const float ix = rcpr(d.x), iy = rcpr(d.y), iz = rcpr(d.z);
@@ -139,16 +109,15 @@ __global__ void __launch_bounds__(kThreads, 1) permeation_kernel(const PermArgs 
                     const f3 pc = sub3(o, mk3(c4.x, c4.y, c4.z));
                     if (!obb_sure_miss(pc, obb_cull_c(pc, h), d, dd)) {
                         const float4 qi = a.at.obbQinv[idx];                               // PM:174 (quirk Q4)
-                        f4 q; q.x = qi.x; q.y = qi.y; q.z = qi.z; q.w = qi.w;
-                        float dist;
-                        if (obb_hit(q, qmul3(q, pc), h, d, dist) && dist < best) best = dist;
+                        const float dist = obb_dist_exact(qi.x, qi.y, qi.z, qi.w, pc.x, pc.y, pc.z, h.x, h.y, h.z, d.x, d.y, d.z);
+                        if (dist < best) best = dist;
                     }
                 }
             }
         }
         best = warp_min_f(best);
         if (lane == 0) a.firstHitDist[j] = best;
-        if (!(best != __int_as_float(0x7F800000))) continue;                               // PM:140 / PM:58
+        if (!(best != pos_inf())) continue;                                                // PM:140 / PM:58
         nHitRays++;
         if (lane == 0) atomicMax(&a.lastHitRay[rayIndex / a.batchSize], rayIndex);
 
@@ -168,10 +137,11 @@ __global__ void __launch_bounds__(kThreads, 1) permeation_kernel(const PermArgs 
             }
             __syncwarp();
             const int nIn = min(32, Na - g * 32);
-            for (int sb = 0; sb < nIn; sb += TB) {
-                float acc[TB];
+            for (int t0 = 0; t0 < nIn; t0 += TBK) {
+                const int nT = min(TBK, nIn - t0);
 #pragma unroll
-                for (int t = 0; t < TB; t++) acc[t] = 0.0f;
+                for (int t = 0; t < TBK; t++) acc[t * kAccStride + lane] = 0.0f;
+                __syncwarp();
 
                 for (int base = 0; base < nsPad; base += SC_S) {
                     f3 oc[RS]; float cc[RS], dn[RS];
@@ -182,77 +152,88 @@ __global__ void __launch_bounds__(kThreads, 1) permeation_kernel(const PermArgs 
                         cc[r] = subr(dot3(oc[r], oc[r]), s.w);
                         dn[r] = a.densS[base + r * 32 + lane];
                     }
+                    for (int t = 0; t < nT; t++) {
+                        const float4 r1 = rec[32 + t0 + t];
+                        const f3 qd = mk3(r1.x, r1.y, r1.z);
+                        float bb[RS];
+                        uint32_t need = 0;
 #pragma unroll
-                    for (int t = 0; t < TB; t++) {
-                        if (sb + t < nIn) {
-                            const float4 r1 = rec[32 + sb + t];
-                            const f3 qd = mk3(r1.x, r1.y, r1.z);
+                        for (int r = 0; r < RS; r++)
+                            if (!sphere_loss_fast_miss(oc[r], cc[r], qd, bb[r])) need |= 1u << r;
+                        if (need) {
+                            float s = 0.0f;
 #pragma unroll
-                            for (int r = 0; r < RS; r++) acc[t] = addr(acc[t], sphere_loss(oc[r], cc[r], qd, dn[r]));
+                            for (int r = 0; r < RS; r++)
+                                if ((need >> r) & 1u) s = addr(s, sphere_loss_exact(bb[r], cc[r], dn[r]));
+                            acc[t * kAccStride + lane] = addr(acc[t * kAccStride + lane], s);
                         }
                     }
                 }
                 for (int base = 0; base < naPad; base += SC_A) {
-                    float4 A[RA]; float2 B[RA]; float dn[RA];
+                    float lox[RA], loy[RA], loz[RA], hix[RA], hiy[RA], hiz[RA], dn[RA];
 #pragma unroll
                     for (int r = 0; r < RA; r++) {
-                        A[r] = gv.aabbA[base + r * 32 + lane];
-                        B[r] = gv.aabbB[base + r * 32 + lane];
+                        const float4 A = gv.aabbA[base + r * 32 + lane];
+                        const float2 B = gv.aabbB[base + r * 32 + lane];
                         dn[r] = a.densA[base + r * 32 + lane];
-                        // origin-relative planes, shared by the TB targets
-                        A[r].x = subr(A[r].x, Pp.x); A[r].y = subr(A[r].y, Pp.y); A[r].z = subr(A[r].z, Pp.z);
-                        A[r].w = subr(A[r].w, Pp.x); B[r].x = subr(B[r].x, Pp.y); B[r].y = subr(B[r].y, Pp.z);
+                        // origin-relative planes, shared by all targets of the block
+                        lox[r] = subr(A.x, Pp.x); loy[r] = subr(A.y, Pp.y); loz[r] = subr(A.z, Pp.z);
+                        hix[r] = subr(A.w, Pp.x); hiy[r] = subr(B.x, Pp.y); hiz[r] = subr(B.y, Pp.z);
                     }
+                    for (int t = 0; t < nT; t++) {
+                        const float4 r0 = rec[t0 + t];
+                        const int cls = __float_as_int(rec[64 + t0 + t].y);
+                        float s = 0.0f;
+                        auto body = [&](auto clsTag) {
+                            constexpr int CLS = decltype(clsTag)::value;
 #pragma unroll
-                    for (int t = 0; t < TB; t++) {
-                        if (sb + t < nIn) {
-                            const float4 r0 = rec[sb + t];
-                            const int cls = __float_as_int(rec[64 + sb + t].y);
-                            auto body = [&](auto clsTag) {
-                                constexpr int CLS = decltype(clsTag)::value;
-#pragma unroll
-                                for (int r = 0; r < RA; r++) {
-                                    float tEnter, tExit;
-                                    slab<CLS>(A[r].x, A[r].y, A[r].z, A[r].w, B[r].x, B[r].y, r0.x, r0.y, r0.z, tEnter, tExit);
-                                    acc[t] = addr(acc[t], slab_loss(tEnter, tExit, dn[r]));
-                                }
-                            };
-                            switch (cls) {
-                            case 0: body(std::integral_constant<int, 0>{}); break;
-                            case 1: body(std::integral_constant<int, 1>{}); break;
-                            case 2: body(std::integral_constant<int, 2>{}); break;
-                            case 3: body(std::integral_constant<int, 3>{}); break;
-                            case 4: body(std::integral_constant<int, 4>{}); break;
-                            case 5: body(std::integral_constant<int, 5>{}); break;
-                            case 6: body(std::integral_constant<int, 6>{}); break;
-                            case 7: body(std::integral_constant<int, 7>{}); break;
-                            default: body(std::integral_constant<int, 8>{}); break;
+                            for (int r = 0; r < RA; r++) {
+                                float tEnter, tExit;
+                                slab<CLS>(lox[r], loy[r], loz[r], hix[r], hiy[r], hiz[r], r0.x, r0.y, r0.z, tEnter, tExit);
+                                s = addr(s, slab_loss(tEnter, tExit, dn[r]));
                             }
+                        };
+                        switch (cls) {
+                        case 0: body(std::integral_constant<int, 0>{}); break;
+                        case 1: body(std::integral_constant<int, 1>{}); break;
+                        case 2: body(std::integral_constant<int, 2>{}); break;
+                        case 3: body(std::integral_constant<int, 3>{}); break;
+                        case 4: body(std::integral_constant<int, 4>{}); break;
+                        case 5: body(std::integral_constant<int, 5>{}); break;
+                        case 6: body(std::integral_constant<int, 6>{}); break;
+                        case 7: body(std::integral_constant<int, 7>{}); break;
+                        default: body(std::integral_constant<int, 8>{}); break;
                         }
+                        if (s != 0.0f) acc[t * kAccStride + lane] = addr(acc[t * kAccStride + lane], s);
                     }
                 }
                 for (int base = 0; base < noPad; base += SC_O) {
-                    f4 oq[RO]; f3 pc[RO], lo[RO], hh[RO]; float cB[RO], dn[RO];
+                    float4 oq[RO]; f3 pc[RO], hh[RO]; float cB[RO], dn[RO];
 #pragma unroll
                     for (int r = 0; r < RO; r++) {
-                        const float4 q4 = gv.obbQ[base + r * 32 + lane];
+                        oq[r] = gv.obbQ[base + r * 32 + lane];                             // PM:296 stored rotation as is
                         const float4 c4 = gv.obbC[base + r * 32 + lane];
                         const float2 h2 = gv.obbH[base + r * 32 + lane];
-                        oq[r].x = q4.x; oq[r].y = q4.y; oq[r].z = q4.z; oq[r].w = q4.w;
                         hh[r] = mk3(c4.w, h2.x, h2.y);
                         pc[r] = sub3(Pp, mk3(c4.x, c4.y, c4.z));
-                        lo[r] = qmul3(oq[r], pc[r]);                                       // PM:296
                         cB[r] = obb_cull_c(pc[r], hh[r]);
                         dn[r] = a.densO[base + r * 32 + lane];
                     }
+                    for (int t = 0; t < nT; t++) {
+                        const float4 r1 = rec[32 + t0 + t];
+                        const f3 qd = mk3(r1.x, r1.y, r1.z);
+                        uint32_t need = 0;
 #pragma unroll
-                    for (int t = 0; t < TB; t++) {
-                        if (sb + t < nIn) {
-                            const float4 r1 = rec[32 + sb + t];
-                            const f3 qd = mk3(r1.x, r1.y, r1.z);
+                        for (int r = 0; r < RO; r++)
+                            if (!obb_sure_miss(pc[r], cB[r], qd, r1.w)) need |= 1u << r;
+                        if (need) {
+                            float s = 0.0f;
 #pragma unroll
                             for (int r = 0; r < RO; r++)
-                                if (!obb_sure_miss(pc[r], cB[r], qd, r1.w)) acc[t] = addr(acc[t], obb_loss(oq[r], lo[r], hh[r], qd, dn[r]));
+                                if ((need >> r) & 1u)
+                                    s = addr(s, obb_loss_exact(oq[r].x, oq[r].y, oq[r].z, oq[r].w, pc[r].x, pc[r].y, pc[r].z,
+                                                               hh[r].x, hh[r].y, hh[r].z, qd.x, qd.y, qd.z, dn[r]));
+                            acc[t * kAccStride + lane] = addr(acc[t * kAccStride + lane], s);
                         }
                     }
                 }
@@ -261,53 +242,45 @@ __global__ void __launch_bounds__(kThreads, 1) permeation_kernel(const PermArgs 
                 for (int e = lane; e < a.nOwned; e += 32) {
                     const int code = a.ownedList[e];
                     const int sec = code >> 28, idx = code & 0x0FFFFFFF;
-                    int owner; float dens;
-                    if (sec == 0) { const float4 at = a.at.sphAttr[idx]; owner = __float_as_int(at.w); dens = at.z; }
-                    else if (sec == 1) { const float4 at = a.at.aabbAttr[idx]; owner = __float_as_int(at.w); dens = at.z; }
-                    else { const float4 at = a.at.obbAttr[idx]; owner = __float_as_int(at.w); dens = at.z; }
-#pragma unroll
-                    for (int t = 0; t < TB; t++) {
-                        if (sb + t < nIn && owner != g * 32 + sb + t) {
-                            const float4 r0 = rec[sb + t], r1 = rec[32 + sb + t];
-                            const f3 qd = mk3(r1.x, r1.y, r1.z);
-                            float c;
-                            if (sec == 0) {
-                                const float4 s = gv.sph[idx];
-                                const f3 oc = sub3(Pp, mk3(s.x, s.y, s.z));
-                                c = sphere_loss(oc, subr(dot3(oc, oc), s.w), qd, dens);
-                            } else if (sec == 1) {
-                                c = aabb_loss<8>(gv.aabbA[idx], gv.aabbB[idx], Pp, r0.x, r0.y, r0.z, dens);
-                            } else {
-                                const float4 q4 = gv.obbQ[idx], c4 = gv.obbC[idx]; const float2 h2 = gv.obbH[idx];
-                                f4 q; q.x = q4.x; q.y = q4.y; q.z = q4.z; q.w = q4.w;
-                                c = obb_loss(q, qmul3(q, sub3(Pp, mk3(c4.x, c4.y, c4.z))), mk3(c4.w, h2.x, h2.y), qd, dens);
-                            }
-                            acc[t] = addr(acc[t], c);
+                    const float4 at = sec == 0 ? a.at.sphAttr[idx] : (sec == 1 ? a.at.aabbAttr[idx] : a.at.obbAttr[idx]);
+                    const int owner = __float_as_int(at.w);
+                    const float dens = at.z;
+                    for (int t = 0; t < nT; t++) {
+                        if (owner == g * 32 + t0 + t) continue;
+                        const float4 r0 = rec[t0 + t], r1 = rec[32 + t0 + t];
+                        const f3 qd = mk3(r1.x, r1.y, r1.z);
+                        float c;
+                        if (sec == 0) {
+                            const float4 s = gv.sph[idx];
+                            const f3 oc = sub3(Pp, mk3(s.x, s.y, s.z));
+                            c = sphere_loss_exact(dot3(oc, qd), subr(dot3(oc, oc), s.w), dens);
+                        } else if (sec == 1) {
+                            c = aabb_loss<8>(gv.aabbA[idx], gv.aabbB[idx], Pp, r0.x, r0.y, r0.z, dens);
+                        } else {
+                            const float4 q4 = gv.obbQ[idx], c4 = gv.obbC[idx]; const float2 h2 = gv.obbH[idx];
+                            const f3 pc = sub3(Pp, mk3(c4.x, c4.y, c4.z));
+                            c = obb_loss_exact(q4.x, q4.y, q4.z, q4.w, pc.x, pc.y, pc.z, c4.w, h2.x, h2.y, qd.x, qd.y, qd.z, dens);
                         }
+                        acc[t * kAccStride + lane] = addr(acc[t * kAccStride + lane], c);
                     }
                 }
-                // fixed-order butterfly, then value = N*S - loss (PM:260)
-#pragma unroll
-                for (int t = 0; t < TB; t++) {
-                    float s = acc[t];
-#pragma unroll
-                    for (int o2 = 16; o2 > 0; o2 >>= 1) s = addr(s, __shfl_xor_sync(kFull, s, o2));
-                    acc[t] = subr(a.nTimesS, s);
-                }
-                if (lane < TB && sb + lane < nIn) {
-                    float v = 0.0f;
-#pragma unroll
-                    for (int t = 0; t < TB; t++) if (t == lane) v = acc[t];
-                    const int tgt = g * 32 + sb + lane;
-                    // deterministic accumulation: integer part + 36-bit fixed-point fraction
+                __syncwarp();
+                // lane t adds its target's 32 per-lane partials in lane order (fixed order); value = N*S - loss (PM:260)
+                if (lane < nT) {
+                    float loss = 0.0f;
+#pragma unroll 8
+                    for (int i = 0; i < 32; i++) loss = addr(loss, acc[lane * kAccStride + i]);
+                    const float v = subr(a.nTimesS, loss);
+                    const int tgt = g * 32 + t0 + lane;
+                    // deterministic accumulation over rays: integer part + 36-bit fixed-point fraction
                     const float ip = truncf(v);
                     const long long ipart = (long long)ip;
                     const long long fpart = (long long)(((double)v - (double)ip) * 68719476736.0);
                     atomicAdd(reinterpret_cast<unsigned long long*>(&a.permSumInt[tgt]), (unsigned long long)ipart);
                     atomicAdd(reinterpret_cast<unsigned long long*>(&a.permSumFrac[tgt]), (unsigned long long)fpart);
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
     if (lane == 0) {
@@ -357,7 +330,7 @@ __global__ void __launch_bounds__(128) perm_last_kernel(const PermArgs a, int T)
         if (i < a.L.ns && (int)a.at.ownS[i] != tgt) {
             const float4 s = gv.sph[i];
             const f3 oc = sub3(Pp, mk3(s.x, s.y, s.z));
-            c = sphere_loss(oc, subr(dot3(oc, oc), s.w), dir, a.at.sphAttr[i].z);
+            c = sphere_loss_exact(dot3(oc, dir), subr(dot3(oc, oc), s.w), a.at.sphAttr[i].z);
         }
         fold(c);
     }
@@ -372,8 +345,8 @@ __global__ void __launch_bounds__(128) perm_last_kernel(const PermArgs a, int T)
         float c = 0.0f;
         if (i < a.L.no && (int)a.at.ownO[i] != tgt) {
             const float4 q4 = gv.obbQ[i], c4 = gv.obbC[i]; const float2 h2 = gv.obbH[i];
-            f4 q; q.x = q4.x; q.y = q4.y; q.z = q4.z; q.w = q4.w;
-            c = obb_loss(q, qmul3(q, sub3(Pp, mk3(c4.x, c4.y, c4.z))), mk3(c4.w, h2.x, h2.y), dir, a.at.obbAttr[i].z);
+            const f3 pc = sub3(Pp, mk3(c4.x, c4.y, c4.z));
+            c = obb_loss_exact(q4.x, q4.y, q4.z, q4.w, pc.x, pc.y, pc.z, c4.w, h2.x, h2.y, dir.x, dir.y, dir.z, a.at.obbAttr[i].z);
         }
         fold(c);
     }
@@ -382,7 +355,7 @@ __global__ void __launch_bounds__(128) perm_last_kernel(const PermArgs a, int T)
 
 size_t perm_smem_bytes(const GeomLayout& L, bool geomInSmem)
 {
-    return (geomInSmem ? L.bytes : 0) + (size_t)kWarpsPerCta * kPermRecFloat4PerWarp * sizeof(float4);
+    return (geomInSmem ? L.bytes : 0) + (size_t)kWarpsPerCta * kPermWarpBytes;
 }
 
 cudaError_t launch_permeation(const PermArgs& a, int numCtas, bool geomInSmem, int T, cudaStream_t stream)

@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- ray-bounce segments/s of the batched acoustic hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one frame of the hot path: AudioRaytracerJobBatched + AudioPermeationJobBatched +
+ProcessAudioDataJob over one synthetic batch (BASELINE.json configs). The default workload is C3
+(64 sources, 1M rays x 12 bounces, 4,096 colliders) -- the configuration BASELINE.json quotes "at 1/2/4/8 B200";
+with N > 1 the SAME batch is ray-sharded over the ranks (strong scaling), no data-path collective, and only the
+per-source partial results (a few KB) are all-gathered over NCCL.
+
+Prints ONE JSON line (rank 0). `value` = segments/s with scene and rays resident in HBM, device-timed (CUDA events
+on the library's stream, max over ranks). `e2e` = the same metric through the C ABI with HOST buffers: scene + ray
+upload and all per-ray outputs copied back inside the timed region (wall clock around schedule -> complete).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic flops per primitive test; index order sphere, AABB, OBB
+FLOPS_TRACE = (38, 35, 98)      # trace / echo / muffle tests (RT)
+FLOPS_PERM_FIRST = (38, 35, 98)  # PM first-hit tests
+FLOPS_PERM_LOSS = (29, 38, 101)  # PM loss tests
+METRIC = "ray-bounce segments/sec (device-timed)"
+UNIT = "segments/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=None, help="override the ray count (debug only; marks the line)")
+    ap.add_argument("--chunk", type=int, default=256, help="rays per interleaved shard chunk (N > 1)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target size of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, device_index: int, period_s: float = 0.1):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.period = period_s
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def run(self):
+        if self.h is None:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._halt.wait(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        med = int(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def flops_of(counters: dict):
+    """Algorithmic flops of a frame from its oracle-equivalent test counters."""
+    g = lambda k: counters.get(k) or counters.get({"traceTests": "trace_tests", "echoTests": "echo_tests",
+                                                   "muffleTests": "muffle_tests", "permFirstTests": "perm_first_tests",
+                                                   "permLossTests": "perm_loss_tests"}[k])
+    trace = sum(f * (a + b + c) for f, a, b, c in zip(FLOPS_TRACE, g("traceTests"), g("echoTests"), g("muffleTests")))
+    perm = sum(f * a for f, a in zip(FLOPS_PERM_FIRST, g("permFirstTests"))) + \
+        sum(f * a for f, a in zip(FLOPS_PERM_LOSS, g("permLossTests")))
+    return trace, perm
+
+
+def cpu_reference_sample(scene, seconds: float, threads: int):
+    """The reference algorithm on the host cores (oracle port, RT + PM) over a bounded, spread-out sample of
+    the workload's rays. Returns (segments/s, description, threads, seconds, segments)."""
+    from oracle import oracle as orc
+    N = scene.n_rays
+    # calibrate on a few rays, then size 4 windows spread over the sphere
+    t0 = time.perf_counter()
+    c = orc.trace_range(scene, N // 2, min(32, N), threads=threads, with_outputs=False)
+    orc.permeation_range(scene, N // 2, min(32, N), threads=threads)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    per_ray = dt / min(32, N)
+    total = int(max(64, min(N, seconds / per_ray)))
+    win = max(16, total // 4)
+    starts = [int(f * (N - win)) for f in (0.1, 0.35, 0.6, 0.85)]
+    seg, t = 0, 0.0
+    for s0 in starts:
+        t0 = time.perf_counter()
+        c = orc.trace_range(scene, s0, win, threads=threads, with_outputs=False)
+        orc.permeation_range(scene, s0, win, threads=threads)
+        t += time.perf_counter() - t0
+        seg += c["segments"]
+    desc = f"{4 * win} of {N} rays (4 windows of {win} at 10/35/60/85% of the Fibonacci index), RT+PM jobs, full scene and targets"
+    return seg / t, desc, threads, t, seg
+
+
+def run_reference(args, scene, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals = []
+    desc = ""
+    for i in range(args.warmup + args.steps):
+        v, desc, th, t, seg = cpu_reference_sample(scene, max(2.0, args.cpu_seconds / max(1, args.steps)), threads)
+        if i >= args.warmup:
+            vals.append((v, t))
+    value = float(np.mean([v for v, _ in vals]))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean([t for _, t in vals]) * 1e3), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, scene, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is C#/Unity and cannot run here (no .NET toolchain); this is the C restatement "
+                "oracle/audiort_oracle.c of its Execute() bodies on all host threads",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, scene, world):
+    return {"workload": f"{args.workload}: {scene.n_targets} sources, {scene.n_rays} rays x {scene.max_hits_per_ray} hits, "
+                        f"{len(scene.aabbs)} AABB + {len(scene.obbs)} OBB + {len(scene.spheres)} spheres",
+            "rays": scene.n_rays, "max_hits_per_ray": scene.max_hits_per_ray, "targets": scene.n_targets,
+            "colliders": scene.n_colliders, "batch_count": scene.batch_count,
+            "sharding": "none" if world == 1 else f"rays interleaved in chunks of {args.chunk} over {world} ranks",
+            "l2": "flushed between steps (256 MiB write)", "reverb_reduction": "exact integer",
+            "rays_override": args.rays is not None}
+
+
+def main():
+    args = parse_args()
+    rank, world, local = dist_env()
+    from audio_raytracer_b200 import scenes
+    scene = scenes.make_config(args.workload, batch_count=max(1, args.gpus), n_rays=args.rays)
+
+    if args.impl == "reference":
+        run_reference(args, scene, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from audio_raytracer_b200 import build, native
+    build.build()
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+
+    ctx = native.Context(device=local)
+    native.upload(ctx, scene)
+    if world > 1:
+        ctx.set_ray_shard(rank, world, args.chunk)
+    n_local = ctx.local_ray_count()
+    H, Na, T = scene.max_hits_per_ray, scene.n_targets, scene.batch_count
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    blob_bytes = int(native.load_library().art_partials_size(Na, T))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def exchange(blob_np):
+        """all-gather the per-source partial blobs (a few KB) over NCCL and merge; returns (merged, ms)."""
+        if world == 1:
+            return blob_np, 0.0
+        mine = torch.from_numpy(blob_np).cuda()
+        out = [torch.empty_like(mine) for _ in range(world)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_gather(out, mine)
+        e1.record()
+        torch.cuda.synchronize()
+        merged = native.merge_partials([o.cpu().numpy() for o in out])
+        return merged, e0.elapsed_time(e1)
+
+    partial_flag = native.FRAME_PARTIALS_ONLY if world > 1 else 0
+
+    def device_step(flags=0):
+        flush.zero_()
+        torch.cuda.synchronize()
+        r = ctx.run_frame(scene, flags=flags | native.FRAME_NO_HOST_OUTPUTS | partial_flag, want=())
+        blob, ex_ms = exchange(ctx.get_partials(Na, T))
+        if world > 1:
+            native.finalize(blob, scene, scene.n_rays)
+        return r.counters, ex_ms
+
+    # ---- one untimed counting pass: oracle-equivalent test counts -> algorithmic flops of a step
+    barrier()
+    cnt, _ = device_step(native.FRAME_COUNTERS)
+    trace_flops_local, perm_flops_local = flops_of(cnt)
+
+    for _ in range(args.warmup):
+        device_step()
+
+    # ---- timed: device-resident inputs, CUDA events on the library stream
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
+    dev_ms, trace_ms, perm_ms, reduce_ms, ex_ms_tot, launches, segs = [], [], [], [], 0.0, 0, 0
+    for _ in range(args.steps):
+        c, ex_ms = device_step()
+        dev_ms.append(c["deviceMs"]); trace_ms.append(c["traceMs"]); perm_ms.append(c["permeationMs"]); reduce_ms.append(c["reduceMs"])
+        ex_ms_tot += ex_ms
+        launches += c["kernelLaunches"]
+        segs += c["segments"]
+    barrier()
+    wall_dev = time.perf_counter() - wall0
+    clocks = sampler.stop()
+
+    # ---- e2e: host buffers through the C ABI, uploads and read-backs inside the timed region
+    out = native.FrameResult()
+    for _ in range(max(1, min(args.warmup, 2))):
+        native.upload(ctx, scene)
+        ctx.run_frame(scene, flags=partial_flag, result=out, want=("echo", "hit_points", "hit_counts"))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_segs = 0
+    for _ in range(args.steps):
+        native.upload(ctx, scene)                                  # H2D: scene structs + ray directions (+ targets)
+        r = ctx.run_frame(scene, flags=partial_flag, result=out, want=("echo", "hit_points", "hit_counts"))
+        blob, _ = exchange(ctx.get_partials(Na, T))
+        if world > 1:
+            native.finalize(blob, scene, scene.n_rays)
+        e2e_segs += r.counters["segments"]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = scene.n_rays * 6 + len(scene.aabbs) * 20 + len(scene.obbs) * 26 + len(scene.spheres) * 16 + Na * 12
+    d2h = n_local * H * (2 + 6) + n_local + blob_bytes
+
+    # ---- reduce over ranks
+    def allmax(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    step_ms = allmax(sum(dev_ms) + ex_ms_tot) / args.steps
+    total_segs = allsum(segs)
+    value = total_segs / args.steps / (step_ms * 1e-3)
+    e2e_value = allsum(e2e_segs) / allmax(e2e_s)
+    trace_ms_avg = float(np.mean(trace_ms))
+    trace_flops_all = allsum(trace_flops_local)
+    perm_flops_all = allsum(perm_flops_local)
+    launches_all = int(allsum(launches))
+    wall_dev_max = allmax(wall_dev)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        sm_max = clocks.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        n_sms = 148
+        peak_tflops = n_sms * 128 * sm_max * 1e6 / 1e12          # FP32 instruction issue, no FMA
+        achieved = trace_flops_local / (trace_ms_avg * 1e-3) / 1e12
+        micro = {}
+        try:
+            micro = {"fadd_fmul_tops": ctx.microbench(0) / 1e3, "fmnmx_tops": ctx.microbench(1) / 1e3,
+                     "ffma_tops": ctx.microbench(2) / 1e3}
+        except Exception as ex:  # pragma: no cover
+            micro = {"error": str(ex)}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, desc, th, t, seg = cpu_reference_sample(scene, args.cpu_seconds, threads)
+            cpu = {"value": v, "unit": UNIT, "cores": th, "kind": "port", "sample": desc, "seconds": t}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, scene, world),
+            "segments_per_step": total_segs / args.steps,
+            "kernel_ms": {"trace": trace_ms_avg, "permeation": float(np.mean(perm_ms)), "reduce": float(np.mean(reduce_ms)),
+                          "partials_allgather": ex_ms_tot / args.steps},
+            "wall_ms_per_step_device_mode": wall_dev_max / args.steps * 1e3,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": allmax(e2e_s) / args.steps * 1e3 if world == 1 else None},
+            "gpu_launches": launches_all,
+            "roofline": {"bound": "fp32", "kernel": "trace_kernel (K1)", "achieved": achieved, "peak": peak_tflops,
+                         "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": None,
+                         "peak_source": f"148 SM x 128 FP32 lanes x {sm_max:.0f} MHz, un-fused issue rate (no FP32 figure in "
+                                        "MEASURED_PEAKS.json; parity forbids FMA contraction, SURVEY 8d); on-box microbenchmarks in 'measured_issue_rates'",
+                         "algorithmic_flops_per_launch": trace_flops_local,
+                         "flops_per_test": {"sphere": 38, "aabb": 35, "obb": 98},
+                         "measured_issue_rates": micro,
+                         "permeation_kernel": {"achieved": perm_flops_local / (float(np.mean(perm_ms)) * 1e-3) / 1e12 if np.mean(perm_ms) > 0 else None,
+                                               "algorithmic_flops_per_launch": perm_flops_local}},
+            "cpu_baseline": cpu,
+            "counters_first_step": {k: cnt[k] for k in ("segments", "segmentHits", "traceTests", "echoTests", "muffleTests",
+                                                        "echoQueries", "muffleQueries", "permHitRays")},
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Run a few frames of one workload through the C ABI (for ncu / compute-sanitizer captures).
+
+    python tools/prof_frame.py --workload c3 --rays 32768 --frames 2 [--jobs 7] [--counters]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from audio_raytracer_b200 import build, native, scenes  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="c3")
+    ap.add_argument("--rays", type=int, default=None)
+    ap.add_argument("--frames", type=int, default=2)
+    ap.add_argument("--jobs", type=int, default=native.JOB_ALL)
+    ap.add_argument("--counters", action="store_true")
+    ap.add_argument("--seq", action="store_true")
+    a = ap.parse_args()
+    build.build()
+    s = scenes.make_config(a.workload, n_rays=a.rays)
+    flags = native.FRAME_NO_HOST_OUTPUTS | (native.FRAME_COUNTERS if a.counters else 0) | (native.FRAME_REVERB_SEQ_FP32 if a.seq else 0)
+    with native.Context(0) as ctx:
+        native.upload(ctx, s)
+        for i in range(a.frames):
+            r = ctx.run_frame(s, jobs=a.jobs, flags=flags, want=())
+            c = r.counters
+            print(f"frame {i}: segments {c['segments']} trace {c['traceMs']:.3f} ms perm {c['permeationMs']:.3f} ms "
+                  f"reduce {c['reduceMs']:.3f} ms launches {c['kernelLaunches']}")
+
+
+if __name__ == "__main__":
+    main()
