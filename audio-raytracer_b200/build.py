@@ -46,24 +46,27 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """Compile and link. ``defines``/``out`` build an experimental variant next to the product library."""
+    if out is None and os.environ.get("AUDIORT_LIB"):
+        return os.environ["AUDIORT_LIB"]          # an explicitly selected prebuilt variant
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if out is None else "build_" + os.path.basename(out))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     log = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + ARCH + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + ARCH + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False
     for src, cmd, p in procs:
-        out, _ = p.communicate()
-        log.append(f"$ {' '.join(cmd)}\n{out}")
+        text, _ = p.communicate()
+        log.append("$ " + " ".join(cmd) + "\n" + text)
         if p.returncode != 0:
             failed = True
     with open(os.path.join(objdir, "nvcc.log"), "w") as f:
@@ -71,11 +74,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         sys.stderr.write("\n".join(log))
         raise RuntimeError("nvcc failed, see audio-raytracer_b200/build/nvcc.log")
-    link = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+    target = out or LIB
+    link = [nvcc] + ARCH + ["-shared", "-o", target] + objs + ["-lcudart"]
     subprocess.check_call(link)
     if verbose:
         sys.stdout.write("\n".join(log))
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

@@ -27,7 +27,7 @@ namespace art {
 
 constexpr int TBK = 16;          // targets per accumulator block
 constexpr int kAccStride = 33;   // acc[t * 33 + lane]: conflict free per target and in the final per-lane sums
-constexpr int kPermRecFloat4PerWarp = 96;
+constexpr int kPermRecFloat4PerWarp = 64;   // rec[q] = (inv.xyz, class bits), rec[32+q] = (d.xyz, dot(d,d))
 constexpr int kPermWarpBytes = kPermRecFloat4PerWarp * 16 + ((TBK * kAccStride * 4 + 15) / 16) * 16;
 
 template <bool SMEM>
@@ -131,9 +131,8 @@ __global__ void __launch_bounds__(kThreads, 1) permeation_kernel(const PermArgs 
                 const f3 T = mk3(a.targets[3 * tslot], a.targets[3 * tslot + 1], a.targets[3 * tslot + 2]);
                 const f3 dir = normalize3(sub3(T, Pp));                                    // PM:76
                 const float ix = rcpr(dir.x), iy = rcpr(dir.y), iz = rcpr(dir.z);
-                rec[lane] = make_float4(ix, iy, iz, 0.0f);
+                rec[lane] = make_float4(ix, iy, iz, __int_as_float(slab_class(ix, iy, iz)));
                 rec[32 + lane] = make_float4(dir.x, dir.y, dir.z, dot3(dir, dir));
-                rec[64 + lane] = make_float4(__int_as_float(tslot), __int_as_float(slab_class(ix, iy, iz)), 0.0f, 0.0f);
             }
             __syncwarp();
             const int nIn = min(32, Na - g * 32);
@@ -182,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) permeation_kernel(const PermArgs 
                     }
                     for (int t = 0; t < nT; t++) {
                         const float4 r0 = rec[t0 + t];
-                        const int cls = __float_as_int(rec[64 + t0 + t].y);
+                        const int cls = __float_as_int(r0.w);
                         float s = 0.0f;
                         auto body = [&](auto clsTag) {
                             constexpr int CLS = decltype(clsTag)::value;

@@ -14,7 +14,10 @@
 
 namespace art {
 
-constexpr int kWarpsPerCta = 16;
+#ifndef ART_WARPS
+#define ART_WARPS 32
+#endif
+constexpr int kWarpsPerCta = ART_WARPS;
 constexpr int kThreads = kWarpsPerCta * 32;
 // colliders held in registers per lane per "super-chunk"
 constexpr int RS = 4;   // spheres

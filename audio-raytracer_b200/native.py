@@ -16,7 +16,7 @@ import numpy as np
 from .layouts import AABB_DT, OBB_DT, SPHERE_DT, SETTINGS_DT
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaudiort_cuda.so")
+LIB_PATH = os.environ.get("AUDIORT_LIB") or os.path.join(_HERE, "libaudiort_cuda.so")
 
 ART_ABI_VERSION = 1
 ART_OK, ART_E_ARG, ART_E_CUDA, ART_E_PENDING, ART_E_NO_DEVICE, ART_E_STATE, ART_E_NOMEM = 0, -1, -2, -3, -4, -5, -6
