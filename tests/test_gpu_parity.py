@@ -293,3 +293,22 @@ def test_c3_full_size_properties(gpu_ctx, oracle):
         np.testing.assert_array_equal(g.hit_ids[sl], o.hit_ids[sl])
         np.testing.assert_array_equal(g.echo[sl], o.echo[sl])
         np.testing.assert_array_equal(g.hit_counts[first:first + 64], o.hit_counts[first:first + 64])
+
+
+def test_jobs_mirror_one_frame_latency(art_lib, oracle):
+    """jobs.AudioRayTracer mirrors ART:92-238: results are consumed one frame after they were scheduled."""
+    from audio_raytracer_b200 import jobs
+    s = scenes.make_config("c2", n_rays=314)
+    rt = jobs.AudioRayTracer(rayCount=314, maxBounces=4, maxRayLife=125.0, maxMuffleHitDistance=250.0,
+                             maxReverbDistance=35.0, toUseThreadCount=1)
+    rt.set_colliders(s.aabbs, s.obbs, s.spheres)
+    assert rt.OnUpdate((0, 0, 0), s.targets) is None                 # first frame: nothing to consume yet
+    res = None
+    while res is None:
+        res = rt.OnUpdate((0, 0, 0), s.targets)
+    s.max_hits_per_ray, s.max_ray_life, s.max_muffle_hit_distance = 5, 125.0, 250.0
+    s.ray_directions = oracle.fibonacci_directions(314)
+    o = oracle.run_frame(s)
+    np.testing.assert_array_equal(res.hit_counts, o.hit_counts)
+    np.testing.assert_array_equal(res.muffle, o.muffle)
+    rt.OnDestroy()
