@@ -281,17 +281,18 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a)
                     while (m) {
                         const int q = __ffs(m) - 1;
                         m &= m - 1;
-                        const float4 r0 = rec[q], r1 = rec[32 + q];
+                        const float4 r1 = rec[32 + q];
                         const f3 qd = mk3(r1.x, r1.y, r1.z);
                         uint32_t need = 0, hm = 0;
 #pragma unroll
                         for (int r = 0; r < RS; r++)
                             if (!sphere_fast_miss(oc[r], cc[r], qd, r1.w)) need |= 1u << r;
                         if (need) {
+                            const float limit = rec[q].w;
 #pragma unroll
                             for (int r = 0; r < RS; r++)
                                 if ((need >> r) & 1u)
-                                    if (sphere_dist_exact(oc[r].x, oc[r].y, oc[r].z, cc[r], qd.x, qd.y, qd.z, r1.w) < r0.w) hm |= 1u << r;
+                                    if (sphere_dist_exact(oc[r].x, oc[r].y, oc[r].z, cc[r], qd.x, qd.y, qd.z, r1.w) < limit) hm |= 1u << r;
                         }
                         if (__any_sync(kFull, hm != 0)) {
                             hm = owner_filter<RS>(hm, a.at.ownS, base, lane, __float_as_int(rec[64 + q].x));
@@ -323,14 +324,14 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a)
                         m &= m - 1;
                         const float4 r0 = rec[q];
                         const int cls = __float_as_int(rec[64 + q].y);
-                        uint32_t hm = 0;
+                        bool hb[RA];
                         auto body = [&](auto clsTag) {
                             constexpr int CLS = decltype(clsTag)::value;
 #pragma unroll
                             for (int r = 0; r < RA; r++) {
                                 float tNear, tFar, dist;
                                 slab<CLS>(lox[r], loy[r], loz[r], hix[r], hiy[r], hiz[r], r0.x, r0.y, r0.z, tNear, tFar);
-                                if (slab_hit(tNear, tFar, dist) && dist < r0.w) hm |= 1u << r;
+                                hb[r] = slab_hit(tNear, tFar, dist) && dist < r0.w;
                             }
                         };
                         switch (cls) {
@@ -344,7 +345,13 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a)
                         case 7: body(std::integral_constant<int, 7>{}); break;
                         default: body(std::integral_constant<int, 8>{}); break;
                         }
-                        if (__any_sync(kFull, hm != 0)) {
+                        bool anyb = false;
+#pragma unroll
+                        for (int r = 0; r < RA; r++) anyb |= hb[r];
+                        if (__any_sync(kFull, anyb)) {
+                            uint32_t hm = 0;
+#pragma unroll
+                            for (int r = 0; r < RA; r++) hm |= hb[r] ? (1u << r) : 0u;
                             hm = owner_filter<RA>(hm, a.at.ownA, base, lane, __float_as_int(rec[64 + q].x));
                             const uint32_t bal = __ballot_sync(kFull, hm != 0);
                             if (bal) {
@@ -374,18 +381,19 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a)
                     while (m) {
                         const int q = __ffs(m) - 1;
                         m &= m - 1;
-                        const float4 r0 = rec[q], r1 = rec[32 + q];
+                        const float4 r1 = rec[32 + q];
                         const f3 qd = mk3(r1.x, r1.y, r1.z);
                         uint32_t need = 0, hm = 0;
 #pragma unroll
                         for (int r = 0; r < RO; r++)
                             if (!obb_sure_miss(pc[r], cB[r], qd, r1.w)) need |= 1u << r;
                         if (need) {
+                            const float limit = rec[q].w;
 #pragma unroll
                             for (int r = 0; r < RO; r++)
                                 if ((need >> r) & 1u)
                                     if (obb_dist_exact(oq[r].x, oq[r].y, oq[r].z, oq[r].w, pc[r].x, pc[r].y, pc[r].z,
-                                                       hh[r].x, hh[r].y, hh[r].z, qd.x, qd.y, qd.z) < r0.w) hm |= 1u << r;
+                                                       hh[r].x, hh[r].y, hh[r].z, qd.x, qd.y, qd.z) < limit) hm |= 1u << r;
                         }
                         if (__any_sync(kFull, hm != 0)) {
                             hm = owner_filter<RO>(hm, a.at.ownO, base, lane, __float_as_int(rec[64 + q].x));

@@ -192,6 +192,7 @@ def main():
     from audio_raytracer_b200 import build, native
     build.build()
     torch.cuda.set_device(local)
+    os.environ["NCCL_DEBUG"] = os.environ.get("ART_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
