@@ -674,6 +674,11 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         bool geomInSmem = trace_smem_bytes(L, Na, true, false) <= (size_t)ctx->maxSmemOptin;
         bool muffleInSmem = trace_smem_bytes(L, Na, geomInSmem, true) <= (size_t)ctx->maxSmemOptin;
         ta.muffleInSmem = muffleInSmem ? 1 : 0;
+        for (int sec = 0; sec < 3; sec++) {
+            long long owned = 0;
+            for (int t = 0; t < Na; t++) owned += ownedCount[(size_t)sec * Na + t];
+            ta.anyOwned[sec] = owned > 0 ? 1 : 0;
+        }
         CK(launch_trace(ta, ctx->numSms, geomInSmem, count, ctx->stream));
         ctx->kernelLaunches++;
     }

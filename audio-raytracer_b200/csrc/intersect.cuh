@@ -57,6 +57,16 @@ __device__ __forceinline__ bool sphere_fast_miss(f3 oc, float cc, f3 d, float a)
     const float dt = dot3(oc, d);
     return mulr(dt, dt) < mulr(a, cc);
 }
+// Conservative variant for the occlusion loops (the exact path re-evaluates survivors, so this only has
+// to be SAFE): the dot product is formed with FMAs (1 FMUL + 2 FFMA instead of 3 FMUL + 2 FADD); its
+// difference from the reference's rounding is at most 3*2^-23*|oc||d|, hence dot^2 moves by less than
+// 2^-20*|oc|^2*a; ccm = cc - 2^-19*|oc|^2 (sphere_cull_c) absorbs that with a 2x margin.
+__device__ __forceinline__ float sphere_cull_c(float cc, float rr) { return fmaf(-1.9073486328125e-06f, cc + rr, cc); }
+__device__ __forceinline__ bool sphere_sure_miss(f3 oc, float ccm, f3 d, float a)
+{
+    const float dt = fmaf(oc.z, d.z, fmaf(oc.y, d.y, oc.x * d.x));
+    return dt * dt < a * ccm;
+}
 // Exact distance in the reference's operation order, or NaN for a miss (NaN fails every `dist < x`).
 static __device__ __noinline__ float sphere_dist_exact(float ocx, float ocy, float ocz, float cc, float dx, float dy, float dz, float a)
 {

@@ -270,12 +270,12 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a)
 
                 // ---- spheres (RT:370-377 / 408-419)
                 for (int base = 0; base < nsPad && open; base += SC_S) {
-                    f3 oc[RS]; float cc[RS];
+                    f3 oc[RS]; float ccm[RS];
 #pragma unroll
                     for (int r = 0; r < RS; r++) {
                         const float4 s = gv.sph[base + r * 32 + lane];
                         oc[r] = sub3(Pp, mk3(s.x, s.y, s.z));
-                        cc[r] = subr(dot3(oc[r], oc[r]), s.w);
+                        ccm[r] = sphere_cull_c(subr(dot3(oc[r], oc[r]), s.w), s.w);
                     }
                     uint32_t m = open;
                     while (m) {
@@ -286,16 +286,18 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a)
                         uint32_t need = 0, hm = 0;
 #pragma unroll
                         for (int r = 0; r < RS; r++)
-                            if (!sphere_fast_miss(oc[r], cc[r], qd, r1.w)) need |= 1u << r;
+                            if (!sphere_sure_miss(oc[r], ccm[r], qd, r1.w)) need |= 1u << r;
                         if (need) {
                             const float limit = rec[q].w;
 #pragma unroll
                             for (int r = 0; r < RS; r++)
-                                if ((need >> r) & 1u)
-                                    if (sphere_dist_exact(oc[r].x, oc[r].y, oc[r].z, cc[r], qd.x, qd.y, qd.z, r1.w) < limit) hm |= 1u << r;
+                                if ((need >> r) & 1u) {
+                                    const float cc = subr(dot3(oc[r], oc[r]), gv.sph[base + r * 32 + lane].w);   // RT:328
+                                    if (sphere_dist_exact(oc[r].x, oc[r].y, oc[r].z, cc, qd.x, qd.y, qd.z, r1.w) < limit) hm |= 1u << r;
+                                }
                         }
                         if (__any_sync(kFull, hm != 0)) {
-                            hm = owner_filter<RS>(hm, a.at.ownS, base, lane, __float_as_int(rec[64 + q].x));
+                            if (a.anyOwned[0]) hm = owner_filter<RS>(hm, a.at.ownS, base, lane, __float_as_int(rec[64 + q].x));
                             const uint32_t bal = __ballot_sync(kFull, hm != 0);
                             if (bal) {
                                 open &= ~(1u << q);
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a)
                             uint32_t hm = 0;
 #pragma unroll
                             for (int r = 0; r < RA; r++) hm |= hb[r] ? (1u << r) : 0u;
-                            hm = owner_filter<RA>(hm, a.at.ownA, base, lane, __float_as_int(rec[64 + q].x));
+                            if (a.anyOwned[1]) hm = owner_filter<RA>(hm, a.at.ownA, base, lane, __float_as_int(rec[64 + q].x));
                             const uint32_t bal = __ballot_sync(kFull, hm != 0);
                             if (bal) {
                                 open &= ~(1u << q);
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a)
                                                        hh[r].x, hh[r].y, hh[r].z, qd.x, qd.y, qd.z) < limit) hm |= 1u << r;
                         }
                         if (__any_sync(kFull, hm != 0)) {
-                            hm = owner_filter<RO>(hm, a.at.ownO, base, lane, __float_as_int(rec[64 + q].x));
+                            if (a.anyOwned[2]) hm = owner_filter<RO>(hm, a.at.ownO, base, lane, __float_as_int(rec[64 + q].x));
                             const uint32_t bal = __ballot_sync(kFull, hm != 0);
                             if (bal) {
                                 open &= ~(1u << q);

@@ -122,6 +122,7 @@ struct TraceArgs {
     unsigned long long* counters;  // [C_COUNT]
     unsigned int* nextRay;         // dynamic ray queue
     int muffleInSmem;              // per-warp shared counters fit
+    int anyOwned[3];               // does any sphere / AABB / OBB belong to a target < nTargets (RT:413/426/439)
 };
 
 // K0 arguments
