@@ -186,8 +186,35 @@ CONFIGS: Dict[str, dict] = {
 }
 
 
+def load_demo_scene(n_targets: int | None = None, batch_count: int | None = None, n_rays: int | None = None) -> Scene:
+    """BASELINE config 1: the reference's demo level (Assets/Scenes/Sample Scene.unity) as the job structs see it on
+    the first frame, with the demo's own parameters (Prefabs/Player.prefab:223-234 + scene overrides: 314 rays,
+    maxBounces 4, maxRayLife 125, maxMuffleHitDistance 250, permeation effectiveness 0, 1 worker thread).
+
+    ``data/c1_demo_scene.npz`` is written by tools/export_demo_scene.py, which restates the collider bake of
+    Audio/Colliders/*.cs offline; at run time the scene has 52 AABB + 38 OBB + 8 sphere colliders and 2 audio targets
+    (the third MusicBox and 13 more colliders sit under the inactive "Environment (Box)" root and never register).
+    ``n_targets=1`` keeps only the first MusicBox, as BASELINE.json words the config ("1 audio source").
+    """
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "c1_demo_scene.npz"))
+    p = z["params"]
+    targets = z["targets"] if n_targets is None else z["targets"][:n_targets]
+    n = int(z["ray_count"][0]) if n_rays is None else n_rays
+    return Scene(aabbs=z["aabbs"].view(AABB_DT), obbs=z["obbs"].view(OBB_DT), spheres=z["spheres"].view(SPHERE_DT),
+                 targets=np.ascontiguousarray(targets, dtype=np.float32), ray_directions=fibonacci_directions(n),
+                 ray_origin=z["ray_origin"].astype(np.float32), max_ray_life=float(p[0]), max_hits_per_ray=int(p[1]),
+                 max_muffle_hit_distance=float(p[2]), permeation_strength_per_ray=float(p[3]),
+                 muffle_effectiveness=float(p[4]), permeation_effectiveness=float(p[5]), max_reverb_distance=float(p[6]),
+                 batch_count=int(p[7]) if batch_count is None else batch_count, name="c1")
+
+
 def make_config(name: str, batch_count: int = 1, n_rays: int | None = None) -> Scene:
     """Build a BASELINE config. ``n_rays`` overrides the ray count (scaled-down parity cases)."""
+    if name == "c1":
+        return load_demo_scene(batch_count=batch_count, n_rays=n_rays)
+    if name == "c1_1src":
+        return load_demo_scene(n_targets=1, batch_count=batch_count, n_rays=n_rays)
     cfg = dict(CONFIGS[name])
     if n_rays is not None:
         cfg["n_rays"] = n_rays

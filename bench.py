@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c1_1src", "c2", "c3", "c4", "c5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=None, help="override the ray count (debug only; marks the line)")
     ap.add_argument("--chunk", type=int, default=256, help="rays per interleaved shard chunk (N > 1)")

@@ -26,6 +26,9 @@ CASES = {
     "c3_n48_t2": ("c3", 48, 2, {}),
     "c4_n24_t1": ("c4", 24, 1, {}),
     "c2_n512_gated": ("c2", 512, 2, {"max_muffle_hit_distance": 20.0, "max_ray_life": 30.0}),
+    # BASELINE config 1: the reference demo level with the demo's own parameters (tools/export_demo_scene.py)
+    "c1_demo": ("c1", None, 1, {}),
+    "c1_demo_1src_t3": ("c1_1src", None, 3, {}),
 }
 
 
@@ -51,5 +54,5 @@ def make(name):
 
 
 if __name__ == "__main__":
-    for n in CASES:
+    for n in (sys.argv[1:] or CASES):
         make(n)

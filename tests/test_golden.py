@@ -5,7 +5,7 @@ import pytest
 
 from helpers import load_golden
 
-CASES = ["c2_n768_t3", "c3_n48_t2", "c4_n24_t1", "c2_n512_gated"]
+CASES = ["c2_n768_t3", "c3_n48_t2", "c4_n24_t1", "c2_n512_gated", "c1_demo", "c1_demo_1src_t3"]
 
 
 @pytest.mark.parametrize("name", CASES)
