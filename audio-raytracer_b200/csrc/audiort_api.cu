@@ -5,6 +5,7 @@
 // every intersection test, sum and count is produced by the kernels in k0..k3.
 #include "../../include/audiort.h"
 
+#include "grid_host.h"
 #include "launchers.h"
 #include "scene_dev.cuh"
 #include "um_math.cuh"
@@ -12,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -170,6 +172,11 @@ struct ArtCtx {
     std::vector<uint16_t> hostS, hostA, hostO;     // raw words, kept for host-side prep
     PinBuf pinScene;
     DevBuf rawScene, geom, attrs, owners, perm;    // perm: dens arrays + owned list
+    HostGrid grid;                                 // uniform grid over the scene (grid_host.h)
+    DevBuf gridCells, gridEntries;
+    bool gridDisabled = false;                     // ART_DISABLE_GRID=1
+    float gridCellScale = 1.0f;                    // ART_GRID_CELL_SCALE
+    uint32_t frameGridUsed = 0;
     GeomLayout L{};
     bool haveScene = false, sceneDirty = false;
     int permPreparedForTargets = -1;
@@ -379,6 +386,8 @@ ART_API int32_t art_create(const ArtConfig* cfg, ArtCtx** out)
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     for (auto& ev : ctx->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if (const char* v = getenv("ART_DISABLE_GRID")) ctx->gridDisabled = atoi(v) != 0;
+    if (const char* v = getenv("ART_GRID_CELL_SCALE")) { const float f = (float)atof(v); if (f > 0.05f && f < 50.0f) ctx->gridCellScale = f; }
     *out = ctx;
     return ART_OK;
 }
@@ -388,7 +397,7 @@ ART_API void art_destroy(ArtCtx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
+    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
                        &ctx->outEcho, &ctx->outHitPts, &ctx->outHitCnt, &ctx->outHitIds, &ctx->firstHit, &ctx->partials, &ctx->queue })
         b->release();
     for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinEcho,
@@ -522,6 +531,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     }
     cudaSetDevice(ctx->device);
     ctx->kernelLaunches = 0;
+    ctx->frameGridUsed = 0;
 
     const int chunk = effective_chunk(ctx);
     ShardMap map;
@@ -563,6 +573,18 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         pa.ownS = ow; pa.ownA = ow + L.nsPad; pa.ownO = ow + L.nsPad + L.naPad;
         CK(launch_pack(pa, ctx->stream));
         ctx->kernelLaunches++;
+        // uniform grid over the new scene (host build, two small uploads)
+        ctx->grid.ok = false;
+        if (!ctx->gridDisabled) {
+            build_grid(ctx->hostS, ctx->hostA, ctx->hostO, ctx->gridCellScale, ctx->grid);
+            if (ctx->grid.ok) {
+                CK(ctx->gridCells.ensure(ctx->grid.cells.size() * sizeof(uint2)));
+                CK(ctx->gridEntries.ensure(ctx->grid.entries.size() * sizeof(uint16_t)));
+                CK(cudaMemcpyAsync(ctx->gridCells.p, ctx->grid.cells.data(), ctx->grid.cells.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(ctx->gridEntries.p, ctx->grid.entries.data(), ctx->grid.entries.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));   // pageable host vectors
+            }
+        }
         ctx->sceneDirty = false;
     }
     if (ctx->raysDirty) {
@@ -679,7 +701,22 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             for (int t = 0; t < Na; t++) owned += ownedCount[(size_t)sec * Na + t];
             ta.anyOwned[sec] = owned > 0 ? 1 : 0;
         }
-        CK(launch_trace(ta, ctx->numSms, geomInSmem, count, ctx->stream));
+        // acceleration structure: same exact tests on the colliders near each ray only (bit-identical outputs);
+        // the work counters are defined by the reference's full scans, so counting frames use the brute-force kernel
+        bool useGrid = ctx->grid.ok && !count && !(prm->flags & ART_FRAME_BRUTE_FORCE);
+        if (useGrid) {
+            const float dx = prm->rayOrigin[0] - ctx->grid.cx, dy = prm->rayOrigin[1] - ctx->grid.cy, dz = prm->rayOrigin[2] - ctx->grid.cz;
+            useGrid = std::sqrt(dx * dx + dy * dy + dz * dz) <= ctx->grid.listenerRange;   // else the error bounds of grid_host.h do not hold
+        }
+        if (useGrid) {
+            GridDesc gd = ctx->grid.d;
+            gd.cells = ctx->gridCells.as<uint2>(); gd.entries = ctx->gridEntries.as<uint16_t>();
+            const bool gInSmem = trace_grid_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
+            CK(launch_trace_grid(ta, gd, ctx->numSms, gInSmem, ctx->stream));
+            ctx->frameGridUsed |= 1u;
+        } else {
+            CK(launch_trace(ta, ctx->numSms, geomInSmem, count, ctx->stream));
+        }
         ctx->kernelLaunches++;
     }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -803,6 +840,7 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
     cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[4]); c.deviceMs = ms;
     cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); c.d2hMs = ms;
     c.kernelLaunches = ctx->kernelLaunches;
+    c.gridUsed = ctx->frameGridUsed;
 
     // per-ray outputs: pinned staging -> caller arrays
     const ArtOutputs& uo = ctx->userOut;

@@ -116,6 +116,42 @@ static __device__ __noinline__ float obb_dist_exact(float qx, float qy, float qz
     return slab_hit(tNear, tFar, dist) ? dist : quiet_nan();
 }
 
+// Conservative OBB pre-test for the grid kernels: a full slab test in cheap arithmetic (FMA rotations,
+// approximate reciprocals) against the box inflated by eta. Returns false only when the exact test
+// (obb_dist_exact / obb_loss_exact with this q) certainly reports a miss.
+// Why it is safe: the cheap and the exact evaluation of local = q*(o-C), ld = q*d differ by less than
+// 4e-6*|pc| and 4e-6*|d| (a dozen roundings of magnitude <= |v|), and the exact FP32 slab comparison can
+// accept a graze that misses by at most ~6e-7 of the distance travelled. Any parameter t* >= 0 at which
+// the exact evaluation is inside the box is therefore inside the inflated box (eta = 2e-5*(|pc|_1 +
+// errScale), errScale >= distance travelled, > 4x the bound above) for the cheap ray as well, with room
+// that dwarfs the rounding of the cheap slab itself. NaNs (0*Inf) drop out of fminf/fmaxf, i.e. an axis
+// that cannot be evaluated imposes no constraint.
+__device__ __forceinline__ float rcp_fast(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ f3 qrot_fast(float4 q, f3 v)
+{
+    const float cx = fmaf(q.y, v.z, -(q.z * v.y)), cy = fmaf(q.z, v.x, -(q.x * v.z)), cz = fmaf(q.x, v.y, -(q.y * v.x));
+    const float ex = fmaf(q.y, cz, -(q.z * cy)), ey = fmaf(q.z, cx, -(q.x * cz)), ez = fmaf(q.x, cy, -(q.y * cx));
+    return mk3(fmaf(2.0f, fmaf(q.w, cx, ex), v.x), fmaf(2.0f, fmaf(q.w, cy, ey), v.y), fmaf(2.0f, fmaf(q.w, cz, ez), v.z));
+}
+__device__ __forceinline__ bool obb_maybe_hit(float4 q, f3 pc, f3 h, f3 d, float errScale)
+{
+    const float eta = 2e-5f * (fabsf(pc.x) + fabsf(pc.y) + fabsf(pc.z) + errScale);
+    const f3 lo = qrot_fast(q, pc), ld = qrot_fast(q, d);
+    const float rx = rcp_fast(ld.x), ry = rcp_fast(ld.y), rz = rcp_fast(ld.z);
+    const float hx = h.x + eta, hy = h.y + eta, hz = h.z + eta;
+    const float ax = (-hx - lo.x) * rx, bx = (hx - lo.x) * rx;
+    const float ay = (-hy - lo.y) * ry, by = (hy - lo.y) * ry;
+    const float az = (-hz - lo.z) * rz, bz = (hz - lo.z) * rz;
+    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    return !(tn > tf) && !(tf < 0.0f);
+}
+
 // ---- permeation variants (PM:265-328) -------------------------------------------------------------
 __device__ __forceinline__ float slab_loss(float tEnter, float tExit, float dens)
 {

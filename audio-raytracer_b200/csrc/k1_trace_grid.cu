@@ -1,0 +1,461 @@
+// k1_trace_grid.cu -- K1 with the uniform-grid acceleration structure: the per-ray
+// bounce loop of AudioRaytracerJobBatched.Execute (Assets/C# Scripts/Jobs/AudioRaytracerJobBatched.cs:61-215).
+//
+// Mapping: ONE THREAD OWNS ONE RAY, one warp owns 32 rays (refilled from a global queue as rays die).
+// Each round every live lane walks its segment through the grid (3D-DDA) to the nearest hit
+// (ShootRayCast, RT:225-280); the warp then evaluates the echo-return ray (RT:124-145) and the Na
+// muffle rays (RT:153-173) of all 32 hit points as ONE POOL of (ray, target) queries that lanes take
+// from dynamically, one grid cell per step, so a lane whose query is blocked early immediately starts
+// the next one. Finally every lane reflects its own ray (RT:456-532).
+//
+// Results are bit-identical with the brute-force kernel (k1_trace.cu) and the oracle: the per-collider
+// tests are the same un-fused IEEE FP32 functions in the reference's operation order (intersect.cuh),
+// the nearest hit is the lexicographic (t, sphere<AABB<OBB, index) minimum -- "strict <, first in
+// canonical order wins" (RT:244, 257, 270) -- and an occlusion query is an "any"; the grid only skips
+// colliders whose conservative bounds the ray does not come near (grid_host.h).
+#include "device_util.cuh"
+#include "intersect.cuh"
+#include "scene_dev.cuh"
+#include "um_math.cuh"
+
+namespace art {
+
+constexpr int kGridWarps = 16;
+constexpr int kGridThreads = kGridWarps * 32;
+constexpr int kQueryWords = 16;          // per prepared query in the per-warp ring (3 x float4 + uint2, padded)
+constexpr uint32_t kNoHit = 0xFFFFFFFFu;
+
+// ---- per-lane 3D-DDA ------------------------------------------------------------------------------
+struct Dda {
+    int ix, iy, iz;
+    float tmx, tmy, tmz;      // parameter at which the ray leaves the current cell along each axis
+    float tdx, tdy, tdz;      // parameter step per cell
+    float tEnd;               // stop once the next cell starts beyond this
+};
+
+// Clip the ray o + t*d, t in [0, tLimit], to the grid and set up the walk. inv = 1/d (may be +-Inf).
+// Returns false when the ray misses the grid altogether (then it misses every collider).
+__device__ __forceinline__ bool dda_init(const GridDesc& g, f3 o, f3 d, f3 inv, float tLimit, Dda& w)
+{
+    // fminf/fmaxf drop NaNs (0 * Inf when the origin sits on a bound with a zero direction component):
+    // that axis then imposes no constraint, which is the conservative reading.
+    const float ax = (g.g0x - o.x) * inv.x, bx = (g.g1x - o.x) * inv.x;
+    const float ay = (g.g0y - o.y) * inv.y, by = (g.g1y - o.y) * inv.y;
+    const float az = (g.g0z - o.z) * inv.z, bz = (g.g1z - o.z) * inv.z;
+    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    const float tStart = fmaxf(tn, 0.0f);
+    w.tEnd = fminf(tf, tLimit);
+    if (!(tStart <= w.tEnd)) return false;
+    const float sx = fmaf(d.x, tStart, o.x), sy = fmaf(d.y, tStart, o.y), sz = fmaf(d.z, tStart, o.z);
+    w.ix = min(max((int)floorf((sx - g.g0x) * g.icx), 0), g.nx - 1);
+    w.iy = min(max((int)floorf((sy - g.g0y) * g.icy), 0), g.ny - 1);
+    w.iz = min(max((int)floorf((sz - g.g0z) * g.icz), 0), g.nz - 1);
+    const float inf = pos_inf();
+    if (d.x > 0.0f) { w.tmx = (g.g0x + (float)(w.ix + 1) * g.csx - o.x) * inv.x; w.tdx = g.csx * inv.x; }
+    else if (d.x < 0.0f) { w.tmx = (g.g0x + (float)w.ix * g.csx - o.x) * inv.x; w.tdx = -g.csx * inv.x; }
+    else { w.tmx = inf; w.tdx = 0.0f; }
+    if (d.y > 0.0f) { w.tmy = (g.g0y + (float)(w.iy + 1) * g.csy - o.y) * inv.y; w.tdy = g.csy * inv.y; }
+    else if (d.y < 0.0f) { w.tmy = (g.g0y + (float)w.iy * g.csy - o.y) * inv.y; w.tdy = -g.csy * inv.y; }
+    else { w.tmy = inf; w.tdy = 0.0f; }
+    if (d.z > 0.0f) { w.tmz = (g.g0z + (float)(w.iz + 1) * g.csz - o.z) * inv.z; w.tdz = g.csz * inv.z; }
+    else if (d.z < 0.0f) { w.tmz = (g.g0z + (float)w.iz * g.csz - o.z) * inv.z; w.tdz = -g.csz * inv.z; }
+    else { w.tmz = inf; w.tdz = 0.0f; }
+    return true;
+}
+// Parameter at which the ray enters the next cell.
+__device__ __forceinline__ float dda_next_t(const Dda& w) { return fminf(fminf(w.tmx, w.tmy), w.tmz); }
+// Advance one cell; false when the walk leaves the grid.
+__device__ __forceinline__ bool dda_step(const GridDesc& g, f3 d, Dda& w)
+{
+    if (w.tmx <= w.tmy && w.tmx <= w.tmz) {
+        w.ix += d.x > 0.0f ? 1 : -1; w.tmx += w.tdx;
+        return (unsigned)w.ix < (unsigned)g.nx;
+    }
+    if (w.tmy <= w.tmz) {
+        w.iy += d.y > 0.0f ? 1 : -1; w.tmy += w.tdy;
+        return (unsigned)w.iy < (unsigned)g.ny;
+    }
+    w.iz += d.z > 0.0f ? 1 : -1; w.tmz += w.tdz;
+    return (unsigned)w.iz < (unsigned)g.nz;
+}
+__device__ __forceinline__ uint2 dda_cell(const GridDesc& g, const Dda& w)
+{
+    return __ldg(&g.cells[((size_t)w.iz * g.ny + w.iy) * g.nx + w.ix]);
+}
+
+// ---- exact per-collider distances (NaN = miss), reference operation order ---------------------------
+__device__ __forceinline__ float sphere_dist(const GeomView& gv, int id, f3 o, f3 d, float dd)
+{
+    const float4 s = gv.sph[id];
+    const f3 oc = sub3(o, mk3(s.x, s.y, s.z));                       // RT:325
+    const float cc = subr(dot3(oc, oc), s.w);                        // RT:328
+    if (sphere_fast_miss(oc, cc, d, dd)) return quiet_nan();         // disc < 0 (RT:331)
+    return sphere_dist_exact(oc.x, oc.y, oc.z, cc, d.x, d.y, d.z, dd);
+}
+__device__ __forceinline__ float aabb_dist(const GeomView& gv, int id, f3 o, f3 inv)
+{
+    const float4 A = gv.aabbA[id];
+    const float2 B = gv.aabbB[id];
+    float tNear, tFar, dist;
+    slab<8>(subr(A.x, o.x), subr(A.y, o.y), subr(A.z, o.z), subr(A.w, o.x), subr(B.x, o.y), subr(B.y, o.z),
+            inv.x, inv.y, inv.z, tNear, tFar);                       // RT:291-298
+    return slab_hit(tNear, tFar, dist) ? dist : quiet_nan();         // RT:300-307
+}
+__device__ __forceinline__ float obb_dist(const GeomView& gv, int id, f3 o, f3 d, float dd, float errScale)
+{
+    const float4 c4 = gv.obbC[id];
+    const float2 h2 = gv.obbH[id];
+    const f3 h = mk3(c4.w, h2.x, h2.y);
+    const f3 pc = sub3(o, mk3(c4.x, c4.y, c4.z));                    // RT:316
+    if (obb_sure_miss(pc, obb_cull_c(pc, h), d, dd)) return quiet_nan();
+    const float4 q4 = gv.obbQ[id];
+    if (!obb_maybe_hit(q4, pc, h, d, errScale)) return quiet_nan();
+    return obb_dist_exact(q4.x, q4.y, q4.z, q4.w, pc.x, pc.y, pc.z, h.x, h.y, h.z, d.x, d.y, d.z);
+}
+
+struct HitRec {            // per hit point, shared memory (one per lane)
+    float px, py, pz;      // Pp = hit - eps*d   (RT:124 == RT:158)
+    float echoL;           // distance(RayOrigin, hit)  (RT:130)
+    float echoMul;         // material Echo of the hit collider (RT:135-141)
+    int resultId;          // rayResultId (RT:115), local indexing
+    int row;               // batch index of the ray
+    int pad;
+};
+
+template <bool SMEM>
+__global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const TraceArgs a, const GridDesc g)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int Na = a.nTargets;
+    const int slots = Na + 1;                    // slot 0 = echo ray, slot 1+t = muffle ray to target t
+
+    unsigned char* p = smem;
+    const unsigned char* geomBase = a.geom;
+    if (SMEM) {
+        stage_blob_to_smem(p, a.geom, a.L.bytes, &bar);
+        geomBase = p;
+        p += a.L.bytes;
+    }
+    HitRec* rec = reinterpret_cast<HitRec*>(p) + warp * 32;
+    p += (size_t)kGridWarps * 32 * sizeof(HitRec);
+    float4* qbase = reinterpret_cast<float4*>(p);
+    float4* qbuf0 = qbase + warp * 32;                                // (dir.xyz, limit)
+    float4* qbuf1 = qbase + (kGridWarps + warp) * 32;                 // (1/dir.xyz, tEnd)
+    float4* qbuf2 = qbase + (2 * kGridWarps + warp) * 32;             // (tMax.xyz, cell | rec << 24)
+    int* qbuf3 = reinterpret_cast<int*>(qbase + 3 * kGridWarps * 32) + warp * 32;   // slot
+    const GeomView gv = make_view(geomBase, a.L);
+    const f3 RayOrigin = mk3(a.ox, a.oy, a.oz);
+    const uint32_t ltMask = (1u << lane) - 1u;
+
+    // ---- per-lane ray state
+    bool hasRay = false, queueEmpty = false;
+    int j = 0, hits = 0, row = 0;
+    f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0);
+    float life = 0.0f;
+    unsigned int nSegments = 0, nSegHits = 0;
+
+    for (;;) {
+        // ================= refill dead lanes from the ray queue =================
+        const uint32_t dead = __ballot_sync(kFull, !hasRay);
+        if (dead && !queueEmpty) {
+            int base = 0;
+            if (lane == 0) base = (int)atomicAdd(a.nextRay, (unsigned)__popc(dead));
+            base = __shfl_sync(kFull, base, 0);
+            if (!hasRay) {
+                const int jj = base + __popc(dead & ltMask);
+                if (jj < a.map.nLocal) {
+                    j = jj;
+                    const int rayIndex = a.map.to_global(j);
+                    row = rayIndex / a.batchSize;                              // ART:161/191 batch k
+                    d = mk3(um_f16tof32(a.dirs[3 * (size_t)rayIndex]), um_f16tof32(a.dirs[3 * (size_t)rayIndex + 1]),
+                            um_f16tof32(a.dirs[3 * (size_t)rayIndex + 2]));    // RT:94
+                    o = RayOrigin;                                             // RT:95
+                    hits = 0;                                                  // RT:97
+                    life = a.maxRayLife;                                       // RT:99
+                    hasRay = true;
+                }
+            }
+            if (base + __popc(dead) >= a.map.nLocal) queueEmpty = true;
+        }
+        if (!__any_sync(kFull, hasRay)) break;
+
+        // ================= ShootRayCast (RT:225-280), one lane = one ray =================
+        float best = kFloatMax;
+        uint32_t bkey = kNoHit;            // (typeOrder << 28) | index ; typeOrder sphere 0, AABB 1, OBB 2
+        if (hasRay) {
+            nSegments++;
+            const float dd = dot3(d, d);                                       // RT:326
+            const f3 inv = mk3(rcpr(d.x), rcpr(d.y), rcpr(d.z));               // RT:289
+            Dda w;
+            bool walking = dda_init(g, o, d, inv, pos_inf(), w);
+            while (walking) {
+                const uint2 hdr = dda_cell(g, w);
+                const uint16_t* e = g.entries + hdr.x;
+                const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
+                for (int k = 0; k < nS; k++) {
+                    const int id = __ldg(e + k);
+                    const float dist = sphere_dist(gv, id, o, d, dd);
+                    const uint32_t key = (uint32_t)id;
+                    if (dist < best || (dist == best && key < bkey)) { best = dist; bkey = key; }
+                }
+                e += nS;
+                for (int k = 0; k < nA; k++) {
+                    const int id = __ldg(e + k);
+                    const float dist = aabb_dist(gv, id, o, inv);
+                    const uint32_t key = (1u << 28) | (uint32_t)id;
+                    if (dist < best || (dist == best && key < bkey)) { best = dist; bkey = key; }
+                }
+                e += nA;
+                for (int k = 0; k < nO; k++) {
+                    const int id = __ldg(e + k);
+                    const float dist = obb_dist(gv, id, o, d, dd, g.errScale);
+                    const uint32_t key = (2u << 28) | (uint32_t)id;
+                    if (dist < best || (dist == best && key < bkey)) { best = dist; bkey = key; }
+                }
+                // colliders listed only in later cells lie beyond the next cell boundary
+                const float tNext = dda_next_t(w);
+                if (tNext > w.tEnd || tNext > best) break;
+                walking = dda_step(g, d, w);
+            }
+        }
+        const bool hit = hasRay && bkey != kNoHit;
+        int hitType = 0, hitIdx = 0;
+        float4 attr = make_float4(0, 0, 0, 0);
+        if (hasRay && !hit) {                                                  // RT:201-207 ray left the scene
+            if (a.hitCounts) a.hitCounts[j] = (uint8_t)hits;
+            hasRay = false;
+        }
+        if (hit) {
+            nSegHits++;
+            hitType = (int)(bkey >> 28);
+            hitIdx = (int)(bkey & 0x0FFFFFFFu);
+            o = add3(o, mul3s(d, best));                                       // RT:111
+            life = subr(life, best);                                           // RT:112
+            hits += 1;                                                         // RT:113
+            const size_t rayResultId = (size_t)j * a.H + hits - 1;             // RT:115
+            attr = hitType == 0 ? a.at.sphAttr[hitIdx] : (hitType == 1 ? a.at.aabbAttr[hitIdx] : a.at.obbAttr[hitIdx]);
+            if (a.hitPoints) {                                                 // RT:118, 197
+                a.hitPoints[3 * rayResultId] = um_f32tof16(o.x);
+                a.hitPoints[3 * rayResultId + 1] = um_f32tof16(o.y);
+                a.hitPoints[3 * rayResultId + 2] = um_f32tof16(o.z);
+            }
+            if (a.hitIds) {
+                const uint32_t refType = hitType == 0 ? 3u : (hitType == 1 ? 1u : 2u);   // Enums/ColliderType.cs
+                a.hitIds[rayResultId] = (refType << 30) | (uint32_t)hitIdx;
+            }
+            const f3 Pp = sub3(o, mul3s(d, kEpsilon));                         // RT:124 == RT:158
+            const f3 wv = sub3(o, RayOrigin);                                  // RT:130
+            HitRec r;
+            r.px = Pp.x; r.py = Pp.y; r.pz = Pp.z;
+            r.echoL = sqrtr(dot3(wv, wv));
+            r.echoMul = attr.y;
+            r.resultId = (int)rayResultId;
+            r.row = row;
+            r.pad = 0;
+            rec[lane] = r;
+        }
+        __syncwarp();
+
+        // ================= echo + muffle queries of all hit points (RT:121-175) =================
+        // Queries are PREPARED 32 at a time by the whole warp (direction, exact reciprocals, DDA start) into a
+        // per-warp ring in shared memory, and CONSUMED one grid cell per step by whichever lanes are idle.
+        const uint32_t hitMask = __ballot_sync(kFull, hit);
+        const int total = __popc(hitMask) * slots;
+        {
+            int nextQ = 0, bufNext = 0, bufCount = 0;
+            bool have = false;
+            f3 qo = mk3(0, 0, 0), qd = mk3(0, 0, 0), qinv = mk3(0, 0, 0);
+            float qL = 0.0f, qdd = 0.0f;
+            int qslot = 0, qrec = 0;
+            Dda w;
+            w.ix = w.iy = w.iz = 0; w.tmx = w.tmy = w.tmz = 0; w.tdx = w.tdy = w.tdz = 0; w.tEnd = 0;
+            for (;;) {
+                const uint32_t idle = __ballot_sync(kFull, !have);
+                if (idle) {
+                    if (bufNext == bufCount && nextQ < total) {
+                        // ---- prepare the next 32 queries (all lanes)
+                        const int q = nextQ + lane;
+                        nextQ += 32;
+                        bool active = false;
+                        f3 nd = mk3(0, 0, 0), ninv = mk3(0, 0, 0);
+                        float nL = 0.0f;
+                        int nslot = 0, nrec = 0;
+                        Dda nw;
+                        nw.ix = nw.iy = nw.iz = 0; nw.tmx = nw.tmy = nw.tmz = 0; nw.tdx = nw.tdy = nw.tdz = 0; nw.tEnd = 0;
+                        if (q < total) {
+                            const int ord = q / slots;
+                            nslot = q - ord * slots;
+                            nrec = __fns(hitMask, 0, ord + 1);
+                            const HitRec r = rec[nrec];
+                            const f3 no = mk3(r.px, r.py, r.pz);
+                            f3 T = RayOrigin;
+                            if (nslot > 0) T = mk3(a.targets[3 * (nslot - 1)], a.targets[3 * (nslot - 1) + 1], a.targets[3 * (nslot - 1) + 2]);
+                            const f3 v = sub3(T, no);                          // RT:127 / RT:162
+                            const float len = sqrtr(dot3(v, v));
+                            nd = smul3(rcpr(len), v);                          // normalize = rsqrt(dot) * v
+                            bool gate = true;
+                            if (nslot == 0) nL = r.echoL;                      // RT:130
+                            else { nL = len; gate = nL < a.maxMuffle; }        // RT:165, 168
+                            if (gate) {
+                                ninv = mk3(rcpr(nd.x), rcpr(nd.y), rcpr(nd.z));
+                                active = dda_init(g, no, nd, ninv, nL, nw);
+                                if (!active) {                                 // nothing near the segment: the ray sees its goal
+                                    if (nslot == 0) a.echo[r.resultId] = um_f32tof16(mulr(nL, r.echoMul));   // RT:142-144
+                                    else atomicAdd(&a.muffleCounts[r.row * Na + (nslot - 1)], 1u);            // RT:171
+                                }
+                            }
+                        }
+                        const uint32_t act = __ballot_sync(kFull, active);
+                        if (active) {
+                            const int pos = __popc(act & ltMask);
+                            qbuf0[pos] = make_float4(nd.x, nd.y, nd.z, nL);
+                            qbuf1[pos] = make_float4(ninv.x, ninv.y, ninv.z, nw.tEnd);
+                            qbuf2[pos] = make_float4(nw.tmx, nw.tmy, nw.tmz,
+                                                     __int_as_float(nw.ix | (nw.iy << 8) | (nw.iz << 16) | (nrec << 24)));
+                            qbuf3[pos] = nslot;
+                        }
+                        bufNext = 0;
+                        bufCount = __popc(act);
+                        __syncwarp();
+                    }
+                    if (bufNext < bufCount) {
+                        // ---- idle lanes take prepared queries
+                        const int pos = bufNext + __popc(idle & ltMask);
+                        if (!have && pos < bufCount) {
+                            const float4 v0 = qbuf0[pos], v1 = qbuf1[pos], v2 = qbuf2[pos];
+                            qslot = qbuf3[pos];
+                            qd = mk3(v0.x, v0.y, v0.z); qL = v0.w;
+                            qinv = mk3(v1.x, v1.y, v1.z); w.tEnd = v1.w;
+                            w.tmx = v2.x; w.tmy = v2.y; w.tmz = v2.z;
+                            const int packed = __float_as_int(v2.w);
+                            w.ix = packed & 255; w.iy = (packed >> 8) & 255; w.iz = (packed >> 16) & 255;
+                            qrec = (packed >> 24) & 31;
+                            w.tdx = fabsf(g.csx * qinv.x); w.tdy = fabsf(g.csy * qinv.y); w.tdz = fabsf(g.csz * qinv.z);
+                            qdd = dot3(qd, qd);
+                            const HitRec r = rec[qrec];
+                            qo = mk3(r.px, r.py, r.pz);
+                            have = true;
+                        }
+                        bufNext = min(bufCount, bufNext + __popc(idle));
+                        __syncwarp();
+                    }
+                }
+                if (!__any_sync(kFull, have)) {
+                    if (bufNext == bufCount && nextQ >= total) break;
+                    continue;
+                }
+                if (have) {
+                    // ---- one grid cell of this lane's query: CanRaySeePoint / CanRaySeeAudioTarget (RT:365-449)
+                    const uint2 hdr = dda_cell(g, w);
+                    const uint16_t* e = g.entries + hdr.x;
+                    const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
+                    const int ownerId = qslot - 1;         // -1 for the echo ray: never equals a valid owner below
+                    bool blocked = false;
+                    for (int k = 0; k < nA && !blocked; k++) {
+                        const int id = __ldg(e + nS + k);
+                        if (aabb_dist(gv, id, qo, qinv) < qL)
+                            blocked = !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
+                    }
+                    for (int k = 0; k < nS && !blocked; k++) {
+                        const int id = __ldg(e + k);
+                        if (sphere_dist(gv, id, qo, qd, qdd) < qL)
+                            blocked = !(qslot > 0 && a.anyOwned[0] && (int)a.at.ownS[id] == ownerId);   // RT:413
+                    }
+                    for (int k = 0; k < nO && !blocked; k++) {
+                        const int id = __ldg(e + nS + nA + k);
+                        if (obb_dist(gv, id, qo, qd, qdd, g.errScale) < qL)
+                            blocked = !(qslot > 0 && a.anyOwned[2] && (int)a.at.ownO[id] == ownerId);   // RT:439
+                    }
+                    bool done = blocked;
+                    if (!blocked) {
+                        const float tNext = dda_next_t(w);
+                        if (tNext > w.tEnd || !dda_step(g, qd, w)) {
+                            // walked the whole segment: the query ray sees its goal
+                            done = true;
+                            const HitRec r = rec[qrec];
+                            if (qslot == 0) a.echo[r.resultId] = um_f32tof16(mulr(qL, r.echoMul));       // RT:133-145
+                            else atomicAdd(&a.muffleCounts[r.row * Na + (qslot - 1)], 1u);                // RT:168-172
+                        }
+                    }
+                    if (done) have = false;
+                }
+            }
+        }
+        __syncwarp();
+
+        // ================= termination / reflection (RT:178-193) =================
+        if (hit) {
+            bool alive = true;
+            if (hits >= a.H || life <= 0.0f) {
+                alive = false;
+            } else {
+                f3 normal = mk3(0.0f, 0.0f, 0.0f);
+                if (hitType == 1) {
+                    const float4 C = a.at.aabbCtr[hitIdx], Hx = a.at.aabbHalf[hitIdx];
+                    const f3 lp = sub3(o, mk3(C.x, C.y, C.z));                                    // RT:465
+                    const float ex = subr(Hx.x, fabsf(lp.x)), ey = subr(Hx.y, fabsf(lp.y)), ez = subr(Hx.z, fabsf(lp.z));
+                    if (ex < ey && ex < ez) normal.x = um_sign(lp.x);                             // RT:471-482
+                    else if (ey < ex && ey < ez) normal.y = um_sign(lp.y);
+                    else normal.z = um_sign(lp.z);
+                } else if (hitType == 2) {
+                    const float4 qi = a.at.obbQinv[hitIdx], q4 = gv.obbQ[hitIdx], c4 = gv.obbC[hitIdx];
+                    const float4 Hx = a.at.obbHalf[hitIdx];                                       // raw OBB Size
+                    f4 qinv; qinv.x = qi.x; qinv.y = qi.y; qinv.z = qi.z; qinv.w = qi.w;
+                    f4 q; q.x = q4.x; q.y = q4.y; q.z = q4.z; q.w = q4.w;
+                    const f3 lh = qmul3(qinv, sub3(o, mk3(c4.x, c4.y, c4.z)));                    // RT:489 (quirk Q3)
+                    const float ex = subr(Hx.x, fabsf(lh.x)), ey = subr(Hx.y, fabsf(lh.y)), ez = subr(Hx.z, fabsf(lh.z));
+                    f3 ln = mk3(0.0f, 0.0f, 0.0f);
+                    if (ex < ey && ex < ez) ln.x = um_sign(lh.x);                                 // RT:497-508
+                    else if (ey < ex && ey < ez) ln.y = um_sign(lh.y);
+                    else ln.z = um_sign(lh.z);
+                    normal = qmul3(q, ln);                                                        // RT:510
+                } else {
+                    const float4 s = gv.sph[hitIdx];
+                    normal = normalize3(sub3(o, mk3(s.x, s.y, s.z)));                             // RT:516
+                }
+                d = reflect3(d, normal);                                                          // RT:525
+                o = add3(o, mul3s(d, kEpsilon));                                                  // RT:528
+                life = subr(life, mulr(a.maxRayLife, attr.x));                                    // RT:531
+                if (life < 0.0f) alive = false;                                                   // RT:189
+            }
+            if (!alive) {
+                if (a.hitCounts) a.hitCounts[j] = (uint8_t)hits;                                  // RT:204, 212
+                hasRay = false;
+            }
+        }
+    }
+
+    // segment counters: warp sum -> one atomic per warp
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        nSegments += __shfl_xor_sync(kFull, nSegments, s);
+        nSegHits += __shfl_xor_sync(kFull, nSegHits, s);
+    }
+    if (lane == 0) {
+        atomicAdd(&a.counters[C_SEGMENTS], (unsigned long long)nSegments);
+        atomicAdd(&a.counters[C_SEGMENT_HITS], (unsigned long long)nSegHits);
+    }
+}
+
+// ---- launcher -----------------------------------------------------------------------------------
+size_t trace_grid_smem_bytes(const GeomLayout& L, bool geomInSmem)
+{
+    return (geomInSmem ? L.bytes : 0) + (size_t)kGridWarps * 32 * (sizeof(HitRec) + kQueryWords * 4);
+}
+
+cudaError_t launch_trace_grid(const TraceArgs& a, const GridDesc& g, int numCtas, bool geomInSmem, cudaStream_t stream)
+{
+    const size_t smem = trace_grid_smem_bytes(a.L, geomInSmem);
+    void (*k)(const TraceArgs, const GridDesc) = geomInSmem ? trace_grid_kernel<true> : trace_grid_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<numCtas, kGridThreads, smem, stream>>>(a, g);
+    return cudaGetLastError();
+}
+
+}  // namespace art

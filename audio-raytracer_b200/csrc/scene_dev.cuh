@@ -125,6 +125,24 @@ struct TraceArgs {
     int anyOwned[3];               // does any sphere / AABB / OBB belong to a target < nTargets (RT:413/426/439)
 };
 
+// Uniform grid over the collider scene (acceleration structure). Built on the host at
+// scene upload (grid_host.h); cell (ix,iy,iz) lists the canonical indices of every collider whose
+// conservatively inflated bounds overlap it, grouped spheres | AABBs | OBBs. The kernels walk a ray
+// through the cells (3D-DDA) and run the SAME exact per-collider tests as the brute-force kernels on
+// the listed colliders only; since the nearest-hit rule is a (t, canonical index) minimum and the
+// occlusion rule an "any", the results do not depend on which non-hitting colliders were skipped.
+struct GridDesc {
+    float g0x, g0y, g0z;          // min corner
+    float g1x, g1y, g1z;          // max corner
+    float csx, csy, csz;          // cell size
+    float icx, icy, icz;          // 1 / cell size
+    int nx, ny, nz;
+    float errScale;               // >= any distance a ray travels inside the scene (conservative pre-tests)
+    const uint2* cells;           // [nz*ny*nx]  x = first entry, y = nS | nA << 10 | nO << 21
+    const uint16_t* entries;      // collider indices, per cell: spheres, AABBs, OBBs
+};
+constexpr int kGridMaxS = 1023, kGridMaxA = 2047, kGridMaxO = 2047;
+
 // K0 arguments
 struct PackArgs {
     const uint16_t* rawS;   // ColliderSphereStruct[ns] as 8 x u16

@@ -108,6 +108,10 @@ typedef struct ArtConfig {
                                           with the reference, serial tail). Default: exact integer accumulation. */
 #define ART_FRAME_NO_HOST_OUTPUTS  4u  /* keep per-ray outputs in HBM, copy back only the per-target results */
 #define ART_FRAME_PARTIALS_ONLY    8u  /* sharded run: skip the PA finalisation, caller combines partials */
+#define ART_FRAME_BRUTE_FORCE     16u  /* scan every collider for every query exactly as the reference's loops do
+                                          (no acceleration structure). Default: uniform-grid traversal, which runs
+                                          the same exact tests on the colliders near each ray only; all outputs are
+                                          bit-identical. ART_FRAME_COUNTERS implies brute force. */
 
 /* One field per job-struct field (RT:12-52, PM:10-27, PA:10-25). */
 typedef struct ArtParams {
@@ -164,6 +168,7 @@ typedef struct ArtCounters {
     float    deviceMs;          /* first kernel start -> last kernel end, this frame */
     float    h2dMs, d2hMs;      /* copy time on the stream (0 when nothing was copied) */
     uint32_t kernelLaunches;    /* kernels of this library launched for the frame */
+    uint32_t gridUsed;          /* bit 0: trace job used the uniform grid, bit 1: permeation job did */
 } ArtCounters;
 
 /* ≙ AudioRayTracer.Awake/InitializeAudioRaytraceSystem (ART:53-87): one context per AudioRayTracer. */

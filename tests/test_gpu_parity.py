@@ -18,9 +18,33 @@ pytestmark = pytest.mark.gpu
 C = native.FRAME_COUNTERS
 
 
+def assert_same_frame(a, b, what):
+    """two GPU frames of the same inputs (e.g. uniform-grid traversal vs brute-force scans): bit-identical outputs."""
+    for k in ("hit_counts", "hit_ids", "echo", "hit_points", "muffle", "muffle_totals"):
+        x, y = getattr(a, k), getattr(b, k)
+        if x is not None and y is not None:
+            np.testing.assert_array_equal(x, y, err_msg=f"{what}: {k}")
+    if a.permeation is not None and b.permeation is not None:
+        np.testing.assert_array_equal(a.permeation.view(np.uint32), b.permeation.view(np.uint32), err_msg=f"{what}: permeation")
+    if a.settings is not None and b.settings is not None:
+        np.testing.assert_array_equal(a.settings.view(np.uint8), b.settings.view(np.uint8), err_msg=f"{what}: settings")
+    assert a.counters["segments"] == b.counters["segments"] and a.counters["segmentHits"] == b.counters["segmentHits"]
+
+
 def run_gpu(ctx, scene, jobs=native.JOB_ALL, flags=C):
+    """The counting frame (brute-force kernels, oracle-equivalent work counters) is what the caller compares with the
+    oracle; the same inputs are also run through the default path (uniform-grid traversal) and must match it bit for bit."""
     native.upload(ctx, scene)
-    return ctx.run_frame(scene, jobs=jobs, flags=flags)
+    r = ctx.run_frame(scene, jobs=jobs, flags=flags)
+    if flags & C:
+        fast = ctx.run_frame(scene, jobs=jobs, flags=flags & ~C)
+        if scene.name != "custom" and jobs & native.JOB_RAYTRACE:
+            assert fast.counters["gridUsed"] & 1, "default path did not use the grid"
+        assert_same_frame(fast, r, "grid vs brute force")
+        if r.permeation_sum is not None and fast.permeation_sum is not None:
+            scale = scene.n_rays * scene.permeation_strength_per_ray * max(1, r.counters["permHitRays"])
+            np.testing.assert_allclose(fast.permeation_sum, r.permeation_sum, rtol=0, atol=1e-5 * scale)
+    return r
 
 
 def assert_rt_equal(g, o, scene, check_counters=True):
