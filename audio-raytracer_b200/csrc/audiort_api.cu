@@ -175,7 +175,7 @@ struct ArtCtx {
     HostGrid grid;                                 // uniform grid over the scene (grid_host.h)
     DevBuf gridCells, gridEntries;
     bool gridDisabled = false;                     // ART_DISABLE_GRID=1
-    float gridCellScale = 1.0f;                    // ART_GRID_CELL_SCALE
+    float gridCellScale = 0.8f;                    // ART_GRID_CELL_SCALE
     uint32_t frameGridUsed = 0;
     GeomLayout L{};
     bool haveScene = false, sceneDirty = false;
@@ -677,6 +677,16 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         at.ownedCount = ctx->ownedCount.as<int>();
     }
 
+    // acceleration structure: the same exact tests on the colliders near each ray only (bit-identical outputs);
+    // the work counters are defined by the reference's full scans, so counting frames use the brute-force kernels
+    bool useGrid = ctx->grid.ok && !count && !(prm->flags & ART_FRAME_BRUTE_FORCE);
+    if (useGrid) {
+        const float dx = prm->rayOrigin[0] - ctx->grid.cx, dy = prm->rayOrigin[1] - ctx->grid.cy, dz = prm->rayOrigin[2] - ctx->grid.cz;
+        useGrid = std::sqrt(dx * dx + dy * dy + dz * dz) <= ctx->grid.listenerRange;   // else the error bounds of grid_host.h do not hold
+    }
+    GridDesc gd = ctx->grid.d;
+    gd.cells = ctx->gridCells.as<uint2>(); gd.entries = ctx->gridEntries.as<uint16_t>();
+
     // ---------------- K1 ----------------
     if (wantRT) {
         TraceArgs ta;
@@ -701,16 +711,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             for (int t = 0; t < Na; t++) owned += ownedCount[(size_t)sec * Na + t];
             ta.anyOwned[sec] = owned > 0 ? 1 : 0;
         }
-        // acceleration structure: same exact tests on the colliders near each ray only (bit-identical outputs);
-        // the work counters are defined by the reference's full scans, so counting frames use the brute-force kernel
-        bool useGrid = ctx->grid.ok && !count && !(prm->flags & ART_FRAME_BRUTE_FORCE);
         if (useGrid) {
-            const float dx = prm->rayOrigin[0] - ctx->grid.cx, dy = prm->rayOrigin[1] - ctx->grid.cy, dz = prm->rayOrigin[2] - ctx->grid.cz;
-            useGrid = std::sqrt(dx * dx + dy * dy + dz * dz) <= ctx->grid.listenerRange;   // else the error bounds of grid_host.h do not hold
-        }
-        if (useGrid) {
-            GridDesc gd = ctx->grid.d;
-            gd.cells = ctx->gridCells.as<uint2>(); gd.entries = ctx->gridEntries.as<uint16_t>();
             const bool gInSmem = trace_grid_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
             CK(launch_trace_grid(ta, gd, ctx->numSms, gInSmem, ctx->stream));
             ctx->frameGridUsed |= 1u;
@@ -741,8 +742,15 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         pa.permLast = reinterpret_cast<float*>(pb + bl.offPermLast);
         pa.counters = dh->counters;
         pa.nextRay = ctx->queue.as<unsigned int>() + 8;
-        const bool geomInSmem = perm_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
-        CK(launch_permeation(pa, ctx->numSms, geomInSmem, T, ctx->stream));
+        if (useGrid) {
+            const bool gInSmem = perm_grid_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
+            CK(launch_permeation_grid(pa, gd, ctx->numSms, gInSmem, ctx->stream));
+            CK(launch_perm_last(pa, T, ctx->stream));
+            ctx->frameGridUsed |= 2u;
+        } else {
+            const bool geomInSmem = perm_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
+            CK(launch_permeation(pa, ctx->numSms, geomInSmem, T, ctx->stream));
+        }
         ctx->kernelLaunches += 2;
     }
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));

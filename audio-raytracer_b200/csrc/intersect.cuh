@@ -138,18 +138,53 @@ __device__ __forceinline__ f3 qrot_fast(float4 q, f3 v)
     const float ex = fmaf(q.y, cz, -(q.z * cy)), ey = fmaf(q.z, cx, -(q.x * cz)), ez = fmaf(q.x, cy, -(q.y * cx));
     return mk3(fmaf(2.0f, fmaf(q.w, cx, ex), v.x), fmaf(2.0f, fmaf(q.w, cy, ey), v.y), fmaf(2.0f, fmaf(q.w, cz, ez), v.z));
 }
-__device__ __forceinline__ bool obb_maybe_hit(float4 q, f3 pc, f3 h, f3 d, float errScale)
+// Cheap slab intervals of the ray against the box inflated by eta (tnI, tfI) and, if DEFL, deflated by eta
+// (tnD, tfD; tnD > tfD when the deflated box is empty).
+template <bool DEFL>
+__device__ __forceinline__ void obb_pretest(float4 q, f3 pc, f3 h, f3 d, float errScale, float& tnI, float& tfI, float& tnD, float& tfD)
 {
     const float eta = 2e-5f * (fabsf(pc.x) + fabsf(pc.y) + fabsf(pc.z) + errScale);
     const f3 lo = qrot_fast(q, pc), ld = qrot_fast(q, d);
     const float rx = rcp_fast(ld.x), ry = rcp_fast(ld.y), rz = rcp_fast(ld.z);
-    const float hx = h.x + eta, hy = h.y + eta, hz = h.z + eta;
-    const float ax = (-hx - lo.x) * rx, bx = (hx - lo.x) * rx;
-    const float ay = (-hy - lo.y) * ry, by = (hy - lo.y) * ry;
-    const float az = (-hz - lo.z) * rz, bz = (hz - lo.z) * rz;
-    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-    return !(tn > tf) && !(tf < 0.0f);
+    {
+        const float hx = h.x + eta, hy = h.y + eta, hz = h.z + eta;
+        const float ax = (-hx - lo.x) * rx, bx = (hx - lo.x) * rx;
+        const float ay = (-hy - lo.y) * ry, by = (hy - lo.y) * ry;
+        const float az = (-hz - lo.z) * rz, bz = (hz - lo.z) * rz;
+        tnI = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+        tfI = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    }
+    if (DEFL) {
+        const float hx = h.x - eta, hy = h.y - eta, hz = h.z - eta;
+        const float ax = (-hx - lo.x) * rx, bx = (hx - lo.x) * rx;
+        const float ay = (-hy - lo.y) * ry, by = (hy - lo.y) * ry;
+        const float az = (-hz - lo.z) * rz, bz = (hz - lo.z) * rz;
+        tnD = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+        tfD = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+        if (!(hx > 0.0f && hy > 0.0f && hz > 0.0f)) { tnD = pos_inf(); tfD = -pos_inf(); }
+    }
+}
+// Nearest-hit use: false only if the exact test certainly misses or its distance certainly exceeds `best`
+// (the exact distance is >= the entry into the inflated box up to rounding far below eta).
+__device__ __forceinline__ bool obb_maybe_nearer(float4 q, f3 pc, f3 h, f3 d, float errScale, float best)
+{
+    float tnI, tfI, tnD, tfD;
+    obb_pretest<false>(q, pc, h, d, errScale, tnI, tfI, tnD, tfD);
+    return !(tnI > tfI) && !(tfI < 0.0f) && !(tnI > best);
+}
+// Any-hit use against a distance limit: 0 = the exact test certainly misses, 1 = it certainly reports a hit
+// with distance < limit, 2 = undecided (run the exact test).
+// "Certainly hits": the origin is outside the inflated box (tnI > 0), so the exact evaluation's origin is outside
+// the real box and its distance is its entry parameter tNear; the cheap ray is inside the DEFLATED box at tnD, so
+// the exact evaluation is inside the real box there with ~eta to spare (the FP32 slab comparison cannot miss
+// that), hence tNear <= tnD * (1 + 2e-6) < limit when tnD < limit * (1 - 1e-4).
+__device__ __forceinline__ int obb_classify(float4 q, f3 pc, f3 h, f3 d, float errScale, float limit)
+{
+    float tnI, tfI, tnD, tfD;
+    obb_pretest<true>(q, pc, h, d, errScale, tnI, tfI, tnD, tfD);
+    if ((tnI > tfI) || (tfI < 0.0f)) return 0;
+    const bool sure = tnI > 0.0f && tnD <= tfD && tnD < limit * 0.9999f;
+    return sure ? 1 : 2;
 }
 
 // ---- permeation variants (PM:265-328) -------------------------------------------------------------

@@ -14,95 +14,33 @@
 // canonical order wins" (RT:244, 257, 270) -- and an occlusion query is an "any"; the grid only skips
 // colliders whose conservative bounds the ray does not come near (grid_host.h).
 #include "device_util.cuh"
+#include "grid_dev.cuh"
 #include "intersect.cuh"
 #include "scene_dev.cuh"
 #include "um_math.cuh"
 
 namespace art {
 
-constexpr int kGridWarps = 16;
+#ifndef ART_GRID_WARPS
+#define ART_GRID_WARPS 24
+#endif
+constexpr int kGridWarps = ART_GRID_WARPS;
 constexpr int kGridThreads = kGridWarps * 32;
 constexpr int kQueryWords = 16;          // per prepared query in the per-warp ring (3 x float4 + uint2, padded)
 constexpr uint32_t kNoHit = 0xFFFFFFFFu;
+#ifndef ART_CAP_A
+#define ART_CAP_A 4
+#endif
+#ifndef ART_CAP_S
+#define ART_CAP_S 1
+#endif
+#ifndef ART_CAP_O
+#define ART_CAP_O 2
+#endif
+constexpr int kCapA = ART_CAP_A, kCapS = ART_CAP_S, kCapO = ART_CAP_O;   // tests per type per step of an occlusion query
 
-// ---- per-lane 3D-DDA ------------------------------------------------------------------------------
-struct Dda {
-    int ix, iy, iz;
-    float tmx, tmy, tmz;      // parameter at which the ray leaves the current cell along each axis
-    float tdx, tdy, tdz;      // parameter step per cell
-    float tEnd;               // stop once the next cell starts beyond this
-};
-
-// Clip the ray o + t*d, t in [0, tLimit], to the grid and set up the walk. inv = 1/d (may be +-Inf).
-// Returns false when the ray misses the grid altogether (then it misses every collider).
-__device__ __forceinline__ bool dda_init(const GridDesc& g, f3 o, f3 d, f3 inv, float tLimit, Dda& w)
-{
-    // fminf/fmaxf drop NaNs (0 * Inf when the origin sits on a bound with a zero direction component):
-    // that axis then imposes no constraint, which is the conservative reading.
-    const float ax = (g.g0x - o.x) * inv.x, bx = (g.g1x - o.x) * inv.x;
-    const float ay = (g.g0y - o.y) * inv.y, by = (g.g1y - o.y) * inv.y;
-    const float az = (g.g0z - o.z) * inv.z, bz = (g.g1z - o.z) * inv.z;
-    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
-    const float tStart = fmaxf(tn, 0.0f);
-    w.tEnd = fminf(tf, tLimit);
-    if (!(tStart <= w.tEnd)) return false;
-    const float sx = fmaf(d.x, tStart, o.x), sy = fmaf(d.y, tStart, o.y), sz = fmaf(d.z, tStart, o.z);
-    w.ix = min(max((int)floorf((sx - g.g0x) * g.icx), 0), g.nx - 1);
-    w.iy = min(max((int)floorf((sy - g.g0y) * g.icy), 0), g.ny - 1);
-    w.iz = min(max((int)floorf((sz - g.g0z) * g.icz), 0), g.nz - 1);
-    const float inf = pos_inf();
-    if (d.x > 0.0f) { w.tmx = (g.g0x + (float)(w.ix + 1) * g.csx - o.x) * inv.x; w.tdx = g.csx * inv.x; }
-    else if (d.x < 0.0f) { w.tmx = (g.g0x + (float)w.ix * g.csx - o.x) * inv.x; w.tdx = -g.csx * inv.x; }
-    else { w.tmx = inf; w.tdx = 0.0f; }
-    if (d.y > 0.0f) { w.tmy = (g.g0y + (float)(w.iy + 1) * g.csy - o.y) * inv.y; w.tdy = g.csy * inv.y; }
-    else if (d.y < 0.0f) { w.tmy = (g.g0y + (float)w.iy * g.csy - o.y) * inv.y; w.tdy = -g.csy * inv.y; }
-    else { w.tmy = inf; w.tdy = 0.0f; }
-    if (d.z > 0.0f) { w.tmz = (g.g0z + (float)(w.iz + 1) * g.csz - o.z) * inv.z; w.tdz = g.csz * inv.z; }
-    else if (d.z < 0.0f) { w.tmz = (g.g0z + (float)w.iz * g.csz - o.z) * inv.z; w.tdz = -g.csz * inv.z; }
-    else { w.tmz = inf; w.tdz = 0.0f; }
-    return true;
-}
-// Parameter at which the ray enters the next cell.
-__device__ __forceinline__ float dda_next_t(const Dda& w) { return fminf(fminf(w.tmx, w.tmy), w.tmz); }
-// Advance one cell; false when the walk leaves the grid.
-__device__ __forceinline__ bool dda_step(const GridDesc& g, f3 d, Dda& w)
-{
-    if (w.tmx <= w.tmy && w.tmx <= w.tmz) {
-        w.ix += d.x > 0.0f ? 1 : -1; w.tmx += w.tdx;
-        return (unsigned)w.ix < (unsigned)g.nx;
-    }
-    if (w.tmy <= w.tmz) {
-        w.iy += d.y > 0.0f ? 1 : -1; w.tmy += w.tdy;
-        return (unsigned)w.iy < (unsigned)g.ny;
-    }
-    w.iz += d.z > 0.0f ? 1 : -1; w.tmz += w.tdz;
-    return (unsigned)w.iz < (unsigned)g.nz;
-}
-__device__ __forceinline__ uint2 dda_cell(const GridDesc& g, const Dda& w)
-{
-    return __ldg(&g.cells[((size_t)w.iz * g.ny + w.iy) * g.nx + w.ix]);
-}
-
-// ---- exact per-collider distances (NaN = miss), reference operation order ---------------------------
-__device__ __forceinline__ float sphere_dist(const GeomView& gv, int id, f3 o, f3 d, float dd)
-{
-    const float4 s = gv.sph[id];
-    const f3 oc = sub3(o, mk3(s.x, s.y, s.z));                       // RT:325
-    const float cc = subr(dot3(oc, oc), s.w);                        // RT:328
-    if (sphere_fast_miss(oc, cc, d, dd)) return quiet_nan();         // disc < 0 (RT:331)
-    return sphere_dist_exact(oc.x, oc.y, oc.z, cc, d.x, d.y, d.z, dd);
-}
-__device__ __forceinline__ float aabb_dist(const GeomView& gv, int id, f3 o, f3 inv)
-{
-    const float4 A = gv.aabbA[id];
-    const float2 B = gv.aabbB[id];
-    float tNear, tFar, dist;
-    slab<8>(subr(A.x, o.x), subr(A.y, o.y), subr(A.z, o.z), subr(A.w, o.x), subr(B.x, o.y), subr(B.y, o.z),
-            inv.x, inv.y, inv.z, tNear, tFar);                       // RT:291-298
-    return slab_hit(tNear, tFar, dist) ? dist : quiet_nan();         // RT:300-307
-}
-__device__ __forceinline__ float obb_dist(const GeomView& gv, int id, f3 o, f3 d, float dd, float errScale)
+// nearest-hit: exact distance, or NaN when the collider misses or certainly lies beyond `best`
+__device__ __forceinline__ float obb_dist_nearest(const GeomView& gv, int id, f3 o, f3 d, float dd, float errScale, float best)
 {
     const float4 c4 = gv.obbC[id];
     const float2 h2 = gv.obbH[id];
@@ -110,8 +48,21 @@ __device__ __forceinline__ float obb_dist(const GeomView& gv, int id, f3 o, f3 d
     const f3 pc = sub3(o, mk3(c4.x, c4.y, c4.z));                    // RT:316
     if (obb_sure_miss(pc, obb_cull_c(pc, h), d, dd)) return quiet_nan();
     const float4 q4 = gv.obbQ[id];
-    if (!obb_maybe_hit(q4, pc, h, d, errScale)) return quiet_nan();
+    if (!obb_maybe_nearer(q4, pc, h, d, errScale, best)) return quiet_nan();
     return obb_dist_exact(q4.x, q4.y, q4.z, q4.w, pc.x, pc.y, pc.z, h.x, h.y, h.z, d.x, d.y, d.z);
+}
+// any-hit: does the exact test report a distance < limit (RT:390 / RT:441)?
+__device__ __forceinline__ bool obb_blocks(const GeomView& gv, int id, f3 o, f3 d, float dd, float errScale, float limit)
+{
+    const float4 c4 = gv.obbC[id];
+    const float2 h2 = gv.obbH[id];
+    const f3 h = mk3(c4.w, h2.x, h2.y);
+    const f3 pc = sub3(o, mk3(c4.x, c4.y, c4.z));
+    if (obb_sure_miss(pc, obb_cull_c(pc, h), d, dd)) return false;
+    const float4 q4 = gv.obbQ[id];
+    const int cls = obb_classify(q4, pc, h, d, errScale, limit);
+    if (cls != 2) return cls == 1;
+    return obb_dist_exact(q4.x, q4.y, q4.z, q4.w, pc.x, pc.y, pc.z, h.x, h.y, h.z, d.x, d.y, d.z) < limit;
 }
 
 struct HitRec {            // per hit point, shared memory (one per lane)
@@ -213,7 +164,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
                 e += nA;
                 for (int k = 0; k < nO; k++) {
                     const int id = __ldg(e + k);
-                    const float dist = obb_dist(gv, id, o, d, dd, g.errScale);
+                    const float dist = obb_dist_nearest(gv, id, o, d, dd, g.errScale, best);
                     const uint32_t key = (2u << 28) | (uint32_t)id;
                     if (dist < best || (dist == best && key < bkey)) { best = dist; bkey = key; }
                 }
@@ -272,8 +223,10 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
             f3 qo = mk3(0, 0, 0), qd = mk3(0, 0, 0), qinv = mk3(0, 0, 0);
             float qL = 0.0f, qdd = 0.0f;
             int qslot = 0, qrec = 0;
+            uint32_t cur = kNoHit;            // cursor inside the current cell (kA | kS << 11 | kO << 21), all ones = fetch the cell
+            uint2 hdr = make_uint2(0, 0);
             Dda w;
-            w.ix = w.iy = w.iz = 0; w.tmx = w.tmy = w.tmz = 0; w.tdx = w.tdy = w.tdz = 0; w.tEnd = 0;
+            w.ix = w.iy = w.iz = 0; w.tmx = w.tmy = w.tmz = 0; w.tdx = w.tdy = w.tdz = 0; w.tEnd = 0; w.tCur = 0;
             for (;;) {
                 const uint32_t idle = __ballot_sync(kFull, !have);
                 if (idle) {
@@ -286,7 +239,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
                         float nL = 0.0f;
                         int nslot = 0, nrec = 0;
                         Dda nw;
-                        nw.ix = nw.iy = nw.iz = 0; nw.tmx = nw.tmy = nw.tmz = 0; nw.tdx = nw.tdy = nw.tdz = 0; nw.tEnd = 0;
+                        nw.ix = nw.iy = nw.iz = 0; nw.tmx = nw.tmy = nw.tmz = 0; nw.tdx = nw.tdy = nw.tdz = 0; nw.tEnd = 0; nw.tCur = 0;
                         if (q < total) {
                             const int ord = q / slots;
                             nslot = q - ord * slots;
@@ -339,6 +292,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
                             qdd = dot3(qd, qd);
                             const HitRec r = rec[qrec];
                             qo = mk3(r.px, r.py, r.pz);
+                            cur = kNoHit;
                             have = true;
                         }
                         bufNext = min(bufCount, bufNext + __popc(idle));
@@ -350,36 +304,43 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
                     continue;
                 }
                 if (have) {
-                    // ---- one grid cell of this lane's query: CanRaySeePoint / CanRaySeeAudioTarget (RT:365-449)
-                    const uint2 hdr = dda_cell(g, w);
+                    // ---- a bounded slice of the current cell's lists: CanRaySeePoint / CanRaySeeAudioTarget (RT:365-449).
+                    //      At most kCapA/kCapS/kCapO tests per step keep the lanes of a warp in step with each other.
+                    if (cur == kNoHit) { hdr = dda_cell(g, w); cur = 0; }
                     const uint16_t* e = g.entries + hdr.x;
                     const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
+                    int kA = (int)(cur & 2047u), kS = (int)((cur >> 11) & 1023u), kO = (int)(cur >> 21);
                     const int ownerId = qslot - 1;         // -1 for the echo ray: never equals a valid owner below
                     bool blocked = false;
-                    for (int k = 0; k < nA && !blocked; k++) {
-                        const int id = __ldg(e + nS + k);
+                    for (int c = 0; c < kCapA && kA < nA && !blocked; c++, kA++) {
+                        const int id = __ldg(e + nS + kA);
                         if (aabb_dist(gv, id, qo, qinv) < qL)
                             blocked = !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
                     }
-                    for (int k = 0; k < nS && !blocked; k++) {
-                        const int id = __ldg(e + k);
+                    for (int c = 0; c < kCapS && kS < nS && !blocked; c++, kS++) {
+                        const int id = __ldg(e + kS);
                         if (sphere_dist(gv, id, qo, qd, qdd) < qL)
                             blocked = !(qslot > 0 && a.anyOwned[0] && (int)a.at.ownS[id] == ownerId);   // RT:413
                     }
-                    for (int k = 0; k < nO && !blocked; k++) {
-                        const int id = __ldg(e + nS + nA + k);
-                        if (obb_dist(gv, id, qo, qd, qdd, g.errScale) < qL)
+                    for (int c = 0; c < kCapO && kO < nO && !blocked; c++, kO++) {
+                        const int id = __ldg(e + nS + nA + kO);
+                        if (obb_blocks(gv, id, qo, qd, qdd, g.errScale, qL))
                             blocked = !(qslot > 0 && a.anyOwned[2] && (int)a.at.ownO[id] == ownerId);   // RT:439
                     }
                     bool done = blocked;
                     if (!blocked) {
-                        const float tNext = dda_next_t(w);
-                        if (tNext > w.tEnd || !dda_step(g, qd, w)) {
-                            // walked the whole segment: the query ray sees its goal
-                            done = true;
-                            const HitRec r = rec[qrec];
-                            if (qslot == 0) a.echo[r.resultId] = um_f32tof16(mulr(qL, r.echoMul));       // RT:133-145
-                            else atomicAdd(&a.muffleCounts[r.row * Na + (qslot - 1)], 1u);                // RT:168-172
+                        if (kA >= nA && kS >= nS && kO >= nO) {
+                            cur = kNoHit;                   // cell finished: move on
+                            const float tNext = dda_next_t(w);
+                            if (tNext > w.tEnd || !dda_step(g, qd, w)) {
+                                // walked the whole segment: the query ray sees its goal
+                                done = true;
+                                const HitRec r = rec[qrec];
+                                if (qslot == 0) a.echo[r.resultId] = um_f32tof16(mulr(qL, r.echoMul));       // RT:133-145
+                                else atomicAdd(&a.muffleCounts[r.row * Na + (qslot - 1)], 1u);                // RT:168-172
+                            }
+                        } else {
+                            cur = (uint32_t)kA | ((uint32_t)kS << 11) | ((uint32_t)kO << 21);
                         }
                     }
                     if (done) have = false;

@@ -352,6 +352,8 @@ __global__ void __launch_bounds__(128) perm_last_kernel(const PermArgs a, int T)
     if (lane == 0) a.permLast[k * a.nTargets + tgt] = subr(a.nTimesS, loss);   // PM:260
 }
 
+cudaError_t launch_perm_last(const PermArgs& a, int T, cudaStream_t stream);
+
 size_t perm_smem_bytes(const GeomLayout& L, bool geomInSmem)
 {
     return (geomInSmem ? L.bytes : 0) + (size_t)kWarpsPerCta * kPermWarpBytes;
@@ -366,6 +368,11 @@ cudaError_t launch_permeation(const PermArgs& a, int numCtas, bool geomInSmem, i
     k<<<numCtas, kThreads, smem, stream>>>(a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    return launch_perm_last(a, T, stream);
+}
+
+cudaError_t launch_perm_last(const PermArgs& a, int T, cudaStream_t stream)
+{
     dim3 grid((unsigned)T, (unsigned)((a.nTargets + 3) / 4));
     perm_last_kernel<<<grid, 128, 0, stream>>>(a, T);
     return cudaGetLastError();

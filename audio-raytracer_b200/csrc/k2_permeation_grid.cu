@@ -1,0 +1,243 @@
+// k2_permeation_grid.cu -- K2 with the uniform-grid acceleration structure:
+// AudioPermeationJobBatched.Execute (Assets/C# Scripts/Jobs/AudioPermeationJobBatched.cs:34-91).
+//
+// Mapping: a warp takes 32 rays at a time from the queue.
+//   Phase 1, one thread = one ray: first-hit DISTANCE by a 3D-DDA walk (PM:101-141; the OBB test uses the
+//            inverse of the stored rotation, PM:174, quirk Q4). Exact tests, so firstHitDist -- the input of
+//            perm_last_kernel, which produces the canonical PermeationPowerRemains bit-exactly -- is the same
+//            float the brute-force kernel writes.
+//   Phase 2, one thread = one (ray, target) pair: the through-material loss of PM:225-261 (no early exit, no
+//            distance clip -- quirk Q7) accumulated cell by cell along the whole line, each collider's interval
+//            clipped to the cell so that a collider listed in several cells is counted once. A lane keeps the
+//            same target for all 32 rays, so the per-target sums live in registers and are flushed with two
+//            integer atomics per target block (deterministic: integer part + 36-bit fixed-point fraction).
+// The per-pair values feed only the permeationSum extension (tolerance 1e-5 relative to N*S, include/audiort.h);
+// they are evaluated in cheap arithmetic (FMA, approximate reciprocals). What the reference keeps of this job --
+// the last hitting ray of each batch (PM:85, quirk Q5/Q6) -- is recomputed by perm_last_kernel in the
+// reference's own operation and summation order.
+#include "device_util.cuh"
+#include "grid_dev.cuh"
+#include "intersect.cuh"
+#include "scene_dev.cuh"
+#include "um_math.cuh"
+
+namespace art {
+
+#ifndef ART_PGRID_WARPS
+#define ART_PGRID_WARPS 24
+#endif
+constexpr int kPGridWarps = ART_PGRID_WARPS;
+constexpr int kPGridThreads = kPGridWarps * 32;
+
+// length of [tEnter, tExit] inside the cell interval [tIn, tOut]
+__device__ __forceinline__ float clip_len(float tEnter, float tExit, float tIn, float tOut)
+{
+    return fmaxf(0.0f, fminf(tExit, tOut) - fmaxf(tEnter, tIn));
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const PermArgs a, const GridDesc g)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int Na = a.nTargets;
+
+    unsigned char* p = smem;
+    const unsigned char* geomBase = a.geom;
+    if (SMEM) {
+        stage_blob_to_smem(p, a.geom, a.L.bytes, &bar);
+        geomBase = p;
+        p += a.L.bytes;
+    }
+    float4* rec = reinterpret_cast<float4*>(p) + warp * 32;      // (Pp.xyz, hit flag) per ray of the warp
+    const GeomView gv = make_view(geomBase, a.L);
+    const f3 RayOrigin = mk3(a.ox, a.oy, a.oz);
+    unsigned int nRays = 0, nHitRays = 0;
+
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = (int)atomicAdd(a.nextRay, 32u);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= a.map.nLocal) break;
+        const int j = base + lane;
+        const bool hasRay = j < a.map.nLocal;
+
+        // ================= Phase 1: ShootRayCast, distance only (PM:101-141) =================
+        float best = pos_inf();                                                // math.INFINITY
+        if (hasRay) {
+            nRays++;
+            const int rayIndex = a.map.to_global(j);
+            const f3 d = mk3(um_f16tof32(a.dirs[3 * (size_t)rayIndex]), um_f16tof32(a.dirs[3 * (size_t)rayIndex + 1]),
+                             um_f16tof32(a.dirs[3 * (size_t)rayIndex + 2]));   // PM:53
+            const f3 o = RayOrigin;
+            const float dd = dot3(d, d);
+            const f3 inv = mk3(rcpr(d.x), rcpr(d.y), rcpr(d.z));
+            Dda w;
+            bool walking = dda_init(g, o, d, inv, pos_inf(), w);
+            while (walking) {
+                const uint2 hdr = dda_cell(g, w);
+                const uint16_t* e = g.entries + hdr.x;
+                const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
+                for (int k = 0; k < nS; k++) {
+                    const float dist = sphere_dist(gv, __ldg(e + k), o, d, dd);
+                    if (dist < best) best = dist;
+                }
+                e += nS;
+                for (int k = 0; k < nA; k++) {
+                    const float dist = aabb_dist(gv, __ldg(e + k), o, inv);
+                    if (dist < best) best = dist;
+                }
+                e += nA;
+                for (int k = 0; k < nO; k++) {
+                    const int id = __ldg(e + k);
+                    const float dist = obb_dist_nearest_q(gv, a.at.obbQinv[id], id, o, d, dd, g.errScale, best);   // PM:174 (quirk Q4)
+                    if (dist < best) best = dist;
+                }
+                const float tNext = dda_next_t(w);
+                if (tNext > w.tEnd || tNext > best) break;
+                walking = dda_step(g, d, w);
+            }
+            a.firstHitDist[j] = best;
+            const bool hit = best != pos_inf();                                // PM:140 / PM:58
+            if (hit) {
+                nHitRays++;
+                atomicMax(&a.lastHitRay[rayIndex / a.batchSize], rayIndex);
+                const f3 P = add3(o, mul3s(d, best));                          // PM:61
+                const f3 Pp = sub3(P, mul3s(d, kEpsilon));                     // PM:72
+                rec[lane] = make_float4(Pp.x, Pp.y, Pp.z, 1.0f);
+            } else {
+                rec[lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+        } else {
+            rec[lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        __syncwarp();
+
+        // ================= Phase 2: per-target loss rays (PM:67-86), one lane = one (ray, target) pair =================
+        for (int tb = 0; tb * 32 < Na; tb++) {
+            const int tpb = min(32, Na - tb * 32);          // targets in this block
+            const int rp = 32 / tpb;                        // rays handled side by side
+            const int rsub = lane / tpb;
+            const int tgt = tb * 32 + (lane - rsub * tpb);
+            const bool laneOn = rsub < rp;
+            const f3 T = laneOn ? mk3(a.targets[3 * tgt], a.targets[3 * tgt + 1], a.targets[3 * tgt + 2]) : mk3(0, 0, 0);
+            long long accInt = 0, accFrac = 0;
+            for (int r0 = 0; r0 < 32; r0 += rp) {
+                const int r = r0 + rsub;
+                float4 rr = make_float4(0, 0, 0, 0);
+                if (laneOn && r < 32) rr = rec[r];
+                if (rr.w != 0.0f) {
+                    const f3 Pp = mk3(rr.x, rr.y, rr.z);
+                    const f3 dir = normalize3(sub3(T, Pp));                    // PM:76
+                    const f3 inv = mk3(rcpr(dir.x), rcpr(dir.y), rcpr(dir.z));             // PM:270
+                    float loss = 0.0f;
+                    Dda w;
+                    bool walking = dda_init(g, Pp, dir, inv, pos_inf(), w);
+                    while (walking) {
+                        const uint2 hdr = dda_cell(g, w);
+                        const uint16_t* e = g.entries + hdr.x;
+                        const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
+                        const float tIn = w.tCur;
+                        const float tOut = fminf(dda_next_t(w), w.tEnd);
+                        // AABB and sphere intervals are evaluated in the reference's own operation order, so tEnter/tExit are
+                        // the reference's floats (a near-tangent sphere crossing, 2*sqrt(disc) with disc ~ 0, would otherwise
+                        // amplify harmless rounding into a visible difference); only the per-cell clipping is new.
+                        for (int k = 0; k < nA; k++) {                          // PM:265-288
+                            const int id = __ldg(e + nS + k);
+                            const float4 A = gv.aabbA[id];
+                            const float2 B = gv.aabbB[id];
+                            float tEnter, tExit;
+                            slab<8>(subr(A.x, Pp.x), subr(A.y, Pp.y), subr(A.z, Pp.z), subr(A.w, Pp.x), subr(B.x, Pp.y), subr(B.y, Pp.z),
+                                    inv.x, inv.y, inv.z, tEnter, tExit);
+                            const float len = clip_len(tEnter, tExit, tIn, tOut);
+                            if (len > 0.0f) {
+                                const float4 at = a.at.aabbAttr[id];
+                                if (__float_as_int(at.w) != tgt) loss = fmaf(len, at.z, loss);     // PM:245 owner skip
+                            }
+                        }
+                        for (int k = 0; k < nS; k++) {                          // PM:303-328 (unit direction)
+                            const int id = __ldg(e + k);
+                            const float4 s = gv.sph[id];
+                            const f3 oc = sub3(Pp, mk3(s.x, s.y, s.z));
+                            const float cc = subr(dot3(oc, oc), s.w);
+                            float b;
+                            if (sphere_loss_fast_miss(oc, cc, dir, b)) continue;   // disc < 0 (PM:311)
+                            const float sq = sqrtr(subr(mulr(b, b), cc));
+                            const float len = clip_len(subr(-b, sq), addr(-b, sq), tIn, tOut);
+                            if (len > 0.0f) {
+                                const float4 at = a.at.sphAttr[id];
+                                if (__float_as_int(at.w) != tgt) loss = fmaf(len, at.z, loss);     // PM:235
+                            }
+                        }
+                        for (int k = 0; k < nO; k++) {                          // PM:294-300 (stored rotation as is)
+                            const int id = __ldg(e + nS + nA + k);
+                            const float4 c4 = gv.obbC[id];
+                            const float2 h2 = gv.obbH[id];
+                            const f3 pc = mk3(Pp.x - c4.x, Pp.y - c4.y, Pp.z - c4.z);
+                            // bounding sphere first: |pc x dir|^2 > r^2 means the line passes the box
+                            const float bq = fmaf(pc.z, dir.z, fmaf(pc.y, dir.y, pc.x * dir.x));
+                            const float pp = fmaf(pc.z, pc.z, fmaf(pc.y, pc.y, pc.x * pc.x));
+                            const float r2 = fmaf(h2.y, h2.y, fmaf(h2.x, h2.x, c4.w * c4.w));
+                            if (pp - bq * bq > r2 * 1.001f + 1e-4f) continue;
+                            const float4 q4 = gv.obbQ[id];
+                            // rotate the point of closest approach (|pn| <= r) instead of pc (|pc| can be the whole room):
+                            // the rounding of the cheap rotation then scales with the box, not with the distance to it
+                            const f3 pn = mk3(fmaf(dir.x, -bq, pc.x), fmaf(dir.y, -bq, pc.y), fmaf(dir.z, -bq, pc.z));
+                            const f3 lo = qrot_fast(q4, pn), ld = qrot_fast(q4, dir);
+                            const float rx = rcp_fast(ld.x), ry = rcp_fast(ld.y), rz = rcp_fast(ld.z);
+                            const float ax = (-c4.w - lo.x) * rx, bx = (c4.w - lo.x) * rx;
+                            const float ay = (-h2.x - lo.y) * ry, by = (h2.x - lo.y) * ry;
+                            const float az = (-h2.y - lo.z) * rz, bz = (h2.y - lo.z) * rz;
+                            const float tEnter = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)) - bq;
+                            const float tExit = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) - bq;
+                            const float len = clip_len(tEnter, tExit, tIn, tOut);
+                            if (len > 0.0f) {
+                                const float4 at = a.at.obbAttr[id];
+                                if (__float_as_int(at.w) != tgt) loss = fmaf(len, at.z, loss);     // PM:255
+                            }
+                        }
+                        if (dda_next_t(w) > w.tEnd) break;
+                        walking = dda_step(g, dir, w);
+                    }
+                    const float v = subr(a.nTimesS, loss);                     // PM:260
+                    const float ip = truncf(v);
+                    accInt += (long long)ip;
+                    accFrac += (long long)(((double)v - (double)ip) * 68719476736.0);
+                }
+            }
+            if (laneOn && (accInt != 0 || accFrac != 0)) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(&a.permSumInt[tgt]), (unsigned long long)accInt);
+                atomicAdd(reinterpret_cast<unsigned long long*>(&a.permSumFrac[tgt]), (unsigned long long)accFrac);
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        nRays += __shfl_xor_sync(kFull, nRays, s);
+        nHitRays += __shfl_xor_sync(kFull, nHitRays, s);
+    }
+    if (lane == 0) {
+        atomicAdd(&a.counters[C_PERM_RAYS], (unsigned long long)nRays);
+        atomicAdd(&a.counters[C_PERM_HIT_RAYS], (unsigned long long)nHitRays);
+    }
+}
+
+size_t perm_grid_smem_bytes(const GeomLayout& L, bool geomInSmem)
+{
+    return (geomInSmem ? L.bytes : 0) + (size_t)kPGridWarps * 32 * sizeof(float4);
+}
+
+cudaError_t launch_permeation_grid(const PermArgs& a, const GridDesc& g, int numCtas, bool geomInSmem, cudaStream_t stream)
+{
+    const size_t smem = perm_grid_smem_bytes(a.L, geomInSmem);
+    void (*k)(const PermArgs, const GridDesc) = geomInSmem ? permeation_grid_kernel<true> : permeation_grid_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<numCtas, kPGridThreads, smem, stream>>>(a, g);
+    return cudaGetLastError();
+}
+
+}  // namespace art

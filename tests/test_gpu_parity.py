@@ -216,8 +216,14 @@ def test_determinism_and_no_counter_variant(gpu_ctx, oracle):
         np.testing.assert_array_equal(a.hit_ids, x.hit_ids)
         np.testing.assert_array_equal(a.muffle, x.muffle)
         np.testing.assert_array_equal(a.permeation.view(np.uint32), x.permeation.view(np.uint32))
-        np.testing.assert_array_equal(a.permeation_sum, x.permeation_sum)          # deterministic reduction
         np.testing.assert_array_equal(a.settings.view(np.uint8), x.settings.view(np.uint8))
+    np.testing.assert_array_equal(a.permeation_sum, b.permeation_sum)              # deterministic reduction
+    # the counting frame runs the brute-force kernels: same per-ray values up to the documented tolerance
+    np.testing.assert_allclose(a.permeation_sum, c.permeation_sum, rtol=0, atol=1e-5 * s.n_rays * s.n_rays)
+    d = gpu_ctx.run_frame(s, flags=native.FRAME_BRUTE_FORCE)
+    assert d.counters["gridUsed"] == 0 and a.counters["gridUsed"] == 3
+    np.testing.assert_array_equal(c.permeation_sum, d.permeation_sum)
+    np.testing.assert_array_equal(a.echo, d.echo)
 
 
 def test_sharded_contexts_merge_to_the_unsharded_result(art_lib, oracle):
