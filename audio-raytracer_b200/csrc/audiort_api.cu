@@ -10,6 +10,7 @@
 #include "scene_dev.cuh"
 #include "um_math.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -17,6 +18,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace art {
@@ -173,9 +175,9 @@ struct ArtCtx {
     PinBuf pinScene;
     DevBuf rawScene, geom, attrs, owners, perm;    // perm: dens arrays + owned list
     HostGrid grid;                                 // uniform grid over the scene (grid_host.h)
-    DevBuf gridCells, gridEntries;
+    DevBuf gridCells, gridEntries, gridScratch;
     bool gridDisabled = false;                     // ART_DISABLE_GRID=1
-    float gridCellScale = 0.8f;                    // ART_GRID_CELL_SCALE
+    float gridCellScale = 1.1f;                    // ART_GRID_CELL_SCALE
     uint32_t frameGridUsed = 0;
     GeomLayout L{};
     bool haveScene = false, sceneDirty = false;
@@ -397,7 +399,7 @@ ART_API void art_destroy(ArtCtx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
+    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridScratch, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
                        &ctx->outEcho, &ctx->outHitPts, &ctx->outHitCnt, &ctx->outHitIds, &ctx->firstHit, &ctx->partials, &ctx->queue })
         b->release();
     for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinEcho,
@@ -592,10 +594,35 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         CK(cudaMemcpyAsync(ctx->dirs.p, ctx->pinRays.p, 6 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
         ctx->raysDirty = false;
     }
-    CK(ctx->pinTargets.ensure(12 * (size_t)Na));
-    CK(ctx->targets.ensure(12 * (size_t)Na));
+    CK(ctx->pinTargets.ensure(16 * (size_t)Na));
+    CK(ctx->targets.ensure(16 * (size_t)Na));
     memcpy(ctx->pinTargets.p, prm->audioTargetPositions, 12 * (size_t)Na);
-    CK(cudaMemcpyAsync(ctx->targets.p, ctx->pinTargets.p, 12 * (size_t)Na, cudaMemcpyHostToDevice, ctx->stream));
+    {   // Morton order of the targets: neighbouring lanes of the grid kernels then walk towards neighbouring targets
+        // (same cells, same list lengths). Results do not depend on the order.
+        int* order = reinterpret_cast<int*>(ctx->pinTargets.as<unsigned char>() + 12 * (size_t)Na);
+        const float* tp = prm->audioTargetPositions;
+        float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+        for (int t = 0; t < Na; t++)
+            for (int k = 0; k < 3; k++) { lo[k] = std::fmin(lo[k], tp[3 * t + k]); hi[k] = std::fmax(hi[k], tp[3 * t + k]); }
+        std::vector<std::pair<uint32_t, int>> keys((size_t)Na);
+        for (int t = 0; t < Na; t++) {
+            uint32_t code = 0;
+            uint32_t q[3];
+            for (int k = 0; k < 3; k++) {
+                const float ext = hi[k] - lo[k];
+                float u = ext > 0.0f ? (tp[3 * t + k] - lo[k]) / ext : 0.0f;
+                if (!(u >= 0.0f)) u = 0.0f;
+                if (u > 1.0f) u = 1.0f;
+                q[k] = (uint32_t)(u * 1023.0f);
+            }
+            for (int b = 9; b >= 0; b--)
+                for (int k = 0; k < 3; k++) code = (code << 1) | ((q[k] >> b) & 1u);
+            keys[(size_t)t] = { code, t };
+        }
+        std::sort(keys.begin(), keys.end());
+        for (int t = 0; t < Na; t++) order[t] = keys[(size_t)t].second;
+    }
+    CK(cudaMemcpyAsync(ctx->targets.p, ctx->pinTargets.p, 16 * (size_t)Na, cudaMemcpyHostToDevice, ctx->stream));
 
     // owned-collider bookkeeping (depends on the target count): counts per (section, target) for the
     // counters, density planes + owned list for K2
@@ -694,6 +721,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         ta.dirs = ctx->dirs.as<uint16_t>(); ta.map = map;
         ta.ox = prm->rayOrigin[0]; ta.oy = prm->rayOrigin[1]; ta.oz = prm->rayOrigin[2];
         ta.targets = ctx->targets.as<float>(); ta.nTargets = Na;
+        ta.targetOrder = reinterpret_cast<const int*>(ctx->targets.as<unsigned char>() + 12 * (size_t)Na);
         ta.maxRayLife = prm->maxRayLife; ta.H = H; ta.maxMuffle = prm->maxMuffleHitDistance;
         ta.batchSize = b;
         ta.echo = ctx->outEcho.as<uint16_t>();
@@ -711,7 +739,10 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             for (int t = 0; t < Na; t++) owned += ownedCount[(size_t)sec * Na + t];
             ta.anyOwned[sec] = owned > 0 ? 1 : 0;
         }
+        ta.scratch = nullptr;
         if (useGrid) {
+            CK(ctx->gridScratch.ensure(trace_grid_scratch_bytes(ctx->numSms)));
+            ta.scratch = ctx->gridScratch.as<uint32_t>();
             const bool gInSmem = trace_grid_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
             CK(launch_trace_grid(ta, gd, ctx->numSms, gInSmem, ctx->stream));
             ctx->frameGridUsed |= 1u;
@@ -733,6 +764,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         pa.dirs = ctx->dirs.as<uint16_t>(); pa.map = map;
         pa.ox = prm->rayOrigin[0]; pa.oy = prm->rayOrigin[1]; pa.oz = prm->rayOrigin[2];
         pa.targets = ctx->targets.as<float>(); pa.nTargets = Na;
+        pa.targetOrder = reinterpret_cast<const int*>(ctx->targets.as<unsigned char>() + 12 * (size_t)Na);
         pa.nTimesS = (float)N * prm->permeationStrengthPerRay;                     // PM:260
         pa.batchSize = b;
         pa.firstHitDist = ctx->firstHit.as<float>();

@@ -74,6 +74,229 @@ struct HitRec {            // per hit point, shared memory (one per lane)
     int pad;
 };
 
+
+// ---- pooled occlusion queries -----------------------------------------------------------------------
+constexpr int kChunkQ = 4096;            // queries per pool pass (bounds the survivor list: 16 KB of scratch per warp)
+constexpr int kSkipCells = 4;
+constexpr int kTwoStageSlots = 16;       // queries per hit point from which the AABB-first two-stage pool pays off            // empty cells a lane may step over in one pool step
+
+struct PoolEnv {
+    const TraceArgs& a;
+    const GridDesc& g;
+    const GeomView& gv;
+    const HitRec* rec;                   // per-warp hit records (shared memory)
+    float4* qbuf0; float4* qbuf1; float4* qbuf2; int* qbuf3;   // per-warp ring of prepared queries (shared memory)
+    uint32_t* surv;                      // per-warp survivor list (global scratch): slot | rec << 16
+    f3 RayOrigin;
+    uint32_t hitMask;
+    int slots, lane;
+    uint32_t ltMask;
+};
+
+__device__ __forceinline__ void query_visible(const PoolEnv& E, int slot, int recIdx, float L)
+{
+    const HitRec r = E.rec[recIdx];
+    if (slot == 0) E.a.echo[r.resultId] = um_f32tof16(mulr(L, r.echoMul));             // RT:133-145
+    else atomicAdd(&E.a.muffleCounts[r.row * E.a.nTargets + (slot - 1)], 1u);          // RT:168-172
+}
+
+// One pass over `count` queries. Queries are PREPARED 32 at a time by the whole warp (direction, exact
+// reciprocals, DDA start) into the per-warp ring and CONSUMED by whichever lanes are idle, a bounded slice of
+// one grid cell per step, so the lanes of a warp stay in step while early exits are taken at once.
+//   STAGE 0: every (hit point, slot) query of the round, tested against the AABB lists only (the cheapest and
+//            most numerous blockers). A query the AABBs do not block is appended to the survivor list.
+//   STAGE 1: the survivors, against the sphere and OBB lists. A query that survives this too sees its goal.
+//   STAGE 2: (few queries per hit point) all three lists in one pass.
+// An occlusion query is an "any" over all colliders (RT:365-449), so the order of the tests is free.
+template <int STAGE>
+__device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count, bool noSO)
+{
+    const TraceArgs& a = E.a;
+    const GridDesc& g = E.g;
+    const GeomView& gv = E.gv;
+    const int lane = E.lane;
+    const uint32_t ltMask = E.ltMask;
+    int nextQ = 0, bufNext = 0, bufCount = 0, survCount = 0;
+    bool have = false;
+    f3 qo = mk3(0, 0, 0), qd = mk3(0, 0, 0), qinv = mk3(0, 0, 0);
+    float qL = 0.0f, qdd = 0.0f;
+    int qslot = 0, qrec = 0;
+    bool fresh = true;                // no cell fetched yet for this query
+    uint2 hdr = make_uint2(0, 0);
+    int kA = 0, kB = 0, kC = 0;       // cursors inside the current cell: AABB, sphere, OBB lists
+    Dda w;
+    w.ix = w.iy = w.iz = 0; w.tmx = w.tmy = w.tmz = 0; w.tdx = w.tdy = w.tdz = 0; w.tEnd = 0; w.tCur = 0;
+    for (;;) {
+        const uint32_t idle = __ballot_sync(kFull, !have);
+        if (idle) {
+            if (bufNext == bufCount && nextQ < count) {
+                // ---- prepare the next 32 queries (all lanes)
+                const int qi = nextQ + lane;
+                nextQ += 32;
+                bool active = false;
+                f3 nd = mk3(0, 0, 0), ninv = mk3(0, 0, 0);
+                float nL = 0.0f;
+                int nslot = 0, nrec = 0;
+                Dda nw;
+                nw.ix = nw.iy = nw.iz = 0; nw.tmx = nw.tmy = nw.tmz = 0; nw.tdx = nw.tdy = nw.tdz = 0; nw.tEnd = 0; nw.tCur = 0;
+                if (qi < count) {
+                    if (STAGE != 1) {
+                        const int q = qFirst + qi;
+                        const int ord = q / E.slots;
+                        nslot = q - ord * E.slots;
+                        if (nslot > 0) nslot = a.targetOrder[nslot - 1] + 1;       // spatially sorted pool order
+                        nrec = __fns(E.hitMask, 0, ord + 1);
+                    } else {
+                        const uint32_t packed = E.surv[qi];   // STAGE 1
+                        nslot = (int)(packed & 0xFFFFu);
+                        nrec = (int)(packed >> 16);
+                    }
+                    const HitRec r = E.rec[nrec];
+                    const f3 no = mk3(r.px, r.py, r.pz);
+                    f3 T = E.RayOrigin;
+                    if (nslot > 0) T = mk3(a.targets[3 * (nslot - 1)], a.targets[3 * (nslot - 1) + 1], a.targets[3 * (nslot - 1) + 2]);
+                    const f3 v = sub3(T, no);                                      // RT:127 / RT:162
+                    const float len = sqrtr(dot3(v, v));
+                    nd = smul3(rcpr(len), v);                                      // normalize = rsqrt(dot) * v
+                    bool gate = true;
+                    if (nslot == 0) nL = r.echoL;                                  // RT:130
+                    else { nL = len; gate = nL < a.maxMuffle; }                    // RT:165, 168
+                    if (gate) {
+                        ninv = mk3(rcpr(nd.x), rcpr(nd.y), rcpr(nd.z));
+                        active = dda_init(g, no, nd, ninv, nL, nw);
+                        if (!active) query_visible(E, nslot, nrec, nL);            // nothing near the segment
+                    }
+                }
+                const uint32_t act = __ballot_sync(kFull, active);
+                if (active) {
+                    const int pos = __popc(act & ltMask);
+                    E.qbuf0[pos] = make_float4(nd.x, nd.y, nd.z, nL);
+                    E.qbuf1[pos] = make_float4(ninv.x, ninv.y, ninv.z, nw.tEnd);
+                    E.qbuf2[pos] = make_float4(nw.tmx, nw.tmy, nw.tmz,
+                                               __int_as_float(nw.ix | (nw.iy << 8) | (nw.iz << 16) | (nrec << 24)));
+                    E.qbuf3[pos] = nslot;
+                }
+                bufNext = 0;
+                bufCount = __popc(act);
+                __syncwarp();
+            }
+            if (bufNext < bufCount) {
+                // ---- idle lanes take prepared queries
+                const int pos = bufNext + __popc(idle & ltMask);
+                if (!have && pos < bufCount) {
+                    const float4 v0 = E.qbuf0[pos], v1 = E.qbuf1[pos], v2 = E.qbuf2[pos];
+                    qslot = E.qbuf3[pos];
+                    qd = mk3(v0.x, v0.y, v0.z); qL = v0.w;
+                    qinv = mk3(v1.x, v1.y, v1.z); w.tEnd = v1.w;
+                    w.tmx = v2.x; w.tmy = v2.y; w.tmz = v2.z;
+                    const int packed = __float_as_int(v2.w);
+                    w.ix = packed & 255; w.iy = (packed >> 8) & 255; w.iz = (packed >> 16) & 255;
+                    qrec = (packed >> 24) & 31;
+                    w.tdx = fabsf(g.csx * qinv.x); w.tdy = fabsf(g.csy * qinv.y); w.tdz = fabsf(g.csz * qinv.z);
+                    qdd = dot3(qd, qd);
+                    const HitRec r = E.rec[qrec];
+                    qo = mk3(r.px, r.py, r.pz);
+                    fresh = true; kA = kB = kC = 0; hdr = make_uint2(0, 0);
+                    have = true;
+                }
+                bufNext = min(bufCount, bufNext + __popc(idle));
+                __syncwarp();
+            }
+        }
+        if (!__any_sync(kFull, have)) {
+            if (bufNext == bufCount && nextQ >= count) break;
+            continue;
+        }
+        bool survived = false;
+        if (have && STAGE == 0) {
+            // ---- a slice of up to kCapA AABB entries of the current cell (stepping over at most kSkipCells empty cells first)
+            bool walkDone = false;
+            for (int s = 0; s < kSkipCells; s++) {
+                if (kA < (int)((hdr.y >> 10) & 2047)) break;
+                if (!fresh) {
+                    const float tNext = dda_next_t(w);
+                    if (tNext > w.tEnd || !dda_step(g, qd, w)) { walkDone = true; break; }
+                }
+                fresh = false;
+                hdr = dda_cell(g, w);
+                kA = 0;
+            }
+            bool blocked = false;
+            if (!walkDone) {
+                const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047;
+                const uint16_t* e = g.entries + hdr.x + nS;
+                const int ownerId = qslot - 1;         // -1 for the echo ray: never equals a valid owner below
+                for (int c = 0; c < kCapA && kA < nA && !blocked; c++, kA++) {
+                    const int id = __ldg(e + kA);
+                    if (aabb_dist(gv, id, qo, qinv) < qL)
+                        blocked = !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
+                }
+            }
+            if (blocked) {
+                have = false;
+            } else if (walkDone) {
+                have = false;
+                if (noSO) query_visible(E, qslot, qrec, qL);
+                else survived = true;
+            }
+        }
+        if (have && STAGE != 0) {
+            // ---- a bounded slice of the current cell's lists (STAGE 1: spheres + OBBs, STAGE 2: all three types)
+            bool walkDone = false;
+            for (int s = 0; s < kSkipCells; s++) {
+                const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
+                const bool pending = kB < nS || kC < nO || (STAGE == 2 && kA < nA);
+                if (pending) break;
+                if (!fresh) {
+                    const float tNext = dda_next_t(w);
+                    if (tNext > w.tEnd || !dda_step(g, qd, w)) { walkDone = true; break; }
+                }
+                fresh = false;
+                hdr = dda_cell(g, w);
+                kA = kB = kC = 0;
+            }
+            bool blocked = false;
+            if (!walkDone) {
+                const uint16_t* e = g.entries + hdr.x;
+                const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
+                const int ownerId = qslot - 1;
+                if (STAGE == 2) {
+                    for (int c = 0; c < kCapA && kA < nA && !blocked; c++, kA++) {
+                        const int id = __ldg(e + nS + kA);
+                        if (aabb_dist(gv, id, qo, qinv) < qL)
+                            blocked = !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
+                    }
+                }
+                for (int c = 0; c < kCapS && kB < nS && !blocked; c++, kB++) {
+                    const int id = __ldg(e + kB);
+                    if (sphere_dist(gv, id, qo, qd, qdd) < qL)
+                        blocked = !(qslot > 0 && a.anyOwned[0] && (int)a.at.ownS[id] == ownerId);       // RT:413
+                }
+                for (int c = 0; c < kCapO && kC < nO && !blocked; c++, kC++) {
+                    const int id = __ldg(e + nS + nA + kC);
+                    if (obb_blocks(gv, id, qo, qd, qdd, g.errScale, qL))
+                        blocked = !(qslot > 0 && a.anyOwned[2] && (int)a.at.ownO[id] == ownerId);       // RT:439
+                }
+            }
+            if (blocked) {
+                have = false;
+            } else if (walkDone) {
+                have = false;
+                query_visible(E, qslot, qrec, qL);     // walked the whole segment: the ray sees its goal
+            }
+        }
+        if (STAGE == 0) {
+            const uint32_t push = __ballot_sync(kFull, survived);
+            if (push) {
+                if (survived) E.surv[survCount + __popc(push & ltMask)] = (uint32_t)qslot | ((uint32_t)qrec << 16);
+                survCount += __popc(push);
+            }
+        }
+    }
+    __syncwarp();
+    return survCount;
+}
+
 template <bool SMEM>
 __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const TraceArgs a, const GridDesc g)
 {
@@ -102,6 +325,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
     const GeomView gv = make_view(geomBase, a.L);
     const f3 RayOrigin = mk3(a.ox, a.oy, a.oz);
     const uint32_t ltMask = (1u << lane) - 1u;
+    uint32_t* surv = a.scratch + ((size_t)blockIdx.x * kGridWarps + warp) * kChunkQ;
 
     // ---- per-lane ray state
     bool hasRay = false, queueEmpty = false;
@@ -213,137 +437,17 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
         __syncwarp();
 
         // ================= echo + muffle queries of all hit points (RT:121-175) =================
-        // Queries are PREPARED 32 at a time by the whole warp (direction, exact reciprocals, DDA start) into a
-        // per-warp ring in shared memory, and CONSUMED one grid cell per step by whichever lanes are idle.
-        const uint32_t hitMask = __ballot_sync(kFull, hit);
-        const int total = __popc(hitMask) * slots;
         {
-            int nextQ = 0, bufNext = 0, bufCount = 0;
-            bool have = false;
-            f3 qo = mk3(0, 0, 0), qd = mk3(0, 0, 0), qinv = mk3(0, 0, 0);
-            float qL = 0.0f, qdd = 0.0f;
-            int qslot = 0, qrec = 0;
-            uint32_t cur = kNoHit;            // cursor inside the current cell (kA | kS << 11 | kO << 21), all ones = fetch the cell
-            uint2 hdr = make_uint2(0, 0);
-            Dda w;
-            w.ix = w.iy = w.iz = 0; w.tmx = w.tmy = w.tmz = 0; w.tdx = w.tdy = w.tdz = 0; w.tEnd = 0; w.tCur = 0;
-            for (;;) {
-                const uint32_t idle = __ballot_sync(kFull, !have);
-                if (idle) {
-                    if (bufNext == bufCount && nextQ < total) {
-                        // ---- prepare the next 32 queries (all lanes)
-                        const int q = nextQ + lane;
-                        nextQ += 32;
-                        bool active = false;
-                        f3 nd = mk3(0, 0, 0), ninv = mk3(0, 0, 0);
-                        float nL = 0.0f;
-                        int nslot = 0, nrec = 0;
-                        Dda nw;
-                        nw.ix = nw.iy = nw.iz = 0; nw.tmx = nw.tmy = nw.tmz = 0; nw.tdx = nw.tdy = nw.tdz = 0; nw.tEnd = 0; nw.tCur = 0;
-                        if (q < total) {
-                            const int ord = q / slots;
-                            nslot = q - ord * slots;
-                            nrec = __fns(hitMask, 0, ord + 1);
-                            const HitRec r = rec[nrec];
-                            const f3 no = mk3(r.px, r.py, r.pz);
-                            f3 T = RayOrigin;
-                            if (nslot > 0) T = mk3(a.targets[3 * (nslot - 1)], a.targets[3 * (nslot - 1) + 1], a.targets[3 * (nslot - 1) + 2]);
-                            const f3 v = sub3(T, no);                          // RT:127 / RT:162
-                            const float len = sqrtr(dot3(v, v));
-                            nd = smul3(rcpr(len), v);                          // normalize = rsqrt(dot) * v
-                            bool gate = true;
-                            if (nslot == 0) nL = r.echoL;                      // RT:130
-                            else { nL = len; gate = nL < a.maxMuffle; }        // RT:165, 168
-                            if (gate) {
-                                ninv = mk3(rcpr(nd.x), rcpr(nd.y), rcpr(nd.z));
-                                active = dda_init(g, no, nd, ninv, nL, nw);
-                                if (!active) {                                 // nothing near the segment: the ray sees its goal
-                                    if (nslot == 0) a.echo[r.resultId] = um_f32tof16(mulr(nL, r.echoMul));   // RT:142-144
-                                    else atomicAdd(&a.muffleCounts[r.row * Na + (nslot - 1)], 1u);            // RT:171
-                                }
-                            }
-                        }
-                        const uint32_t act = __ballot_sync(kFull, active);
-                        if (active) {
-                            const int pos = __popc(act & ltMask);
-                            qbuf0[pos] = make_float4(nd.x, nd.y, nd.z, nL);
-                            qbuf1[pos] = make_float4(ninv.x, ninv.y, ninv.z, nw.tEnd);
-                            qbuf2[pos] = make_float4(nw.tmx, nw.tmy, nw.tmz,
-                                                     __int_as_float(nw.ix | (nw.iy << 8) | (nw.iz << 16) | (nrec << 24)));
-                            qbuf3[pos] = nslot;
-                        }
-                        bufNext = 0;
-                        bufCount = __popc(act);
-                        __syncwarp();
-                    }
-                    if (bufNext < bufCount) {
-                        // ---- idle lanes take prepared queries
-                        const int pos = bufNext + __popc(idle & ltMask);
-                        if (!have && pos < bufCount) {
-                            const float4 v0 = qbuf0[pos], v1 = qbuf1[pos], v2 = qbuf2[pos];
-                            qslot = qbuf3[pos];
-                            qd = mk3(v0.x, v0.y, v0.z); qL = v0.w;
-                            qinv = mk3(v1.x, v1.y, v1.z); w.tEnd = v1.w;
-                            w.tmx = v2.x; w.tmy = v2.y; w.tmz = v2.z;
-                            const int packed = __float_as_int(v2.w);
-                            w.ix = packed & 255; w.iy = (packed >> 8) & 255; w.iz = (packed >> 16) & 255;
-                            qrec = (packed >> 24) & 31;
-                            w.tdx = fabsf(g.csx * qinv.x); w.tdy = fabsf(g.csy * qinv.y); w.tdz = fabsf(g.csz * qinv.z);
-                            qdd = dot3(qd, qd);
-                            const HitRec r = rec[qrec];
-                            qo = mk3(r.px, r.py, r.pz);
-                            cur = kNoHit;
-                            have = true;
-                        }
-                        bufNext = min(bufCount, bufNext + __popc(idle));
-                        __syncwarp();
-                    }
-                }
-                if (!__any_sync(kFull, have)) {
-                    if (bufNext == bufCount && nextQ >= total) break;
-                    continue;
-                }
-                if (have) {
-                    // ---- a bounded slice of the current cell's lists: CanRaySeePoint / CanRaySeeAudioTarget (RT:365-449).
-                    //      At most kCapA/kCapS/kCapO tests per step keep the lanes of a warp in step with each other.
-                    if (cur == kNoHit) { hdr = dda_cell(g, w); cur = 0; }
-                    const uint16_t* e = g.entries + hdr.x;
-                    const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
-                    int kA = (int)(cur & 2047u), kS = (int)((cur >> 11) & 1023u), kO = (int)(cur >> 21);
-                    const int ownerId = qslot - 1;         // -1 for the echo ray: never equals a valid owner below
-                    bool blocked = false;
-                    for (int c = 0; c < kCapA && kA < nA && !blocked; c++, kA++) {
-                        const int id = __ldg(e + nS + kA);
-                        if (aabb_dist(gv, id, qo, qinv) < qL)
-                            blocked = !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
-                    }
-                    for (int c = 0; c < kCapS && kS < nS && !blocked; c++, kS++) {
-                        const int id = __ldg(e + kS);
-                        if (sphere_dist(gv, id, qo, qd, qdd) < qL)
-                            blocked = !(qslot > 0 && a.anyOwned[0] && (int)a.at.ownS[id] == ownerId);   // RT:413
-                    }
-                    for (int c = 0; c < kCapO && kO < nO && !blocked; c++, kO++) {
-                        const int id = __ldg(e + nS + nA + kO);
-                        if (obb_blocks(gv, id, qo, qd, qdd, g.errScale, qL))
-                            blocked = !(qslot > 0 && a.anyOwned[2] && (int)a.at.ownO[id] == ownerId);   // RT:439
-                    }
-                    bool done = blocked;
-                    if (!blocked) {
-                        if (kA >= nA && kS >= nS && kO >= nO) {
-                            cur = kNoHit;                   // cell finished: move on
-                            const float tNext = dda_next_t(w);
-                            if (tNext > w.tEnd || !dda_step(g, qd, w)) {
-                                // walked the whole segment: the query ray sees its goal
-                                done = true;
-                                const HitRec r = rec[qrec];
-                                if (qslot == 0) a.echo[r.resultId] = um_f32tof16(mulr(qL, r.echoMul));       // RT:133-145
-                                else atomicAdd(&a.muffleCounts[r.row * Na + (qslot - 1)], 1u);                // RT:168-172
-                            }
-                        } else {
-                            cur = (uint32_t)kA | ((uint32_t)kS << 11) | ((uint32_t)kO << 21);
-                        }
-                    }
-                    if (done) have = false;
+            const uint32_t hitMask = __ballot_sync(kFull, hit);
+            const int total = __popc(hitMask) * slots;
+            const PoolEnv E = { a, g, gv, rec, qbuf0, qbuf1, qbuf2, qbuf3, surv, RayOrigin, hitMask, slots, lane, ltMask };
+            const bool noSO = a.L.ns + a.L.no == 0;
+            for (int q0 = 0; q0 < total; q0 += kChunkQ) {
+                if (slots >= kTwoStageSlots) {
+                    const int nSurv = run_pool<0>(E, q0, min(kChunkQ, total - q0), noSO);
+                    if (nSurv > 0) run_pool<1>(E, 0, nSurv, noSO);
+                } else {
+                    run_pool<2>(E, q0, min(kChunkQ, total - q0), noSO);   // few queries per hit point: one pass over all types
                 }
             }
         }
@@ -404,6 +508,8 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
 }
 
 // ---- launcher -----------------------------------------------------------------------------------
+size_t trace_grid_scratch_bytes(int numCtas) { return (size_t)numCtas * kGridWarps * kChunkQ * sizeof(uint32_t); }
+
 size_t trace_grid_smem_bytes(const GeomLayout& L, bool geomInSmem)
 {
     return (geomInSmem ? L.bytes : 0) + (size_t)kGridWarps * 32 * (sizeof(HitRec) + kQueryWords * 4);

@@ -120,8 +120,8 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
             const int tpb = min(32, Na - tb * 32);          // targets in this block
             const int rp = 32 / tpb;                        // rays handled side by side
             const int rsub = lane / tpb;
-            const int tgt = tb * 32 + (lane - rsub * tpb);
             const bool laneOn = rsub < rp;
+            const int tgt = laneOn ? a.targetOrder[tb * 32 + (lane - rsub * tpb)] : 0;   // spatially sorted lane order
             const f3 T = laneOn ? mk3(a.targets[3 * tgt], a.targets[3 * tgt + 1], a.targets[3 * tgt + 2]) : mk3(0, 0, 0);
             long long accInt = 0, accFrac = 0;
             for (int r0 = 0; r0 < 32; r0 += rp) {
@@ -181,6 +181,9 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
                             const float pp = fmaf(pc.z, pc.z, fmaf(pc.y, pc.y, pc.x * pc.x));
                             const float r2 = fmaf(h2.y, h2.y, fmaf(h2.x, h2.x, c4.w * c4.w));
                             if (pp - bq * bq > r2 * 1.001f + 1e-4f) continue;
+                            // the chord lies within rb of the point of closest approach (t = -bq): skip cells it cannot reach
+                            const float rb = sqrtf(r2) * 1.001f + 1e-3f;
+                            if (-bq + rb < tIn || -bq - rb > tOut) continue;
                             const float4 q4 = gv.obbQ[id];
                             // rotate the point of closest approach (|pn| <= r) instead of pc (|pc| can be the whole room):
                             // the rounding of the cheap rotation then scales with the box, not with the distance to it

@@ -8,6 +8,7 @@ cudaError_t launch_pack(const PackArgs& a, cudaStream_t stream);
 size_t trace_smem_bytes(const GeomLayout& L, int nTargets, bool geomInSmem, bool muffleInSmem);
 cudaError_t launch_trace(const TraceArgs& a, int numCtas, bool geomInSmem, bool count, cudaStream_t stream);
 size_t trace_grid_smem_bytes(const GeomLayout& L, bool geomInSmem);
+size_t trace_grid_scratch_bytes(int numCtas);
 cudaError_t launch_trace_grid(const TraceArgs& a, const GridDesc& g, int numCtas, bool geomInSmem, cudaStream_t stream);
 size_t perm_smem_bytes(const GeomLayout& L, bool geomInSmem);
 cudaError_t launch_permeation(const PermArgs& a, int numCtas, bool geomInSmem, int T, cudaStream_t stream);

@@ -108,6 +108,7 @@ struct TraceArgs {
     ShardMap map;
     float ox, oy, oz;              // RayOrigin
     const float* targets;          // float3 [nTargets]
+    const int* targetOrder;        // grid kernels: spatially sorted permutation of the targets (coherent lanes), or null
     int nTargets;
     float maxRayLife;
     int H;                         // MaxHitsPerRay
@@ -121,6 +122,7 @@ struct TraceArgs {
     uint32_t* muffleCounts;        // u32 [T*Na], row = batch index k = rayIndex / batchSize
     unsigned long long* counters;  // [C_COUNT]
     unsigned int* nextRay;         // dynamic ray queue
+    uint32_t* scratch;             // grid kernel: per-warp survivor lists (trace_grid_scratch_bytes)
     int muffleInSmem;              // per-warp shared counters fit
     int anyOwned[3];               // does any sphere / AABB / OBB belong to a target < nTargets (RT:413/426/439)
 };
@@ -167,6 +169,7 @@ struct PermArgs {
     ShardMap map;
     float ox, oy, oz;
     const float* targets;
+    const int* targetOrder;    // grid kernel: spatially sorted permutation of the targets, or null
     int nTargets;
     float nTimesS;             // (float)RayDirections.Length * PermeationStrengthPerRay (PM:260)
     int batchSize;
