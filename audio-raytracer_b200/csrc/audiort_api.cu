@@ -740,11 +740,12 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             ta.anyOwned[sec] = owned > 0 ? 1 : 0;
         }
         ta.scratch = nullptr;
+        ta.raysPerWarp = trace_grid_rays_per_warp(map.nLocal, Na, ctx->numSms);
         if (useGrid) {
             CK(ctx->gridScratch.ensure(trace_grid_scratch_bytes(ctx->numSms)));
             ta.scratch = ctx->gridScratch.as<uint32_t>();
             const bool gInSmem = trace_grid_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
-            CK(launch_trace_grid(ta, gd, ctx->numSms, gInSmem, ctx->stream));
+            CK(launch_trace_grid(ta, gd, ctx->numSms, gInSmem, (prm->flags & ART_FRAME_GRID_STATS) != 0, ctx->stream));
             ctx->frameGridUsed |= 1u;
         } else {
             CK(launch_trace(ta, ctx->numSms, geomInSmem, count, ctx->stream));
@@ -774,9 +775,10 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         pa.permLast = reinterpret_cast<float*>(pb + bl.offPermLast);
         pa.counters = dh->counters;
         pa.nextRay = ctx->queue.as<unsigned int>() + 8;
+        pa.raysPerWarp = perm_grid_rays_per_warp(map.nLocal, Na, ctx->numSms);
         if (useGrid) {
             const bool gInSmem = perm_grid_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
-            CK(launch_permeation_grid(pa, gd, ctx->numSms, gInSmem, ctx->stream));
+            CK(launch_permeation_grid(pa, gd, ctx->numSms, gInSmem, (prm->flags & ART_FRAME_GRID_STATS) != 0, ctx->stream));
             CK(launch_perm_last(pa, T, ctx->stream));
             ctx->frameGridUsed |= 2u;
         } else {
@@ -856,6 +858,10 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
     for (int k = 0; k < 3; k++) { c.traceTests[k] = dc[C_TRACE_S + k]; c.echoTests[k] = dc[C_ECHO_S + k]; c.muffleTests[k] = dc[C_MUFFLE_S + k]; }
     c.echoQueries = dc[C_ECHO_Q]; c.muffleQueries = dc[C_MUFFLE_Q];
     c.permRays = dc[C_PERM_RAYS]; c.permHitRays = dc[C_PERM_HIT_RAYS];
+    for (int k = 0; k < 3; k++) {
+        c.gridTraceTests[k] = dc[C_GRID_RT_S + k]; c.gridPermFirstTests[k] = dc[C_GRID_PF_S + k]; c.gridPermLossTests[k] = dc[C_GRID_PL_S + k];
+    }
+    c.gridTraceCells = dc[C_GRID_RT_CELLS]; c.gridPermCells = dc[C_GRID_PM_CELLS];
     {
         const int* ownedCount = ctx->frameOwnedCount.data();
         const uint64_t nSec[3] = { (uint64_t)ctx->L.ns, (uint64_t)ctx->L.na, (uint64_t)ctx->L.no };

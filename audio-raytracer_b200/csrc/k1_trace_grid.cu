@@ -91,6 +91,7 @@ struct PoolEnv {
     uint32_t hitMask;
     int slots, lane;
     uint32_t ltMask;
+    unsigned int* st;                    // STATS: per-lane counters {sphere, AABB, OBB tests, cells}
 };
 
 __device__ __forceinline__ void query_visible(const PoolEnv& E, int slot, int recIdx, float L)
@@ -108,7 +109,7 @@ __device__ __forceinline__ void query_visible(const PoolEnv& E, int slot, int re
 //   STAGE 1: the survivors, against the sphere and OBB lists. A query that survives this too sees its goal.
 //   STAGE 2: (few queries per hit point) all three lists in one pass.
 // An occlusion query is an "any" over all colliders (RT:365-449), so the order of the tests is free.
-template <int STAGE>
+template <int STAGE, bool STATS>
 __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count, bool noSO)
 {
     const TraceArgs& a = E.a;
@@ -219,6 +220,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                 }
                 fresh = false;
                 hdr = dda_cell(g, w);
+                if (STATS) E.st[3]++;
                 kA = 0;
             }
             bool blocked = false;
@@ -228,6 +230,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                 const int ownerId = qslot - 1;         // -1 for the echo ray: never equals a valid owner below
                 for (int c = 0; c < kCapA && kA < nA && !blocked; c++, kA++) {
                     const int id = __ldg(e + kA);
+                    if (STATS) E.st[1]++;
                     if (aabb_dist(gv, id, qo, qinv) < qL)
                         blocked = !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
                 }
@@ -253,6 +256,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                 }
                 fresh = false;
                 hdr = dda_cell(g, w);
+                if (STATS) E.st[3]++;
                 kA = kB = kC = 0;
             }
             bool blocked = false;
@@ -263,17 +267,20 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                 if (STAGE == 2) {
                     for (int c = 0; c < kCapA && kA < nA && !blocked; c++, kA++) {
                         const int id = __ldg(e + nS + kA);
+                        if (STATS) E.st[1]++;
                         if (aabb_dist(gv, id, qo, qinv) < qL)
                             blocked = !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
                     }
                 }
                 for (int c = 0; c < kCapS && kB < nS && !blocked; c++, kB++) {
                     const int id = __ldg(e + kB);
+                    if (STATS) E.st[0]++;
                     if (sphere_dist(gv, id, qo, qd, qdd) < qL)
                         blocked = !(qslot > 0 && a.anyOwned[0] && (int)a.at.ownS[id] == ownerId);       // RT:413
                 }
                 for (int c = 0; c < kCapO && kC < nO && !blocked; c++, kC++) {
                     const int id = __ldg(e + nS + nA + kC);
+                    if (STATS) E.st[2]++;
                     if (obb_blocks(gv, id, qo, qd, qdd, g.errScale, qL))
                         blocked = !(qslot > 0 && a.anyOwned[2] && (int)a.at.ownO[id] == ownerId);       // RT:439
                 }
@@ -297,7 +304,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
     return survCount;
 }
 
-template <bool SMEM>
+template <bool SMEM, bool STATS>
 __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const TraceArgs a, const GridDesc g)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -333,15 +340,16 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
     f3 o = mk3(0, 0, 0), d = mk3(0, 0, 0);
     float life = 0.0f;
     unsigned int nSegments = 0, nSegHits = 0;
+    unsigned int st[4] = { 0, 0, 0, 0 };          // STATS: sphere / AABB / OBB tests, cells visited (this lane)
 
     for (;;) {
         // ================= refill dead lanes from the ray queue =================
-        const uint32_t dead = __ballot_sync(kFull, !hasRay);
+        const uint32_t dead = __ballot_sync(kFull, !hasRay && lane < a.raysPerWarp);
         if (dead && !queueEmpty) {
             int base = 0;
             if (lane == 0) base = (int)atomicAdd(a.nextRay, (unsigned)__popc(dead));
             base = __shfl_sync(kFull, base, 0);
-            if (!hasRay) {
+            if ((dead >> lane) & 1u) {
                 const int jj = base + __popc(dead & ltMask);
                 if (jj < a.map.nLocal) {
                     j = jj;
@@ -372,6 +380,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
                 const uint2 hdr = dda_cell(g, w);
                 const uint16_t* e = g.entries + hdr.x;
                 const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
+                if (STATS) { st[0] += nS; st[1] += nA; st[2] += nO; st[3]++; }
                 for (int k = 0; k < nS; k++) {
                     const int id = __ldg(e + k);
                     const float dist = sphere_dist(gv, id, o, d, dd);
@@ -440,14 +449,14 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
         {
             const uint32_t hitMask = __ballot_sync(kFull, hit);
             const int total = __popc(hitMask) * slots;
-            const PoolEnv E = { a, g, gv, rec, qbuf0, qbuf1, qbuf2, qbuf3, surv, RayOrigin, hitMask, slots, lane, ltMask };
+            const PoolEnv E = { a, g, gv, rec, qbuf0, qbuf1, qbuf2, qbuf3, surv, RayOrigin, hitMask, slots, lane, ltMask, st };
             const bool noSO = a.L.ns + a.L.no == 0;
             for (int q0 = 0; q0 < total; q0 += kChunkQ) {
                 if (slots >= kTwoStageSlots) {
-                    const int nSurv = run_pool<0>(E, q0, min(kChunkQ, total - q0), noSO);
-                    if (nSurv > 0) run_pool<1>(E, 0, nSurv, noSO);
+                    const int nSurv = run_pool<0, STATS>(E, q0, min(kChunkQ, total - q0), noSO);
+                    if (nSurv > 0) run_pool<1, STATS>(E, 0, nSurv, noSO);
                 } else {
-                    run_pool<2>(E, q0, min(kChunkQ, total - q0), noSO);   // few queries per hit point: one pass over all types
+                    run_pool<2, STATS>(E, q0, min(kChunkQ, total - q0), noSO);   // few queries per hit point: one pass over all types
                 }
             }
         }
@@ -505,9 +514,28 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
         atomicAdd(&a.counters[C_SEGMENTS], (unsigned long long)nSegments);
         atomicAdd(&a.counters[C_SEGMENT_HITS], (unsigned long long)nSegHits);
     }
+    if (STATS) {
+        atomicAdd(&a.counters[C_GRID_RT_S], (unsigned long long)st[0]);
+        atomicAdd(&a.counters[C_GRID_RT_A], (unsigned long long)st[1]);
+        atomicAdd(&a.counters[C_GRID_RT_O], (unsigned long long)st[2]);
+        atomicAdd(&a.counters[C_GRID_RT_CELLS], (unsigned long long)st[3]);
+    }
 }
 
 // ---- launcher -----------------------------------------------------------------------------------
+// Lanes per warp that own a ray. With R = 32 a batch of n rays takes k = ceil(n / (32 * warps)) rounds per lane and the
+// last round is mostly empty when n is small (one shard of a ray-sharded frame); R = ceil(n / (k * warps)) fills all k
+// rounds evenly instead. At least ~256 queries are kept in a round's pool.
+int trace_grid_rays_per_warp(int nLocal, int nTargets, int numCtas)
+{
+    const long long warps = (long long)numCtas * kGridWarps;
+    const long long k = (nLocal + warps * 32 - 1) / (warps * 32);
+    long long r = k > 0 ? (nLocal + warps * k - 1) / (warps * k) : 32;
+    const long long minPool = (256 + nTargets) / (nTargets + 1);
+    if (r < minPool) r = minPool;
+    return (int)(r < 1 ? 1 : (r > 32 ? 32 : r));
+}
+
 size_t trace_grid_scratch_bytes(int numCtas) { return (size_t)numCtas * kGridWarps * kChunkQ * sizeof(uint32_t); }
 
 size_t trace_grid_smem_bytes(const GeomLayout& L, bool geomInSmem)
@@ -515,10 +543,12 @@ size_t trace_grid_smem_bytes(const GeomLayout& L, bool geomInSmem)
     return (geomInSmem ? L.bytes : 0) + (size_t)kGridWarps * 32 * (sizeof(HitRec) + kQueryWords * 4);
 }
 
-cudaError_t launch_trace_grid(const TraceArgs& a, const GridDesc& g, int numCtas, bool geomInSmem, cudaStream_t stream)
+cudaError_t launch_trace_grid(const TraceArgs& a, const GridDesc& g, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream)
 {
     const size_t smem = trace_grid_smem_bytes(a.L, geomInSmem);
-    void (*k)(const TraceArgs, const GridDesc) = geomInSmem ? trace_grid_kernel<true> : trace_grid_kernel<false>;
+    void (*k)(const TraceArgs, const GridDesc) = nullptr;
+    if (geomInSmem) k = stats ? trace_grid_kernel<true, true> : trace_grid_kernel<true, false>;
+    else k = stats ? trace_grid_kernel<false, true> : trace_grid_kernel<false, false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<numCtas, kGridThreads, smem, stream>>>(a, g);

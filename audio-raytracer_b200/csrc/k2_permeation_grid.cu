@@ -35,7 +35,7 @@ __device__ __forceinline__ float clip_len(float tEnter, float tExit, float tIn, 
     return fmaxf(0.0f, fminf(tExit, tOut) - fmaxf(tEnter, tIn));
 }
 
-template <bool SMEM>
+template <bool SMEM, bool STATS>
 __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const PermArgs a, const GridDesc g)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -55,14 +55,15 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
     const GeomView gv = make_view(geomBase, a.L);
     const f3 RayOrigin = mk3(a.ox, a.oy, a.oz);
     unsigned int nRays = 0, nHitRays = 0;
+    unsigned long long st[7] = { 0, 0, 0, 0, 0, 0, 0 };   // STATS: first-hit S/A/O tests, loss S/A/O tests, cells
 
     for (;;) {
         int base = 0;
-        if (lane == 0) base = (int)atomicAdd(a.nextRay, 32u);
+        if (lane == 0) base = (int)atomicAdd(a.nextRay, (unsigned)a.raysPerWarp);
         base = __shfl_sync(kFull, base, 0);
         if (base >= a.map.nLocal) break;
         const int j = base + lane;
-        const bool hasRay = j < a.map.nLocal;
+        const bool hasRay = lane < a.raysPerWarp && j < a.map.nLocal;
 
         // ================= Phase 1: ShootRayCast, distance only (PM:101-141) =================
         float best = pos_inf();                                                // math.INFINITY
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
                 const uint2 hdr = dda_cell(g, w);
                 const uint16_t* e = g.entries + hdr.x;
                 const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
+                if (STATS) { st[0] += nS; st[1] += nA; st[2] += nO; st[6]++; }
                 for (int k = 0; k < nS; k++) {
                     const float dist = sphere_dist(gv, __ldg(e + k), o, d, dd);
                     if (dist < best) best = dist;
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
             const int tgt = laneOn ? a.targetOrder[tb * 32 + (lane - rsub * tpb)] : 0;   // spatially sorted lane order
             const f3 T = laneOn ? mk3(a.targets[3 * tgt], a.targets[3 * tgt + 1], a.targets[3 * tgt + 2]) : mk3(0, 0, 0);
             long long accInt = 0, accFrac = 0;
-            for (int r0 = 0; r0 < 32; r0 += rp) {
+            for (int r0 = 0; r0 < a.raysPerWarp; r0 += rp) {
                 const int r = r0 + rsub;
                 float4 rr = make_float4(0, 0, 0, 0);
                 if (laneOn && r < 32) rr = rec[r];
@@ -141,6 +143,7 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
                         const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
                         const float tIn = w.tCur;
                         const float tOut = fminf(dda_next_t(w), w.tEnd);
+                        if (STATS) { st[3] += nS; st[4] += nA; st[5] += nO; st[6]++; }
                         // AABB and sphere intervals are evaluated in the reference's own operation order, so tEnter/tExit are
                         // the reference's floats (a near-tangent sphere crossing, 2*sqrt(disc) with disc ~ 0, would otherwise
                         // amplify harmless rounding into a visible difference); only the per-cell clipping is new.
@@ -226,6 +229,25 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
         atomicAdd(&a.counters[C_PERM_RAYS], (unsigned long long)nRays);
         atomicAdd(&a.counters[C_PERM_HIT_RAYS], (unsigned long long)nHitRays);
     }
+    if (STATS) {
+        for (int k = 0; k < 3; k++) {
+            atomicAdd(&a.counters[C_GRID_PF_S + k], st[k]);
+            atomicAdd(&a.counters[C_GRID_PL_S + k], st[3 + k]);
+        }
+        atomicAdd(&a.counters[C_GRID_PM_CELLS], st[6]);
+    }
+}
+
+// Rays a warp takes at a time: chosen like trace_grid_rays_per_warp so that small batches are spread evenly over the
+// warps (a multiple of the rays handled side by side when there are fewer than 32 targets).
+int perm_grid_rays_per_warp(int nLocal, int nTargets, int numCtas)
+{
+    const long long warps = (long long)numCtas * kPGridWarps;
+    const long long k = (nLocal + warps * 32 - 1) / (warps * 32);
+    long long r = k > 0 ? (nLocal + warps * k - 1) / (warps * k) : 32;
+    const int side = nTargets >= 32 ? 1 : 32 / nTargets;
+    r = (r + side - 1) / side * side;
+    return (int)(r < side ? side : (r > 32 ? 32 : r));
 }
 
 size_t perm_grid_smem_bytes(const GeomLayout& L, bool geomInSmem)
@@ -233,10 +255,12 @@ size_t perm_grid_smem_bytes(const GeomLayout& L, bool geomInSmem)
     return (geomInSmem ? L.bytes : 0) + (size_t)kPGridWarps * 32 * sizeof(float4);
 }
 
-cudaError_t launch_permeation_grid(const PermArgs& a, const GridDesc& g, int numCtas, bool geomInSmem, cudaStream_t stream)
+cudaError_t launch_permeation_grid(const PermArgs& a, const GridDesc& g, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream)
 {
     const size_t smem = perm_grid_smem_bytes(a.L, geomInSmem);
-    void (*k)(const PermArgs, const GridDesc) = geomInSmem ? permeation_grid_kernel<true> : permeation_grid_kernel<false>;
+    void (*k)(const PermArgs, const GridDesc) = nullptr;
+    if (geomInSmem) k = stats ? permeation_grid_kernel<true, true> : permeation_grid_kernel<true, false>;
+    else k = stats ? permeation_grid_kernel<false, true> : permeation_grid_kernel<false, false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<numCtas, kPGridThreads, smem, stream>>>(a, g);

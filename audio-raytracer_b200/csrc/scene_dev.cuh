@@ -85,6 +85,11 @@ enum CounterIdx {
     C_MUFFLE_Q, C_MUFFLE_S, C_MUFFLE_A, C_MUFFLE_O,
     C_PERM_RAYS, C_PERM_HIT_RAYS, C_PERM_FIRST_S, C_PERM_FIRST_A, C_PERM_FIRST_O,
     C_PERM_PAIRS, C_PERM_LOSS_S, C_PERM_LOSS_A, C_PERM_LOSS_O,
+    // tests the grid kernels actually executed (ART_FRAME_GRID_STATS): trace job, permeation first hit, permeation loss
+    C_GRID_RT_S, C_GRID_RT_A, C_GRID_RT_O,
+    C_GRID_PF_S, C_GRID_PF_A, C_GRID_PF_O,
+    C_GRID_PL_S, C_GRID_PL_A, C_GRID_PL_O,
+    C_GRID_RT_CELLS, C_GRID_PM_CELLS,
     C_COUNT
 };
 
@@ -123,6 +128,7 @@ struct TraceArgs {
     unsigned long long* counters;  // [C_COUNT]
     unsigned int* nextRay;         // dynamic ray queue
     uint32_t* scratch;             // grid kernel: per-warp survivor lists (trace_grid_scratch_bytes)
+    int raysPerWarp;               // grid kernel: lanes of a warp that own a ray (32 unless the batch is too small to fill the GPU)
     int muffleInSmem;              // per-warp shared counters fit
     int anyOwned[3];               // does any sphere / AABB / OBB belong to a target < nTargets (RT:413/426/439)
 };
@@ -180,6 +186,7 @@ struct PermArgs {
     float* permLast;           // [T*Na] values of the last hitting ray of batch k (perm_last_kernel)
     unsigned long long* counters;
     unsigned int* nextRay;
+    int raysPerWarp;           // grid kernel: rays a warp takes from the queue at a time (<= 32)
 };
 
 // K3 output (also part of the partial-result blob)

@@ -18,10 +18,10 @@ from .layouts import AABB_DT, OBB_DT, SPHERE_DT, SETTINGS_DT
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AUDIORT_LIB") or os.path.join(_HERE, "libaudiort_cuda.so")
 
-ART_ABI_VERSION = 1
+ART_ABI_VERSION = 2
 ART_OK, ART_E_ARG, ART_E_CUDA, ART_E_PENDING, ART_E_NO_DEVICE, ART_E_STATE, ART_E_NOMEM = 0, -1, -2, -3, -4, -5, -6
 JOB_RAYTRACE, JOB_PERMEATION, JOB_PROCESS, JOB_ALL = 1, 2, 4, 7
-FRAME_COUNTERS, FRAME_REVERB_SEQ_FP32, FRAME_NO_HOST_OUTPUTS, FRAME_PARTIALS_ONLY, FRAME_BRUTE_FORCE = 1, 2, 4, 8, 16
+FRAME_COUNTERS, FRAME_REVERB_SEQ_FP32, FRAME_NO_HOST_OUTPUTS, FRAME_PARTIALS_ONLY, FRAME_BRUTE_FORCE, FRAME_GRID_STATS = 1, 2, 4, 8, 16, 32
 
 EXPORTS = [
     "art_create", "art_destroy", "art_set_scene", "art_set_rays", "art_generate_fibonacci_rays", "art_get_rays",
@@ -62,7 +62,9 @@ class ArtCounters(C.Structure):
                 ("permRays", C.c_uint64), ("permHitRays", C.c_uint64), ("permFirstTests", C.c_uint64 * 3),
                 ("permPairs", C.c_uint64), ("permLossTests", C.c_uint64 * 3),
                 ("traceMs", C.c_float), ("permeationMs", C.c_float), ("reduceMs", C.c_float), ("deviceMs", C.c_float),
-                ("h2dMs", C.c_float), ("d2hMs", C.c_float), ("kernelLaunches", C.c_uint32), ("gridUsed", C.c_uint32)]
+                ("h2dMs", C.c_float), ("d2hMs", C.c_float), ("kernelLaunches", C.c_uint32), ("gridUsed", C.c_uint32),
+                ("gridTraceTests", C.c_uint64 * 3), ("gridPermFirstTests", C.c_uint64 * 3), ("gridPermLossTests", C.c_uint64 * 3),
+                ("gridTraceCells", C.c_uint64), ("gridPermCells", C.c_uint64)]
 
     def as_dict(self) -> dict:
         out = {}

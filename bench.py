@@ -124,11 +124,12 @@ def cpu_reference_sample(scene, seconds: float, threads: int):
     from oracle import oracle as orc
     N = scene.n_rays
     # calibrate on a few rays, then size 4 windows spread over the sphere
+    ncal = min(N, max(32, 8 * threads))
     t0 = time.perf_counter()
-    c = orc.trace_range(scene, N // 2, min(32, N), threads=threads, with_outputs=False)
-    orc.permeation_range(scene, N // 2, min(32, N), threads=threads)
+    c = orc.trace_range(scene, N // 2, ncal, threads=threads, with_outputs=False)
+    orc.permeation_range(scene, N // 2, ncal, threads=threads)
     dt = max(time.perf_counter() - t0, 1e-4)
-    per_ray = dt / min(32, N)
+    per_ray = dt / ncal
     total = int(max(64, min(N, seconds / per_ray)))
     win = max(16, total // 4)
     starts = [int(f * (N - win)) for f in (0.1, 0.35, 0.6, 0.85)]
@@ -174,6 +175,7 @@ def workload_config(args, scene, world):
             "colliders": scene.n_colliders, "batch_count": scene.batch_count,
             "sharding": "none" if world == 1 else f"rays interleaved in chunks of {args.chunk} over {world} ranks",
             "l2": "flushed between steps (256 MiB write)", "reverb_reduction": "exact integer",
+            "path": "default: uniform-grid traversal, bit-identical to the brute-force scans (ART_FRAME_BRUTE_FORCE timed beside it)",
             "rays_override": args.rays is not None}
 
 
@@ -236,10 +238,19 @@ def main():
             native.finalize(blob, scene, scene.n_rays)
         return r.counters, ex_ms
 
-    # ---- one untimed counting pass: oracle-equivalent test counts -> algorithmic flops of a step
+    # ---- untimed passes: (1) oracle-equivalent test counts of the reference's full scans -> reference-formulation flops
+    #      of a step; (2) the brute-force kernels without counters -> their own roofline; (3) the tests the default
+    #      (uniform-grid) kernels actually execute
     barrier()
     cnt, _ = device_step(native.FRAME_COUNTERS)
     trace_flops_local, perm_flops_local = flops_of(cnt)
+    device_step(native.FRAME_BRUTE_FORCE)
+    bf, _ = device_step(native.FRAME_BRUTE_FORCE)
+    gst, _ = device_step(native.FRAME_GRID_STATS)
+    grid_used = int(gst.get("gridUsed", 0))
+    exec_trace_flops = sum(f * n for f, n in zip(FLOPS_TRACE, gst["gridTraceTests"]))
+    exec_perm_flops = sum(f * n for f, n in zip(FLOPS_PERM_FIRST, gst["gridPermFirstTests"])) + \
+        sum(f * n for f, n in zip(FLOPS_PERM_LOSS, gst["gridPermLossTests"]))
 
     for _ in range(args.warmup):
         device_step()
@@ -314,7 +325,27 @@ def main():
         sm_max = clocks.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
         n_sms = 148
         peak_tflops = n_sms * 128 * sm_max * 1e6 / 1e12          # FP32 instruction issue, no FMA
-        achieved = trace_flops_local / (trace_ms_avg * 1e-3) / 1e12
+        perm_ms_avg = float(np.mean(perm_ms))
+        tfl = lambda flops, ms: (flops / (ms * 1e-3) / 1e12) if ms and ms > 0 else None
+        if grid_used & 1:
+            achieved = tfl(exec_trace_flops, trace_ms_avg)
+            kernel_name = "trace_grid_kernel (K1, default path: uniform-grid traversal)"
+            accounting = ("collider tests the kernel actually executed (ART_FRAME_GRID_STATS) x reference flops per test; "
+                          "the acceleration structure changes WHICH tests run, so the full-scan count is reported beside it "
+                          "(SURVEY 8f-4). The kernel is traversal/divergence bound, not FP32 bound: see profiles/ for issue-slot "
+                          "and lane utilisation.")
+        else:
+            achieved = tfl(trace_flops_local, trace_ms_avg)
+            kernel_name = "trace_kernel (K1, brute force)"
+            accounting = "tests of the reference's full scans (early exits honoured) x reference flops per test"
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            key = f"{args.workload}:{scene.n_rays}:{world}"
+            if key in tr:
+                traffic = tr[key]
+        except Exception:
+            pass
         micro = {}
         try:
             micro = {"fadd_fmul_tops": ctx.microbench(0) / 1e3, "fmnmx_tops": ctx.microbench(1) / 1e3,
@@ -338,15 +369,35 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": allmax(e2e_s) / args.steps * 1e3 if world == 1 else None},
             "gpu_launches": launches_all,
-            "roofline": {"bound": "fp32", "kernel": "trace_kernel (K1)", "achieved": achieved, "peak": peak_tflops,
-                         "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": None,
+            "roofline": {"bound": "fp32", "kernel": kernel_name, "achieved": achieved, "peak": peak_tflops,
+                         "unit": "TFLOP/s", "frac": (achieved / peak_tflops) if achieved else None, "traffic": traffic,
+                         "accounting": accounting,
                          "peak_source": f"148 SM x 128 FP32 lanes x {sm_max:.0f} MHz, un-fused issue rate (no FP32 figure in "
-                                        "MEASURED_PEAKS.json; parity forbids FMA contraction, SURVEY 8d); on-box microbenchmarks in 'measured_issue_rates'",
-                         "algorithmic_flops_per_launch": trace_flops_local,
+                                        "MEASURED_PEAKS.json; parity forbids FMA contraction, SURVEY 8d); FMA peak = 2x; "
+                                        "on-box microbenchmarks in 'measured_issue_rates'",
+                         "peak_fma": 2 * peak_tflops,
+                         "executed_flops_per_launch": exec_trace_flops if grid_used & 1 else trace_flops_local,
                          "flops_per_test": {"sphere": 38, "aabb": 35, "obb": 98},
                          "measured_issue_rates": micro,
-                         "permeation_kernel": {"achieved": perm_flops_local / (float(np.mean(perm_ms)) * 1e-3) / 1e12 if np.mean(perm_ms) > 0 else None,
-                                               "algorithmic_flops_per_launch": perm_flops_local}},
+                         "reference_formulation": {
+                             "what": "the reference's own full linear scans (early exits honoured), counted by the brute-force kernels' COUNT variant",
+                             "algorithmic_flops_per_launch": trace_flops_local,
+                             "equivalent_tflops_of_default_path": tfl(trace_flops_local, trace_ms_avg),
+                             "tests_full_scan": [int(a + b + c) for a, b, c in zip(cnt["traceTests"], cnt["echoTests"], cnt["muffleTests"])],
+                             "tests_executed": [int(x) for x in gst["gridTraceTests"]],
+                             "cells_visited": int(gst["gridTraceCells"])},
+                         "brute_force_kernel": {
+                             "kernel": "trace_kernel (ART_FRAME_BRUTE_FORCE: every collider for every query, as the reference loops do)",
+                             "ms": bf["traceMs"], "achieved": tfl(trace_flops_local, bf["traceMs"]),
+                             "frac": (tfl(trace_flops_local, bf["traceMs"]) or 0) / peak_tflops,
+                             "step_ms": bf["deviceMs"], "segments_per_s": bf["segments"] / (bf["deviceMs"] * 1e-3) if bf["deviceMs"] else None},
+                         "permeation_kernel": {
+                             "kernel": "permeation_grid_kernel (K2)" if grid_used & 2 else "permeation_kernel (K2, brute force)",
+                             "achieved": tfl(exec_perm_flops if grid_used & 2 else perm_flops_local, perm_ms_avg),
+                             "executed_flops_per_launch": exec_perm_flops if grid_used & 2 else perm_flops_local,
+                             "algorithmic_flops_per_launch": perm_flops_local,
+                             "equivalent_tflops_of_default_path": tfl(perm_flops_local, perm_ms_avg),
+                             "brute_force_ms": bf["permeationMs"], "brute_force_achieved": tfl(perm_flops_local, bf["permeationMs"])}},
             "cpu_baseline": cpu,
             "counters_first_step": {k: cnt[k] for k in ("segments", "segmentHits", "traceTests", "echoTests", "muffleTests",
                                                         "echoQueries", "muffleQueries", "permHitRays")},

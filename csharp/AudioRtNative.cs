@@ -11,7 +11,7 @@ using Unity.Mathematics;
 public static unsafe class AudioRtNative
 {
     const string Lib = "audiort_cuda";
-    public const int ART_ABI_VERSION = 1;
+    public const int ART_ABI_VERSION = 2;
 
     public const uint JOB_RAYTRACE = 1, JOB_PERMEATION = 2, JOB_PROCESS = 4, JOB_ALL = 7;
     public const uint FRAME_COUNTERS = 1, FRAME_REVERB_SEQ_FP32 = 2, FRAME_NO_HOST_OUTPUTS = 4, FRAME_PARTIALS_ONLY = 8;

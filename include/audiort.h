@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ART_ABI_VERSION 1
+#define ART_ABI_VERSION 2
 
 typedef enum ArtStatus {
     ART_OK          =  0,
@@ -112,6 +112,8 @@ typedef struct ArtConfig {
                                           (no acceleration structure). Default: uniform-grid traversal, which runs
                                           the same exact tests on the colliders near each ray only; all outputs are
                                           bit-identical. ART_FRAME_COUNTERS implies brute force. */
+#define ART_FRAME_GRID_STATS      32u  /* grid kernels also count the collider tests and cells they actually visit
+                                          (ArtCounters.grid*); slightly slower kernel variant */
 
 /* One field per job-struct field (RT:12-52, PM:10-27, PA:10-25). */
 typedef struct ArtParams {
@@ -169,6 +171,13 @@ typedef struct ArtCounters {
     float    h2dMs, d2hMs;      /* copy time on the stream (0 when nothing was copied) */
     uint32_t kernelLaunches;    /* kernels of this library launched for the frame */
     uint32_t gridUsed;          /* bit 0: trace job used the uniform grid, bit 1: permeation job did */
+    /* ART_FRAME_GRID_STATS: collider tests the grid kernels actually executed ([3] = sphere, AABB, OBB) and grid
+     * cells they visited; compare with traceTests + echoTests + muffleTests / permFirstTests / permLossTests, the
+     * counts of the reference's full scans */
+    uint64_t gridTraceTests[3];
+    uint64_t gridPermFirstTests[3];
+    uint64_t gridPermLossTests[3];
+    uint64_t gridTraceCells, gridPermCells;
 } ArtCounters;
 
 /* ≙ AudioRayTracer.Awake/InitializeAudioRaytraceSystem (ART:53-87): one context per AudioRayTracer. */
