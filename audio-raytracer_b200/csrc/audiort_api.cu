@@ -970,6 +970,36 @@ ART_API int32_t art_finalize(const void* blob, int64_t blobBytes, const ArtParam
     return finalize_blob(static_cast<const unsigned char*>(blob), (size_t)blobBytes, params, rayCount, outputs, nullptr);
 }
 
+ART_API int32_t art_grid_build_host(const ArtAABB* aabbs, int32_t nAABB, const ArtOBB* obbs, int32_t nOBB,
+                                    const ArtSphere* spheres, int32_t nSphere, float cellScale, ArtGridInfo* info,
+                                    uint32_t* cells, int64_t cellsCapacity, uint16_t* entries, int64_t entriesCapacity)
+{
+    if (!info || nAABB < 0 || nOBB < 0 || nSphere < 0 || (nAABB && !aabbs) || (nOBB && !obbs) || (nSphere && !spheres)) return ART_E_ARG;
+    std::vector<uint16_t> hS(reinterpret_cast<const uint16_t*>(spheres), reinterpret_cast<const uint16_t*>(spheres) + 8 * (size_t)nSphere);
+    std::vector<uint16_t> hA(reinterpret_cast<const uint16_t*>(aabbs), reinterpret_cast<const uint16_t*>(aabbs) + 10 * (size_t)nAABB);
+    std::vector<uint16_t> hO(reinterpret_cast<const uint16_t*>(obbs), reinterpret_cast<const uint16_t*>(obbs) + 13 * (size_t)nOBB);
+    HostGrid g;
+    build_grid(hS, hA, hO, cellScale > 0.0f ? cellScale : 1.1f, g);
+    memset(info, 0, sizeof *info);
+    if (!g.ok) return ART_E_STATE;
+    info->nx = g.d.nx; info->ny = g.d.ny; info->nz = g.d.nz;
+    info->g0[0] = g.d.g0x; info->g0[1] = g.d.g0y; info->g0[2] = g.d.g0z;
+    info->g1[0] = g.d.g1x; info->g1[1] = g.d.g1y; info->g1[2] = g.d.g1z;
+    info->cellSize[0] = g.d.csx; info->cellSize[1] = g.d.csy; info->cellSize[2] = g.d.csz;
+    info->margin = g.margin;
+    info->nCells = (int64_t)g.cells.size();
+    info->nEntries = (int64_t)g.entries.size();
+    if (cells) {
+        if (cellsCapacity < 2 * info->nCells) return ART_E_ARG;
+        for (size_t i = 0; i < g.cells.size(); i++) { cells[2 * i] = g.cells[i].x; cells[2 * i + 1] = g.cells[i].y; }
+    }
+    if (entries) {
+        if (entriesCapacity < info->nEntries) return ART_E_ARG;
+        memcpy(entries, g.entries.data(), g.entries.size() * sizeof(uint16_t));
+    }
+    return ART_OK;
+}
+
 ART_API int32_t art_microbench(ArtCtx* ctx, int32_t kind, double* gops)
 {
     if (!ctx || !gops || kind < 0 || kind > 2) return ART_E_ARG;

@@ -30,6 +30,7 @@ struct HostGrid {
     float diag = 0.0f;                  // un-inflated scene diagonal
     float cx = 0, cy = 0, cz = 0;       // scene centre
     float listenerRange = 0.0f;         // ray origins farther than this from the centre -> brute force
+    float margin = 0.0f;                // m: inflation of every collider's bounds
     bool ok = false;
     const char* why = "";
 };
@@ -126,6 +127,7 @@ inline void build_grid(const std::vector<uint16_t>& rawS, const std::vector<uint
     // error scale: |oc| can reach the listener range plus half the diagonal
     const float D = 2.0f * g.diag + 33.0f;
     const float m = 1e-3f + 1e-4f * D;
+    g.margin = m;
     for (int k = 0; k < 3; k++) { lo[k] -= 2.0f * m; hi[k] += 2.0f * m; }
 
     const size_t nc = ns + na + no;

@@ -27,8 +27,13 @@ EXPORTS = [
     "art_create", "art_destroy", "art_set_scene", "art_set_rays", "art_generate_fibonacci_rays", "art_get_rays",
     "art_set_ray_shard", "art_local_ray_count", "art_trace_schedule", "art_is_completed", "art_complete",
     "art_get_counters", "art_last_error", "art_partials_size", "art_get_partials", "art_partials_merge",
-    "art_finalize", "art_microbench",
+    "art_finalize", "art_microbench", "art_grid_build_host",
 ]
+
+
+class ArtGridInfo(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("g0", C.c_float * 3), ("g1", C.c_float * 3),
+                ("cellSize", C.c_float * 3), ("margin", C.c_float), ("nCells", C.c_int64), ("nEntries", C.c_int64)]
 
 
 class ArtError(RuntimeError):
@@ -114,6 +119,8 @@ def load_library(path: Optional[str] = None):
     lib.art_get_counters.argtypes = [vp, i32, C.POINTER(ArtCounters)]
     lib.art_last_error.restype = C.c_char_p
     lib.art_last_error.argtypes = [vp]
+    lib.art_grid_build_host.restype = i32
+    lib.art_grid_build_host.argtypes = [vp, i32, vp, i32, vp, i32, C.c_float, C.POINTER(ArtGridInfo), vp, i64, vp, i64]
     lib.art_partials_size.restype = i64
     lib.art_partials_size.argtypes = [i32, i32]
     lib.art_get_partials.restype = i32
@@ -343,3 +350,24 @@ def upload(ctx: Context, scene):
     """set_scene + set_rays for a scenes.Scene."""
     ctx.set_scene(scene.aabbs, scene.obbs, scene.spheres)
     ctx.set_rays(scene.ray_directions)
+
+
+def build_grid_host(scene, cell_scale: float = 1.1):
+    """The uniform grid art_set_scene would build for ``scene`` (host only, no GPU): (ArtGridInfo, cells [nCells, 2]
+    uint32 = {first entry, nS | nA << 10 | nO << 21}, entries uint16), or None when the scene cannot be gridded."""
+    lib = load_library()
+    a, o, s = (np.ascontiguousarray(x) for x in (scene.aabbs, scene.obbs, scene.spheres))
+    ptr = lambda x: x.ctypes.data_as(C.c_void_p) if len(x) else None
+    info = ArtGridInfo()
+    rc = lib.art_grid_build_host(ptr(a), len(a), ptr(o), len(o), ptr(s), len(s), cell_scale, C.byref(info), None, 0, None, 0)
+    if rc == ART_E_STATE:
+        return None
+    if rc != ART_OK:
+        raise ArtError(rc, "art_grid_build_host")
+    cells = np.zeros((info.nCells, 2), dtype=np.uint32)
+    entries = np.zeros(info.nEntries, dtype=np.uint16)
+    rc = lib.art_grid_build_host(ptr(a), len(a), ptr(o), len(o), ptr(s), len(s), cell_scale, C.byref(info),
+                                 cells.ctypes.data_as(C.c_void_p), cells.size, entries.ctypes.data_as(C.c_void_p), entries.size)
+    if rc != ART_OK:
+        raise ArtError(rc, "art_grid_build_host")
+    return info, cells, entries

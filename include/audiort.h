@@ -232,6 +232,21 @@ ART_API int32_t art_partials_merge(void* accumBlob, const void* otherBlob, int64
 ART_API int32_t art_finalize(const void* blob, int64_t blobBytes, const ArtParams* params, int32_t rayCount,
                              const ArtOutputs* outputs /* only the per-target arrays are used */);
 
+/* Host-only inspection of the acceleration structure art_set_scene builds (a uniform grid over the colliders;
+ * csrc/grid_host.h): cell (x,y,z) = cells[2*((z*ny + y)*nx + x) + {0,1}] = {first entry, nS | nA << 10 | nO << 21},
+ * entries = canonical collider indices, per cell spheres | AABBs | OBBs. Needs no context and no GPU (tests, tooling).
+ * cells / entries may be NULL to query the sizes first. Returns ART_OK, or ART_E_STATE when the scene cannot be gridded
+ * (the library then uses the brute-force kernels). */
+typedef struct ArtGridInfo {
+    int32_t nx, ny, nz;
+    float   g0[3], g1[3], cellSize[3];
+    float   margin;             /* m of grid_host.h */
+    int64_t nCells, nEntries;
+} ArtGridInfo;
+ART_API int32_t art_grid_build_host(const ArtAABB* aabbs, int32_t nAABB, const ArtOBB* obbs, int32_t nOBB,
+                                    const ArtSphere* spheres, int32_t nSphere, float cellScale, ArtGridInfo* info,
+                                    uint32_t* cells, int64_t cellsCapacity, uint16_t* entries, int64_t entriesCapacity);
+
 /* Device-side FP32 issue-rate microbenchmarks used for the roofline denominator (bench.py):
  * kind 0 = un-fused FADD/FMUL, 1 = FMNMX, 2 = FFMA. Returns achieved Gop/s (lane-ops). */
 ART_API int32_t art_microbench(ArtCtx* ctx, int32_t kind, double* gops);
