@@ -19,7 +19,13 @@ public static class Program
     }
     static half H(BinaryReader r) { half h; h.value = r.ReadUInt16(); return h; }
     static half3 H3(BinaryReader r) { half3 v; v.x = H(r); v.y = H(r); v.z = H(r); return v; }
-    static AudioMaterialProperties Mat(BinaryReader r) => new AudioMaterialProperties { Absorption = H(r), Density = H(r), Echo = H(r) };
+    static T[] ReadBlittable<T>(BinaryReader r, int n, int size) where T : struct
+    {
+        if (System.Runtime.InteropServices.Marshal.SizeOf<T>() != size) throw new InvalidOperationException($"{typeof(T).Name} is not {size} bytes");
+        var a = new T[n];
+        for (int i = 0; i < n; i++) a[i] = System.Runtime.InteropServices.MemoryMarshal.Read<T>(r.ReadBytes(size));
+        return a;
+    }
 
     public static int Main(string[] args)
     {
@@ -31,18 +37,11 @@ public static class Program
         var origin = new float3(r.ReadSingle(), r.ReadSingle(), r.ReadSingle());
         float maxRayLife = r.ReadSingle(), maxMuffle = r.ReadSingle(), strength = r.ReadSingle(), muffleEff = r.ReadSingle(),
               permEff = r.ReadSingle(), maxReverb = r.ReadSingle();
-        var aabbs = ReadStructs(r, nA, b => new ColliderAABBStruct { Center = H3(b), Size = H3(b), MaterialProperties = Mat(b), AudioTargetId = b.ReadInt16() });
-        var obbs = ReadStructs(r, nO, b =>
-        {
-            var o = new ColliderOBBStruct { Center = H3(b), Size = H3(b) };
-            // the private halfQuaternion field sits between Size and MaterialProperties (ColliderOBBStruct.cs:8-24):
-            // feed its three halves through the public setter's inverse, i.e. reconstruct the quaternion the getter returns
-            halfQuaternion hq; hq.x = H(b); hq.y = H(b); hq.z = H(b);
-            o.Rotation = hq.QuaternionValue;
-            o.MaterialProperties = Mat(b); o.AudioTargetId = b.ReadInt16();
-            return o;
-        });
-        var spheres = ReadStructs(r, nS, b => new ColliderSphereStruct { Center = H3(b), Radius = H(b), MaterialProperties = Mat(b), AudioTargetId = b.ReadInt16() });
+        // the collider structs are blittable, sequential and made of 2-byte members only (20 / 26 / 16 bytes, no padding):
+        // read them as raw bytes so that the private halfQuaternion of ColliderOBBStruct keeps its exact stored bits
+        var aabbs = ReadBlittable<ColliderAABBStruct>(r, nA, 20);
+        var obbs = ReadBlittable<ColliderOBBStruct>(r, nO, 26);
+        var spheres = ReadBlittable<ColliderSphereStruct>(r, nS, 16);
         var targets = ReadStructs(r, Na, b => new float3(b.ReadSingle(), b.ReadSingle(), b.ReadSingle()));
         var dirs = ReadStructs(r, N, H3);
 
