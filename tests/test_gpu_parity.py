@@ -343,3 +343,77 @@ def test_jobs_mirror_one_frame_latency(art_lib, oracle):
     np.testing.assert_array_equal(res.hit_counts, o.hit_counts)
     np.testing.assert_array_equal(res.muffle, o.muffle)
     rt.OnDestroy()
+
+
+# ---------------------------------------------------------------- uniform-grid path: edge cases of the traversal
+def _grid_vs_oracle(ctx, oracle, s, expect_grid=True):
+    o = oracle.run_frame(s, threads=8)
+    native.upload(ctx, s)
+    g = ctx.run_frame(s)                                   # default path
+    assert bool(g.counters["gridUsed"] & 1) == expect_grid
+    for k in ("hit_counts", "hit_ids", "echo", "muffle", "muffle_totals"):
+        np.testing.assert_array_equal(getattr(g, k), getattr(o, k), err_msg=k)
+    gp, op = g.hit_points.copy(), o.hit_points.copy()
+    gp[gp == 0x8000] = 0
+    op[op == 0x8000] = 0
+    np.testing.assert_array_equal(gp, op)
+    np.testing.assert_array_equal(g.permeation.view(np.uint32), o.permeation.view(np.uint32))
+    scale = max(s.n_rays * s.permeation_strength_per_ray, 50.0) * max(1, o.counters["perm_hit_rays"])
+    np.testing.assert_allclose(g.permeation_sum, o.permeation_sum, rtol=0, atol=1e-5 * scale)
+    assert g.counters["segments"] == o.counters["segments"]
+    return g, o
+
+
+def test_grid_listener_and_targets_outside_the_scene(gpu_ctx, oracle):
+    """rays that start outside the grid (clip to the grid first) and targets far outside it"""
+    s = scenes.make_scene(n_aabb=40, n_obb=20, n_sphere=12, n_targets=5, seed=901, n_rays=600, max_hits=4, batch_count=2,
+                          room_half=(6.0, 3.0, 6.0))
+    s.ray_origin = np.array([14.0, 1.0, -11.0], dtype=np.float32)           # outside the room, inside the listener range
+    s.targets[0] = [40.0, 2.0, 3.0]
+    s.targets[1] = [-25.0, -30.0, 0.5]
+    _grid_vs_oracle(gpu_ctx, oracle, s)
+    s.ray_origin = np.array([400.0, 0.0, 0.0], dtype=np.float32)            # beyond the listener range: brute-force fallback
+    _grid_vs_oracle(gpu_ctx, oracle, s, expect_grid=False)
+
+
+def test_grid_owned_colliders_of_every_type(gpu_ctx, oracle):
+    """the owner skip (RT:413/426/439, PM:235/245/255) inside the traversal, for spheres, AABBs and OBBs"""
+    s = scenes.make_scene(n_aabb=60, n_obb=30, n_sphere=20, n_targets=6, seed=902, n_rays=700, max_hits=5, batch_count=1,
+                          room_half=(8.0, 4.0, 8.0))
+    from audio_raytracer_b200.layouts import f32tof16
+    for t in range(6):                                                      # wrap every target in owned colliders
+        s.spheres["center"][t] = f32tof16(s.targets[t]); s.spheres["radius"][t] = f32tof16(np.float32([1.2]))[0]
+        s.spheres["audioTargetId"][t] = t
+        s.aabbs["center"][6 + t] = f32tof16(s.targets[t]); s.aabbs["size"][6 + t] = f32tof16(np.float32([0.9, 0.7, 0.8]))
+        s.aabbs["audioTargetId"][6 + t] = t if t % 2 else (t + 1) % 6         # even: owned by a DIFFERENT target (blocks), odd: own
+    g, o = _grid_vs_oracle(gpu_ctx, oracle, s)
+    assert o.muffle_totals.sum() > 0
+
+
+def test_grid_large_coordinates_and_mixed_sizes(gpu_ctx, oracle):
+    """a 20x larger room (half precision spacing up to 0.5 at these coordinates), walls spanning the whole grid next to small boxes"""
+    s = scenes.make_scene(n_aabb=80, n_obb=40, n_sphere=30, n_targets=4, seed=903, n_rays=500, max_hits=6, batch_count=1,
+                          room_half=(640.0, 160.0, 640.0), size_range=(2.0, 60.0))
+    s.ray_origin = np.array([3.0, 13.0, -7.0], dtype=np.float32)
+    s.max_ray_life = 1e6
+    s.max_muffle_hit_distance = 1e6
+    _grid_vs_oracle(gpu_ctx, oracle, s)
+
+
+def test_grid_rebuilds_when_the_scene_changes(gpu_ctx, oracle):
+    a = scenes.make_config("c2", n_rays=300)
+    b = scenes.make_scene(n_aabb=30, n_obb=10, n_sphere=50, n_targets=2, seed=904, n_rays=300, max_hits=3)
+    for s in (a, b, a):
+        _grid_vs_oracle(gpu_ctx, oracle, s)
+
+
+def test_grid_stats_are_reported(gpu_ctx):
+    s = scenes.make_config("c3", n_rays=256)
+    native.upload(gpu_ctx, s)
+    c = gpu_ctx.run_frame(s, flags=native.FRAME_GRID_STATS).counters
+    full = gpu_ctx.run_frame(s, flags=C).counters
+    assert c["gridUsed"] == 3 and c["gridTraceCells"] > 0 and c["gridPermCells"] > 0
+    executed = sum(c["gridTraceTests"])
+    scanned = sum(full["traceTests"]) + sum(full["echoTests"]) + sum(full["muffleTests"])
+    assert 0 < executed < scanned / 10                     # the traversal runs a small fraction of the full scans' tests
+    assert 0 < sum(c["gridPermLossTests"]) < sum(full["permLossTests"]) / 5
