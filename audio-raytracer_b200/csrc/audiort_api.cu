@@ -18,6 +18,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -166,7 +167,9 @@ struct ArtCtx {
     int numSms = 0;
     int maxSmemOptin = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copyStream = nullptr;             // per-ray outputs go back to the host while the permeation job runs
     cudaEvent_t ev[6] = {};
+    cudaEvent_t evTraceDone = nullptr, evCopyDone = nullptr;
     std::string err;
     bool poisoned = false;
 
@@ -209,6 +212,26 @@ struct ArtCtx {
 };
 
 namespace {
+
+// pinned staging -> caller arrays; large arrays are copied by a few threads (one memcpy stream saturates ~10 GB/s)
+void big_memcpy(void* dst, const void* src, size_t bytes)
+{
+    constexpr size_t kMinPerThread = (size_t)4 << 20;
+    unsigned n = (unsigned)(bytes / kMinPerThread);
+    const unsigned hw = std::thread::hardware_concurrency();
+    if (n > 6) n = 6;
+    if (hw && n > hw) n = hw;
+    if (n <= 1) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / n) + 63) & ~(size_t)63;
+    for (unsigned i = 0; i < n; i++) {
+        const size_t off = (size_t)i * per;
+        if (off >= bytes) break;
+        const size_t len = std::min(per, bytes - off);
+        th.emplace_back([=] { memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
+    }
+    for (auto& t : th) t.join();
+}
 
 int32_t fail(ArtCtx* c, int32_t code, const char* fmt, ...)
 {
@@ -386,6 +409,9 @@ ART_API int32_t art_create(const ArtConfig* cfg, ArtCtx** out)
     ctx->numSms = prop.multiProcessorCount;
     ctx->maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->evTraceDone, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->evCopyDone, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     for (auto& ev : ctx->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if (const char* v = getenv("ART_DISABLE_GRID")) ctx->gridDisabled = atoi(v) != 0;
@@ -406,6 +432,9 @@ ART_API void art_destroy(ArtCtx* ctx)
                        &ctx->pinHitPts, &ctx->pinHitCnt, &ctx->pinHitIds })
         b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->evTraceDone) cudaEventDestroy(ctx->evTraceDone);
+    if (ctx->evCopyDone) cudaEventDestroy(ctx->evCopyDone);
+    if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -753,6 +782,18 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         ctx->kernelLaunches++;
     }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    // per-ray outputs are final once K1 has run: copy them back on a second stream while K2 / K3 execute
+    bool copiedEarly = false;
+    if (hostOut && wantRT && outputs) {
+        CK(cudaEventRecord(ctx->evTraceDone, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evTraceDone, 0));
+        if (outputs->echoRayDistances) { CK(ctx->pinEcho.ensure(NH * 2)); CK(cudaMemcpyAsync(ctx->pinEcho.p, ctx->outEcho.p, NH * 2, cudaMemcpyDeviceToHost, ctx->copyStream)); }
+        if (wantHitPts) { CK(ctx->pinHitPts.ensure(NH * 6)); CK(cudaMemcpyAsync(ctx->pinHitPts.p, ctx->outHitPts.p, NH * 6, cudaMemcpyDeviceToHost, ctx->copyStream)); }
+        if (wantHitCnt) { CK(ctx->pinHitCnt.ensure(nLoc)); CK(cudaMemcpyAsync(ctx->pinHitCnt.p, ctx->outHitCnt.p, nLoc, cudaMemcpyDeviceToHost, ctx->copyStream)); }
+        if (wantHitIds) { CK(ctx->pinHitIds.ensure(NH * 4)); CK(cudaMemcpyAsync(ctx->pinHitIds.p, ctx->outHitIds.p, NH * 4, cudaMemcpyDeviceToHost, ctx->copyStream)); }
+        CK(cudaEventRecord(ctx->evCopyDone, ctx->copyStream));
+        copiedEarly = true;
+    }
     // ---------------- K2 ----------------
     if (wantPM) {
         CK(ctx->firstHit.ensure(nLoc * 4 + 16));
@@ -796,12 +837,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     // ---------------- read back ----------------
     CK(cudaMemcpyAsync(ctx->pinPartials.p, ctx->partials.p, bl.bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    if (hostOut && wantRT && outputs) {
-        if (outputs->echoRayDistances) { CK(ctx->pinEcho.ensure(NH * 2)); CK(cudaMemcpyAsync(ctx->pinEcho.p, ctx->outEcho.p, NH * 2, cudaMemcpyDeviceToHost, ctx->stream)); }
-        if (wantHitPts) { CK(ctx->pinHitPts.ensure(NH * 6)); CK(cudaMemcpyAsync(ctx->pinHitPts.p, ctx->outHitPts.p, NH * 6, cudaMemcpyDeviceToHost, ctx->stream)); }
-        if (wantHitCnt) { CK(ctx->pinHitCnt.ensure(nLoc)); CK(cudaMemcpyAsync(ctx->pinHitCnt.p, ctx->outHitCnt.p, nLoc, cudaMemcpyDeviceToHost, ctx->stream)); }
-        if (wantHitIds) { CK(ctx->pinHitIds.ensure(NH * 4)); CK(cudaMemcpyAsync(ctx->pinHitIds.p, ctx->outHitIds.p, NH * 4, cudaMemcpyDeviceToHost, ctx->stream)); }
-    }
+    if (copiedEarly) CK(cudaStreamWaitEvent(ctx->stream, ctx->evCopyDone, 0));
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
 
     ctx->params = *prm;
@@ -892,10 +928,10 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
     const ArtOutputs& uo = ctx->userOut;
     const bool hostOut = !(ctx->frameFlags & ART_FRAME_NO_HOST_OUTPUTS);
     if (hostOut && (ctx->frameJobs & ART_JOB_RAYTRACE) && ctx->haveUserOut) {
-        if (uo.echoRayDistances) memcpy(uo.echoRayDistances, ctx->pinEcho.p, NH * 2);
-        if (uo.rayHitResults) memcpy(uo.rayHitResults, ctx->pinHitPts.p, NH * 6);
-        if (uo.rayHitResultCounts) memcpy(uo.rayHitResultCounts, ctx->pinHitCnt.p, nLoc);
-        if (uo.hitColliderIds) memcpy(uo.hitColliderIds, ctx->pinHitIds.p, NH * 4);
+        if (uo.echoRayDistances) big_memcpy(uo.echoRayDistances, ctx->pinEcho.p, NH * 2);
+        if (uo.rayHitResults) big_memcpy(uo.rayHitResults, ctx->pinHitPts.p, NH * 6);
+        if (uo.rayHitResultCounts) big_memcpy(uo.rayHitResultCounts, ctx->pinHitCnt.p, nLoc);
+        if (uo.hitColliderIds) big_memcpy(uo.hitColliderIds, ctx->pinHitIds.p, NH * 4);
     }
     ctx->lastBlob.assign(ctx->pinPartials.as<unsigned char>(), ctx->pinPartials.as<unsigned char>() + bl.bytes);
     ctx->frameDone = true;

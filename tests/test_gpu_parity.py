@@ -417,3 +417,19 @@ def test_grid_stats_are_reported(gpu_ctx):
     scanned = sum(full["traceTests"]) + sum(full["echoTests"]) + sum(full["muffleTests"])
     assert 0 < executed < scanned / 10                     # the traversal runs a small fraction of the full scans' tests
     assert 0 < sum(c["gridPermLossTests"]) < sum(full["permLossTests"]) / 5
+
+
+def test_c3_full_size_grid_equals_brute_force(gpu_ctx):
+    """BASELINE config 3 at full size (1,048,576 rays, 12.4 M segments): the default (uniform-grid) path and the brute-force
+    scans must agree on every per-ray and per-source output, bit for bit."""
+    s = scenes.make_config("c3")
+    native.upload(gpu_ctx, s)
+    fast = gpu_ctx.run_frame(s)
+    slow = gpu_ctx.run_frame(s, flags=native.FRAME_BRUTE_FORCE)
+    assert fast.counters["gridUsed"] == 3 and slow.counters["gridUsed"] == 0
+    assert fast.counters["segments"] == slow.counters["segments"] == 12360709
+    for k in ("hit_counts", "hit_ids", "echo", "hit_points", "muffle", "muffle_totals"):
+        assert np.array_equal(getattr(fast, k), getattr(slow, k)), k
+    np.testing.assert_array_equal(fast.permeation.view(np.uint32), slow.permeation.view(np.uint32))
+    np.testing.assert_array_equal(fast.settings.view(np.uint8), slow.settings.view(np.uint8))
+    np.testing.assert_allclose(fast.permeation_sum, slow.permeation_sum, rtol=1e-9, atol=1e-5 * s.n_rays * s.n_rays)
