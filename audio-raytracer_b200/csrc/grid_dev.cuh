@@ -68,7 +68,7 @@ __device__ __forceinline__ bool dda_step(const GridDesc& g, f3 d, Dda& w)
 }
 __device__ __forceinline__ uint2 dda_cell(const GridDesc& g, const Dda& w)
 {
-    return __ldg(&g.cells[((size_t)w.iz * g.ny + w.iy) * g.nx + w.ix]);
+    return __ldg(&g.cells[(w.iz * g.ny + w.iy) * g.nx + w.ix]);   // < 2^23 cells: 32-bit index arithmetic
 }
 
 // ---- exact per-collider distances (NaN = miss), reference operation order ---------------------------
@@ -88,6 +88,17 @@ __device__ __forceinline__ float aabb_dist(const GeomView& gv, int id, f3 o, f3 
     slab<8>(subr(A.x, o.x), subr(A.y, o.y), subr(A.z, o.z), subr(A.w, o.x), subr(B.x, o.y), subr(B.y, o.z),
             inv.x, inv.y, inv.z, tNear, tFar);                       // RT:291-298
     return slab_hit(tNear, tFar, dist) ? dist : quiet_nan();         // RT:300-307
+}
+// any-hit form of aabb_dist: does the slab test report a distance < limit (RT:381-384 / RT:423-430)?
+__device__ __forceinline__ bool aabb_blocks(const GeomView& gv, int id, f3 o, f3 inv, float limit)
+{
+    const float4 A = gv.aabbA[id];
+    const float2 B = gv.aabbB[id];
+    float tNear, tFar;
+    slab<8>(subr(A.x, o.x), subr(A.y, o.y), subr(A.z, o.z), subr(A.w, o.x), subr(B.x, o.y), subr(B.y, o.z),
+            inv.x, inv.y, inv.z, tNear, tFar);                       // RT:291-298
+    const float dist = tNear > 0.0f ? tNear : tFar;                  // RT:306
+    return !(tNear > tFar || tFar < 0.0f) && dist < limit;           // RT:300-304 + caller's compare
 }
 // nearest-hit OBB distance with an explicit rotation q4 (RT:314-320 passes the stored rotation, PM:172-179 its
 // inverse): exact distance, or NaN when the collider misses or certainly lies beyond `best`

@@ -235,7 +235,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                 for (int c = 0; c < kCapA && kA < nA && !blocked; c++, kA++) {
                     const int id = __ldg(e + kA);
                     if (STATS) E.st[1]++;
-                    if (aabb_dist(gv, id, qo, qinv) < qL)
+                    if (aabb_blocks(gv, id, qo, qinv, qL))
                         blocked = !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
                 }
             }
@@ -272,7 +272,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                     for (int c = 0; c < kCapA && kA < nA && !blocked; c++, kA++) {
                         const int id = __ldg(e + nS + kA);
                         if (STATS) E.st[1]++;
-                        if (aabb_dist(gv, id, qo, qinv) < qL)
+                        if (aabb_blocks(gv, id, qo, qinv, qL))
                             blocked = !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
                     }
                 }
