@@ -72,3 +72,8 @@ def test_cuda_matches_oracle_on_demo_scene(gpu_ctx, oracle, name, T):
     np.testing.assert_array_equal(r.permeation.view(np.uint32), f.permeation.view(np.uint32))
     np.testing.assert_array_equal(r.settings.view(np.uint8), f.settings.view(np.uint8))
     assert r.counters["segments"] == f.counters["segments"]
+    for flags in (native.FRAME_REVERB_SEQ_FP32, native.FRAME_REVERB_SEQ_FP32 | native.FRAME_FORCE_GRID):
+        g = gpu_ctx.run_frame(s, flags=flags)                  # default (brute force at 98 colliders) and forced grid
+        for k in ("echo", "hit_counts", "hit_ids", "muffle"):
+            np.testing.assert_array_equal(getattr(g, k), getattr(f, k), err_msg=k)
+        np.testing.assert_array_equal(g.settings.view(np.uint8), f.settings.view(np.uint8))

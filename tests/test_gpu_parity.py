@@ -37,7 +37,7 @@ def run_gpu(ctx, scene, jobs=native.JOB_ALL, flags=C):
     native.upload(ctx, scene)
     r = ctx.run_frame(scene, jobs=jobs, flags=flags)
     if flags & C:
-        fast = ctx.run_frame(scene, jobs=jobs, flags=flags & ~C)
+        fast = ctx.run_frame(scene, jobs=jobs, flags=(flags & ~C) | native.FRAME_FORCE_GRID)
         if scene.name != "custom" and jobs & native.JOB_RAYTRACE:
             assert fast.counters["gridUsed"] & 1, "default path did not use the grid"
         assert_same_frame(fast, r, "grid vs brute force")
@@ -349,7 +349,7 @@ def test_jobs_mirror_one_frame_latency(art_lib, oracle):
 def _grid_vs_oracle(ctx, oracle, s, expect_grid=True):
     o = oracle.run_frame(s, threads=8)
     native.upload(ctx, s)
-    g = ctx.run_frame(s)                                   # default path
+    g = ctx.run_frame(s, flags=native.FRAME_FORCE_GRID)    # grid kernels whatever the scene size
     assert bool(g.counters["gridUsed"] & 1) == expect_grid
     for k in ("hit_counts", "hit_ids", "echo", "muffle", "muffle_totals"):
         np.testing.assert_array_equal(getattr(g, k), getattr(o, k), err_msg=k)
@@ -407,6 +407,19 @@ def test_grid_rebuilds_when_the_scene_changes(gpu_ctx, oracle):
         _grid_vs_oracle(gpu_ctx, oracle, s)
 
 
+def test_small_scenes_default_to_the_brute_force_kernels(gpu_ctx, oracle):
+    """demo scene (98 colliders): the library picks the low-latency brute-force kernels unless told otherwise"""
+    s = scenes.make_config("c1")
+    native.upload(gpu_ctx, s)
+    a = gpu_ctx.run_frame(s)
+    b = gpu_ctx.run_frame(s, flags=native.FRAME_FORCE_GRID)
+    assert a.counters["gridUsed"] == 0 and b.counters["gridUsed"] == 3
+    assert_same_frame(a, b, "default vs forced grid")
+    big = scenes.make_config("c2", n_rays=256)
+    native.upload(gpu_ctx, big)
+    assert gpu_ctx.run_frame(big).counters["gridUsed"] == 3
+
+
 def test_grid_stats_are_reported(gpu_ctx):
     s = scenes.make_config("c3", n_rays=256)
     native.upload(gpu_ctx, s)
@@ -433,3 +446,21 @@ def test_c3_full_size_grid_equals_brute_force(gpu_ctx):
     np.testing.assert_array_equal(fast.permeation.view(np.uint32), slow.permeation.view(np.uint32))
     np.testing.assert_array_equal(fast.settings.view(np.uint8), slow.settings.view(np.uint8))
     np.testing.assert_allclose(fast.permeation_sum, slow.permeation_sum, rtol=1e-9, atol=1e-5 * s.n_rays * s.n_rays)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_scenes_and_parameters(gpu_ctx, oracle, seed):
+    """fuzz: random room sizes, collider mixes (including empty types), target counts around the 15-target switch between
+    the one-pass and the two-stage occlusion pool, ray lives / muffle distances that cut rays short, several batch counts"""
+    rng = np.random.default_rng(7000 + seed)
+    na, no, ns = int(rng.integers(6, 200)), int(rng.integers(0, 90)), int(rng.integers(0, 60))
+    nt = int(rng.choice([1, 2, 7, 14, 15, 16, 33, 50]))
+    no = max(no, nt)
+    room = rng.uniform(3.0, 40.0, size=3)
+    s = scenes.make_scene(n_aabb=na, n_obb=no, n_sphere=ns, n_targets=nt, seed=8000 + seed, n_rays=int(rng.integers(100, 900)),
+                          max_hits=int(rng.integers(1, 10)), batch_count=int(rng.integers(1, 6)), room_half=room,
+                          size_range=(0.1, float(rng.uniform(0.5, 4.0))))
+    s.max_ray_life = float(rng.choice([1000.0, 60.0, 15.0]))
+    s.max_muffle_hit_distance = float(rng.choice([1000.0, 30.0, 8.0]))
+    s.ray_origin = (rng.uniform(-0.5, 0.5, size=3) * room).astype(np.float32)
+    _grid_vs_oracle(gpu_ctx, oracle, s)
