@@ -182,7 +182,7 @@ struct ArtCtx {
     bool gridDisabled = false;                     // ART_DISABLE_GRID=1
     bool gridBuilt = false;                        // grid (or the decision that there is none) is current for the scene
     float gridCellScale = 1.1f;                    // ART_GRID_CELL_SCALE
-    int gridMinColliders = 192;                    // ART_GRID_MIN_COLLIDERS: smaller scenes use the brute-force kernels
+    int gridMinRays = -1;                          // ART_GRID_MIN_RAYS: smaller batches use the brute-force kernels (-1: heuristic)
     uint32_t frameGridUsed = 0;
     GeomLayout L{};
     bool haveScene = false, sceneDirty = false;
@@ -417,7 +417,7 @@ ART_API int32_t art_create(const ArtConfig* cfg, ArtCtx** out)
     for (auto& ev : ctx->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if (const char* v = getenv("ART_DISABLE_GRID")) ctx->gridDisabled = atoi(v) != 0;
-    if (const char* v = getenv("ART_GRID_MIN_COLLIDERS")) ctx->gridMinColliders = atoi(v);
+    if (const char* v = getenv("ART_GRID_MIN_RAYS")) ctx->gridMinRays = atoi(v);
     if (const char* v = getenv("ART_GRID_CELL_SCALE")) { const float f = (float)atof(v); if (f > 0.05f && f < 50.0f) ctx->gridCellScale = f; }
     *out = ctx;
     return ART_OK;
@@ -729,9 +729,19 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     // acceleration structure: the same exact tests on the colliders near each ray only (bit-identical outputs);
     // the work counters are defined by the reference's full scans, so counting frames use the brute-force kernels
     bool useGrid = !ctx->gridDisabled && !count && !(prm->flags & ART_FRAME_BRUTE_FORCE);
-    // small scenes: a full scan is a handful of instructions per query and the warp-per-ray brute-force mapping has the
-    // lower latency (demo scene, 98 colliders x 314 rays: 0.05 ms vs 0.26 ms)
-    if (useGrid && !(prm->flags & ART_FRAME_FORCE_GRID) && L.ns + L.na + L.no < ctx->gridMinColliders) useGrid = false;
+    // Small batches: the brute-force kernels give a whole warp to every ray (32 colliders per step), the grid kernels one
+    // lane; below a few thousand rays the GPU is not full and the brute-force mapping has the lower latency whatever the
+    // scene size (tools/path_crossover.py: 4,096 rays vs 1,023 colliders 0.23 ms vs 0.74 ms; 65,536 rays 2.46 vs 0.96 ms).
+    if (useGrid && !(prm->flags & ART_FRAME_FORCE_GRID)) {
+        const long long nc = (long long)L.ns + L.na + L.no;
+        long long minRays = ctx->gridMinRays;
+        if (minRays < 0) {
+            minRays = nc > 0 ? 32768LL * 1024 / nc : 32768;
+            if (minRays > 32768) minRays = 32768;
+            if (minRays < 4096) minRays = 4096;
+        }
+        if (map.nLocal < minRays) useGrid = false;
+    }
     if (useGrid && !ctx->gridBuilt) {
         // uniform grid over the current scene (host build, two small uploads)
         build_grid(ctx->hostS, ctx->hostA, ctx->hostO, ctx->gridCellScale, ctx->grid);

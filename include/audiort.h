@@ -111,10 +111,10 @@ typedef struct ArtConfig {
 #define ART_FRAME_BRUTE_FORCE     16u  /* scan every collider for every query exactly as the reference's loops do
                                           (no acceleration structure). Default: uniform-grid traversal, which runs
                                           the same exact tests on the colliders near each ray only; all outputs are
-                                          bit-identical. ART_FRAME_COUNTERS implies brute force, and so do scenes with fewer
-                                          than 192 colliders (ART_GRID_MIN_COLLIDERS) unless ART_FRAME_FORCE_GRID is set. */
-#define ART_FRAME_FORCE_GRID      64u  /* use the grid kernels even for scenes so small (< 192 colliders) that the library would
-                                          pick the brute-force kernels, whose warp-per-ray mapping has the lower latency there */
+                                          bit-identical. ART_FRAME_COUNTERS implies brute force, and so do batches of fewer
+                                          than 4,096..32,768 rays (by scene size; ART_GRID_MIN_RAYS) unless ART_FRAME_FORCE_GRID is set. */
+#define ART_FRAME_FORCE_GRID      64u  /* use the grid kernels even for batches so small (a few thousand rays) that the library
+                                          would pick the brute-force kernels, whose warp-per-ray mapping has the lower latency there */
 #define ART_FRAME_GRID_STATS      32u  /* grid kernels also count the collider tests and cells they actually visit
                                           (ArtCounters.grid*); slightly slower kernel variant */
 

@@ -208,8 +208,9 @@ def test_reverb_sequential_fp32_is_bit_exact(gpu_ctx, oracle):
 def test_determinism_and_no_counter_variant(gpu_ctx, oracle):
     s = scenes.make_config("c3", n_rays=512)
     native.upload(gpu_ctx, s)
-    a = gpu_ctx.run_frame(s, flags=0)
-    b = gpu_ctx.run_frame(s, flags=0)
+    F = native.FRAME_FORCE_GRID                     # 512 rays: the library itself would pick the brute-force kernels
+    a = gpu_ctx.run_frame(s, flags=F)
+    b = gpu_ctx.run_frame(s, flags=F)
     c = gpu_ctx.run_frame(s, flags=C)
     for x in (b, c):
         np.testing.assert_array_equal(a.echo, x.echo)
@@ -408,22 +409,25 @@ def test_grid_rebuilds_when_the_scene_changes(gpu_ctx, oracle):
 
 
 def test_small_scenes_default_to_the_brute_force_kernels(gpu_ctx, oracle):
-    """demo scene (98 colliders): the library picks the low-latency brute-force kernels unless told otherwise"""
+    """demo scene (314 rays): the library picks the low-latency brute-force kernels unless told otherwise"""
     s = scenes.make_config("c1")
     native.upload(gpu_ctx, s)
     a = gpu_ctx.run_frame(s)
     b = gpu_ctx.run_frame(s, flags=native.FRAME_FORCE_GRID)
     assert a.counters["gridUsed"] == 0 and b.counters["gridUsed"] == 3
     assert_same_frame(a, b, "default vs forced grid")
-    big = scenes.make_config("c2", n_rays=256)
+    big = scenes.make_config("c2")                  # 65,536 rays: the grid kernels
     native.upload(gpu_ctx, big)
     assert gpu_ctx.run_frame(big).counters["gridUsed"] == 3
+    small = scenes.make_config("c2", n_rays=2048)
+    native.upload(gpu_ctx, small)
+    assert gpu_ctx.run_frame(small).counters["gridUsed"] == 0
 
 
 def test_grid_stats_are_reported(gpu_ctx):
     s = scenes.make_config("c3", n_rays=256)
     native.upload(gpu_ctx, s)
-    c = gpu_ctx.run_frame(s, flags=native.FRAME_GRID_STATS).counters
+    c = gpu_ctx.run_frame(s, flags=native.FRAME_GRID_STATS | native.FRAME_FORCE_GRID).counters
     full = gpu_ctx.run_frame(s, flags=C).counters
     assert c["gridUsed"] == 3 and c["gridTraceCells"] > 0 and c["gridPermCells"] > 0
     executed = sum(c["gridTraceTests"])
