@@ -917,6 +917,7 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
         c.gridTraceTests[k] = dc[C_GRID_RT_S + k]; c.gridPermFirstTests[k] = dc[C_GRID_PF_S + k]; c.gridPermLossTests[k] = dc[C_GRID_PL_S + k];
     }
     c.gridTraceCells = dc[C_GRID_RT_CELLS]; c.gridPermCells = dc[C_GRID_PM_CELLS];
+    c.debugViolations = dc[C_DEBUG_VIOLATIONS];
     {
         const int* ownedCount = ctx->frameOwnedCount.data();
         const uint64_t nSec[3] = { (uint64_t)ctx->L.ns, (uint64_t)ctx->L.na, (uint64_t)ctx->L.no };

@@ -7,6 +7,14 @@
 
 namespace art {
 
+// -DART_DEBUG_BOUNDS: every index the grid kernels form is checked and violations are counted (ArtCounters.debugViolations);
+// the GPU tests are run once against such a build (compute-sanitizer is not available on the test pool).
+#ifdef ART_DEBUG_BOUNDS
+#define ART_CHECK(counters, cond) do { if (!(cond)) atomicAdd(&(counters)[C_DEBUG_VIOLATIONS], 1ull); } while (0)
+#else
+#define ART_CHECK(counters, cond) do { } while (0)
+#endif
+
 // ---- per-lane 3D-DDA ------------------------------------------------------------------------------
 struct Dda {
     int ix, iy, iz;

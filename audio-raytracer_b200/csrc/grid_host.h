@@ -188,6 +188,7 @@ inline void build_grid(const std::vector<uint16_t>& rawS, const std::vector<uint
         off += s + a + o;
     }
     g.entries.resize((size_t)off + 8);
+    d.nEntries = (int)off;
     auto fill = [&](size_t cell, int type, uint16_t id) { g.entries[cursor[cell * 3 + type]++] = id; };
     visit(bS, 0, fill); visit(bA, 1, fill); visit(bO, 2, fill);   // ascending canonical index inside each list
     g.ok = true;

@@ -156,6 +156,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                         nslot = (int)(packed & 0xFFFFu);
                         nrec = (int)(packed >> 16);
                     }
+                    ART_CHECK(a.counters, (unsigned)nrec < 32u && nslot >= 0 && nslot <= a.nTargets);
                     const HitRec r = E.rec[nrec];
                     const f3 no = mk3(r.px, r.py, r.pz);
                     f3 T = E.RayOrigin;
@@ -234,6 +235,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                 const int ownerId = qslot - 1;         // -1 for the echo ray: never equals a valid owner below
                 for (int c = 0; c < kCapA && kA < nA && !blocked; c++, kA++) {
                     const int id = __ldg(e + kA);
+                    ART_CHECK(a.counters, id < a.L.na && hdr.x + nS + nA <= (unsigned)g.nEntries);
                     if (STATS) E.st[1]++;
                     if (aabb_blocks(gv, id, qo, qinv, qL))
                         blocked = !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
@@ -271,6 +273,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                 if (STAGE == 2) {
                     for (int c = 0; c < kCapA && kA < nA && !blocked; c++, kA++) {
                         const int id = __ldg(e + nS + kA);
+                        ART_CHECK(a.counters, id < a.L.na);
                         if (STATS) E.st[1]++;
                         if (aabb_blocks(gv, id, qo, qinv, qL))
                             blocked = !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
@@ -278,12 +281,14 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                 }
                 for (int c = 0; c < kCapS && kB < nS && !blocked; c++, kB++) {
                     const int id = __ldg(e + kB);
+                    ART_CHECK(a.counters, id < a.L.ns);
                     if (STATS) E.st[0]++;
                     if (sphere_dist(gv, id, qo, qd, qdd) < qL)
                         blocked = !(qslot > 0 && a.anyOwned[0] && (int)a.at.ownS[id] == ownerId);       // RT:413
                 }
                 for (int c = 0; c < kCapO && kC < nO && !blocked; c++, kC++) {
                     const int id = __ldg(e + nS + nA + kC);
+                    ART_CHECK(a.counters, id < a.L.no && hdr.x + nS + nA + nO <= (unsigned)g.nEntries);
                     if (STATS) E.st[2]++;
                     if (obb_blocks(gv, id, qo, qd, qdd, g.errScale, qL))
                         blocked = !(qslot > 0 && a.anyOwned[2] && (int)a.at.ownO[id] == ownerId);       // RT:439
@@ -299,6 +304,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
         if (STAGE == 0) {
             const uint32_t push = __ballot_sync(kFull, survived);
             if (push) {
+                ART_CHECK(a.counters, survCount + __popc(push) <= kChunkQ);
                 if (survived) E.surv[survCount + __popc(push & ltMask)] = (uint32_t)qslot | ((uint32_t)qrec << 16);
                 survCount += __popc(push);
             }
@@ -385,8 +391,11 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
                 const uint16_t* e = g.entries + hdr.x;
                 const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
                 if (STATS) { st[0] += nS; st[1] += nA; st[2] += nO; st[3]++; }
+                ART_CHECK(a.counters, (unsigned)w.ix < (unsigned)g.nx && (unsigned)w.iy < (unsigned)g.ny && (unsigned)w.iz < (unsigned)g.nz);
+                ART_CHECK(a.counters, hdr.x + nS + nA + nO <= (unsigned)g.nEntries);
                 for (int k = 0; k < nS; k++) {
                     const int id = __ldg(e + k);
+                    ART_CHECK(a.counters, id < a.L.ns);
                     const float dist = sphere_dist(gv, id, o, d, dd);
                     const uint32_t key = (uint32_t)id;
                     if (dist < best || (dist == best && key < bkey)) { best = dist; bkey = key; }
@@ -394,6 +403,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
                 e += nS;
                 for (int k = 0; k < nA; k++) {
                     const int id = __ldg(e + k);
+                    ART_CHECK(a.counters, id < a.L.na);
                     const float dist = aabb_dist(gv, id, o, inv);
                     const uint32_t key = (1u << 28) | (uint32_t)id;
                     if (dist < best || (dist == best && key < bkey)) { best = dist; bkey = key; }
@@ -401,6 +411,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
                 e += nA;
                 for (int k = 0; k < nO; k++) {
                     const int id = __ldg(e + k);
+                    ART_CHECK(a.counters, id < a.L.no);
                     const float dist = obb_dist_nearest(gv, id, o, d, dd, g.errScale, best);
                     const uint32_t key = (2u << 28) | (uint32_t)id;
                     if (dist < best || (dist == best && key < bkey)) { best = dist; bkey = key; }
@@ -426,6 +437,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
             life = subr(life, best);                                           // RT:112
             hits += 1;                                                         // RT:113
             const size_t rayResultId = (size_t)j * a.H + hits - 1;             // RT:115
+            ART_CHECK(a.counters, j < a.map.nLocal && hits <= a.H && hitIdx < (hitType == 0 ? a.L.ns : (hitType == 1 ? a.L.na : a.L.no)));
             attr = hitType == 0 ? a.at.sphAttr[hitIdx] : (hitType == 1 ? a.at.aabbAttr[hitIdx] : a.at.obbAttr[hitIdx]);
             if (a.hitPoints) {                                                 // RT:118, 197
                 a.hitPoints[3 * rayResultId] = um_f32tof16(o.x);

@@ -82,6 +82,8 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
                 const uint16_t* e = g.entries + hdr.x;
                 const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
                 if (STATS) { st[0] += nS; st[1] += nA; st[2] += nO; st[6]++; }
+                ART_CHECK(a.counters, (unsigned)w.ix < (unsigned)g.nx && (unsigned)w.iy < (unsigned)g.ny && (unsigned)w.iz < (unsigned)g.nz);
+                ART_CHECK(a.counters, hdr.x + nS + nA + nO <= (unsigned)g.nEntries);
                 for (int k = 0; k < nS; k++) {
                     const float dist = sphere_dist(gv, __ldg(e + k), o, d, dd);
                     if (dist < best) best = dist;
@@ -144,11 +146,14 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
                         const float tIn = w.tCur;
                         const float tOut = fminf(dda_next_t(w), w.tEnd);
                         if (STATS) { st[3] += nS; st[4] += nA; st[5] += nO; st[6]++; }
+                        ART_CHECK(a.counters, (unsigned)w.ix < (unsigned)g.nx && (unsigned)w.iy < (unsigned)g.ny && (unsigned)w.iz < (unsigned)g.nz);
+                        ART_CHECK(a.counters, hdr.x + nS + nA + nO <= (unsigned)g.nEntries && tgt >= 0 && tgt < Na);
                         // AABB and sphere intervals are evaluated in the reference's own operation order, so tEnter/tExit are
                         // the reference's floats (a near-tangent sphere crossing, 2*sqrt(disc) with disc ~ 0, would otherwise
                         // amplify harmless rounding into a visible difference); only the per-cell clipping is new.
                         for (int k = 0; k < nA; k++) {                          // PM:265-288
                             const int id = __ldg(e + nS + k);
+                            ART_CHECK(a.counters, id < a.L.na);
                             const float4 A = gv.aabbA[id];
                             const float2 B = gv.aabbB[id];
                             float tEnter, tExit;
@@ -176,6 +181,7 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
                         }
                         for (int k = 0; k < nO; k++) {                          // PM:294-300 (stored rotation as is)
                             const int id = __ldg(e + nS + nA + k);
+                            ART_CHECK(a.counters, id < a.L.no);
                             const float4 c4 = gv.obbC[id];
                             const float2 h2 = gv.obbH[id];
                             const f3 pc = mk3(Pp.x - c4.x, Pp.y - c4.y, Pp.z - c4.z);

@@ -90,6 +90,7 @@ enum CounterIdx {
     C_GRID_PF_S, C_GRID_PF_A, C_GRID_PF_O,
     C_GRID_PL_S, C_GRID_PL_A, C_GRID_PL_O,
     C_GRID_RT_CELLS, C_GRID_PM_CELLS,
+    C_DEBUG_VIOLATIONS,        // -DART_DEBUG_BOUNDS builds: index checks that failed in the grid kernels (must stay 0)
     C_COUNT
 };
 
@@ -146,6 +147,7 @@ struct GridDesc {
     float icx, icy, icz;          // 1 / cell size
     int nx, ny, nz;
     float errScale;               // >= any distance a ray travels inside the scene (conservative pre-tests)
+    int nEntries;                 // length of entries (bounds checks of debug builds)
     const uint2* cells;           // [nz*ny*nx]  x = first entry, y = nS | nA << 10 | nO << 21
     const uint16_t* entries;      // collider indices, per cell: spheres, AABBs, OBBs
 };

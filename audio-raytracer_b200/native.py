@@ -69,7 +69,7 @@ class ArtCounters(C.Structure):
                 ("traceMs", C.c_float), ("permeationMs", C.c_float), ("reduceMs", C.c_float), ("deviceMs", C.c_float),
                 ("h2dMs", C.c_float), ("d2hMs", C.c_float), ("kernelLaunches", C.c_uint32), ("gridUsed", C.c_uint32),
                 ("gridTraceTests", C.c_uint64 * 3), ("gridPermFirstTests", C.c_uint64 * 3), ("gridPermLossTests", C.c_uint64 * 3),
-                ("gridTraceCells", C.c_uint64), ("gridPermCells", C.c_uint64)]
+                ("gridTraceCells", C.c_uint64), ("gridPermCells", C.c_uint64), ("debugViolations", C.c_uint64)]
 
     def as_dict(self) -> dict:
         out = {}

@@ -181,6 +181,7 @@ typedef struct ArtCounters {
     uint64_t gridPermFirstTests[3];
     uint64_t gridPermLossTests[3];
     uint64_t gridTraceCells, gridPermCells;
+    uint64_t debugViolations;   /* builds with -DART_DEBUG_BOUNDS: failed index checks in the grid kernels (0 otherwise) */
 } ArtCounters;
 
 /* ≙ AudioRayTracer.Awake/InitializeAudioRaytraceSystem (ART:53-87): one context per AudioRayTracer. */

@@ -29,6 +29,7 @@ def assert_same_frame(a, b, what):
     if a.settings is not None and b.settings is not None:
         np.testing.assert_array_equal(a.settings.view(np.uint8), b.settings.view(np.uint8), err_msg=f"{what}: settings")
     assert a.counters["segments"] == b.counters["segments"] and a.counters["segmentHits"] == b.counters["segmentHits"]
+    assert a.counters["debugViolations"] == 0 and b.counters["debugViolations"] == 0
 
 
 def run_gpu(ctx, scene, jobs=native.JOB_ALL, flags=C):
@@ -362,6 +363,7 @@ def _grid_vs_oracle(ctx, oracle, s, expect_grid=True):
     scale = max(s.n_rays * s.permeation_strength_per_ray, 50.0) * max(1, o.counters["perm_hit_rays"])
     np.testing.assert_allclose(g.permeation_sum, o.permeation_sum, rtol=0, atol=1e-5 * scale)
     assert g.counters["segments"] == o.counters["segments"]
+    assert g.counters["debugViolations"] == 0
     return g, o
 
 
