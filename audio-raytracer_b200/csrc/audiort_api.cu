@@ -178,7 +178,7 @@ struct ArtCtx {
     PinBuf pinScene;
     DevBuf rawScene, geom, attrs, owners, perm;    // perm: dens arrays + owned list
     HostGrid grid;                                 // uniform grid over the scene (grid_host.h)
-    DevBuf gridCells, gridEntries, gridScratch;
+    DevBuf gridCells, gridEntries, gridRangeO, gridScratch;
     bool gridDisabled = false;                     // ART_DISABLE_GRID=1
     bool gridBuilt = false;                        // grid (or the decision that there is none) is current for the scene
     float gridCellScale = 1.1f;                    // ART_GRID_CELL_SCALE
@@ -428,7 +428,7 @@ ART_API void art_destroy(ArtCtx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridScratch, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
+    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
                        &ctx->outEcho, &ctx->outHitPts, &ctx->outHitCnt, &ctx->outHitIds, &ctx->firstHit, &ctx->partials, &ctx->queue })
         b->release();
     for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinEcho,
@@ -748,6 +748,8 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         if (ctx->grid.ok) {
             CK(ctx->gridCells.ensure(ctx->grid.cells.size() * sizeof(uint2)));
             CK(ctx->gridEntries.ensure(ctx->grid.entries.size() * sizeof(uint16_t)));
+            CK(ctx->gridRangeO.ensure(ctx->grid.rangeO.size() * sizeof(uint2)));
+            CK(cudaMemcpyAsync(ctx->gridRangeO.p, ctx->grid.rangeO.data(), ctx->grid.rangeO.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
             CK(cudaMemcpyAsync(ctx->gridCells.p, ctx->grid.cells.data(), ctx->grid.cells.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
             CK(cudaMemcpyAsync(ctx->gridEntries.p, ctx->grid.entries.data(), ctx->grid.entries.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));   // pageable host vectors
@@ -760,7 +762,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         useGrid = std::sqrt(dx * dx + dy * dy + dz * dz) <= ctx->grid.listenerRange;   // else the error bounds of grid_host.h do not hold
     }
     GridDesc gd = ctx->grid.d;
-    gd.cells = ctx->gridCells.as<uint2>(); gd.entries = ctx->gridEntries.as<uint16_t>();
+    gd.cells = ctx->gridCells.as<uint2>(); gd.entries = ctx->gridEntries.as<uint16_t>(); gd.rangeO = ctx->gridRangeO.as<uint2>();
 
     // ---------------- K1 ----------------
     if (wantRT) {

@@ -22,6 +22,7 @@ struct Dda {
     float tdx, tdy, tdz;      // parameter step per cell
     float tEnd;               // stop once the next cell starts beyond this
     float tCur;               // parameter at which the ray entered the current cell (>= 0)
+    int lastAxis;             // axis of the last step (0,1,2), -1 in the first cell
 };
 
 // Clip the ray o + t*d, t in [0, tLimit], to the grid and set up the walk. inv = 1/d (may be +-Inf).
@@ -38,6 +39,7 @@ __device__ __forceinline__ bool dda_init(const GridDesc& g, f3 o, f3 d, f3 inv, 
     const float tStart = fmaxf(tn, 0.0f);
     w.tEnd = fminf(tf, tLimit);
     w.tCur = tStart;
+    w.lastAxis = -1;
     if (!(tStart <= w.tEnd)) return false;
     const float sx = fmaf(d.x, tStart, o.x), sy = fmaf(d.y, tStart, o.y), sz = fmaf(d.z, tStart, o.z);
     w.ix = min(max((int)floorf((sx - g.g0x) * g.icx), 0), g.nx - 1);
@@ -61,16 +63,16 @@ __device__ __forceinline__ float dda_next_t(const Dda& w) { return fminf(fminf(w
 __device__ __forceinline__ bool dda_step(const GridDesc& g, f3 d, Dda& w)
 {
     if (w.tmx <= w.tmy && w.tmx <= w.tmz) {
-        w.tCur = w.tmx;
+        w.tCur = w.tmx; w.lastAxis = 0;
         w.ix += d.x > 0.0f ? 1 : -1; w.tmx += w.tdx;
         return (unsigned)w.ix < (unsigned)g.nx;
     }
     if (w.tmy <= w.tmz) {
-        w.tCur = w.tmy;
+        w.tCur = w.tmy; w.lastAxis = 1;
         w.iy += d.y > 0.0f ? 1 : -1; w.tmy += w.tdy;
         return (unsigned)w.iy < (unsigned)g.ny;
     }
-    w.tCur = w.tmz;
+    w.tCur = w.tmz; w.lastAxis = 2;
     w.iz += d.z > 0.0f ? 1 : -1; w.tmz += w.tdz;
     return (unsigned)w.iz < (unsigned)g.nz;
 }

@@ -27,6 +27,7 @@ struct HostGrid {
     GridDesc d{};                       // device pointers left null
     std::vector<uint2> cells;
     std::vector<uint16_t> entries;
+    std::vector<uint2> rangeO;          // per OBB: the cell range it is listed in (packed 8 bits per axis)
     float diag = 0.0f;                  // un-inflated scene diagonal
     float cx = 0, cy = 0, cz = 0;       // scene centre
     float listenerRange = 0.0f;         // ray origins farther than this from the centre -> brute force
@@ -56,7 +57,7 @@ inline void build_grid(const std::vector<uint16_t>& rawS, const std::vector<uint
                        float cellScale, HostGrid& g)
 {
     using namespace gridimpl;
-    g.ok = false; g.cells.clear(); g.entries.clear();
+    g.ok = false; g.cells.clear(); g.entries.clear(); g.rangeO.clear();
     const size_t ns = rawS.size() / 8, na = rawA.size() / 10, no = rawO.size() / 13;
     if (ns + na + no == 0) { g.why = "empty scene"; return; }
     if (ns > 65535 || na > 65535 || no > 65535) { g.why = "more than 65535 colliders of one type"; return; }
@@ -150,7 +151,7 @@ inline void build_grid(const std::vector<uint16_t>& rawS, const std::vector<uint
     d.icx = 1.0f / csz[0]; d.icy = 1.0f / csz[1]; d.icz = 1.0f / csz[2];
     d.nx = dim[0]; d.ny = dim[1]; d.nz = dim[2];
     d.errScale = D;
-    d.cells = nullptr; d.entries = nullptr;
+    d.cells = nullptr; d.entries = nullptr; d.rangeO = nullptr;
     const size_t nCells = (size_t)dim[0] * dim[1] * dim[2];
 
     auto range = [&](const Box& b, float extra, int i0[3], int i1[3]) {
@@ -191,6 +192,12 @@ inline void build_grid(const std::vector<uint16_t>& rawS, const std::vector<uint
     d.nEntries = (int)off;
     auto fill = [&](size_t cell, int type, uint16_t id) { g.entries[cursor[cell * 3 + type]++] = id; };
     visit(bS, 0, fill); visit(bA, 1, fill); visit(bO, 2, fill);   // ascending canonical index inside each list
+    g.rangeO.resize(no + 1);
+    for (size_t i = 0; i < no; i++) {
+        int i0[3], i1[3];
+        range(bO[i], 0.0f, i0, i1);
+        g.rangeO[i] = make_uint2((uint32_t)(i0[0] | (i0[1] << 8) | (i0[2] << 16)), (uint32_t)(i1[0] | (i1[1] << 8) | (i1[2] << 16)));
+    }
     g.ok = true;
     g.why = "";
 }

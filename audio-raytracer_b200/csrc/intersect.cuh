@@ -132,6 +132,12 @@ __device__ __forceinline__ float rcp_fast(float x)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ float sqrt_fast(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ f3 qrot_fast(float4 q, f3 v)
 {
     const float cx = fmaf(q.y, v.z, -(q.z * v.y)), cy = fmaf(q.z, v.x, -(q.x * v.z)), cz = fmaf(q.x, v.y, -(q.y * v.x));

@@ -130,7 +130,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
     uint2 hdr = make_uint2(0, 0);
     int kA = 0, kB = 0, kC = 0;       // cursors inside the current cell: AABB, sphere, OBB lists
     Dda w;
-    w.ix = w.iy = w.iz = 0; w.tmx = w.tmy = w.tmz = 0; w.tdx = w.tdy = w.tdz = 0; w.tEnd = 0; w.tCur = 0;
+    w.ix = w.iy = w.iz = 0; w.tmx = w.tmy = w.tmz = 0; w.tdx = w.tdy = w.tdz = 0; w.tEnd = 0; w.tCur = 0; w.lastAxis = -1;
     for (;;) {
         const uint32_t idle = __ballot_sync(kFull, !have);
         if (idle) {
@@ -143,7 +143,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                 float nL = 0.0f;
                 int nslot = 0, nrec = 0;
                 Dda nw;
-                nw.ix = nw.iy = nw.iz = 0; nw.tmx = nw.tmy = nw.tmz = 0; nw.tdx = nw.tdy = nw.tdz = 0; nw.tEnd = 0; nw.tCur = 0;
+                nw.ix = nw.iy = nw.iz = 0; nw.tmx = nw.tmy = nw.tmz = 0; nw.tdx = nw.tdy = nw.tdz = 0; nw.tEnd = 0; nw.tCur = 0; nw.lastAxis = -1;
                 if (qi < count) {
                     if (STAGE != 1) {
                         const int q = qFirst + qi;

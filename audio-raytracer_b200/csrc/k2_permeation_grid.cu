@@ -139,10 +139,16 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
                     float loss = 0.0f;
                     Dda w;
                     bool walking = dda_init(g, Pp, dir, inv, pos_inf(), w);
+                    const float tRay0 = w.tCur;                 // where the line enters the grid (0 inside it)
                     while (walking) {
                         const uint2 hdr = dda_cell(g, w);
                         const uint16_t* e = g.entries + hdr.x;
                         const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
+                        // the cell the walk came from differs along one axis: an OBB whose cell range contains that
+                        // coordinate was already met there (the cells of a convex range along a line are contiguous)
+                        const int axShift = 8 * w.lastAxis;
+                        const int prevCoord = w.lastAxis == 0 ? w.ix - (dir.x > 0.0f ? 1 : -1)
+                                            : (w.lastAxis == 1 ? w.iy - (dir.y > 0.0f ? 1 : -1) : w.iz - (dir.z > 0.0f ? 1 : -1));
                         const float tIn = w.tCur;
                         const float tOut = fminf(dda_next_t(w), w.tEnd);
                         if (STATS) { st[3] += nS; st[4] += nA; st[5] += nO; st[6]++; }
@@ -190,9 +196,11 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
                             const float pp = fmaf(pc.z, pc.z, fmaf(pc.y, pc.y, pc.x * pc.x));
                             const float r2 = fmaf(h2.y, h2.y, fmaf(h2.x, h2.x, c4.w * c4.w));
                             if (pp - bq * bq > r2 * 1.001f + 1e-4f) continue;
-                            // the chord lies within rb of the point of closest approach (t = -bq): skip cells it cannot reach
-                            const float rb = sqrtf(r2) * 1.001f + 1e-3f;
-                            if (-bq + rb < tIn || -bq - rb > tOut) continue;
+                            if (w.lastAxis >= 0) {              // count every OBB once: where the walk first meets it
+                                const uint2 rg = __ldg(&g.rangeO[id]);
+                                const int lo = (int)((rg.x >> axShift) & 255u), hi = (int)((rg.y >> axShift) & 255u);
+                                if (prevCoord >= lo && prevCoord <= hi) continue;
+                            }
                             const float4 q4 = gv.obbQ[id];
                             // rotate the point of closest approach (|pn| <= r) instead of pc (|pc| can be the whole room):
                             // the rounding of the cheap rotation then scales with the box, not with the distance to it
@@ -204,7 +212,7 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
                             const float az = (-h2.y - lo.z) * rz, bz = (h2.y - lo.z) * rz;
                             const float tEnter = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)) - bq;
                             const float tExit = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) - bq;
-                            const float len = clip_len(tEnter, tExit, tIn, tOut);
+                            const float len = fmaxf(0.0f, tExit - fmaxf(tEnter, tRay0));   // the whole chord, once (PM:286-287)
                             if (len > 0.0f) {
                                 const float4 at = a.at.obbAttr[id];
                                 if (__float_as_int(at.w) != tgt) loss = fmaf(len, at.z, loss);     // PM:255

@@ -150,6 +150,7 @@ struct GridDesc {
     int nEntries;                 // length of entries (bounds checks of debug builds)
     const uint2* cells;           // [nz*ny*nx]  x = first entry, y = nS | nA << 10 | nO << 21
     const uint16_t* entries;      // collider indices, per cell: spheres, AABBs, OBBs
+    const uint2* rangeO;          // per OBB: cell range it is listed in, x = ix0 | iy0 << 8 | iz0 << 16, y = ix1 | iy1 << 8 | iz1 << 16
 };
 constexpr int kGridMaxS = 1023, kGridMaxA = 2047, kGridMaxO = 2047;
 
