@@ -196,8 +196,9 @@ struct ArtCtx {
     int shardIndex = 0, shardCount = 1, chunkRays = 0;
 
     // frame
-    DevBuf targets, ownedCount, outEcho, outHitPts, outHitCnt, outHitIds, firstHit, partials, queue;
-    PinBuf pinTargets, pinOwnedCount, pinPartials, pinEcho, pinHitPts, pinHitCnt, pinHitIds;
+    DevBuf targets, ownedCount, outAll, firstHit, partials, queue;   // outAll: echo | hit ids | hit points | hit counts, one memset, one copy
+    PinBuf pinTargets, pinOwnedCount, pinPartials, pinAll;
+    size_t offEcho = 0, offHitIds = 0, offHitPts = 0, offHitCnt = 0, outBytes = 0;
     ArtParams params{};
     ArtOutputs userOut{};
     bool haveUserOut = false;
@@ -429,10 +430,9 @@ ART_API void art_destroy(ArtCtx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
-                       &ctx->outEcho, &ctx->outHitPts, &ctx->outHitCnt, &ctx->outHitIds, &ctx->firstHit, &ctx->partials, &ctx->queue })
+                       &ctx->outAll, &ctx->firstHit, &ctx->partials, &ctx->queue })
         b->release();
-    for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinEcho,
-                       &ctx->pinHitPts, &ctx->pinHitCnt, &ctx->pinHitIds })
+    for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinAll })
         b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->evTraceDone) cudaEventDestroy(ctx->evTraceDone);
@@ -692,22 +692,26 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
 
     // ---------------- device outputs ----------------
     const BlobLayout bl = blob_layout(Na, T);
-    CK(ctx->partials.ensure(bl.bytes));
+    const size_t queueOff = (bl.bytes + 63) & ~(size_t)63;         // the two ray-queue counters live behind the blob: one memset
+    CK(ctx->partials.ensure(queueOff + 64));
     CK(ctx->pinPartials.ensure(bl.bytes));
-    CK(ctx->queue.ensure(64));
-    CK(cudaMemsetAsync(ctx->partials.p, 0, bl.bytes, ctx->stream));
+    CK(cudaMemsetAsync(ctx->partials.p, 0, queueOff + 64, ctx->stream));
     CK(cudaMemsetAsync(ctx->partials.as<unsigned char>() + bl.offLastHit, 0xFF, sizeof(int32_t) * (size_t)T, ctx->stream));
-    CK(cudaMemsetAsync(ctx->queue.p, 0, 64, ctx->stream));
     unsigned char* pb = ctx->partials.as<unsigned char>();
     BlobHeader* dh = reinterpret_cast<BlobHeader*>(pb);
     const bool wantHitPts = outputs && outputs->rayHitResults, wantHitCnt = outputs && outputs->rayHitResultCounts,
                wantHitIds = outputs && outputs->hitColliderIds;
     if (wantRT) {
-        CK(ctx->outEcho.ensure(NH * 2 + 16));
-        CK(cudaMemsetAsync(ctx->outEcho.p, 0, NH * 2, ctx->stream));
-        if (wantHitPts) { CK(ctx->outHitPts.ensure(NH * 6 + 16)); CK(cudaMemsetAsync(ctx->outHitPts.p, 0, NH * 6, ctx->stream)); }
-        if (wantHitCnt) { CK(ctx->outHitCnt.ensure(nLoc + 16)); CK(cudaMemsetAsync(ctx->outHitCnt.p, 0, nLoc, ctx->stream)); }
-        if (wantHitIds) { CK(ctx->outHitIds.ensure(NH * 4 + 16)); CK(cudaMemsetAsync(ctx->outHitIds.p, 0, NH * 4, ctx->stream)); }
+        // echo | hit ids | hit points | hit counts in one allocation: one memset now, one copy back later
+        auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        size_t o = 0;
+        ctx->offEcho = o; o = up(o + NH * 2);
+        ctx->offHitIds = o; if (wantHitIds) o = up(o + NH * 4);
+        ctx->offHitPts = o; if (wantHitPts) o = up(o + NH * 6);
+        ctx->offHitCnt = o; if (wantHitCnt) o = up(o + nLoc);
+        ctx->outBytes = o;
+        CK(ctx->outAll.ensure(o + 256));
+        CK(cudaMemsetAsync(ctx->outAll.p, 0, o, ctx->stream));
     }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
 
@@ -774,13 +778,14 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         ta.targetOrder = reinterpret_cast<const int*>(ctx->targets.as<unsigned char>() + 12 * (size_t)Na);
         ta.maxRayLife = prm->maxRayLife; ta.H = H; ta.maxMuffle = prm->maxMuffleHitDistance;
         ta.batchSize = b;
-        ta.echo = ctx->outEcho.as<uint16_t>();
-        ta.hitPoints = wantHitPts ? ctx->outHitPts.as<uint16_t>() : nullptr;
-        ta.hitCounts = wantHitCnt ? ctx->outHitCnt.as<uint8_t>() : nullptr;
-        ta.hitIds = wantHitIds ? ctx->outHitIds.as<uint32_t>() : nullptr;
+        unsigned char* ob = ctx->outAll.as<unsigned char>();
+        ta.echo = reinterpret_cast<uint16_t*>(ob + ctx->offEcho);
+        ta.hitPoints = wantHitPts ? reinterpret_cast<uint16_t*>(ob + ctx->offHitPts) : nullptr;
+        ta.hitCounts = wantHitCnt ? ob + ctx->offHitCnt : nullptr;
+        ta.hitIds = wantHitIds ? reinterpret_cast<uint32_t*>(ob + ctx->offHitIds) : nullptr;
         ta.muffleCounts = reinterpret_cast<uint32_t*>(pb + bl.offMuffle);
         ta.counters = dh->counters;
-        ta.nextRay = ctx->queue.as<unsigned int>();
+        ta.nextRay = reinterpret_cast<unsigned int*>(ctx->partials.as<unsigned char>() + queueOff);
         bool geomInSmem = trace_smem_bytes(L, Na, true, false) <= (size_t)ctx->maxSmemOptin;
         bool muffleInSmem = trace_smem_bytes(L, Na, geomInSmem, true) <= (size_t)ctx->maxSmemOptin;
         ta.muffleInSmem = muffleInSmem ? 1 : 0;
@@ -808,10 +813,13 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     if (hostOut && wantRT && outputs) {
         CK(cudaEventRecord(ctx->evTraceDone, ctx->stream));
         CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evTraceDone, 0));
-        if (outputs->echoRayDistances) { CK(ctx->pinEcho.ensure(NH * 2)); CK(cudaMemcpyAsync(ctx->pinEcho.p, ctx->outEcho.p, NH * 2, cudaMemcpyDeviceToHost, ctx->copyStream)); }
-        if (wantHitPts) { CK(ctx->pinHitPts.ensure(NH * 6)); CK(cudaMemcpyAsync(ctx->pinHitPts.p, ctx->outHitPts.p, NH * 6, cudaMemcpyDeviceToHost, ctx->copyStream)); }
-        if (wantHitCnt) { CK(ctx->pinHitCnt.ensure(nLoc)); CK(cudaMemcpyAsync(ctx->pinHitCnt.p, ctx->outHitCnt.p, nLoc, cudaMemcpyDeviceToHost, ctx->copyStream)); }
-        if (wantHitIds) { CK(ctx->pinHitIds.ensure(NH * 4)); CK(cudaMemcpyAsync(ctx->pinHitIds.p, ctx->outHitIds.p, NH * 4, cudaMemcpyDeviceToHost, ctx->copyStream)); }
+        // one copy covers every requested array (the echo halves come first and are skipped when not wanted)
+        const size_t from = outputs->echoRayDistances ? 0 : ctx->offHitIds;
+        if (ctx->outBytes > from) {
+            CK(ctx->pinAll.ensure(ctx->outBytes));
+            CK(cudaMemcpyAsync(ctx->pinAll.as<unsigned char>() + from, ctx->outAll.as<unsigned char>() + from, ctx->outBytes - from,
+                               cudaMemcpyDeviceToHost, ctx->copyStream));
+        }
         CK(cudaEventRecord(ctx->evCopyDone, ctx->copyStream));
         copiedEarly = true;
     }
@@ -836,7 +844,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         pa.permSumFrac = reinterpret_cast<long long*>(pb + bl.offSumFrac);
         pa.permLast = reinterpret_cast<float*>(pb + bl.offPermLast);
         pa.counters = dh->counters;
-        pa.nextRay = ctx->queue.as<unsigned int>() + 8;
+        pa.nextRay = reinterpret_cast<unsigned int*>(ctx->partials.as<unsigned char>() + queueOff) + 8;
         pa.raysPerWarp = perm_grid_rays_per_warp(map.nLocal, Na, ctx->numSms);
         if (useGrid) {
             const bool gInSmem = perm_grid_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
@@ -852,7 +860,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     // ---------------- K3 ----------------
     if (wantRT) {
-        CK(launch_echo_stats(ctx->outEcho.as<uint16_t>(), NH, &dh->echo, (prm->flags & ART_FRAME_REVERB_SEQ_FP32) != 0, ctx->numSms, ctx->stream));
+        CK(launch_echo_stats(reinterpret_cast<const uint16_t*>(ctx->outAll.as<unsigned char>() + ctx->offEcho), NH, &dh->echo, (prm->flags & ART_FRAME_REVERB_SEQ_FP32) != 0, ctx->numSms, ctx->stream));
         ctx->kernelLaunches += (prm->flags & ART_FRAME_REVERB_SEQ_FP32) ? 2 : 1;
     }
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
@@ -950,10 +958,11 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
     const ArtOutputs& uo = ctx->userOut;
     const bool hostOut = !(ctx->frameFlags & ART_FRAME_NO_HOST_OUTPUTS);
     if (hostOut && (ctx->frameJobs & ART_JOB_RAYTRACE) && ctx->haveUserOut) {
-        if (uo.echoRayDistances) big_memcpy(uo.echoRayDistances, ctx->pinEcho.p, NH * 2);
-        if (uo.rayHitResults) big_memcpy(uo.rayHitResults, ctx->pinHitPts.p, NH * 6);
-        if (uo.rayHitResultCounts) big_memcpy(uo.rayHitResultCounts, ctx->pinHitCnt.p, nLoc);
-        if (uo.hitColliderIds) big_memcpy(uo.hitColliderIds, ctx->pinHitIds.p, NH * 4);
+        const unsigned char* pb = ctx->pinAll.as<unsigned char>();
+        if (uo.echoRayDistances) big_memcpy(uo.echoRayDistances, pb + ctx->offEcho, NH * 2);
+        if (uo.rayHitResults) big_memcpy(uo.rayHitResults, pb + ctx->offHitPts, NH * 6);
+        if (uo.rayHitResultCounts) big_memcpy(uo.rayHitResultCounts, pb + ctx->offHitCnt, nLoc);
+        if (uo.hitColliderIds) big_memcpy(uo.hitColliderIds, pb + ctx->offHitIds, NH * 4);
     }
     ctx->lastBlob.assign(ctx->pinPartials.as<unsigned char>(), ctx->pinPartials.as<unsigned char>() + bl.bytes);
     ctx->frameDone = true;
