@@ -168,8 +168,10 @@ struct ArtCtx {
     int maxSmemOptin = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr;             // per-ray outputs go back to the host while the permeation job runs
-    cudaEvent_t ev[6] = {};
-    cudaEvent_t evTraceDone = nullptr, evCopyDone = nullptr;
+    cudaStream_t stream2 = nullptr;                // small frames: the permeation job runs beside the trace job (ART:213 does the same)
+    cudaEvent_t ev[7] = {};
+    cudaEvent_t evTraceDone = nullptr, evCopyDone = nullptr, evReady = nullptr, evP0 = nullptr, evP1 = nullptr;
+    bool frameOverlap = false;
     std::string err;
     bool poisoned = false;
 
@@ -413,6 +415,9 @@ ART_API int32_t art_create(const ArtConfig* cfg, ArtCtx** out)
     ctx->maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->evReady, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&ctx->evP0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evP1)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&ctx->evTraceDone, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&ctx->evCopyDone, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     for (auto& ev : ctx->ev)
@@ -435,6 +440,8 @@ ART_API void art_destroy(ArtCtx* ctx)
     for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinAll })
         b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t evx : { ctx->evReady, ctx->evP0, ctx->evP1 }) if (evx) cudaEventDestroy(evx);
+    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
     if (ctx->evTraceDone) cudaEventDestroy(ctx->evTraceDone);
     if (ctx->evCopyDone) cudaEventDestroy(ctx->evCopyDone);
     if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
@@ -768,6 +775,16 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     GridDesc gd = ctx->grid.d;
     gd.cells = ctx->gridCells.as<uint2>(); gd.entries = ctx->gridEntries.as<uint16_t>(); gd.rangeO = ctx->gridRangeO.as<uint2>();
 
+    // Small frames (brute-force kernels, GPU far from full): run the permeation job on a second stream beside the trace
+    // job, as the reference schedules them (ART:191, 213). Large frames stay serial so that each kernel is timed alone.
+    const bool overlapJobs = !useGrid && wantRT && wantPM && map.nLocal <= 16384;
+    ctx->frameOverlap = overlapJobs;
+    if (overlapJobs) {
+        CK(cudaEventRecord(ctx->evReady, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->evReady, 0));
+    }
+    cudaStream_t pmStream = overlapJobs ? ctx->stream2 : ctx->stream;
+
     // ---------------- K1 ----------------
     if (wantRT) {
         TraceArgs ta;
@@ -848,12 +865,14 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         pa.raysPerWarp = perm_grid_rays_per_warp(map.nLocal, Na, ctx->numSms);
         if (useGrid) {
             const bool gInSmem = perm_grid_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
-            CK(launch_permeation_grid(pa, gd, ctx->numSms, gInSmem, (prm->flags & ART_FRAME_GRID_STATS) != 0, ctx->stream));
-            CK(launch_perm_last(pa, T, ctx->stream));
+            CK(launch_permeation_grid(pa, gd, ctx->numSms, gInSmem, (prm->flags & ART_FRAME_GRID_STATS) != 0, pmStream));
+            CK(launch_perm_last(pa, T, pmStream));
             ctx->frameGridUsed |= 2u;
         } else {
             const bool geomInSmem = perm_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
-            CK(launch_permeation(pa, ctx->numSms, geomInSmem, T, ctx->stream));
+            if (overlapJobs) CK(cudaEventRecord(ctx->evP0, pmStream));
+            CK(launch_permeation(pa, ctx->numSms, geomInSmem, T, pmStream));
+            if (overlapJobs) CK(cudaEventRecord(ctx->evP1, pmStream));
         }
         ctx->kernelLaunches += 2;
     }
@@ -864,6 +883,8 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         ctx->kernelLaunches += (prm->flags & ART_FRAME_REVERB_SEQ_FP32) ? 2 : 1;
     }
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (overlapJobs) CK(cudaStreamWaitEvent(ctx->stream, ctx->evP1, 0));      // join the permeation job
+    CK(cudaEventRecord(ctx->ev[6], ctx->stream));
     // ---------------- read back ----------------
     CK(cudaMemcpyAsync(ctx->pinPartials.p, ctx->partials.p, bl.bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (copiedEarly) CK(cudaStreamWaitEvent(ctx->stream, ctx->evCopyDone, 0));
@@ -949,7 +970,8 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
     cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); c.traceMs = ms;
     cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); c.permeationMs = ms;
     cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); c.reduceMs = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[4]); c.deviceMs = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[6]); c.deviceMs = ms;
+    if (ctx->frameOverlap) { cudaEventElapsedTime(&ms, ctx->evP0, ctx->evP1); c.permeationMs = ms; }
     cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); c.d2hMs = ms;
     c.kernelLaunches = ctx->kernelLaunches;
     c.gridUsed = ctx->frameGridUsed;
