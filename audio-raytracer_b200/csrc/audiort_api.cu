@@ -199,7 +199,7 @@ struct ArtCtx {
 
     // frame
     DevBuf targets, ownedCount, outAll, firstHit, partials, queue;   // outAll: echo | hit ids | hit points | hit counts, one memset, one copy
-    PinBuf pinTargets, pinOwnedCount, pinPartials, pinAll;
+    PinBuf pinTargets, pinOwnedCount, pinPartials, pinAll, pinPerm;
     size_t offEcho = 0, offHitIds = 0, offHitPts = 0, offHitCnt = 0, outBytes = 0;
     ArtParams params{};
     ArtOutputs userOut{};
@@ -437,7 +437,7 @@ ART_API void art_destroy(ArtCtx* ctx)
     for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
                        &ctx->outAll, &ctx->firstHit, &ctx->partials, &ctx->queue })
         b->release();
-    for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinAll })
+    for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinAll, &ctx->pinPerm })
         b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t evx : { ctx->evReady, ctx->evP0, ctx->evP1 }) if (evx) cudaEventDestroy(evx);
@@ -674,26 +674,26 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     }
     const size_t nPad = (size_t)L.nsPad + L.naPad + L.noPad;
     if (wantPM && ctx->permPreparedForTargets != Na) {
-        // [dens S | dens A | dens O | ownedList]
-        std::vector<float> dens(nPad, 0.0f);
-        std::vector<int> owned;
+        // [dens S | dens A | dens O | ownedList] staged in pinned memory and copied asynchronously (a dynamic scene comes
+        // through here every frame)
+        const size_t bytes = nPad * 8 + 16;
+        CK(ctx->pinPerm.ensure(bytes));
+        CK(ctx->perm.ensure(bytes));
+        float* dens = ctx->pinPerm.as<float>();
+        int* owned = reinterpret_cast<int*>(ctx->pinPerm.as<unsigned char>() + nPad * 4);
+        memset(dens, 0, nPad * 4);
+        int nOwned = 0;
         auto fill = [&](const std::vector<uint16_t>& raw, int words, int densWord, int sec, size_t off) {
             const size_t n = raw.size() / words;
             for (size_t i = 0; i < n; i++) {
                 const int t = (int)(short)raw[i * words + words - 1];
-                if (t >= 0 && t < Na) owned.push_back((sec << 28) | (int)i);
+                if (t >= 0 && t < Na) owned[nOwned++] = (sec << 28) | (int)i;
                 else dens[off + i] = h2f(raw[i * words + densWord]);
             }
         };
         fill(ctx->hostS, 8, 5, 0, 0); fill(ctx->hostA, 10, 7, 1, L.nsPad); fill(ctx->hostO, 13, 10, 2, (size_t)L.nsPad + L.naPad);
-        ctx->nOwned = (int)owned.size();
-        const size_t bytes = nPad * 4 + owned.size() * 4 + 16;
-        CK(ctx->perm.ensure(bytes));
-        // synchronous small copies (rare: only when the scene or the target count changes)
-        CK(cudaMemcpyAsync(ctx->perm.p, dens.data(), nPad * 4, cudaMemcpyHostToDevice, ctx->stream));
-        if (!owned.empty())
-            CK(cudaMemcpyAsync(ctx->perm.as<unsigned char>() + nPad * 4, owned.data(), owned.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->nOwned = nOwned;
+        CK(cudaMemcpyAsync(ctx->perm.p, ctx->pinPerm.p, nPad * 4 + (size_t)nOwned * 4, cudaMemcpyHostToDevice, ctx->stream));
         ctx->permPreparedForTargets = Na;
     }
 

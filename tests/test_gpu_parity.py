@@ -470,3 +470,40 @@ def test_random_scenes_and_parameters(gpu_ctx, oracle, seed):
     s.max_muffle_hit_distance = float(rng.choice([1000.0, 30.0, 8.0]))
     s.ray_origin = (rng.uniform(-0.5, 0.5, size=3) * room).astype(np.float32)
     _grid_vs_oracle(gpu_ctx, oracle, s)
+
+
+def test_small_frames_in_a_loop(gpu_ctx, oracle):
+    """the reference's own frame sizes, frame after frame on one context (two jobs side by side on two streams, per-ray
+    outputs copied back on a third): a moving listener, moving targets, a scene re-uploaded every frame, another frame shape
+    in between -- every frame must still give the oracle's results"""
+    s = scenes.make_config("c1")
+    native.upload(gpu_ctx, s)
+    for step in range(6):
+        s.ray_origin = (np.float32([15.51, -1.45, -3.11]) + np.float32([0.37 * step, 0.05 * step, -0.21 * step])).astype(np.float32)
+        s.targets[0] = s.targets[0] + np.float32([0.0, 0.1 * step, 0.0])
+        g = gpu_ctx.run_frame(s, flags=native.FRAME_REVERB_SEQ_FP32)
+        o = oracle.run_frame(s)
+        for k in ("echo", "hit_counts", "hit_ids", "muffle", "muffle_totals"):
+            np.testing.assert_array_equal(getattr(g, k), getattr(o, k), err_msg=f"step {step}: {k}")
+        np.testing.assert_array_equal(g.permeation.view(np.uint32), o.permeation.view(np.uint32))
+        np.testing.assert_array_equal(g.settings.view(np.uint8), o.settings.view(np.uint8))
+    # dynamic scene: art_set_scene every frame (colliders re-baked)
+    for step in range(5):
+        s.aabbs["center"][10, 1] += 8          # move one collider (raw half bits: a small change of the value)
+        native.upload(gpu_ctx, s)
+        g = gpu_ctx.run_frame(s, flags=native.FRAME_REVERB_SEQ_FP32)
+        o = oracle.run_frame(s)
+        np.testing.assert_array_equal(g.echo, o.echo)
+        np.testing.assert_array_equal(g.muffle, o.muffle)
+        np.testing.assert_array_equal(g.permeation.view(np.uint32), o.permeation.view(np.uint32))
+    # another frame shape in between
+    t = scenes.make_config("c2", n_rays=700)
+    native.upload(gpu_ctx, t)
+    g = gpu_ctx.run_frame(t)
+    o = oracle.run_frame(t, threads=8)
+    np.testing.assert_array_equal(g.echo, o.echo)
+    native.upload(gpu_ctx, s)
+    g = gpu_ctx.run_frame(s, flags=native.FRAME_REVERB_SEQ_FP32)
+    o = oracle.run_frame(s)
+    np.testing.assert_array_equal(g.echo, o.echo)
+    np.testing.assert_array_equal(g.settings.view(np.uint8), o.settings.view(np.uint8))

@@ -58,21 +58,27 @@ int main(int argc, char** argv)
     CK(art_set_scene(ctx, aabbs, nA, obbs, nO, sph, nS));
     CK(art_set_rays(ctx, dirs, N));
     double* us = malloc(sizeof(double) * frames);
+    double tSet = 0, tSched = 0, tDone = 0;
     ArtHandle hnd = 0;
     for (int i = -20; i < frames; i++) {
         const double t0 = now_us();
         if (!staticScene) CK(art_set_scene(ctx, aabbs, nA, obbs, nO, sph, nS));
+        const double t1 = now_us();
         CK(art_trace_schedule(ctx, &prm, &out, &hnd));
+        const double t2 = now_us();
         CK(art_complete(ctx, hnd));
-        if (i >= 0) us[i] = now_us() - t0;
+        const double t3 = now_us();
+        if (i >= 0) { us[i] = t3 - t0; tSet += t1 - t0; tSched += t2 - t1; tDone += t3 - t2; }
     }
     ArtCounters c; CK(art_get_counters(ctx, hnd, &c));
     qsort(us, frames, sizeof(double), cmp_double);
     double sum = 0; for (int i = 0; i < frames; i++) sum += us[i];
     printf("{\"rays\": %d, \"targets\": %d, \"colliders\": %d, \"frames\": %d, \"scene_upload_per_frame\": %s, \"us_per_frame_mean\": %.1f, "
-           "\"us_per_frame_median\": %.1f, \"us_per_frame_p99\": %.1f, \"device_us\": %.1f, \"segments\": %llu, \"muffle0\": %.6f}\n",
+           "\"us_per_frame_median\": %.1f, \"us_per_frame_p99\": %.1f, \"device_us\": %.1f, \"set_scene_us\": %.1f, \"schedule_us\": %.1f, "
+           "\"complete_us\": %.1f, \"segments\": %llu, \"muffle0\": %.6f}\n",
            N, Na, nA + nO + nS, frames, staticScene ? "false" : "true", sum / frames, us[frames / 2], us[(int)(frames * 0.99)],
-           c.deviceMs * 1e3, (unsigned long long)c.segments, out.audioTargetSettings[0].muffleStrength);
+           c.deviceMs * 1e3, tSet / frames, tSched / frames, tDone / frames, (unsigned long long)c.segments,
+           out.audioTargetSettings[0].muffleStrength);
     art_destroy(ctx);
     return 0;
 }
