@@ -77,10 +77,6 @@ struct HitRec {            // per hit point, shared memory (one per lane)
 
 // ---- pooled occlusion queries -----------------------------------------------------------------------
 constexpr int kChunkQ = 4096;            // queries per pool pass (bounds the survivor list: 16 KB of scratch per warp)
-#ifndef ART_SLICES
-#define ART_SLICES 1
-#endif
-constexpr int kSlicesPerStep = ART_SLICES;   // slices a lane processes back to back before the warp re-synchronises
 constexpr int kSkipCells = 4;
 constexpr int kTwoStageSlots = 16;       // queries per hit point from which the AABB-first two-stage pool pays off            // empty cells a lane may step over in one pool step
 
@@ -214,7 +210,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
             continue;
         }
         bool survived = false;
-        for (int it = 0; it < kSlicesPerStep && have && STAGE == 0; it++) {
+        if (have && STAGE == 0) {   // (more than one slice per step was measured slower: 43 -> 45..70 ms on C3)
             // ---- a slice of up to kCapA AABB entries of the current cell (stepping over at most kSkipCells empty cells first)
             bool walkDone = false;
             for (int s = 0; s < kSkipCells; s++) {
