@@ -181,6 +181,12 @@ struct ArtCtx {
     DevBuf rawScene, geom, attrs, owners, perm;    // perm: dens arrays + owned list
     HostGrid grid;                                 // uniform grid over the scene (grid_host.h)
     DevBuf gridCells, gridEntries, gridRangeO, gridScratch;
+    DevBuf fanBoxes, fanCells, fanEntries, fanCtl;  // target fans (fan_dev.cuh): collider bounds (per scene), lists (per frame)
+    PinBuf pinFanCtl;
+    bool fansDisabled = false;                     // ART_DISABLE_FANS=1
+    size_t fanEntriesPerPair = 64;                 // entry capacity = fans * colliders * this (grows after an overflow); ART_FAN_ENTRIES_PER_PAIR
+    bool frameFans = false;                        // the frame in flight uses the fans
+    bool rerunning = false;                        // art_complete is re-running an overflowed frame without fans
     bool gridDisabled = false;                     // ART_DISABLE_GRID=1
     bool gridBuilt = false;                        // grid (or the decision that there is none) is current for the scene
     float gridCellScale = 1.1f;                    // ART_GRID_CELL_SCALE
@@ -424,6 +430,8 @@ ART_API int32_t art_create(const ArtConfig* cfg, ArtCtx** out)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if (const char* v = getenv("ART_DISABLE_GRID")) ctx->gridDisabled = atoi(v) != 0;
     if (const char* v = getenv("ART_GRID_MIN_RAYS")) ctx->gridMinRays = atoi(v);
+    if (const char* v = getenv("ART_DISABLE_FANS")) ctx->fansDisabled = atoi(v) != 0;
+    if (const char* v = getenv("ART_FAN_ENTRIES_PER_PAIR")) { const long n = atol(v); if (n >= 1 && n <= 65536) ctx->fanEntriesPerPair = (size_t)n; }
     if (const char* v = getenv("ART_GRID_CELL_SCALE")) { const float f = (float)atof(v); if (f > 0.05f && f < 50.0f) ctx->gridCellScale = f; }
     *out = ctx;
     return ART_OK;
@@ -434,10 +442,10 @@ ART_API void art_destroy(ArtCtx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
+    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->fanBoxes, &ctx->fanCells, &ctx->fanEntries, &ctx->fanCtl, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
                        &ctx->outAll, &ctx->firstHit, &ctx->partials, &ctx->queue })
         b->release();
-    for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinAll, &ctx->pinPerm })
+    for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinAll, &ctx->pinPerm, &ctx->pinFanCtl })
         b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t evx : { ctx->evReady, ctx->evP0, ctx->evP1 }) if (evx) cudaEventDestroy(evx);
@@ -625,7 +633,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     }
     CK(ctx->pinTargets.ensure(16 * (size_t)Na));
     CK(ctx->targets.ensure(16 * (size_t)Na));
-    memcpy(ctx->pinTargets.p, prm->audioTargetPositions, 12 * (size_t)Na);
+    memmove(ctx->pinTargets.p, prm->audioTargetPositions, 12 * (size_t)Na);   // (a re-run passes the library-owned copy back in)
     {   // Morton order of the targets: neighbouring lanes of the grid kernels then walk towards neighbouring targets
         // (same cells, same list lengths). Results do not depend on the order.
         int* order = reinterpret_cast<int*>(ctx->pinTargets.as<unsigned char>() + 12 * (size_t)Na);
@@ -763,6 +771,10 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             CK(cudaMemcpyAsync(ctx->gridRangeO.p, ctx->grid.rangeO.data(), ctx->grid.rangeO.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
             CK(cudaMemcpyAsync(ctx->gridCells.p, ctx->grid.cells.data(), ctx->grid.cells.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
             CK(cudaMemcpyAsync(ctx->gridEntries.p, ctx->grid.entries.data(), ctx->grid.entries.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+            const size_t boxBytes = ctx->grid.boxLo.size() * sizeof(float);
+            CK(ctx->fanBoxes.ensure(2 * boxBytes + 32));
+            CK(cudaMemcpyAsync(ctx->fanBoxes.p, ctx->grid.boxLo.data(), boxBytes, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->fanBoxes.as<unsigned char>() + boxBytes, ctx->grid.boxHi.data(), boxBytes, cudaMemcpyHostToDevice, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));   // pageable host vectors
         }
         ctx->gridBuilt = true;
@@ -774,6 +786,39 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     }
     GridDesc gd = ctx->grid.d;
     gd.cells = ctx->gridCells.as<uint2>(); gd.entries = ctx->gridEntries.as<uint16_t>(); gd.rangeO = ctx->gridRangeO.as<uint2>();
+
+    // Target fans (fan_dev.cuh): every echo / muffle / permeation query ends in the listener or an audio target, so the
+    // colliders are binned by direction around those few goals, on the device, every frame (the goals move).
+    FanDesc fd{};
+    bool useFans = useGrid && !ctx->fansDisabled && !ctx->rerunning && !(prm->flags & ART_FRAME_NO_FANS);
+    if (useFans) {
+        const size_t nFans = (size_t)Na + 1, nc = (size_t)L.ns + L.na + L.no;
+        // a collider can subtend every bin of a fan (a wall seen from nearby), a typical one a few dozen
+        const size_t perFan = std::min(nc * (size_t)kFanCells, nc * ctx->fanEntriesPerPair + ((size_t)2048 * ctx->fanEntriesPerPair));
+        const size_t cap = nFans * perFan + 4096;
+        if (cap > ((size_t)1 << 30) || nFans * kFanCells > ((size_t)1 << 28)) useFans = false;   // > 2 GiB of lists: walk the grid instead
+        else {
+            CK(ctx->fanCells.ensure(nFans * kFanCells * sizeof(uint2)));
+            CK(ctx->fanEntries.ensure(cap * sizeof(uint16_t)));
+            CK(ctx->fanCtl.ensure(16));
+            CK(ctx->pinFanCtl.ensure(16));
+            CK(cudaMemsetAsync(ctx->fanCtl.p, 0, 16, ctx->stream));
+            FanBuildArgs fa;
+            fa.boxLo = ctx->fanBoxes.as<float4>(); fa.boxHi = fa.boxLo + nc;
+            fa.ns = L.ns; fa.na = L.na; fa.no = L.no;
+            fa.ownS = at.ownS; fa.ownA = at.ownA; fa.ownO = at.ownO;
+            fa.targets = ctx->targets.as<float>(); fa.nTargets = Na;
+            fa.lx = prm->rayOrigin[0]; fa.ly = prm->rayOrigin[1]; fa.lz = prm->rayOrigin[2];
+            fa.nearDist = 1e-3f * ctx->grid.d.errScale;
+            fa.cells = ctx->fanCells.as<uint2>(); fa.entries = ctx->fanEntries.as<uint16_t>();
+            fa.capacity = (unsigned int)cap; fa.ctl = ctx->fanCtl.as<unsigned int>();
+            CK(launch_fan_build(fa, ctx->stream));
+            ctx->kernelLaunches++;
+            fd.nFans = (int)nFans; fd.cells = fa.cells; fd.entries = fa.entries; fd.nEntries = (int)cap;
+            ctx->frameGridUsed |= 4u;
+        }
+    }
+    ctx->frameFans = useFans;
 
     // Small frames (brute-force kernels, GPU far from full): run the permeation job on a second stream beside the trace
     // job, as the reference schedules them (ART:191, 213). Large frames stay serial so that each kernel is timed alone.
@@ -817,7 +862,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             CK(ctx->gridScratch.ensure(trace_grid_scratch_bytes(ctx->numSms)));
             ta.scratch = ctx->gridScratch.as<uint32_t>();
             const bool gInSmem = trace_grid_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
-            CK(launch_trace_grid(ta, gd, ctx->numSms, gInSmem, (prm->flags & ART_FRAME_GRID_STATS) != 0, ctx->stream));
+            CK(launch_trace_grid(ta, gd, useFans ? &fd : nullptr, ctx->numSms, gInSmem, (prm->flags & ART_FRAME_GRID_STATS) != 0, ctx->stream));
             ctx->frameGridUsed |= 1u;
         } else {
             CK(launch_trace(ta, ctx->numSms, geomInSmem, count, ctx->stream));
@@ -865,7 +910,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         pa.raysPerWarp = perm_grid_rays_per_warp(map.nLocal, Na, ctx->numSms);
         if (useGrid) {
             const bool gInSmem = perm_grid_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
-            CK(launch_permeation_grid(pa, gd, ctx->numSms, gInSmem, (prm->flags & ART_FRAME_GRID_STATS) != 0, pmStream));
+            CK(launch_permeation_grid(pa, gd, useFans ? &fd : nullptr, ctx->numSms, gInSmem, (prm->flags & ART_FRAME_GRID_STATS) != 0, pmStream));
             CK(launch_perm_last(pa, T, pmStream));
             ctx->frameGridUsed |= 2u;
         } else {
@@ -887,6 +932,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     CK(cudaEventRecord(ctx->ev[6], ctx->stream));
     // ---------------- read back ----------------
     CK(cudaMemcpyAsync(ctx->pinPartials.p, ctx->partials.p, bl.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (useFans) CK(cudaMemcpyAsync(ctx->pinFanCtl.p, ctx->fanCtl.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
     if (copiedEarly) CK(cudaStreamWaitEvent(ctx->stream, ctx->evCopyDone, 0));
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
 
@@ -931,6 +977,29 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
         return fail(ctx, ART_E_CUDA, "frame failed: %s", cudaGetErrorString(e));
     }
     ctx->inFlight = false;
+    bool fanOverflow = false;
+    if (ctx->frameFans && ctx->pinFanCtl.as<unsigned int>()[1] != 0) {
+        // the fan lists did not fit their buffer (or a list exceeded its length limit): the frame's results are incomplete.
+        // Run it again on the grid walk and give the next frame a larger buffer.
+        if (ctx->fanEntriesPerPair < 4096) ctx->fanEntriesPerPair *= 4;
+        ArtParams prm = ctx->params;
+        ArtOutputs uo = ctx->userOut;
+        const bool hadOut = ctx->haveUserOut;
+        const ArtHandle keep = ctx->handle;
+        ctx->rerunning = true;
+        ArtHandle h2 = 0;
+        int32_t rc = art_trace_schedule(ctx, &prm, hadOut ? &uo : nullptr, &h2);
+        ctx->rerunning = false;
+        ctx->handle = keep;
+        if (rc != ART_OK) { ctx->inFlight = false; return rc; }
+        e = cudaEventSynchronize(ctx->ev[5]);
+        if (e != cudaSuccess) {
+            ctx->poisoned = true; ctx->inFlight = false;
+            return fail(ctx, ART_E_CUDA, "frame failed: %s", cudaGetErrorString(e));
+        }
+        ctx->inFlight = false;
+        fanOverflow = true;
+    }
     const int Na = ctx->frameNa, T = ctx->frameT, H = ctx->frameH;
     const size_t nLoc = (size_t)ctx->map.nLocal, NH = nLoc * H;
     const BlobLayout bl = blob_layout(Na, T);
@@ -974,7 +1043,7 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
     if (ctx->frameOverlap) { cudaEventElapsedTime(&ms, ctx->evP0, ctx->evP1); c.permeationMs = ms; }
     cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); c.d2hMs = ms;
     c.kernelLaunches = ctx->kernelLaunches;
-    c.gridUsed = ctx->frameGridUsed;
+    c.gridUsed = ctx->frameGridUsed | (fanOverflow ? 8u : 0u);
 
     // per-ray outputs: pinned staging -> caller arrays
     const ArtOutputs& uo = ctx->userOut;

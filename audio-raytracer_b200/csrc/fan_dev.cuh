@@ -1,0 +1,76 @@
+// fan_dev.cuh -- "target fans": per-goal, direction-binned collider lists for the queries that all end in
+// one of a few fixed points -- the listener (echo-return rays, RT:124-145) and the Na audio targets (muffle
+// rays RT:153-173, permeation lines PM:67-86).
+//
+// Every such query runs along a line through its goal G, so seen FROM G it is a single direction. For each
+// goal the directions are binned on a cube map (6 faces x B x B bins); bin (face, ia, ib) lists every
+// collider whose conservative bounds (the same inflated boxes the uniform grid registers, grid_host.h)
+// subtend that bin as seen from G. Colliders whose bounds come within `nearDist` of G -- for which "direction
+// from G" is ill-conditioned -- are kept in one extra "near" list per goal that every query of that goal
+// tests. Colliders owned by target a are left out of fan a (RT:413/426/439, PM:235/245/255 skip them).
+//
+// A query from P towards G therefore tests  near(G) + bin(G, P - G)  (any-hit, K1) or
+// near(G) + bin(G, P - G) + bin(G, G - P)  (whole line, K2) -- about a dozen colliders per list at C3, each
+// exactly once, with no cell walk. The per-collider tests are the same exact FP32 functions as everywhere
+// else (intersect.cuh); the lists only decide WHICH colliders are tested, and they are conservative:
+//   * the exact FP32 test can report collider c at parameter t only if the real ray point X(t) lies in c's
+//     inflated box (the guarantee the grid relies on, grid_host.h);
+//   * the ray leaves P with a direction that is normalize(G - P) up to ~3e-7 rad, so X(t) deviates from the
+//     exact line P -> G by < 1e-6 * errScale; seen from G, at |X - G| >= nearDist = 1e-3 * errScale, that is
+//     < 1e-3 rad, i.e. < 2e-3 in the tangent-plane coordinates of a cube face;
+//   * every collider is registered in all bins its box projects onto, inflated by kFanTanMargin = 4e-3, with
+//     1 % slack on the face-membership constraint, and in the near list when G is within nearDist of the box.
+// The lists are rebuilt on the device every frame (goals move): fan_build_kernel, k4_fan_build.cu.
+#pragma once
+#include "scene_dev.cuh"
+
+namespace art {
+
+constexpr int kFanBins = 32;                         // B: bins per cube-face edge (one CTA thread per bin when building)
+constexpr int kFanCellsPerFace = kFanBins * kFanBins;
+constexpr int kFanCells = 6 * kFanCellsPerFace + 1;  // per goal; the last cell is the near list
+constexpr float kFanTanMargin = 4e-3f;
+constexpr int kFanMaxNear = 512;                     // near-list capacity per goal (else the frame falls back to the grid walk)
+
+struct FanDesc {
+    int nFans;                 // Na + 1: fan a < Na = audio target a, fan Na = the listener (RayOrigin)
+    const uint2* cells;        // [nFans * kFanCells]: x = first entry, y = nS | nA << 10 | nO << 21 (as GridDesc::cells)
+    const uint16_t* entries;   // collider indices per cell: spheres, AABBs, OBBs, ascending
+    int nEntries;              // capacity (bounds checks of debug builds)
+};
+
+// fan_build_kernel arguments (k4_fan_build.cu)
+struct FanBuildArgs {
+    const float4* boxLo;       // [ns + na + no] conservative bounds of every collider, canonical order S | A | O (grid_host.h)
+    const float4* boxHi;
+    int ns, na, no;
+    const short* ownS; const short* ownA; const short* ownO;   // AudioTargetId per collider
+    const float* targets;      // float3 [nTargets]
+    int nTargets;
+    float lx, ly, lz;          // listener = goal of fan nTargets
+    float nearDist;
+    uint2* cells;              // [(nTargets + 1) * kFanCells]
+    uint16_t* entries;
+    unsigned int capacity;     // entries available
+    unsigned int* ctl;         // [0] next free entry, [1] overflow flag (zeroed by the host before the launch)
+};
+
+// Cell index (within one fan) of the bin that direction v (from the goal, any length) falls in.
+// Returns -1 when v has no usable direction (zero or non-finite).
+__device__ __forceinline__ int fan_bin(float vx, float vy, float vz)
+{
+    const float ax = fabsf(vx), ay = fabsf(vy), az = fabsf(vz);
+    int k; float w, p, q, s;
+    if (ax >= ay && ax >= az) { k = 0; w = ax; s = vx; p = vy; q = vz; }
+    else if (ay >= az) { k = 1; w = ay; s = vy; p = vz; q = vx; }
+    else { k = 2; w = az; s = vz; p = vx; q = vy; }
+    if (!(w > 0.0f) || !(w < 3.0e38f)) return -1;
+    const float r = __fdividef(1.0f, w);
+    const float a = p * r, b = q * r;                       // tangent-plane coordinates in [-1, 1]
+    const int ia = min(kFanBins - 1, max(0, (int)floorf((a + 1.0f) * (0.5f * kFanBins))));
+    const int ib = min(kFanBins - 1, max(0, (int)floorf((b + 1.0f) * (0.5f * kFanBins))));
+    const int face = 2 * k + (s < 0.0f ? 1 : 0);
+    return face * kFanCellsPerFace + ib * kFanBins + ia;
+}
+
+}  // namespace art

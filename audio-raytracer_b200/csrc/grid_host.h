@@ -28,6 +28,8 @@ struct HostGrid {
     std::vector<uint2> cells;
     std::vector<uint16_t> entries;
     std::vector<uint2> rangeO;          // per OBB: the cell range it is listed in (packed 8 bits per axis)
+    std::vector<float> boxLo, boxHi;    // float4 per collider, canonical order S | A | O: the conservative bounds the cells
+                                        // were filled from (inflated by m, spheres by mS as well) -- input of the target fans
     float diag = 0.0f;                  // un-inflated scene diagonal
     float cx = 0, cy = 0, cz = 0;       // scene centre
     float listenerRange = 0.0f;         // ray origins farther than this from the centre -> brute force
@@ -57,7 +59,7 @@ inline void build_grid(const std::vector<uint16_t>& rawS, const std::vector<uint
                        float cellScale, HostGrid& g)
 {
     using namespace gridimpl;
-    g.ok = false; g.cells.clear(); g.entries.clear(); g.rangeO.clear();
+    g.ok = false; g.cells.clear(); g.entries.clear(); g.rangeO.clear(); g.boxLo.clear(); g.boxHi.clear();
     const size_t ns = rawS.size() / 8, na = rawA.size() / 10, no = rawO.size() / 13;
     if (ns + na + no == 0) { g.why = "empty scene"; return; }
     if (ns > 65535 || na > 65535 || no > 65535) { g.why = "more than 65535 colliders of one type"; return; }
@@ -192,6 +194,15 @@ inline void build_grid(const std::vector<uint16_t>& rawS, const std::vector<uint
     d.nEntries = (int)off;
     auto fill = [&](size_t cell, int type, uint16_t id) { g.entries[cursor[cell * 3 + type]++] = id; };
     visit(bS, 0, fill); visit(bA, 1, fill); visit(bO, 2, fill);   // ascending canonical index inside each list
+    g.boxLo.reserve(4 * nc + 4); g.boxHi.reserve(4 * nc + 4);
+    auto pushBoxes = [&](const std::vector<Box>& bs, int type) {
+        for (const Box& b : bs) {
+            const float infl = m + (type == 0 ? sphereExtra(b) : 0.0f);
+            for (int k = 0; k < 3; k++) { g.boxLo.push_back(b.lo[k] - infl); g.boxHi.push_back(b.hi[k] + infl); }
+            g.boxLo.push_back(0.0f); g.boxHi.push_back(0.0f);
+        }
+    };
+    pushBoxes(bS, 0); pushBoxes(bA, 1); pushBoxes(bO, 2);
     g.rangeO.resize(no + 1);
     for (size_t i = 0; i < no; i++) {
         int i0[3], i1[3];

@@ -14,6 +14,7 @@
 // canonical order wins" (RT:244, 257, 270) -- and an occlusion query is an "any"; the grid only skips
 // colliders whose conservative bounds the ray does not come near (grid_host.h).
 #include "device_util.cuh"
+#include "fan_dev.cuh"
 #include "grid_dev.cuh"
 #include "intersect.cuh"
 #include "scene_dev.cuh"
@@ -83,6 +84,7 @@ constexpr int kTwoStageSlots = 16;       // queries per hit point from which the
 struct PoolEnv {
     const TraceArgs& a;
     const GridDesc& g;
+    const FanDesc& f;                    // target fans (FAN variants): the pool's queries all end in the listener or a target
     const GeomView& gv;
     const HitRec* rec;                   // per-warp hit records (shared memory)
     float4* qbuf0; float4* qbuf1; float4* qbuf2; int* qbuf3;   // per-warp ring of prepared queries (shared memory)
@@ -109,7 +111,10 @@ __device__ __forceinline__ void query_visible(const PoolEnv& E, int slot, int re
 //   STAGE 1: the survivors, against the sphere and OBB lists. A query that survives this too sees its goal.
 //   STAGE 2: (few queries per hit point) all three lists in one pass.
 // An occlusion query is an "any" over all colliders (RT:365-449), so the order of the tests is free.
-template <int STAGE, bool STATS>
+// FAN: instead of walking the grid cells along the segment, a query tests the two lists its goal's fan holds for
+// it (fan_dev.cuh): the goal's near list and the direction bin of (hit point - goal). Colliders owned by the goal's
+// target are not in its fan, so the owner checks fall away.
+template <int STAGE, bool STATS, bool FAN>
 __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count, bool noSO)
 {
     const TraceArgs& a = E.a;
@@ -117,6 +122,8 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
     const GeomView& gv = E.gv;
     const int lane = E.lane;
     const uint32_t ltMask = E.ltMask;
+    const uint16_t* const ebase = FAN ? E.f.entries : g.entries;
+    int fCell0 = 0, fCell1 = 0, fPos = 2;   // FAN: near cell, bin cell, next of the two to fetch (2 = none left)
     int nextQ = 0, bufNext = 0, bufCount = 0, survCount = 0;
     bool have = false;
     f3 qo = mk3(0, 0, 0), qd = mk3(0, 0, 0), qinv = mk3(0, 0, 0);
@@ -165,7 +172,15 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                     else { nL = len; gate = nL < a.maxMuffle; }                    // RT:165, 168
                     if (gate) {
                         ninv = mk3(rcpr(nd.x), rcpr(nd.y), rcpr(nd.z));
-                        active = dda_init(g, no, nd, ninv, nL, nw);
+                        if (FAN) {
+                            const int bin = fan_bin(-v.x, -v.y, -v.z);             // direction goal -> hit point
+                            const int fanBase = (nslot == 0 ? a.nTargets : nslot - 1) * kFanCells;
+                            nw.ix = fanBase + 6 * kFanCellsPerFace;                // near list of the goal
+                            nw.iy = fanBase + bin;
+                            active = bin >= 0 && len == len;                       // degenerate (hit point == goal): no test can block
+                        } else {
+                            active = dda_init(g, no, nd, ninv, nL, nw);
+                        }
                         if (!active) query_visible(E, nslot, nrec, nL);            // nothing near the segment
                     }
                 }
@@ -174,8 +189,9 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                     const int pos = __popc(act & ltMask);
                     E.qbuf0[pos] = make_float4(nd.x, nd.y, nd.z, nL);
                     E.qbuf1[pos] = make_float4(ninv.x, ninv.y, ninv.z, nw.tEnd);
-                    E.qbuf2[pos] = make_float4(nw.tmx, nw.tmy, nw.tmz,
-                                               __int_as_float(nw.ix | (nw.iy << 8) | (nw.iz << 16) | (nrec << 24)));
+                    if (FAN) E.qbuf2[pos] = make_float4(__int_as_float(nw.ix), __int_as_float(nw.iy), 0.0f, __int_as_float(nrec << 24));
+                    else E.qbuf2[pos] = make_float4(nw.tmx, nw.tmy, nw.tmz,
+                                                    __int_as_float(nw.ix | (nw.iy << 8) | (nw.iz << 16) | (nrec << 24)));
                     E.qbuf3[pos] = nslot;
                 }
                 bufNext = 0;
@@ -190,11 +206,15 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                     qslot = E.qbuf3[pos];
                     qd = mk3(v0.x, v0.y, v0.z); qL = v0.w;
                     qinv = mk3(v1.x, v1.y, v1.z); w.tEnd = v1.w;
-                    w.tmx = v2.x; w.tmy = v2.y; w.tmz = v2.z;
                     const int packed = __float_as_int(v2.w);
-                    w.ix = packed & 255; w.iy = (packed >> 8) & 255; w.iz = (packed >> 16) & 255;
                     qrec = (packed >> 24) & 31;
-                    w.tdx = fabsf(g.csx * qinv.x); w.tdy = fabsf(g.csy * qinv.y); w.tdz = fabsf(g.csz * qinv.z);
+                    if (FAN) {
+                        fCell0 = __float_as_int(v2.x); fCell1 = __float_as_int(v2.y); fPos = 0;
+                    } else {
+                        w.tmx = v2.x; w.tmy = v2.y; w.tmz = v2.z;
+                        w.ix = packed & 255; w.iy = (packed >> 8) & 255; w.iz = (packed >> 16) & 255;
+                        w.tdx = fabsf(g.csx * qinv.x); w.tdy = fabsf(g.csy * qinv.y); w.tdz = fabsf(g.csz * qinv.z);
+                    }
                     qdd = dot3(qd, qd);
                     const HitRec r = E.rec[qrec];
                     qo = mk3(r.px, r.py, r.pz);
@@ -215,26 +235,32 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
             bool walkDone = false;
             for (int s = 0; s < kSkipCells; s++) {
                 if (kA < (int)((hdr.y >> 10) & 2047)) break;
-                if (!fresh) {
-                    const float tNext = dda_next_t(w);
-                    if (tNext > w.tEnd || !dda_step(g, qd, w)) { walkDone = true; break; }
+                if (FAN) {
+                    if (fPos >= 2) { walkDone = true; break; }
+                    hdr = __ldg(&E.f.cells[fPos == 0 ? fCell0 : fCell1]);
+                    fPos++;
+                } else {
+                    if (!fresh) {
+                        const float tNext = dda_next_t(w);
+                        if (tNext > w.tEnd || !dda_step(g, qd, w)) { walkDone = true; break; }
+                    }
+                    fresh = false;
+                    hdr = dda_cell(g, w);
                 }
-                fresh = false;
-                hdr = dda_cell(g, w);
                 if (STATS) E.st[3]++;
                 kA = 0;
             }
             bool blocked = false;
             if (!walkDone) {
                 const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047;
-                const uint16_t* e = g.entries + hdr.x + nS;
+                const uint16_t* e = ebase + hdr.x + nS;
                 const int ownerId = qslot - 1;         // -1 for the echo ray: never equals a valid owner below
                 for (int c = 0; c < kCapA && kA < nA && !blocked; c++, kA++) {
                     const int id = __ldg(e + kA);
-                    ART_CHECK(a.counters, id < a.L.na && hdr.x + nS + nA <= (unsigned)g.nEntries);
+                    ART_CHECK(a.counters, id < a.L.na && hdr.x + nS + nA <= (unsigned)(FAN ? E.f.nEntries : g.nEntries));
                     if (STATS) E.st[1]++;
                     if (aabb_blocks(gv, id, qo, qinv, qL))
-                        blocked = !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
+                        blocked = FAN || !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
                 }
             }
             if (blocked) {
@@ -252,18 +278,24 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                 const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
                 const bool pending = kB < nS || kC < nO || (STAGE == 2 && kA < nA);
                 if (pending) break;
-                if (!fresh) {
-                    const float tNext = dda_next_t(w);
-                    if (tNext > w.tEnd || !dda_step(g, qd, w)) { walkDone = true; break; }
+                if (FAN) {
+                    if (fPos >= 2) { walkDone = true; break; }
+                    hdr = __ldg(&E.f.cells[fPos == 0 ? fCell0 : fCell1]);
+                    fPos++;
+                } else {
+                    if (!fresh) {
+                        const float tNext = dda_next_t(w);
+                        if (tNext > w.tEnd || !dda_step(g, qd, w)) { walkDone = true; break; }
+                    }
+                    fresh = false;
+                    hdr = dda_cell(g, w);
                 }
-                fresh = false;
-                hdr = dda_cell(g, w);
                 if (STATS) E.st[3]++;
                 kA = kB = kC = 0;
             }
             bool blocked = false;
             if (!walkDone) {
-                const uint16_t* e = g.entries + hdr.x;
+                const uint16_t* e = ebase + hdr.x;
                 const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
                 const int ownerId = qslot - 1;
                 if (STAGE == 2) {
@@ -272,7 +304,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                         ART_CHECK(a.counters, id < a.L.na);
                         if (STATS) E.st[1]++;
                         if (aabb_blocks(gv, id, qo, qinv, qL))
-                            blocked = !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
+                            blocked = FAN || !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
                     }
                 }
                 for (int c = 0; c < kCapS && kB < nS && !blocked; c++, kB++) {
@@ -280,14 +312,14 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                     ART_CHECK(a.counters, id < a.L.ns);
                     if (STATS) E.st[0]++;
                     if (sphere_dist(gv, id, qo, qd, qdd) < qL)
-                        blocked = !(qslot > 0 && a.anyOwned[0] && (int)a.at.ownS[id] == ownerId);       // RT:413
+                        blocked = FAN || !(qslot > 0 && a.anyOwned[0] && (int)a.at.ownS[id] == ownerId);       // RT:413
                 }
                 for (int c = 0; c < kCapO && kC < nO && !blocked; c++, kC++) {
                     const int id = __ldg(e + nS + nA + kC);
-                    ART_CHECK(a.counters, id < a.L.no && hdr.x + nS + nA + nO <= (unsigned)g.nEntries);
+                    ART_CHECK(a.counters, id < a.L.no && hdr.x + nS + nA + nO <= (unsigned)(FAN ? E.f.nEntries : g.nEntries));
                     if (STATS) E.st[2]++;
                     if (obb_blocks(gv, id, qo, qd, qdd, g.errScale, qL))
-                        blocked = !(qslot > 0 && a.anyOwned[2] && (int)a.at.ownO[id] == ownerId);       // RT:439
+                        blocked = FAN || !(qslot > 0 && a.anyOwned[2] && (int)a.at.ownO[id] == ownerId);       // RT:439
                 }
             }
             if (blocked) {
@@ -310,8 +342,8 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
     return survCount;
 }
 
-template <bool SMEM, bool STATS>
-__global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const TraceArgs a, const GridDesc g)
+template <bool SMEM, bool STATS, bool FAN>
+__global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const TraceArgs a, const GridDesc g, const FanDesc f)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -461,14 +493,14 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
         {
             const uint32_t hitMask = __ballot_sync(kFull, hit);
             const int total = __popc(hitMask) * slots;
-            const PoolEnv E = { a, g, gv, rec, qbuf0, qbuf1, qbuf2, qbuf3, surv, RayOrigin, hitMask, slots, lane, ltMask, st };
+            const PoolEnv E = { a, g, f, gv, rec, qbuf0, qbuf1, qbuf2, qbuf3, surv, RayOrigin, hitMask, slots, lane, ltMask, st };
             const bool noSO = a.L.ns + a.L.no == 0;
             for (int q0 = 0; q0 < total; q0 += kChunkQ) {
                 if (slots >= kTwoStageSlots) {
-                    const int nSurv = run_pool<0, STATS>(E, q0, min(kChunkQ, total - q0), noSO);
-                    if (nSurv > 0) run_pool<1, STATS>(E, 0, nSurv, noSO);
+                    const int nSurv = run_pool<0, STATS, FAN>(E, q0, min(kChunkQ, total - q0), noSO);
+                    if (nSurv > 0) run_pool<1, STATS, FAN>(E, 0, nSurv, noSO);
                 } else {
-                    run_pool<2, STATS>(E, q0, min(kChunkQ, total - q0), noSO);   // few queries per hit point: one pass over all types
+                    run_pool<2, STATS, FAN>(E, q0, min(kChunkQ, total - q0), noSO);   // few queries per hit point: one pass over all types
                 }
             }
         }
@@ -555,15 +587,23 @@ size_t trace_grid_smem_bytes(const GeomLayout& L, bool geomInSmem)
     return (geomInSmem ? L.bytes : 0) + (size_t)kGridWarps * 32 * (sizeof(HitRec) + kQueryWords * 4);
 }
 
-cudaError_t launch_trace_grid(const TraceArgs& a, const GridDesc& g, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream)
+// fans == nullptr: the occlusion queries walk the grid cells along their segments instead of using the target fans
+cudaError_t launch_trace_grid(const TraceArgs& a, const GridDesc& g, const FanDesc* fans, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream)
 {
     const size_t smem = trace_grid_smem_bytes(a.L, geomInSmem);
-    void (*k)(const TraceArgs, const GridDesc) = nullptr;
-    if (geomInSmem) k = stats ? trace_grid_kernel<true, true> : trace_grid_kernel<true, false>;
-    else k = stats ? trace_grid_kernel<false, true> : trace_grid_kernel<false, false>;
+    void (*k)(const TraceArgs, const GridDesc, const FanDesc) = nullptr;
+    if (fans) {
+        if (geomInSmem) k = stats ? trace_grid_kernel<true, true, true> : trace_grid_kernel<true, false, true>;
+        else k = stats ? trace_grid_kernel<false, true, true> : trace_grid_kernel<false, false, true>;
+    } else {
+        if (geomInSmem) k = stats ? trace_grid_kernel<true, true, false> : trace_grid_kernel<true, false, false>;
+        else k = stats ? trace_grid_kernel<false, true, false> : trace_grid_kernel<false, false, false>;
+    }
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<numCtas, kGridThreads, smem, stream>>>(a, g);
+    FanDesc fd{};
+    if (fans) fd = *fans;
+    k<<<numCtas, kGridThreads, smem, stream>>>(a, g, fd);
     return cudaGetLastError();
 }
 

@@ -16,6 +16,7 @@
 // the last hitting ray of each batch (PM:85, quirk Q5/Q6) -- is recomputed by perm_last_kernel in the
 // reference's own operation and summation order.
 #include "device_util.cuh"
+#include "fan_dev.cuh"
 #include "grid_dev.cuh"
 #include "intersect.cuh"
 #include "scene_dev.cuh"
@@ -35,8 +36,13 @@ __device__ __forceinline__ float clip_len(float tEnter, float tExit, float tIn, 
     return fmaxf(0.0f, fminf(tExit, tOut) - fmaxf(tEnter, tIn));
 }
 
-template <bool SMEM, bool STATS>
-__global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const PermArgs a, const GridDesc g)
+// FAN: phase 2 does not walk the grid; a (ray, target) line tests the three lists the target's fan holds for it
+// (fan_dev.cuh): the near list, the direction bin of (hit point - target) for the part of the line before the
+// target and the opposite bin for the part behind it (PM:225 ignores the target distance, quirk Q7). Every
+// collider is met once with its whole chord; the two bins are clipped at the target's parameter so that a collider
+// listed in both (possible only for conservatively inflated bounds) is still counted once.
+template <bool SMEM, bool STATS, bool FAN>
+__global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const PermArgs a, const GridDesc g, const FanDesc f)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -134,92 +140,157 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
                 if (laneOn && r < 32) rr = rec[r];
                 if (rr.w != 0.0f) {
                     const f3 Pp = mk3(rr.x, rr.y, rr.z);
-                    const f3 dir = normalize3(sub3(T, Pp));                    // PM:76
+                    const f3 toT = sub3(T, Pp);
+                    const f3 dir = normalize3(toT);                            // PM:76
                     const f3 inv = mk3(rcpr(dir.x), rcpr(dir.y), rcpr(dir.z));             // PM:270
                     float loss = 0.0f;
-                    Dda w;
-                    bool walking = dda_init(g, Pp, dir, inv, pos_inf(), w);
-                    const float tRay0 = w.tCur;                 // where the line enters the grid (0 inside it)
-                    while (walking) {
-                        const uint2 hdr = dda_cell(g, w);
-                        const uint16_t* e = g.entries + hdr.x;
-                        const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
-                        // the cell the walk came from differs along one axis: an OBB whose cell range contains that
-                        // coordinate was already met there (the cells of a convex range along a line are contiguous)
-                        const int axShift = 8 * w.lastAxis;
-                        const int prevCoord = w.lastAxis == 0 ? w.ix - (dir.x > 0.0f ? 1 : -1)
-                                            : (w.lastAxis == 1 ? w.iy - (dir.y > 0.0f ? 1 : -1) : w.iz - (dir.z > 0.0f ? 1 : -1));
-                        const float tIn = w.tCur;
-                        const float tOut = fminf(dda_next_t(w), w.tEnd);
-                        if (STATS) { st[3] += nS; st[4] += nA; st[5] += nO; st[6]++; }
-                        ART_CHECK(a.counters, (unsigned)w.ix < (unsigned)g.nx && (unsigned)w.iy < (unsigned)g.ny && (unsigned)w.iz < (unsigned)g.nz);
-                        ART_CHECK(a.counters, hdr.x + nS + nA + nO <= (unsigned)g.nEntries && tgt >= 0 && tgt < Na);
-                        // AABB and sphere intervals are evaluated in the reference's own operation order, so tEnter/tExit are
-                        // the reference's floats (a near-tangent sphere crossing, 2*sqrt(disc) with disc ~ 0, would otherwise
-                        // amplify harmless rounding into a visible difference); only the per-cell clipping is new.
-                        for (int k = 0; k < nA; k++) {                          // PM:265-288
-                            const int id = __ldg(e + nS + k);
-                            ART_CHECK(a.counters, id < a.L.na);
-                            const float4 A = gv.aabbA[id];
-                            const float2 B = gv.aabbB[id];
-                            float tEnter, tExit;
-                            slab<8>(subr(A.x, Pp.x), subr(A.y, Pp.y), subr(A.z, Pp.z), subr(A.w, Pp.x), subr(B.x, Pp.y), subr(B.y, Pp.z),
-                                    inv.x, inv.y, inv.z, tEnter, tExit);
-                            const float len = clip_len(tEnter, tExit, tIn, tOut);
-                            if (len > 0.0f) {
-                                const float4 at = a.at.aabbAttr[id];
-                                if (__float_as_int(at.w) != tgt) loss = fmaf(len, at.z, loss);     // PM:245 owner skip
+                    if (FAN) {
+                        const int bin = fan_bin(-toT.x, -toT.y, -toT.z);       // direction target -> hit point
+                        const float tT = sqrt_fast(fmaf(toT.z, toT.z, fmaf(toT.y, toT.y, toT.x * toT.x)));   // line parameter of the target
+                        const int fanBase = tgt * kFanCells;
+                        for (int m = 0; m < 3 && bin >= 0; m++) {
+                            // m = 0: near list, whole line; 1: bin towards the hit point, t in [0, tT]; 2: opposite bin, t > tT
+                            int cell = fanBase + 6 * kFanCellsPerFace;
+                            if (m == 1) cell = fanBase + bin;
+                            if (m == 2) { const int face = bin / kFanCellsPerFace, r = bin - face * kFanCellsPerFace;
+                                          cell = fanBase + (face ^ 1) * kFanCellsPerFace + (kFanCellsPerFace - 1 - r); }
+                            const float tIn = m == 2 ? tT : 0.0f, tOut = m == 1 ? tT : pos_inf();
+                            const uint2 hdr = __ldg(&f.cells[cell]);
+                            const uint16_t* e = f.entries + hdr.x;
+                            const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
+                            if (STATS) { st[3] += nS; st[4] += nA; st[5] += nO; st[6]++; }
+                            ART_CHECK(a.counters, hdr.x + nS + nA + nO <= (unsigned)f.nEntries && tgt >= 0 && tgt < Na);
+                            for (int k = 0; k < nA; k++) {                      // PM:265-288, reference operation order
+                                const int id = __ldg(e + nS + k);
+                                ART_CHECK(a.counters, id < a.L.na);
+                                const float4 A = gv.aabbA[id];
+                                const float2 B = gv.aabbB[id];
+                                float tEnter, tExit;
+                                slab<8>(subr(A.x, Pp.x), subr(A.y, Pp.y), subr(A.z, Pp.z), subr(A.w, Pp.x), subr(B.x, Pp.y), subr(B.y, Pp.z),
+                                        inv.x, inv.y, inv.z, tEnter, tExit);
+                                const float len = clip_len(tEnter, tExit, tIn, tOut);
+                                if (len > 0.0f) loss = fmaf(len, a.at.aabbAttr[id].z, loss);
+                            }
+                            for (int k = 0; k < nS; k++) {                      // PM:303-328 (unit direction)
+                                const int id = __ldg(e + k);
+                                ART_CHECK(a.counters, id < a.L.ns);
+                                const float4 s = gv.sph[id];
+                                const f3 oc = sub3(Pp, mk3(s.x, s.y, s.z));
+                                const float cc = subr(dot3(oc, oc), s.w);
+                                float b;
+                                if (sphere_loss_fast_miss(oc, cc, dir, b)) continue;   // disc < 0 (PM:311)
+                                const float sq = sqrtr(subr(mulr(b, b), cc));
+                                const float len = clip_len(subr(-b, sq), addr(-b, sq), tIn, tOut);
+                                if (len > 0.0f) loss = fmaf(len, a.at.sphAttr[id].z, loss);
+                            }
+                            for (int k = 0; k < nO; k++) {                      // PM:294-300 (stored rotation as is)
+                                const int id = __ldg(e + nS + nA + k);
+                                ART_CHECK(a.counters, id < a.L.no);
+                                const float4 c4 = gv.obbC[id];
+                                const float2 h2 = gv.obbH[id];
+                                const f3 pc = mk3(Pp.x - c4.x, Pp.y - c4.y, Pp.z - c4.z);
+                                const float bq = fmaf(pc.z, dir.z, fmaf(pc.y, dir.y, pc.x * dir.x));
+                                const float pp = fmaf(pc.z, pc.z, fmaf(pc.y, pc.y, pc.x * pc.x));
+                                const float r2 = fmaf(h2.y, h2.y, fmaf(h2.x, h2.x, c4.w * c4.w));
+                                if (pp - bq * bq > r2 * 1.001f + 1e-4f) continue;   // the line passes the bounding sphere
+                                const float4 q4 = gv.obbQ[id];
+                                const f3 pn = mk3(fmaf(dir.x, -bq, pc.x), fmaf(dir.y, -bq, pc.y), fmaf(dir.z, -bq, pc.z));
+                                const f3 lo = qrot_fast(q4, pn), ld = qrot_fast(q4, dir);
+                                const float rx = rcp_fast(ld.x), ry = rcp_fast(ld.y), rz = rcp_fast(ld.z);
+                                const float ax = (-c4.w - lo.x) * rx, bx = (c4.w - lo.x) * rx;
+                                const float ay = (-h2.x - lo.y) * ry, by = (h2.x - lo.y) * ry;
+                                const float az = (-h2.y - lo.z) * rz, bz = (h2.y - lo.z) * rz;
+                                const float tEnter = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)) - bq;
+                                const float tExit = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) - bq;
+                                const float len = clip_len(tEnter, tExit, tIn, tOut);
+                                if (len > 0.0f) loss = fmaf(len, a.at.obbAttr[id].z, loss);
                             }
                         }
-                        for (int k = 0; k < nS; k++) {                          // PM:303-328 (unit direction)
-                            const int id = __ldg(e + k);
-                            const float4 s = gv.sph[id];
-                            const f3 oc = sub3(Pp, mk3(s.x, s.y, s.z));
-                            const float cc = subr(dot3(oc, oc), s.w);
-                            float b;
-                            if (sphere_loss_fast_miss(oc, cc, dir, b)) continue;   // disc < 0 (PM:311)
-                            const float sq = sqrtr(subr(mulr(b, b), cc));
-                            const float len = clip_len(subr(-b, sq), addr(-b, sq), tIn, tOut);
-                            if (len > 0.0f) {
-                                const float4 at = a.at.sphAttr[id];
-                                if (__float_as_int(at.w) != tgt) loss = fmaf(len, at.z, loss);     // PM:235
+                    } else {
+                        Dda w;
+                        bool walking = dda_init(g, Pp, dir, inv, pos_inf(), w);
+                        const float tRay0 = w.tCur;                 // where the line enters the grid (0 inside it)
+                        while (walking) {
+                            const uint2 hdr = dda_cell(g, w);
+                            const uint16_t* e = g.entries + hdr.x;
+                            const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
+                            // the cell the walk came from differs along one axis: an OBB whose cell range contains that
+                            // coordinate was already met there (the cells of a convex range along a line are contiguous)
+                            const int axShift = 8 * w.lastAxis;
+                            const int prevCoord = w.lastAxis == 0 ? w.ix - (dir.x > 0.0f ? 1 : -1)
+                                                : (w.lastAxis == 1 ? w.iy - (dir.y > 0.0f ? 1 : -1) : w.iz - (dir.z > 0.0f ? 1 : -1));
+                            const float tIn = w.tCur;
+                            const float tOut = fminf(dda_next_t(w), w.tEnd);
+                            if (STATS) { st[3] += nS; st[4] += nA; st[5] += nO; st[6]++; }
+                            ART_CHECK(a.counters, (unsigned)w.ix < (unsigned)g.nx && (unsigned)w.iy < (unsigned)g.ny && (unsigned)w.iz < (unsigned)g.nz);
+                            ART_CHECK(a.counters, hdr.x + nS + nA + nO <= (unsigned)g.nEntries && tgt >= 0 && tgt < Na);
+                            // AABB and sphere intervals are evaluated in the reference's own operation order, so tEnter/tExit are
+                            // the reference's floats (a near-tangent sphere crossing, 2*sqrt(disc) with disc ~ 0, would otherwise
+                            // amplify harmless rounding into a visible difference); only the per-cell clipping is new.
+                            for (int k = 0; k < nA; k++) {                          // PM:265-288
+                                const int id = __ldg(e + nS + k);
+                                ART_CHECK(a.counters, id < a.L.na);
+                                const float4 A = gv.aabbA[id];
+                                const float2 B = gv.aabbB[id];
+                                float tEnter, tExit;
+                                slab<8>(subr(A.x, Pp.x), subr(A.y, Pp.y), subr(A.z, Pp.z), subr(A.w, Pp.x), subr(B.x, Pp.y), subr(B.y, Pp.z),
+                                        inv.x, inv.y, inv.z, tEnter, tExit);
+                                const float len = clip_len(tEnter, tExit, tIn, tOut);
+                                if (len > 0.0f) {
+                                    const float4 at = a.at.aabbAttr[id];
+                                    if (__float_as_int(at.w) != tgt) loss = fmaf(len, at.z, loss);     // PM:245 owner skip
+                                }
                             }
+                            for (int k = 0; k < nS; k++) {                          // PM:303-328 (unit direction)
+                                const int id = __ldg(e + k);
+                                const float4 s = gv.sph[id];
+                                const f3 oc = sub3(Pp, mk3(s.x, s.y, s.z));
+                                const float cc = subr(dot3(oc, oc), s.w);
+                                float b;
+                                if (sphere_loss_fast_miss(oc, cc, dir, b)) continue;   // disc < 0 (PM:311)
+                                const float sq = sqrtr(subr(mulr(b, b), cc));
+                                const float len = clip_len(subr(-b, sq), addr(-b, sq), tIn, tOut);
+                                if (len > 0.0f) {
+                                    const float4 at = a.at.sphAttr[id];
+                                    if (__float_as_int(at.w) != tgt) loss = fmaf(len, at.z, loss);     // PM:235
+                                }
+                            }
+                            for (int k = 0; k < nO; k++) {                          // PM:294-300 (stored rotation as is)
+                                const int id = __ldg(e + nS + nA + k);
+                                ART_CHECK(a.counters, id < a.L.no);
+                                const float4 c4 = gv.obbC[id];
+                                const float2 h2 = gv.obbH[id];
+                                const f3 pc = mk3(Pp.x - c4.x, Pp.y - c4.y, Pp.z - c4.z);
+                                // bounding sphere first: |pc x dir|^2 > r^2 means the line passes the box
+                                const float bq = fmaf(pc.z, dir.z, fmaf(pc.y, dir.y, pc.x * dir.x));
+                                const float pp = fmaf(pc.z, pc.z, fmaf(pc.y, pc.y, pc.x * pc.x));
+                                const float r2 = fmaf(h2.y, h2.y, fmaf(h2.x, h2.x, c4.w * c4.w));
+                                if (pp - bq * bq > r2 * 1.001f + 1e-4f) continue;
+                                if (w.lastAxis >= 0) {              // count every OBB once: where the walk first meets it
+                                    const uint2 rg = __ldg(&g.rangeO[id]);
+                                    const int lo = (int)((rg.x >> axShift) & 255u), hi = (int)((rg.y >> axShift) & 255u);
+                                    if (prevCoord >= lo && prevCoord <= hi) continue;
+                                }
+                                const float4 q4 = gv.obbQ[id];
+                                // rotate the point of closest approach (|pn| <= r) instead of pc (|pc| can be the whole room):
+                                // the rounding of the cheap rotation then scales with the box, not with the distance to it
+                                const f3 pn = mk3(fmaf(dir.x, -bq, pc.x), fmaf(dir.y, -bq, pc.y), fmaf(dir.z, -bq, pc.z));
+                                const f3 lo = qrot_fast(q4, pn), ld = qrot_fast(q4, dir);
+                                const float rx = rcp_fast(ld.x), ry = rcp_fast(ld.y), rz = rcp_fast(ld.z);
+                                const float ax = (-c4.w - lo.x) * rx, bx = (c4.w - lo.x) * rx;
+                                const float ay = (-h2.x - lo.y) * ry, by = (h2.x - lo.y) * ry;
+                                const float az = (-h2.y - lo.z) * rz, bz = (h2.y - lo.z) * rz;
+                                const float tEnter = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)) - bq;
+                                const float tExit = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) - bq;
+                                const float len = fmaxf(0.0f, tExit - fmaxf(tEnter, tRay0));   // the whole chord, once (PM:286-287)
+                                if (len > 0.0f) {
+                                    const float4 at = a.at.obbAttr[id];
+                                    if (__float_as_int(at.w) != tgt) loss = fmaf(len, at.z, loss);     // PM:255
+                                }
+                            }
+                            if (dda_next_t(w) > w.tEnd) break;
+                            walking = dda_step(g, dir, w);
                         }
-                        for (int k = 0; k < nO; k++) {                          // PM:294-300 (stored rotation as is)
-                            const int id = __ldg(e + nS + nA + k);
-                            ART_CHECK(a.counters, id < a.L.no);
-                            const float4 c4 = gv.obbC[id];
-                            const float2 h2 = gv.obbH[id];
-                            const f3 pc = mk3(Pp.x - c4.x, Pp.y - c4.y, Pp.z - c4.z);
-                            // bounding sphere first: |pc x dir|^2 > r^2 means the line passes the box
-                            const float bq = fmaf(pc.z, dir.z, fmaf(pc.y, dir.y, pc.x * dir.x));
-                            const float pp = fmaf(pc.z, pc.z, fmaf(pc.y, pc.y, pc.x * pc.x));
-                            const float r2 = fmaf(h2.y, h2.y, fmaf(h2.x, h2.x, c4.w * c4.w));
-                            if (pp - bq * bq > r2 * 1.001f + 1e-4f) continue;
-                            if (w.lastAxis >= 0) {              // count every OBB once: where the walk first meets it
-                                const uint2 rg = __ldg(&g.rangeO[id]);
-                                const int lo = (int)((rg.x >> axShift) & 255u), hi = (int)((rg.y >> axShift) & 255u);
-                                if (prevCoord >= lo && prevCoord <= hi) continue;
-                            }
-                            const float4 q4 = gv.obbQ[id];
-                            // rotate the point of closest approach (|pn| <= r) instead of pc (|pc| can be the whole room):
-                            // the rounding of the cheap rotation then scales with the box, not with the distance to it
-                            const f3 pn = mk3(fmaf(dir.x, -bq, pc.x), fmaf(dir.y, -bq, pc.y), fmaf(dir.z, -bq, pc.z));
-                            const f3 lo = qrot_fast(q4, pn), ld = qrot_fast(q4, dir);
-                            const float rx = rcp_fast(ld.x), ry = rcp_fast(ld.y), rz = rcp_fast(ld.z);
-                            const float ax = (-c4.w - lo.x) * rx, bx = (c4.w - lo.x) * rx;
-                            const float ay = (-h2.x - lo.y) * ry, by = (h2.x - lo.y) * ry;
-                            const float az = (-h2.y - lo.z) * rz, bz = (h2.y - lo.z) * rz;
-                            const float tEnter = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)) - bq;
-                            const float tExit = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) - bq;
-                            const float len = fmaxf(0.0f, tExit - fmaxf(tEnter, tRay0));   // the whole chord, once (PM:286-287)
-                            if (len > 0.0f) {
-                                const float4 at = a.at.obbAttr[id];
-                                if (__float_as_int(at.w) != tgt) loss = fmaf(len, at.z, loss);     // PM:255
-                            }
-                        }
-                        if (dda_next_t(w) > w.tEnd) break;
-                        walking = dda_step(g, dir, w);
                     }
                     const float v = subr(a.nTimesS, loss);                     // PM:260
                     const float ip = truncf(v);
@@ -269,15 +340,23 @@ size_t perm_grid_smem_bytes(const GeomLayout& L, bool geomInSmem)
     return (geomInSmem ? L.bytes : 0) + (size_t)kPGridWarps * 32 * sizeof(float4);
 }
 
-cudaError_t launch_permeation_grid(const PermArgs& a, const GridDesc& g, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream)
+// fans == nullptr: the loss lines walk the grid cells instead of using the target fans
+cudaError_t launch_permeation_grid(const PermArgs& a, const GridDesc& g, const FanDesc* fans, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream)
 {
     const size_t smem = perm_grid_smem_bytes(a.L, geomInSmem);
-    void (*k)(const PermArgs, const GridDesc) = nullptr;
-    if (geomInSmem) k = stats ? permeation_grid_kernel<true, true> : permeation_grid_kernel<true, false>;
-    else k = stats ? permeation_grid_kernel<false, true> : permeation_grid_kernel<false, false>;
+    void (*k)(const PermArgs, const GridDesc, const FanDesc) = nullptr;
+    if (fans) {
+        if (geomInSmem) k = stats ? permeation_grid_kernel<true, true, true> : permeation_grid_kernel<true, false, true>;
+        else k = stats ? permeation_grid_kernel<false, true, true> : permeation_grid_kernel<false, false, true>;
+    } else {
+        if (geomInSmem) k = stats ? permeation_grid_kernel<true, true, false> : permeation_grid_kernel<true, false, false>;
+        else k = stats ? permeation_grid_kernel<false, true, false> : permeation_grid_kernel<false, false, false>;
+    }
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<numCtas, kPGridThreads, smem, stream>>>(a, g);
+    FanDesc fd{};
+    if (fans) fd = *fans;
+    k<<<numCtas, kPGridThreads, smem, stream>>>(a, g, fd);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,189 @@
+// k4_fan_build.cu -- per-frame construction of the target fans (fan_dev.cuh) on the device.
+//
+// One CTA per (goal, cube face), one thread per direction bin (32 x 32). The CTA sweeps the colliders in
+// canonical order (spheres | AABBs | OBBs) in chunks of 1,024: every thread projects one collider's
+// conservative box onto the face (a bin rectangle, or nothing), the non-empty rectangles are compacted IN
+// ORDER into shared memory, and every thread then scans the compacted chunk for the rectangles that contain
+// its bin. Pass 0 counts, a block scan + one atomicAdd reserves the CTA's span of the entry array, pass 1
+// repeats the sweep and writes the indices -- so every list is ascending and grouped by type, and its
+// content does not depend on scheduling (only its position in the entry array does).
+#include "device_util.cuh"
+#include "fan_dev.cuh"
+#include "launchers.h"
+
+namespace art {
+
+constexpr uint32_t kRectEmpty = 0x000000FFu;   // a0 = 255 > a1 = 0
+
+// Bin rectangle of the box [lo, hi] (already conservative, grid_host.h) seen from T on cube face (k, sgn),
+// packed a0 | a1 << 8 | b0 << 16 | b1 << 24, or kRectEmpty. near: T lies within nearDist of the box (per axis).
+__device__ __forceinline__ uint32_t fan_rect(const float lo[3], const float hi[3], const float T[3], int k, bool neg, float nearDist, bool& near)
+{
+    float rl[3], rh[3];
+    near = true;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float e = 4e-6f * (fabsf(T[c]) + fabsf(lo[c]) + fabsf(hi[c])) + 1e-6f;   // rounding of the two subtractions
+        rl[c] = lo[c] - T[c] - e;
+        rh[c] = hi[c] - T[c] + e;
+        near = near && rl[c] <= nearDist && rh[c] >= -nearDist;
+    }
+    if (near) return kRectEmpty;
+    const int i = k == 2 ? 0 : k + 1, j = k == 0 ? 2 : k - 1;   // (k+1)%3, (k+2)%3
+    const float w0 = neg ? -rh[k] : rl[k], w1 = neg ? -rl[k] : rh[k];
+    if (!(w1 > 0.0f)) return kRectEmpty;
+    const float x0 = rl[i], x1 = rh[i], y0 = rl[j], y1 = rh[j];
+    const float xmin = (x0 <= 0.0f && x1 >= 0.0f) ? 0.0f : fminf(fabsf(x0), fabsf(x1));
+    const float ymin = (y0 <= 0.0f && y1 >= 0.0f) ? 0.0f : fminf(fabsf(y0), fabsf(y1));
+    // directions on this face have w >= |x|, |y| (1 % slack: a query direction within 2e-3 of the face edge)
+    const float wlo = fmaxf(w0, 0.99f * fmaxf(xmin, ymin));
+    if (wlo > w1) return kRectEmpty;
+    const float inf = __int_as_float(0x7F800000);
+    const float r1 = 1.0f / w1;
+    const bool pos = wlo > 0.0f;
+    const float rlo = pos ? 1.0f / wlo : 0.0f;
+    const float amin = (x0 >= 0.0f ? x0 * r1 : (pos ? x0 * rlo : -inf)) - kFanTanMargin;
+    const float amax = (x1 <= 0.0f ? x1 * r1 : (pos ? x1 * rlo : inf)) + kFanTanMargin;
+    const float bmin = (y0 >= 0.0f ? y0 * r1 : (pos ? y0 * rlo : -inf)) - kFanTanMargin;
+    const float bmax = (y1 <= 0.0f ? y1 * r1 : (pos ? y1 * rlo : inf)) + kFanTanMargin;
+    if (amin > 1.0f || amax < -1.0f || bmin > 1.0f || bmax < -1.0f) return kRectEmpty;
+    const float sc = 0.5f * kFanBins;
+    const uint32_t a0 = (uint32_t)min(kFanBins - 1, max(0, (int)floorf((fmaxf(amin, -1.0f) + 1.0f) * sc)));
+    const uint32_t a1 = (uint32_t)min(kFanBins - 1, max(0, (int)floorf((fminf(amax, 1.0f) + 1.0f) * sc)));
+    const uint32_t b0 = (uint32_t)min(kFanBins - 1, max(0, (int)floorf((fmaxf(bmin, -1.0f) + 1.0f) * sc)));
+    const uint32_t b1 = (uint32_t)min(kFanBins - 1, max(0, (int)floorf((fminf(bmax, 1.0f) + 1.0f) * sc)));
+    return a0 | (a1 << 8) | (b0 << 16) | (b1 << 24);
+}
+
+__global__ void __launch_bounds__(kFanCellsPerFace, 1) fan_build_kernel(const FanBuildArgs a)
+{
+    static_assert(kFanCellsPerFace == 1024 && kFanBins == 32, "one thread per bin, one warp per bin row");
+    __shared__ uint32_t sRect[1024];
+    __shared__ uint32_t sIdT[1024];          // local collider index | type << 16
+    __shared__ uint32_t sNear[kFanMaxNear];
+    __shared__ int sWarpCnt[32], sWarpNear[32], sWarpTot[32];
+    __shared__ int sNearCount;
+    __shared__ unsigned int sBase;
+
+    const int face = blockIdx.x, fan = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t ia = (uint32_t)lane, ib = (uint32_t)warp;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    const int nc = a.ns + a.na + a.no;
+    float T[3];
+    if (fan < a.nTargets) { T[0] = a.targets[3 * fan]; T[1] = a.targets[3 * fan + 1]; T[2] = a.targets[3 * fan + 2]; }
+    else { T[0] = a.lx; T[1] = a.ly; T[2] = a.lz; }
+    const int k = face >> 1;
+    const bool neg = face & 1;
+    const bool nearCta = face == 0;
+    if (tid == 0) sNearCount = 0;
+    __syncthreads();
+
+    int cS = 0, cA = 0, cO = 0;
+    unsigned int wpos = 0;                   // pass 1: next entry of this bin
+    unsigned int blockTotal = 0;
+    int nearTotal = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int base = 0; base < nc; base += 1024) {
+            const int g = base + tid;
+            uint32_t rect = kRectEmpty, idT = 0;
+            bool near = false;
+            if (g < nc) {
+                int type, id; short owner;
+                if (g < a.ns) { type = 0; id = g; owner = a.ownS[id]; }
+                else if (g < a.ns + a.na) { type = 1; id = g - a.ns; owner = a.ownA[id]; }
+                else { type = 2; id = g - a.ns - a.na; owner = a.ownO[id]; }
+                if (!(fan < a.nTargets && (int)owner == fan)) {          // RT:413/426/439, PM:235/245/255
+                    const float4 l4 = a.boxLo[g], h4 = a.boxHi[g];
+                    const float lo[3] = { l4.x, l4.y, l4.z }, hi[3] = { h4.x, h4.y, h4.z };
+                    rect = fan_rect(lo, hi, T, k, neg, a.nearDist, near);
+                    idT = (uint32_t)id | ((uint32_t)type << 16);
+                }
+            }
+            const uint32_t bal = __ballot_sync(kFull, rect != kRectEmpty);
+            const uint32_t nbal = __ballot_sync(kFull, near && nearCta && pass == 0);
+            if (lane == 0) { sWarpCnt[warp] = __popc(bal); sWarpNear[warp] = __popc(nbal); }
+            __syncthreads();
+            int incl = sWarpCnt[lane], nincl = sWarpNear[lane];
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const int v = __shfl_up_sync(kFull, incl, s), nv = __shfl_up_sync(kFull, nincl, s);
+                if (lane >= s) { incl += v; nincl += nv; }
+            }
+            const int M = __shfl_sync(kFull, incl, 31), nM = __shfl_sync(kFull, nincl, 31);
+            const int prefix = warp == 0 ? 0 : __shfl_sync(kFull, incl, warp - 1);
+            const int nprefix = warp == 0 ? 0 : __shfl_sync(kFull, nincl, warp - 1);
+            if (rect != kRectEmpty) {
+                const int pos = prefix + __popc(bal & ltMask);
+                sRect[pos] = rect; sIdT[pos] = idT;
+            }
+            if (near && nearCta && pass == 0) {
+                const int pos = sNearCount + nprefix + __popc(nbal & ltMask);
+                if (pos < kFanMaxNear) sNear[pos] = idT;
+            }
+            __syncthreads();
+            for (int c = 0; c < M; c++) {
+                const uint32_t r = sRect[c];
+                if (ia >= (r & 255u) && ia <= ((r >> 8) & 255u) && ib >= ((r >> 16) & 255u) && ib <= (r >> 24)) {
+                    const uint32_t e = sIdT[c];
+                    if (pass == 0) { const uint32_t t = e >> 16; cS += t == 0; cA += t == 1; cO += t == 2; }
+                    else a.entries[wpos++] = (uint16_t)(e & 0xFFFFu);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) sNearCount += nM;
+        }
+        if (pass == 1) break;
+        // ---- reserve the CTA's span: block scan of the per-bin totals
+        __syncthreads();
+        nearTotal = nearCta ? sNearCount : 0;
+        const int tot = cS + cA + cO;
+        bool bad = cS > kGridMaxS || cA > kGridMaxA || cO > kGridMaxO || nearTotal > kFanMaxNear;
+        int incl = tot;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) { const int v = __shfl_up_sync(kFull, incl, s); if (lane >= s) incl += v; }
+        if (lane == 31) sWarpTot[warp] = incl;
+        __syncthreads();
+        int wincl = sWarpTot[lane];
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) { const int v = __shfl_up_sync(kFull, wincl, s); if (lane >= s) wincl += v; }
+        blockTotal = (unsigned)__shfl_sync(kFull, wincl, 31);
+        const unsigned binOff = (unsigned)((warp == 0 ? 0 : __shfl_sync(kFull, wincl, warp - 1)) + incl - tot);
+        bad = __syncthreads_or(bad);
+        if (tid == 0) {
+            unsigned int b = 0xFFFFFFFFu;
+            if (!bad) {
+                b = atomicAdd(&a.ctl[0], blockTotal + (unsigned)nearTotal);
+                if ((unsigned long long)b + blockTotal + (unsigned)nearTotal > (unsigned long long)a.capacity) b = 0xFFFFFFFFu;
+            }
+            if (b == 0xFFFFFFFFu) atomicExch(&a.ctl[1], 1u);          // the host re-runs the frame without fans
+            sBase = b;
+        }
+        __syncthreads();
+        const unsigned int bs = sBase;
+        uint2* cells = a.cells + (size_t)fan * kFanCells;
+        if (bs == 0xFFFFFFFFu) {
+            cells[face * kFanCellsPerFace + tid] = make_uint2(0u, 0u);
+            if (nearCta && tid == 0) cells[6 * kFanCellsPerFace] = make_uint2(0u, 0u);
+            return;
+        }
+        wpos = bs + binOff;
+        cells[face * kFanCellsPerFace + tid] = make_uint2(wpos, (uint32_t)cS | ((uint32_t)cA << 10) | ((uint32_t)cO << 21));
+        if (nearCta && tid == 0) {
+            uint32_t nS = 0, nA = 0, nO = 0;
+            for (int q = 0; q < nearTotal; q++) { const uint32_t t = sNear[q] >> 16; nS += t == 0; nA += t == 1; nO += t == 2; }
+            cells[6 * kFanCellsPerFace] = make_uint2(bs + blockTotal, nS | (nA << 10) | (nO << 21));
+        }
+        if (nearCta)
+            for (int q = tid; q < nearTotal; q += 1024) a.entries[bs + blockTotal + q] = (uint16_t)(sNear[q] & 0xFFFFu);
+    }
+}
+
+cudaError_t launch_fan_build(const FanBuildArgs& a, cudaStream_t stream)
+{
+    const int nFans = a.nTargets + 1;
+    fan_build_kernel<<<dim3(6, nFans), kFanCellsPerFace, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace art

@@ -1,5 +1,6 @@
 // launchers.h -- host-callable entry points of the kernel translation units.
 #pragma once
+#include "fan_dev.cuh"
 #include "scene_dev.cuh"
 
 namespace art {
@@ -11,12 +12,13 @@ size_t trace_grid_smem_bytes(const GeomLayout& L, bool geomInSmem);
 size_t trace_grid_scratch_bytes(int numCtas);
 int trace_grid_rays_per_warp(int nLocal, int nTargets, int numCtas);
 int perm_grid_rays_per_warp(int nLocal, int nTargets, int numCtas);
-cudaError_t launch_trace_grid(const TraceArgs& a, const GridDesc& g, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream);
+cudaError_t launch_trace_grid(const TraceArgs& a, const GridDesc& g, const FanDesc* fans, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream);
+cudaError_t launch_fan_build(const FanBuildArgs& a, cudaStream_t stream);
 size_t perm_smem_bytes(const GeomLayout& L, bool geomInSmem);
 cudaError_t launch_permeation(const PermArgs& a, int numCtas, bool geomInSmem, int T, cudaStream_t stream);
 cudaError_t launch_perm_last(const PermArgs& a, int T, cudaStream_t stream);
 size_t perm_grid_smem_bytes(const GeomLayout& L, bool geomInSmem);
-cudaError_t launch_permeation_grid(const PermArgs& a, const GridDesc& g, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream);
+cudaError_t launch_permeation_grid(const PermArgs& a, const GridDesc& g, const FanDesc* fans, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream);
 cudaError_t launch_echo_stats(const uint16_t* echo, size_t n, EchoStats* out, bool sequential, int numSms, cudaStream_t stream);
 cudaError_t launch_fibonacci(uint16_t* dirs, int n, cudaStream_t stream);
 cudaError_t launch_microbench(int kind, int numSms, float* sink, long long* laneOps, cudaStream_t stream);

@@ -22,6 +22,7 @@ ART_ABI_VERSION = 2
 ART_OK, ART_E_ARG, ART_E_CUDA, ART_E_PENDING, ART_E_NO_DEVICE, ART_E_STATE, ART_E_NOMEM = 0, -1, -2, -3, -4, -5, -6
 JOB_RAYTRACE, JOB_PERMEATION, JOB_PROCESS, JOB_ALL = 1, 2, 4, 7
 FRAME_COUNTERS, FRAME_REVERB_SEQ_FP32, FRAME_NO_HOST_OUTPUTS, FRAME_PARTIALS_ONLY, FRAME_BRUTE_FORCE, FRAME_GRID_STATS, FRAME_FORCE_GRID = 1, 2, 4, 8, 16, 32, 64
+FRAME_NO_FANS = 128
 
 EXPORTS = [
     "art_create", "art_destroy", "art_set_scene", "art_set_rays", "art_generate_fibonacci_rays", "art_get_rays",

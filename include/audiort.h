@@ -117,6 +117,10 @@ typedef struct ArtConfig {
                                           would pick the brute-force kernels, whose warp-per-ray mapping has the lower latency there */
 #define ART_FRAME_GRID_STATS      32u  /* grid kernels also count the collider tests and cells they actually visit
                                           (ArtCounters.grid*); slightly slower kernel variant */
+#define ART_FRAME_NO_FANS        128u  /* grid kernels: do not build the per-frame target fans (direction-binned collider lists
+                                          around the listener and every audio target); the echo / muffle / permeation queries
+                                          then walk the grid cells along their lines instead. Results are bit-identical
+                                          (permeationSum within its tolerance). ART_DISABLE_FANS=1 does the same for a context. */
 
 /* One field per job-struct field (RT:12-52, PM:10-27, PA:10-25). */
 typedef struct ArtParams {
@@ -173,7 +177,9 @@ typedef struct ArtCounters {
     float    deviceMs;          /* first kernel start -> last kernel end, this frame */
     float    h2dMs, d2hMs;      /* copy time on the stream (0 when nothing was copied) */
     uint32_t kernelLaunches;    /* kernels of this library launched for the frame */
-    uint32_t gridUsed;          /* bit 0: trace job used the uniform grid, bit 1: permeation job did */
+    uint32_t gridUsed;          /* bit 0: trace job used the uniform grid, bit 1: permeation job did, bit 2: the frame's
+                                   goal-directed queries used the target fans, bit 3: the fan build overflowed its entry
+                                   buffer and the frame was re-run on the grid walk (the buffer grows for the next frame) */
     /* ART_FRAME_GRID_STATS: collider tests the grid kernels actually executed ([3] = sphere, AABB, OBB) and grid
      * cells they visited; compare with traceTests + echoTests + muffleTests / permFirstTests / permLossTests, the
      * counts of the reference's full scans */

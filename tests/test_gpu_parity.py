@@ -38,13 +38,18 @@ def run_gpu(ctx, scene, jobs=native.JOB_ALL, flags=C):
     native.upload(ctx, scene)
     r = ctx.run_frame(scene, jobs=jobs, flags=flags)
     if flags & C:
-        fast = ctx.run_frame(scene, jobs=jobs, flags=(flags & ~C) | native.FRAME_FORCE_GRID)
-        if scene.name != "custom" and jobs & native.JOB_RAYTRACE:
-            assert fast.counters["gridUsed"] & 1, "default path did not use the grid"
-        assert_same_frame(fast, r, "grid vs brute force")
-        if r.permeation_sum is not None and fast.permeation_sum is not None:
-            scale = scene.n_rays * scene.permeation_strength_per_ray * max(1, r.counters["permHitRays"])
-            np.testing.assert_allclose(fast.permeation_sum, r.permeation_sum, rtol=0, atol=1e-5 * scale)
+        # default path: uniform grid for the bounce rays + target fans for the echo / muffle / permeation queries;
+        # then the same frame with every query walking the grid (ART_FRAME_NO_FANS)
+        for extra, what in ((0, "grid + fans"), (native.FRAME_NO_FANS, "grid walk")):
+            fast = ctx.run_frame(scene, jobs=jobs, flags=(flags & ~C) | native.FRAME_FORCE_GRID | extra)
+            if scene.name != "custom" and jobs & native.JOB_RAYTRACE:
+                assert fast.counters["gridUsed"] & 1, "default path did not use the grid"
+                assert bool(fast.counters["gridUsed"] & 4) == (extra == 0), "target fans used / not used as requested"
+            assert not fast.counters["gridUsed"] & 8, "fan build overflowed"
+            assert_same_frame(fast, r, what + " vs brute force")
+            if r.permeation_sum is not None and fast.permeation_sum is not None:
+                scale = scene.n_rays * scene.permeation_strength_per_ray * max(1, r.counters["permHitRays"])
+                np.testing.assert_allclose(fast.permeation_sum, r.permeation_sum, rtol=0, atol=1e-5 * scale, err_msg=what)
     return r
 
 
@@ -223,7 +228,7 @@ def test_determinism_and_no_counter_variant(gpu_ctx, oracle):
     # the counting frame runs the brute-force kernels: same per-ray values up to the documented tolerance
     np.testing.assert_allclose(a.permeation_sum, c.permeation_sum, rtol=0, atol=1e-5 * s.n_rays * s.n_rays)
     d = gpu_ctx.run_frame(s, flags=native.FRAME_BRUTE_FORCE)
-    assert d.counters["gridUsed"] == 0 and a.counters["gridUsed"] == 3
+    assert d.counters["gridUsed"] == 0 and a.counters["gridUsed"] == 7
     np.testing.assert_array_equal(c.permeation_sum, d.permeation_sum)
     np.testing.assert_array_equal(a.echo, d.echo)
 
@@ -351,18 +356,20 @@ def test_jobs_mirror_one_frame_latency(art_lib, oracle):
 def _grid_vs_oracle(ctx, oracle, s, expect_grid=True):
     o = oracle.run_frame(s, threads=8)
     native.upload(ctx, s)
-    g = ctx.run_frame(s, flags=native.FRAME_FORCE_GRID)    # grid kernels whatever the scene size
-    assert bool(g.counters["gridUsed"] & 1) == expect_grid
-    for k in ("hit_counts", "hit_ids", "echo", "muffle", "muffle_totals"):
-        np.testing.assert_array_equal(getattr(g, k), getattr(o, k), err_msg=k)
-    gp, op = g.hit_points.copy(), o.hit_points.copy()
-    gp[gp == 0x8000] = 0
-    op[op == 0x8000] = 0
-    np.testing.assert_array_equal(gp, op)
-    np.testing.assert_array_equal(g.permeation.view(np.uint32), o.permeation.view(np.uint32))
-    scale = max(s.n_rays * s.permeation_strength_per_ray, 50.0) * max(1, o.counters["perm_hit_rays"])
-    np.testing.assert_allclose(g.permeation_sum, o.permeation_sum, rtol=0, atol=1e-5 * scale)
-    assert g.counters["segments"] == o.counters["segments"]
+    for extra in (0, native.FRAME_NO_FANS):                    # target fans / every query walking the grid
+        g = ctx.run_frame(s, flags=native.FRAME_FORCE_GRID | extra)    # grid kernels whatever the scene size
+        assert bool(g.counters["gridUsed"] & 1) == expect_grid
+        assert bool(g.counters["gridUsed"] & 4) == (expect_grid and extra == 0) and not g.counters["gridUsed"] & 8
+        for k in ("hit_counts", "hit_ids", "echo", "muffle", "muffle_totals"):
+            np.testing.assert_array_equal(getattr(g, k), getattr(o, k), err_msg=f"{k} (flags {extra})")
+        gp, op = g.hit_points.copy(), o.hit_points.copy()
+        gp[gp == 0x8000] = 0
+        op[op == 0x8000] = 0
+        np.testing.assert_array_equal(gp, op)
+        np.testing.assert_array_equal(g.permeation.view(np.uint32), o.permeation.view(np.uint32))
+        scale = max(s.n_rays * s.permeation_strength_per_ray, 50.0) * max(1, o.counters["perm_hit_rays"])
+        np.testing.assert_allclose(g.permeation_sum, o.permeation_sum, rtol=0, atol=1e-5 * scale)
+        assert g.counters["segments"] == o.counters["segments"]
     assert g.counters["debugViolations"] == 0
     return g, o
 
@@ -416,11 +423,11 @@ def test_small_scenes_default_to_the_brute_force_kernels(gpu_ctx, oracle):
     native.upload(gpu_ctx, s)
     a = gpu_ctx.run_frame(s)
     b = gpu_ctx.run_frame(s, flags=native.FRAME_FORCE_GRID)
-    assert a.counters["gridUsed"] == 0 and b.counters["gridUsed"] == 3
+    assert a.counters["gridUsed"] == 0 and b.counters["gridUsed"] == 7
     assert_same_frame(a, b, "default vs forced grid")
     big = scenes.make_config("c2")                  # 65,536 rays: the grid kernels
     native.upload(gpu_ctx, big)
-    assert gpu_ctx.run_frame(big).counters["gridUsed"] == 3
+    assert gpu_ctx.run_frame(big).counters["gridUsed"] == 7
     small = scenes.make_config("c2", n_rays=2048)
     native.upload(gpu_ctx, small)
     assert gpu_ctx.run_frame(small).counters["gridUsed"] == 0
@@ -431,7 +438,7 @@ def test_grid_stats_are_reported(gpu_ctx):
     native.upload(gpu_ctx, s)
     c = gpu_ctx.run_frame(s, flags=native.FRAME_GRID_STATS | native.FRAME_FORCE_GRID).counters
     full = gpu_ctx.run_frame(s, flags=C).counters
-    assert c["gridUsed"] == 3 and c["gridTraceCells"] > 0 and c["gridPermCells"] > 0
+    assert c["gridUsed"] == 7 and c["gridTraceCells"] > 0 and c["gridPermCells"] > 0
     executed = sum(c["gridTraceTests"])
     scanned = sum(full["traceTests"]) + sum(full["echoTests"]) + sum(full["muffleTests"])
     assert 0 < executed < scanned / 10                     # the traversal runs a small fraction of the full scans' tests
@@ -445,7 +452,7 @@ def test_c3_full_size_grid_equals_brute_force(gpu_ctx):
     native.upload(gpu_ctx, s)
     fast = gpu_ctx.run_frame(s)
     slow = gpu_ctx.run_frame(s, flags=native.FRAME_BRUTE_FORCE)
-    assert fast.counters["gridUsed"] == 3 and slow.counters["gridUsed"] == 0
+    assert fast.counters["gridUsed"] == 7 and slow.counters["gridUsed"] == 0
     assert fast.counters["segments"] == slow.counters["segments"] == 12360709
     for k in ("hit_counts", "hit_ids", "echo", "hit_points", "muffle", "muffle_totals"):
         assert np.array_equal(getattr(fast, k), getattr(slow, k)), k
@@ -507,3 +514,22 @@ def test_small_frames_in_a_loop(gpu_ctx, oracle):
     o = oracle.run_frame(s)
     np.testing.assert_array_equal(g.echo, o.echo)
     np.testing.assert_array_equal(g.settings.view(np.uint8), o.settings.view(np.uint8))
+
+
+def test_fan_overflow_reruns_the_frame_on_the_grid_walk(oracle, monkeypatch):
+    """a fan entry buffer that is too small is detected on the device; art_complete re-runs the frame without fans (same
+    results), reports it in gridUsed bit 3 and grows the buffer so that the next frame fits"""
+    monkeypatch.setenv("ART_FAN_ENTRIES_PER_PAIR", "1")
+    s = scenes.make_config("c3", n_rays=512)
+    o = oracle.run_frame(s, threads=8)
+    with native.Context(0) as ctx:
+        native.upload(ctx, s)
+        seen = []
+        for _ in range(4):
+            g = ctx.run_frame(s, flags=native.FRAME_FORCE_GRID)
+            seen.append(g.counters["gridUsed"])
+            np.testing.assert_array_equal(g.hit_ids, o.hit_ids)
+            np.testing.assert_array_equal(g.echo, o.echo)
+            np.testing.assert_array_equal(g.muffle, o.muffle)
+            np.testing.assert_array_equal(g.permeation.view(np.uint32), o.permeation.view(np.uint32))
+        assert seen[0] & 8 and seen[-1] == 7, seen
