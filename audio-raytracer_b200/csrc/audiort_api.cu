@@ -181,7 +181,7 @@ struct ArtCtx {
     DevBuf rawScene, geom, attrs, owners, perm;    // perm: dens arrays + owned list
     HostGrid grid;                                 // uniform grid over the scene (grid_host.h)
     DevBuf gridCells, gridEntries, gridRangeO, gridScratch;
-    DevBuf fanBoxes, fanCells, fanEntries, fanCtl;  // target fans (fan_dev.cuh): collider bounds (per scene), lists (per frame)
+    DevBuf fanBoxes, fanCells, fanEntries, fanCtl, fanOrder;  // target fans (fan_dev.cuh): collider bounds (per scene), lists (per frame)
     PinBuf pinFanCtl;
     bool fansDisabled = false;                     // ART_DISABLE_FANS=1
     size_t fanEntriesPerPair = 64;                 // entry capacity = fans * colliders * this (grows after an overflow); ART_FAN_ENTRIES_PER_PAIR
@@ -442,7 +442,7 @@ ART_API void art_destroy(ArtCtx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->fanBoxes, &ctx->fanCells, &ctx->fanEntries, &ctx->fanCtl, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
+    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->fanBoxes, &ctx->fanCells, &ctx->fanEntries, &ctx->fanCtl, &ctx->fanOrder, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
                        &ctx->outAll, &ctx->firstHit, &ctx->partials, &ctx->queue })
         b->release();
     for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinAll, &ctx->pinPerm, &ctx->pinFanCtl })
@@ -684,12 +684,14 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     if (wantPM && ctx->permPreparedForTargets != Na) {
         // [dens S | dens A | dens O | ownedList] staged in pinned memory and copied asynchronously (a dynamic scene comes
         // through here every frame)
-        const size_t bytes = nPad * 8 + 16;
+        const size_t bytes = nPad * 12 + 16;      // + true densities (target-fan path)
         CK(ctx->pinPerm.ensure(bytes));
         CK(ctx->perm.ensure(bytes));
         float* dens = ctx->pinPerm.as<float>();
         int* owned = reinterpret_cast<int*>(ctx->pinPerm.as<unsigned char>() + nPad * 4);
+        float* trueDens = reinterpret_cast<float*>(ctx->pinPerm.as<unsigned char>() + nPad * 8);
         memset(dens, 0, nPad * 4);
+        memset(trueDens, 0, nPad * 4);
         int nOwned = 0;
         auto fill = [&](const std::vector<uint16_t>& raw, int words, int densWord, int sec, size_t off) {
             const size_t n = raw.size() / words;
@@ -697,11 +699,13 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
                 const int t = (int)(short)raw[i * words + words - 1];
                 if (t >= 0 && t < Na) owned[nOwned++] = (sec << 28) | (int)i;
                 else dens[off + i] = h2f(raw[i * words + densWord]);
+                trueDens[off + i] = h2f(raw[i * words + densWord]);
             }
         };
         fill(ctx->hostS, 8, 5, 0, 0); fill(ctx->hostA, 10, 7, 1, L.nsPad); fill(ctx->hostO, 13, 10, 2, (size_t)L.nsPad + L.naPad);
         ctx->nOwned = nOwned;
         CK(cudaMemcpyAsync(ctx->perm.p, ctx->pinPerm.p, nPad * 4 + (size_t)nOwned * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->perm.as<unsigned char>() + nPad * 8, trueDens, nPad * 4, cudaMemcpyHostToDevice, ctx->stream));
         ctx->permPreparedForTargets = Na;
     }
 
@@ -812,6 +816,12 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             fa.nearDist = 1e-3f * ctx->grid.d.errScale;
             fa.cells = ctx->fanCells.as<uint2>(); fa.entries = ctx->fanEntries.as<uint16_t>();
             fa.capacity = (unsigned int)cap; fa.ctl = ctx->fanCtl.as<unsigned int>();
+            fa.order = nullptr;
+            if (nc <= 16384) {                       // the per-goal sort runs in one CTA's shared memory
+                CK(ctx->fanOrder.ensure(nFans * nc * sizeof(uint32_t)));
+                fa.order = ctx->fanOrder.as<uint32_t>();
+                ctx->kernelLaunches++;
+            }
             CK(launch_fan_build(fa, ctx->stream));
             ctx->kernelLaunches++;
             fd.nFans = (int)nFans; fd.cells = fa.cells; fd.entries = fa.entries; fd.nEntries = (int)cap;
@@ -892,6 +902,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         pa.geom = ctx->geom.as<unsigned char>(); pa.L = L; pa.at = at;
         const float* dn = ctx->perm.as<float>();
         pa.densS = dn; pa.densA = dn + L.nsPad; pa.densO = dn + L.nsPad + L.naPad;
+        pa.trueDens = reinterpret_cast<const float*>(ctx->perm.as<unsigned char>() + nPad * 8);
         pa.ownedList = reinterpret_cast<const int*>(ctx->perm.as<unsigned char>() + nPad * 4);
         pa.nOwned = ctx->nOwned;
         pa.dirs = ctx->dirs.as<uint16_t>(); pa.map = map;
@@ -909,7 +920,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         pa.nextRay = reinterpret_cast<unsigned int*>(ctx->partials.as<unsigned char>() + queueOff) + 8;
         pa.raysPerWarp = perm_grid_rays_per_warp(map.nLocal, Na, ctx->numSms);
         if (useGrid) {
-            const bool gInSmem = perm_grid_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
+            const bool gInSmem = perm_grid_smem_bytes(L, true, useFans) <= (size_t)ctx->maxSmemOptin;
             CK(launch_permeation_grid(pa, gd, useFans ? &fd : nullptr, ctx->numSms, gInSmem, (prm->flags & ART_FRAME_GRID_STATS) != 0, pmStream));
             CK(launch_perm_last(pa, T, pmStream));
             ctx->frameGridUsed |= 2u;

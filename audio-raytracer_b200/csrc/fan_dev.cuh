@@ -35,7 +35,7 @@ constexpr int kFanMaxNear = 512;                     // near-list capacity per g
 struct FanDesc {
     int nFans;                 // Na + 1: fan a < Na = audio target a, fan Na = the listener (RayOrigin)
     const uint2* cells;        // [nFans * kFanCells]: x = first entry, y = nS | nA << 10 | nO << 21 (as GridDesc::cells)
-    const uint16_t* entries;   // collider indices per cell: spheres, AABBs, OBBs, ascending
+    const uint16_t* entries;   // collider indices per cell: spheres, AABBs, OBBs, each nearest to the goal first
     int nEntries;              // capacity (bounds checks of debug builds)
 };
 
@@ -53,6 +53,7 @@ struct FanBuildArgs {
     uint16_t* entries;
     unsigned int capacity;     // entries available
     unsigned int* ctl;         // [0] next free entry, [1] overflow flag (zeroed by the host before the launch)
+    uint32_t* order;           // [(nTargets + 1) * (ns + na + no)] per-goal sweep order (fan_order_kernel), or null
 };
 
 // Cell index (within one fan) of the bin that direction v (from the goal, any length) falls in.

@@ -58,6 +58,22 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
         p += a.L.bytes;
     }
     float4* rec = reinterpret_cast<float4*>(p) + warp * 32;      // (Pp.xyz, hit flag) per ray of the warp
+    p += (size_t)kPGridWarps * 32 * sizeof(float4);
+    // FAN: true densities (PM:235/245/255 skip owned colliders per TARGET; the fans leave those out of the lists, so unlike
+    // a.dens* these are not zeroed for owned colliders) -- in shared memory beside the geometry when that fits
+    const float* densS = nullptr; const float* densA = nullptr; const float* densO = nullptr;
+    if (FAN) {
+        if (SMEM) {
+            float* d = reinterpret_cast<float*>(p);
+            for (int i = threadIdx.x; i < a.L.nsPad; i += kPGridThreads) d[i] = a.at.sphAttr[i].z;
+            for (int i = threadIdx.x; i < a.L.naPad; i += kPGridThreads) d[a.L.nsPad + i] = a.at.aabbAttr[i].z;
+            for (int i = threadIdx.x; i < a.L.noPad; i += kPGridThreads) d[a.L.nsPad + a.L.naPad + i] = a.at.obbAttr[i].z;
+            __syncthreads();
+            densS = d; densA = d + a.L.nsPad; densO = d + a.L.nsPad + a.L.naPad;
+        } else {
+            densS = a.trueDens; densA = a.trueDens + a.L.nsPad; densO = a.trueDens + a.L.nsPad + a.L.naPad;
+        }
+    }
     const GeomView gv = make_view(geomBase, a.L);
     const f3 RayOrigin = mk3(a.ox, a.oy, a.oz);
     unsigned int nRays = 0, nHitRays = 0;
@@ -146,64 +162,94 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
                     float loss = 0.0f;
                     if (FAN) {
                         const int bin = fan_bin(-toT.x, -toT.y, -toT.z);       // direction target -> hit point
-                        const float tT = sqrt_fast(fmaf(toT.z, toT.z, fmaf(toT.y, toT.y, toT.x * toT.x)));   // line parameter of the target
-                        const int fanBase = tgt * kFanCells;
-                        for (int m = 0; m < 3 && bin >= 0; m++) {
-                            // m = 0: near list, whole line; 1: bin towards the hit point, t in [0, tT]; 2: opposite bin, t > tT
-                            int cell = fanBase + 6 * kFanCellsPerFace;
-                            if (m == 1) cell = fanBase + bin;
-                            if (m == 2) { const int face = bin / kFanCellsPerFace, r = bin - face * kFanCellsPerFace;
-                                          cell = fanBase + (face ^ 1) * kFanCellsPerFace + (kFanCellsPerFace - 1 - r); }
-                            const float tIn = m == 2 ? tT : 0.0f, tOut = m == 1 ? tT : pos_inf();
-                            const uint2 hdr = __ldg(&f.cells[cell]);
-                            const uint16_t* e = f.entries + hdr.x;
-                            const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
-                            if (STATS) { st[3] += nS; st[4] += nA; st[5] += nO; st[6]++; }
-                            ART_CHECK(a.counters, hdr.x + nS + nA + nO <= (unsigned)f.nEntries && tgt >= 0 && tgt < Na);
-                            for (int k = 0; k < nA; k++) {                      // PM:265-288, reference operation order
-                                const int id = __ldg(e + nS + k);
-                                ART_CHECK(a.counters, id < a.L.na);
-                                const float4 A = gv.aabbA[id];
-                                const float2 B = gv.aabbB[id];
-                                float tEnter, tExit;
-                                slab<8>(subr(A.x, Pp.x), subr(A.y, Pp.y), subr(A.z, Pp.z), subr(A.w, Pp.x), subr(B.x, Pp.y), subr(B.y, Pp.z),
-                                        inv.x, inv.y, inv.z, tEnter, tExit);
-                                const float len = clip_len(tEnter, tExit, tIn, tOut);
-                                if (len > 0.0f) loss = fmaf(len, a.at.aabbAttr[id].z, loss);
+                        if (bin >= 0) {
+                            const float tT = sqrt_fast(fmaf(toT.z, toT.z, fmaf(toT.y, toT.y, toT.x * toT.x)));   // line parameter of the target
+                            // cell 0: near list, whole line; 1: bin towards the hit point, t in [0, tT]; 2: opposite bin, t > tT
+                            const int fanBase = tgt * kFanCells;
+                            const int face = bin / kFanCellsPerFace, rb = bin - face * kFanCellsPerFace;
+                            const uint2 h0 = __ldg(&f.cells[fanBase + 6 * kFanCellsPerFace]);
+                            const uint2 h1 = __ldg(&f.cells[fanBase + bin]);
+                            const uint2 h2 = __ldg(&f.cells[fanBase + (face ^ 1) * kFanCellsPerFace + (kFanCellsPerFace - 1 - rb)]);
+                            const int nS0 = h0.y & 1023, nA0 = (h0.y >> 10) & 2047, nO0 = h0.y >> 21;
+                            const int nS1 = h1.y & 1023, nA1 = (h1.y >> 10) & 2047, nO1 = h1.y >> 21;
+                            const int nS2 = h2.y & 1023, nA2 = (h2.y >> 10) & 2047, nO2 = h2.y >> 21;
+                            if (STATS) { st[3] += nS0 + nS1 + nS2; st[4] += nA0 + nA1 + nA2; st[5] += nO0 + nO1 + nO2; st[6] += 3; }
+                            ART_CHECK(a.counters, h0.x + nS0 + nA0 + nO0 <= (unsigned)f.nEntries && h1.x + nS1 + nA1 + nO1 <= (unsigned)f.nEntries &&
+                                                  h2.x + nS2 + nA2 + nO2 <= (unsigned)f.nEntries && tgt >= 0 && tgt < Na);
+                            const float inf = pos_inf();
+                            // each type's lists of the three cells run as ONE loop (the lanes of a warp have lists of different
+                            // lengths: three loops instead of nine), the next index is fetched while the current collider is tested
+                            {   // ---- AABBs, PM:265-288 in the reference's operation order
+                                const int n01 = nA0 + nA1, n = n01 + nA2;
+                                const uint16_t* p0 = f.entries + h0.x + nS0;
+                                const uint16_t* p1 = f.entries + h1.x + nS1 - nA0;
+                                const uint16_t* p2 = f.entries + h2.x + nS2 - n01;
+                                int nxt = n > 0 ? (int)__ldg((0 < nA0 ? p0 : (0 < n01 ? p1 : p2))) : 0;
+                                for (int k = 0; k < n; k++) {
+                                    const int id = nxt;
+                                    const int k1 = k + 1;
+                                    if (k1 < n) nxt = (int)__ldg((k1 < nA0 ? p0 : (k1 < n01 ? p1 : p2)) + k1);
+                                    ART_CHECK(a.counters, id < a.L.na);
+                                    const float tIn = k >= n01 ? tT : 0.0f, tOut = (k >= nA0 && k < n01) ? tT : inf;
+                                    const float4 A = gv.aabbA[id];
+                                    const float2 B = gv.aabbB[id];
+                                    float tEnter, tExit;
+                                    slab<8>(subr(A.x, Pp.x), subr(A.y, Pp.y), subr(A.z, Pp.z), subr(A.w, Pp.x), subr(B.x, Pp.y), subr(B.y, Pp.z),
+                                            inv.x, inv.y, inv.z, tEnter, tExit);
+                                    const float len = clip_len(tEnter, tExit, tIn, tOut);
+                                    if (len > 0.0f) loss = fmaf(len, densA[id], loss);
+                                }
                             }
-                            for (int k = 0; k < nS; k++) {                      // PM:303-328 (unit direction)
-                                const int id = __ldg(e + k);
-                                ART_CHECK(a.counters, id < a.L.ns);
-                                const float4 s = gv.sph[id];
-                                const f3 oc = sub3(Pp, mk3(s.x, s.y, s.z));
-                                const float cc = subr(dot3(oc, oc), s.w);
-                                float b;
-                                if (sphere_loss_fast_miss(oc, cc, dir, b)) continue;   // disc < 0 (PM:311)
-                                const float sq = sqrtr(subr(mulr(b, b), cc));
-                                const float len = clip_len(subr(-b, sq), addr(-b, sq), tIn, tOut);
-                                if (len > 0.0f) loss = fmaf(len, a.at.sphAttr[id].z, loss);
+                            {   // ---- spheres, PM:303-328 (unit direction)
+                                const int n01 = nS0 + nS1, n = n01 + nS2;
+                                const uint16_t* p0 = f.entries + h0.x;
+                                const uint16_t* p1 = f.entries + h1.x - nS0;
+                                const uint16_t* p2 = f.entries + h2.x - n01;
+                                for (int k = 0; k < n; k++) {
+                                    const int id = (int)__ldg((k < nS0 ? p0 : (k < n01 ? p1 : p2)) + k);
+                                    ART_CHECK(a.counters, id < a.L.ns);
+                                    const float tIn = k >= n01 ? tT : 0.0f, tOut = (k >= nS0 && k < n01) ? tT : inf;
+                                    const float4 sp = gv.sph[id];
+                                    const f3 oc = sub3(Pp, mk3(sp.x, sp.y, sp.z));
+                                    const float cc = subr(dot3(oc, oc), sp.w);
+                                    float b;
+                                    if (sphere_loss_fast_miss(oc, cc, dir, b)) continue;   // disc < 0 (PM:311)
+                                    const float sq = sqrtr(subr(mulr(b, b), cc));
+                                    const float len = clip_len(subr(-b, sq), addr(-b, sq), tIn, tOut);
+                                    if (len > 0.0f) loss = fmaf(len, densS[id], loss);
+                                }
                             }
-                            for (int k = 0; k < nO; k++) {                      // PM:294-300 (stored rotation as is)
-                                const int id = __ldg(e + nS + nA + k);
-                                ART_CHECK(a.counters, id < a.L.no);
-                                const float4 c4 = gv.obbC[id];
-                                const float2 h2 = gv.obbH[id];
-                                const f3 pc = mk3(Pp.x - c4.x, Pp.y - c4.y, Pp.z - c4.z);
-                                const float bq = fmaf(pc.z, dir.z, fmaf(pc.y, dir.y, pc.x * dir.x));
-                                const float pp = fmaf(pc.z, pc.z, fmaf(pc.y, pc.y, pc.x * pc.x));
-                                const float r2 = fmaf(h2.y, h2.y, fmaf(h2.x, h2.x, c4.w * c4.w));
-                                if (pp - bq * bq > r2 * 1.001f + 1e-4f) continue;   // the line passes the bounding sphere
-                                const float4 q4 = gv.obbQ[id];
-                                const f3 pn = mk3(fmaf(dir.x, -bq, pc.x), fmaf(dir.y, -bq, pc.y), fmaf(dir.z, -bq, pc.z));
-                                const f3 lo = qrot_fast(q4, pn), ld = qrot_fast(q4, dir);
-                                const float rx = rcp_fast(ld.x), ry = rcp_fast(ld.y), rz = rcp_fast(ld.z);
-                                const float ax = (-c4.w - lo.x) * rx, bx = (c4.w - lo.x) * rx;
-                                const float ay = (-h2.x - lo.y) * ry, by = (h2.x - lo.y) * ry;
-                                const float az = (-h2.y - lo.z) * rz, bz = (h2.y - lo.z) * rz;
-                                const float tEnter = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)) - bq;
-                                const float tExit = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) - bq;
-                                const float len = clip_len(tEnter, tExit, tIn, tOut);
-                                if (len > 0.0f) loss = fmaf(len, a.at.obbAttr[id].z, loss);
+                            {   // ---- OBBs, PM:294-300 (stored rotation as is), cheap arithmetic about the point of closest approach
+                                const int n01 = nO0 + nO1, n = n01 + nO2;
+                                const uint16_t* p0 = f.entries + h0.x + nS0 + nA0;
+                                const uint16_t* p1 = f.entries + h1.x + nS1 + nA1 - nO0;
+                                const uint16_t* p2 = f.entries + h2.x + nS2 + nA2 - n01;
+                                int nxt = n > 0 ? (int)__ldg((0 < nO0 ? p0 : (0 < n01 ? p1 : p2))) : 0;
+                                for (int k = 0; k < n; k++) {
+                                    const int id = nxt;
+                                    const int k1 = k + 1;
+                                    if (k1 < n) nxt = (int)__ldg((k1 < nO0 ? p0 : (k1 < n01 ? p1 : p2)) + k1);
+                                    ART_CHECK(a.counters, id < a.L.no);
+                                    const float tIn = k >= n01 ? tT : 0.0f, tOut = (k >= nO0 && k < n01) ? tT : inf;
+                                    const float4 c4 = gv.obbC[id];
+                                    const float2 h2o = gv.obbH[id];
+                                    const f3 pc = mk3(Pp.x - c4.x, Pp.y - c4.y, Pp.z - c4.z);
+                                    const float bq = fmaf(pc.z, dir.z, fmaf(pc.y, dir.y, pc.x * dir.x));
+                                    const float pp = fmaf(pc.z, pc.z, fmaf(pc.y, pc.y, pc.x * pc.x));
+                                    const float r2 = fmaf(h2o.y, h2o.y, fmaf(h2o.x, h2o.x, c4.w * c4.w));
+                                    if (pp - bq * bq > r2 * 1.001f + 1e-4f) continue;   // the line passes the bounding sphere
+                                    const float4 q4 = gv.obbQ[id];
+                                    const f3 pn = mk3(fmaf(dir.x, -bq, pc.x), fmaf(dir.y, -bq, pc.y), fmaf(dir.z, -bq, pc.z));
+                                    const f3 lo = qrot_fast(q4, pn), ld = qrot_fast(q4, dir);
+                                    const float rx = rcp_fast(ld.x), ry = rcp_fast(ld.y), rz = rcp_fast(ld.z);
+                                    const float ax = (-c4.w - lo.x) * rx, bx = (c4.w - lo.x) * rx;
+                                    const float ay = (-h2o.x - lo.y) * ry, by = (h2o.x - lo.y) * ry;
+                                    const float az = (-h2o.y - lo.z) * rz, bz = (h2o.y - lo.z) * rz;
+                                    const float tEnter = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)) - bq;
+                                    const float tExit = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) - bq;
+                                    const float len = clip_len(tEnter, tExit, tIn, tOut);
+                                    if (len > 0.0f) loss = fmaf(len, densO[id], loss);
+                                }
                             }
                         }
                     } else {
@@ -335,15 +381,15 @@ int perm_grid_rays_per_warp(int nLocal, int nTargets, int numCtas)
     return (int)(r < side ? side : (r > 32 ? 32 : r));
 }
 
-size_t perm_grid_smem_bytes(const GeomLayout& L, bool geomInSmem)
+size_t perm_grid_smem_bytes(const GeomLayout& L, bool geomInSmem, bool fans)
 {
-    return (geomInSmem ? L.bytes : 0) + (size_t)kPGridWarps * 32 * sizeof(float4);
+    return (geomInSmem ? L.bytes + (fans ? ((size_t)L.nsPad + L.naPad + L.noPad) * sizeof(float) : 0) : 0) + (size_t)kPGridWarps * 32 * sizeof(float4);
 }
 
 // fans == nullptr: the loss lines walk the grid cells instead of using the target fans
 cudaError_t launch_permeation_grid(const PermArgs& a, const GridDesc& g, const FanDesc* fans, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream)
 {
-    const size_t smem = perm_grid_smem_bytes(a.L, geomInSmem);
+    const size_t smem = perm_grid_smem_bytes(a.L, geomInSmem, fans != nullptr);
     void (*k)(const PermArgs, const GridDesc, const FanDesc) = nullptr;
     if (fans) {
         if (geomInSmem) k = stats ? permeation_grid_kernel<true, true, true> : permeation_grid_kernel<true, false, true>;

@@ -5,8 +5,9 @@
 // conservative box onto the face (a bin rectangle, or nothing), the non-empty rectangles are compacted IN
 // ORDER into shared memory, and every thread then scans the compacted chunk for the rectangles that contain
 // its bin. Pass 0 counts, a block scan + one atomicAdd reserves the CTA's span of the entry array, pass 1
-// repeats the sweep and writes the indices -- so every list is ascending and grouped by type, and its
-// content does not depend on scheduling (only its position in the entry array does).
+// repeats the sweep and writes the indices -- so every list is grouped by type and ordered like the sweep
+// (fan_order_kernel: nearest to the goal first), and its content does not depend on scheduling (only its
+// position in the entry array does).
 #include "device_util.cuh"
 #include "fan_dev.cuh"
 #include "launchers.h"
@@ -55,6 +56,48 @@ __device__ __forceinline__ uint32_t fan_rect(const float lo[3], const float hi[3
     return a0 | (a1 << 8) | (b0 << 16) | (b1 << 24);
 }
 
+// Per goal: the colliders sorted by (type, distance of their box from the goal, index). The build sweeps them in this
+// order, so every list comes out grouped by type and nearest-first: a collider close to the goal subtends more of the
+// bin and lies between the goal and more hit points, hence an any-hit query (K1) finds its blocker in the first entries.
+// One CTA per goal, bitonic sort of 64-bit (key, index) pairs in shared memory.
+__global__ void __launch_bounds__(1024, 1) fan_order_kernel(const FanBuildArgs a, int nPow2)
+{
+    extern __shared__ unsigned long long sKeys[];
+    const int fan = blockIdx.x, tid = threadIdx.x;
+    const int nc = a.ns + a.na + a.no;
+    float T[3];
+    if (fan < a.nTargets) { T[0] = a.targets[3 * fan]; T[1] = a.targets[3 * fan + 1]; T[2] = a.targets[3 * fan + 2]; }
+    else { T[0] = a.lx; T[1] = a.ly; T[2] = a.lz; }
+    for (int g = tid; g < nPow2; g += 1024) {
+        unsigned long long key = ~0ull;
+        if (g < nc) {
+            const float4 l4 = a.boxLo[g], h4 = a.boxHi[g];
+            const float dx = fmaxf(fmaxf(l4.x - T[0], T[0] - h4.x), 0.0f), dy = fmaxf(fmaxf(l4.y - T[1], T[1] - h4.y), 0.0f),
+                        dz = fmaxf(fmaxf(l4.z - T[2], T[2] - h4.z), 0.0f);
+            float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (!(d2 >= 0.0f)) d2 = 0.0f;
+            const uint32_t type = g < a.ns ? 0u : (g < a.ns + a.na ? 1u : 2u);
+            key = ((unsigned long long)((type << 30) | (__float_as_uint(d2) >> 2)) << 32) | (uint32_t)g;
+        }
+        sKeys[g] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= nPow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < nPow2; i += 1024) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const unsigned long long x = sKeys[i], y = sKeys[p];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { sKeys[i] = y; sKeys[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int g = tid; g < nc; g += 1024) a.order[(size_t)fan * nc + g] = (uint32_t)(sKeys[g] & 0xFFFFFFFFull);
+}
+
 __global__ void __launch_bounds__(kFanCellsPerFace, 1) fan_build_kernel(const FanBuildArgs a)
 {
     static_assert(kFanCellsPerFace == 1024 && kFanBins == 32, "one thread per bin, one warp per bin row");
@@ -85,10 +128,10 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 1) fan_build_kernel(const Fa
     int nearTotal = 0;
     for (int pass = 0; pass < 2; pass++) {
         for (int base = 0; base < nc; base += 1024) {
-            const int g = base + tid;
             uint32_t rect = kRectEmpty, idT = 0;
             bool near = false;
-            if (g < nc) {
+            if (base + tid < nc) {
+                const int g = a.order ? (int)a.order[(size_t)fan * nc + base + tid] : base + tid;
                 int type, id; short owner;
                 if (g < a.ns) { type = 0; id = g; owner = a.ownS[id]; }
                 else if (g < a.ns + a.na) { type = 1; id = g - a.ns; owner = a.ownA[id]; }
@@ -179,9 +222,20 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 1) fan_build_kernel(const Fa
     }
 }
 
+// a.order (may be null: canonical order) needs (nTargets + 1) * (ns + na + no) words
 cudaError_t launch_fan_build(const FanBuildArgs& a, cudaStream_t stream)
 {
     const int nFans = a.nTargets + 1;
+    const int nc = a.ns + a.na + a.no;
+    if (a.order) {
+        int nPow2 = 2;
+        while (nPow2 < nc) nPow2 <<= 1;
+        const size_t smem = (size_t)nPow2 * sizeof(unsigned long long);
+        cudaError_t e = cudaFuncSetAttribute(fan_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        fan_order_kernel<<<nFans, 1024, smem, stream>>>(a, nPow2);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
     fan_build_kernel<<<dim3(6, nFans), kFanCellsPerFace, 0, stream>>>(a);
     return cudaGetLastError();
 }

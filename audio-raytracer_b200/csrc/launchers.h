@@ -17,7 +17,7 @@ cudaError_t launch_fan_build(const FanBuildArgs& a, cudaStream_t stream);
 size_t perm_smem_bytes(const GeomLayout& L, bool geomInSmem);
 cudaError_t launch_permeation(const PermArgs& a, int numCtas, bool geomInSmem, int T, cudaStream_t stream);
 cudaError_t launch_perm_last(const PermArgs& a, int T, cudaStream_t stream);
-size_t perm_grid_smem_bytes(const GeomLayout& L, bool geomInSmem);
+size_t perm_grid_smem_bytes(const GeomLayout& L, bool geomInSmem, bool fans);
 cudaError_t launch_permeation_grid(const PermArgs& a, const GridDesc& g, const FanDesc* fans, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream);
 cudaError_t launch_echo_stats(const uint16_t* echo, size_t n, EchoStats* out, bool sequential, int numSms, cudaStream_t stream);
 cudaError_t launch_fibonacci(uint16_t* dirs, int n, cudaStream_t stream);

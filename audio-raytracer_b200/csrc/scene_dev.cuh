@@ -172,6 +172,7 @@ struct PermArgs {
     GeomLayout L;
     AttrArrays at;
     const float* densS; const float* densA; const float* densO;   // padded; 0 for pads and for colliders owned by a target < Na
+    const float* trueDens;     // padded [S | A | O]: density of every collider, owned or not (target-fan path, geometry not in smem)
     const int* ownedList;      // (section << 28) | index of every collider owned by a target < Na, canonical order (host built)
     int nOwned;
     const uint16_t* dirs;
