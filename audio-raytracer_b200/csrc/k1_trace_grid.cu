@@ -342,7 +342,239 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
     return survCount;
 }
 
-template <bool SMEM, bool STATS, bool FAN>
+// ---- target-fan occlusion queries (FAN kernels, fan_dev.cuh) ---------------------------------------------
+// Every echo / muffle query ends in the listener or an audio target, so instead of walking grid cells it tests the two
+// lists its goal's fan holds for it: the goal's near list and the direction bin of (hit point - goal), AABBs first,
+// nearest to the goal first. Colliders owned by the goal's target are not in its fan (RT:413/426/439 skip them), so the
+// owner checks fall away.
+//
+// Prepare query (slot, rec): 0 = gated out (RT:168), 1 = the goal is visible without any test, 2 = lists to test.
+__device__ __forceinline__ int fan_prepare(const PoolEnv& E, int nslot, int nrec, f3& no, f3& nd, f3& ninv, float& nL, uint2& hN, uint2& hB)
+{
+    const TraceArgs& a = E.a;
+    const HitRec r = E.rec[nrec];
+    no = mk3(r.px, r.py, r.pz);
+    f3 T = E.RayOrigin;
+    if (nslot > 0) T = mk3(a.targets[3 * (nslot - 1)], a.targets[3 * (nslot - 1) + 1], a.targets[3 * (nslot - 1) + 2]);
+    const f3 v = sub3(T, no);                                      // RT:127 / RT:162
+    const float len = sqrtr(dot3(v, v));
+    nd = smul3(rcpr(len), v);                                      // normalize = rsqrt(dot) * v
+    ninv = mk3(0, 0, 0); hN = make_uint2(0, 0); hB = make_uint2(0, 0);
+    if (nslot == 0) nL = r.echoL;                                  // RT:130
+    else { nL = len; if (!(nL < a.maxMuffle)) return 0; }          // RT:165, 168
+    const int bin = fan_bin(-v.x, -v.y, -v.z);                     // direction goal -> hit point
+    if (bin < 0 || len != len) return 1;                           // degenerate (hit point == goal): no test can block
+    ninv = mk3(rcpr(nd.x), rcpr(nd.y), rcpr(nd.z));
+    const int fanBase = (nslot == 0 ? a.nTargets : nslot - 1) * kFanCells;
+    hN = __ldg(&E.f.cells[fanBase + 6 * kFanCellsPerFace]);        // near list of the goal
+    hB = __ldg(&E.f.cells[fanBase + bin]);
+    return 2;
+}
+
+// First pass, full width: every (hit point, slot) query of the round is prepared by its own lane and tested against
+// the FIRST AABB of its lists -- with nearest-first lists that alone blocks most queries. The others go to the
+// survivor list (slot | rec << 16) for the pooled stages below. recOfOrd: lane of the n-th hit point of the round.
+template <bool STATS>
+__device__ __forceinline__ int fan_first_pass(const PoolEnv& E, int qFirst, int count, const int* recOfOrd)
+{
+    const TraceArgs& a = E.a;
+    int survCount = 0;
+    for (int q0 = 0; q0 < count; q0 += 32) {
+        const int q = qFirst + q0 + E.lane;
+        bool survived = false;
+        int nslot = 0, nrec = 0;
+        if (q0 + E.lane < count) {
+            const int ord = q / E.slots;
+            nslot = q - ord * E.slots;
+            if (nslot > 0) nslot = a.targetOrder[nslot - 1] + 1;
+            nrec = recOfOrd[ord];
+            ART_CHECK(a.counters, (unsigned)nrec < 32u && nslot >= 0 && nslot <= a.nTargets);
+            f3 no, nd, ninv; float nL; uint2 hN, hB;
+            const int state = fan_prepare(E, nslot, nrec, no, nd, ninv, nL, hN, hB);
+            if (state == 1) query_visible(E, nslot, nrec, nL);
+            if (state == 2) {
+                const int nS0 = hN.y & 1023, nA0 = (hN.y >> 10) & 2047, nS1 = hB.y & 1023, nA1 = (hB.y >> 10) & 2047;
+                if (STATS) E.st[3] += 2;
+                bool blocked = false;
+                if (nA0 + nA1 > 0) {
+                    const int id = __ldg(nA0 > 0 ? E.f.entries + hN.x + nS0 : E.f.entries + hB.x + nS1);
+                    ART_CHECK(a.counters, id < a.L.na);
+                    if (STATS) E.st[1]++;
+                    blocked = aabb_blocks(E.gv, id, no, ninv, nL);
+                }
+                if (!blocked) {
+                    const bool more = nA0 + nA1 > 1 || (nS0 | nS1 | (hN.y >> 21) | (hB.y >> 21)) != 0;
+                    if (more) survived = true;
+                    else query_visible(E, nslot, nrec, nL);
+                }
+            }
+        }
+        const uint32_t push = __ballot_sync(kFull, survived);
+        if (push) {
+            ART_CHECK(a.counters, survCount + __popc(push) <= kChunkQ);
+            if (survived) E.surv[survCount + __popc(push & E.ltMask)] = (uint32_t)nslot | ((uint32_t)nrec << 16);
+            survCount += __popc(push);
+        }
+    }
+    __syncwarp();
+    return survCount;
+}
+
+// Pooled stages over the survivor list (read and, in stage 0, rewritten in place: a survivor is only ever written below
+// the entries already read). Queries are PREPARED 32 at a time by the whole warp -- including both list headers, so the
+// loads of 32 queries are in flight together -- and CONSUMED by whichever lanes are idle, a bounded slice per step.
+//   STAGE 0: the AABB lists (near list, then bin), skipping the first AABB (tested by fan_first_pass).
+//   STAGE 1: the sphere and OBB lists.
+template <int STAGE, bool STATS>
+__device__ __forceinline__ int run_pool_fan(const PoolEnv& E, int count)
+{
+    const TraceArgs& a = E.a;
+    const GeomView& gv = E.gv;
+    const int lane = E.lane;
+    const uint32_t ltMask = E.ltMask;
+    const uint16_t* const ebase = E.f.entries;
+    int nextQ = 0, bufNext = 0, bufCount = 0, survCount = 0;
+    bool have = false;
+    f3 qo = mk3(0, 0, 0), qd = mk3(0, 0, 0), qinv = mk3(0, 0, 0);
+    float qL = 0.0f, qdd = 0.0f;
+    uint32_t qpacked = 0;
+    uint2 hdr = make_uint2(0, 0), hdr0 = make_uint2(0, 0), hdr1 = make_uint2(0, 0);
+    int fPos = 2;                     // next of the two lists to open (2 = none left)
+    bool skipA = false, anySO = false;
+    int kA = 0, kB = 0, kC = 0;       // cursors inside the current lists: AABB, sphere, OBB
+    for (;;) {
+        const uint32_t idle = __ballot_sync(kFull, !have);
+        if (idle) {
+            if (bufNext == bufCount && nextQ < count) {
+                // ---- prepare the next 32 queries (all lanes)
+                const int qi = nextQ + lane;
+                nextQ += 32;
+                bool active = false;
+                f3 no, nd = mk3(0, 0, 0), ninv = mk3(0, 0, 0);
+                float nL = 0.0f;
+                uint2 hN = make_uint2(0, 0), hB = make_uint2(0, 0);
+                uint32_t packed = 0;
+                if (qi < count) {
+                    packed = E.surv[qi];
+                    const int nslot = (int)(packed & 0xFFFFu), nrec = (int)(packed >> 16);
+                    ART_CHECK(a.counters, (unsigned)nrec < 32u && nslot >= 0 && nslot <= a.nTargets);
+                    const int state = fan_prepare(E, nslot, nrec, no, nd, ninv, nL, hN, hB);
+                    active = state == 2;
+                    if (state == 1) query_visible(E, nslot, nrec, nL);
+                }
+                const uint32_t act = __ballot_sync(kFull, active);
+                if (active) {
+                    const int pos = __popc(act & ltMask);
+                    E.qbuf0[pos] = make_float4(nd.x, nd.y, nd.z, nL);
+                    E.qbuf1[pos] = make_float4(ninv.x, ninv.y, ninv.z, __uint_as_float(packed));
+                    E.qbuf2[pos] = make_float4(__uint_as_float(hN.x), __uint_as_float(hN.y), __uint_as_float(hB.x), __uint_as_float(hB.y));
+                }
+                bufNext = 0;
+                bufCount = __popc(act);
+                __syncwarp();
+            }
+            if (bufNext < bufCount) {
+                // ---- idle lanes take prepared queries
+                const int pos = bufNext + __popc(idle & ltMask);
+                if (!have && pos < bufCount) {
+                    const float4 v0 = E.qbuf0[pos], v1 = E.qbuf1[pos], v2 = E.qbuf2[pos];
+                    qd = mk3(v0.x, v0.y, v0.z); qL = v0.w;
+                    qinv = mk3(v1.x, v1.y, v1.z); qpacked = __float_as_uint(v1.w);
+                    hdr0 = make_uint2(__float_as_uint(v2.x), __float_as_uint(v2.y));
+                    hdr1 = make_uint2(__float_as_uint(v2.z), __float_as_uint(v2.w));
+                    qdd = dot3(qd, qd);
+                    const HitRec r = E.rec[qpacked >> 16];
+                    qo = mk3(r.px, r.py, r.pz);
+                    anySO = ((hdr0.y & 1023) | (hdr0.y >> 21) | (hdr1.y & 1023) | (hdr1.y >> 21)) != 0;
+                    fPos = 0; skipA = STAGE == 0; kA = kB = kC = 0; hdr = make_uint2(0, 0);
+                    have = true;
+                }
+                bufNext = min(bufCount, bufNext + __popc(idle));
+                __syncwarp();
+            }
+        }
+        if (!__any_sync(kFull, have)) {
+            if (bufNext == bufCount && nextQ >= count) break;
+            continue;
+        }
+        bool survived = false;
+        if (have && STAGE == 0) {
+            bool walkDone = false;
+            for (int s = 0; s < 3; s++) {
+                if (kA < (int)((hdr.y >> 10) & 2047)) break;
+                if (fPos >= 2) { walkDone = true; break; }
+                hdr = fPos == 0 ? hdr0 : hdr1;
+                fPos++;
+                kA = 0;
+                if (skipA && ((hdr.y >> 10) & 2047) != 0) { kA = 1; skipA = false; }   // fan_first_pass tested it
+            }
+            bool blocked = false;
+            if (!walkDone) {
+                const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047;
+                const uint16_t* e = ebase + hdr.x + nS;
+                for (int c = 0; c < kCapA && kA < nA && !blocked; c++, kA++) {
+                    const int id = __ldg(e + kA);
+                    ART_CHECK(a.counters, id < a.L.na && hdr.x + nS + nA <= (unsigned)E.f.nEntries);
+                    if (STATS) E.st[1]++;
+                    blocked = aabb_blocks(gv, id, qo, qinv, qL);
+                }
+            }
+            if (blocked) {
+                have = false;
+            } else if (walkDone) {
+                have = false;
+                if (anySO) survived = true;
+                else query_visible(E, (int)(qpacked & 0xFFFFu), (int)(qpacked >> 16), qL);
+            }
+        }
+        if (have && STAGE == 1) {
+            bool walkDone = false;
+            for (int s = 0; s < 3; s++) {
+                if (kB < (int)(hdr.y & 1023) || kC < (int)(hdr.y >> 21)) break;
+                if (fPos >= 2) { walkDone = true; break; }
+                hdr = fPos == 0 ? hdr0 : hdr1;
+                fPos++;
+                kB = kC = 0;
+            }
+            bool blocked = false;
+            if (!walkDone) {
+                const uint16_t* e = ebase + hdr.x;
+                const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
+                for (int c = 0; c < kCapS && kB < nS && !blocked; c++, kB++) {
+                    const int id = __ldg(e + kB);
+                    ART_CHECK(a.counters, id < a.L.ns);
+                    if (STATS) E.st[0]++;
+                    blocked = sphere_dist(gv, id, qo, qd, qdd) < qL;
+                }
+                for (int c = 0; c < kCapO && kC < nO && !blocked; c++, kC++) {
+                    const int id = __ldg(e + nS + nA + kC);
+                    ART_CHECK(a.counters, id < a.L.no && hdr.x + nS + nA + nO <= (unsigned)E.f.nEntries);
+                    if (STATS) E.st[2]++;
+                    blocked = obb_blocks(gv, id, qo, qd, qdd, E.g.errScale, qL);
+                }
+            }
+            if (blocked) {
+                have = false;
+            } else if (walkDone) {
+                have = false;
+                query_visible(E, (int)(qpacked & 0xFFFFu), (int)(qpacked >> 16), qL);   // every list tested: the ray sees its goal
+            }
+        }
+        if (STAGE == 0) {
+            const uint32_t push = __ballot_sync(kFull, survived);
+            if (push) {
+                if (survived) E.surv[survCount + __popc(push & ltMask)] = qpacked;
+                survCount += __popc(push);
+            }
+        }
+    }
+    __syncwarp();
+    return survCount;
+}
+
+// FAN: 0 = every occlusion query walks the grid; 1 = target fans, one-pass pool (few queries per hit point); 2 = target
+// fans, full-width first pass + pooled stages (many queries per hit point)
+template <bool SMEM, bool STATS, int FAN>
 __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const TraceArgs a, const GridDesc g, const FanDesc f)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -495,12 +727,24 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
             const int total = __popc(hitMask) * slots;
             const PoolEnv E = { a, g, f, gv, rec, qbuf0, qbuf1, qbuf2, qbuf3, surv, RayOrigin, hitMask, slots, lane, ltMask, st };
             const bool noSO = a.L.ns + a.L.no == 0;
-            for (int q0 = 0; q0 < total; q0 += kChunkQ) {
-                if (slots >= kTwoStageSlots) {
-                    const int nSurv = run_pool<0, STATS, FAN>(E, q0, min(kChunkQ, total - q0), noSO);
-                    if (nSurv > 0) run_pool<1, STATS, FAN>(E, 0, nSurv, noSO);
-                } else {
-                    run_pool<2, STATS, FAN>(E, q0, min(kChunkQ, total - q0), noSO);   // few queries per hit point: one pass over all types
+            if (FAN == 1) {
+                for (int q0 = 0; q0 < total; q0 += kChunkQ) run_pool<2, STATS, true>(E, q0, min(kChunkQ, total - q0), noSO);
+            } else if (FAN == 2) {
+                if (hit) qbuf3[__popc(hitMask & ltMask)] = lane;       // lane of the n-th hit point of the round
+                __syncwarp();
+                for (int q0 = 0; q0 < total; q0 += kChunkQ) {          // (the survivor list holds kChunkQ queries)
+                    const int n0 = fan_first_pass<STATS>(E, q0, min(kChunkQ, total - q0), qbuf3);
+                    const int n1 = n0 > 0 ? run_pool_fan<0, STATS>(E, n0) : 0;
+                    if (n1 > 0) run_pool_fan<1, STATS>(E, n1);
+                }
+            } else {
+                for (int q0 = 0; q0 < total; q0 += kChunkQ) {
+                    if (slots >= kTwoStageSlots) {
+                        const int nSurv = run_pool<0, STATS, false>(E, q0, min(kChunkQ, total - q0), noSO);
+                        if (nSurv > 0) run_pool<1, STATS, false>(E, 0, nSurv, noSO);
+                    } else {
+                        run_pool<2, STATS, false>(E, q0, min(kChunkQ, total - q0), noSO);   // few queries per hit point: one pass over all types
+                    }
                 }
             }
         }
@@ -592,12 +836,16 @@ cudaError_t launch_trace_grid(const TraceArgs& a, const GridDesc& g, const FanDe
 {
     const size_t smem = trace_grid_smem_bytes(a.L, geomInSmem);
     void (*k)(const TraceArgs, const GridDesc, const FanDesc) = nullptr;
-    if (fans) {
-        if (geomInSmem) k = stats ? trace_grid_kernel<true, true, true> : trace_grid_kernel<true, false, true>;
-        else k = stats ? trace_grid_kernel<false, true, true> : trace_grid_kernel<false, false, true>;
+    const int mode = !fans ? 0 : (a.nTargets + 1 >= kTwoStageSlots ? 2 : 1);
+    if (mode == 2) {
+        if (geomInSmem) k = stats ? trace_grid_kernel<true, true, 2> : trace_grid_kernel<true, false, 2>;
+        else k = stats ? trace_grid_kernel<false, true, 2> : trace_grid_kernel<false, false, 2>;
+    } else if (mode == 1) {
+        if (geomInSmem) k = stats ? trace_grid_kernel<true, true, 1> : trace_grid_kernel<true, false, 1>;
+        else k = stats ? trace_grid_kernel<false, true, 1> : trace_grid_kernel<false, false, 1>;
     } else {
-        if (geomInSmem) k = stats ? trace_grid_kernel<true, true, false> : trace_grid_kernel<true, false, false>;
-        else k = stats ? trace_grid_kernel<false, true, false> : trace_grid_kernel<false, false, false>;
+        if (geomInSmem) k = stats ? trace_grid_kernel<true, true, 0> : trace_grid_kernel<true, false, 0>;
+        else k = stats ? trace_grid_kernel<false, true, 0> : trace_grid_kernel<false, false, 0>;
     }
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -165,12 +165,20 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 1) fan_build_kernel(const Fa
                 if (pos < kFanMaxNear) sNear[pos] = idT;
             }
             __syncthreads();
-            for (int c = 0; c < M; c++) {
-                const uint32_t r = sRect[c];
-                if (ia >= (r & 255u) && ia <= ((r >> 8) & 255u) && ib >= ((r >> 16) & 255u) && ib <= (r >> 24)) {
-                    const uint32_t e = sIdT[c];
-                    if (pass == 0) { const uint32_t t = e >> 16; cS += t == 0; cA += t == 1; cO += t == 2; }
-                    else a.entries[wpos++] = (uint16_t)(e & 0xFFFFu);
+            // a warp owns one bin row: its lanes first pick, 32 rectangles at a time, the ones that overlap the row,
+            // then every lane checks its own column against those only (in order)
+            for (int c0 = 0; c0 < M; c0 += 32) {
+                const uint32_t r = c0 + lane < M ? sRect[c0 + lane] : kRectEmpty;
+                uint32_t rows = __ballot_sync(kFull, ib >= ((r >> 16) & 255u) && ib <= (r >> 24) && (r & 255u) <= ((r >> 8) & 255u));
+                while (rows) {
+                    const int j = __ffs(rows) - 1;
+                    rows &= rows - 1;
+                    const uint32_t rj = __shfl_sync(kFull, r, j);
+                    if (ia >= (rj & 255u) && ia <= ((rj >> 8) & 255u)) {
+                        const uint32_t e = sIdT[c0 + j];
+                        if (pass == 0) { const uint32_t t = e >> 16; cS += t == 0; cA += t == 1; cO += t == 2; }
+                        else a.entries[wpos++] = (uint16_t)(e & 0xFFFFu);
+                    }
                 }
             }
             __syncthreads();

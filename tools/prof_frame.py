@@ -22,12 +22,15 @@ def main():
     ap.add_argument("--seq", action="store_true")
     ap.add_argument("--force-grid", action="store_true")
     ap.add_argument("--brute", action="store_true")
+    ap.add_argument("--muffle-dist", type=float, default=None, help="override MaxMuffleHitDistance (0 gates every muffle ray out)")
     ap.add_argument("--no-fans", action="store_true", help="grid kernels: every query walks the grid (no target fans)")
     ap.add_argument("--stats", action="store_true", help="ART_FRAME_GRID_STATS: tests / cells the grid kernels execute")
     ap.add_argument("--outputs", action="store_true", help="also produce hit points / ids / counts and copy everything back")
     a = ap.parse_args()
     build.build()
     s = scenes.make_config(a.workload, n_rays=a.rays)
+    if a.muffle_dist is not None:
+        s.max_muffle_hit_distance = a.muffle_dist
     flags = (0 if a.outputs else native.FRAME_NO_HOST_OUTPUTS) | (native.FRAME_COUNTERS if a.counters else 0) | (native.FRAME_REVERB_SEQ_FP32 if a.seq else 0)
     flags |= (native.FRAME_FORCE_GRID if a.force_grid else 0) | (native.FRAME_BRUTE_FORCE if a.brute else 0)
     flags |= (native.FRAME_NO_FANS if a.no_fans else 0) | (native.FRAME_GRID_STATS if a.stats else 0)
