@@ -343,6 +343,10 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
 }
 
 // ---- target-fan occlusion queries (FAN kernels, fan_dev.cuh) ---------------------------------------------
+#ifndef ART_FAN_FIRST_TESTS
+#define ART_FAN_FIRST_TESTS 2
+#endif
+constexpr int kFanFirstTests = ART_FAN_FIRST_TESTS;   // AABBs every query tests in the full-width first pass
 // Every echo / muffle query ends in the listener or an audio target, so instead of walking grid cells it tests the two
 // lists its goal's fan holds for it: the goal's near list and the direction bin of (hit point - goal), AABBs first,
 // nearest to the goal first. Colliders owned by the goal's target are not in its fan (RT:413/426/439 skip them), so the
@@ -372,20 +376,23 @@ __device__ __forceinline__ int fan_prepare(const PoolEnv& E, int nslot, int nrec
 }
 
 // First pass, full width: every (hit point, slot) query of the round is prepared by its own lane and tested against
-// the FIRST AABB of its lists -- with nearest-first lists that alone blocks most queries. The others go to the
+// the first kFanFirstTests AABBs of its lists -- with nearest-first lists that alone blocks most queries. The others go to the
 // survivor list (slot | rec << 16) for the pooled stages below. recOfOrd: lane of the n-th hit point of the round.
 template <bool STATS>
 __device__ __forceinline__ int fan_first_pass(const PoolEnv& E, int qFirst, int count, const int* recOfOrd)
 {
     const TraceArgs& a = E.a;
+    const float invSlots = 1.0f / (float)E.slots;
     int survCount = 0;
     for (int q0 = 0; q0 < count; q0 += 32) {
         const int q = qFirst + q0 + E.lane;
         bool survived = false;
         int nslot = 0, nrec = 0;
         if (q0 + E.lane < count) {
-            const int ord = q / E.slots;
+            int ord = (int)((float)q * invSlots);                  // q < 2^24: the product is within one of q / slots
             nslot = q - ord * E.slots;
+            if (nslot < 0) { ord--; nslot += E.slots; }
+            else if (nslot >= E.slots) { ord++; nslot -= E.slots; }
             if (nslot > 0) nslot = a.targetOrder[nslot - 1] + 1;
             nrec = recOfOrd[ord];
             ART_CHECK(a.counters, (unsigned)nrec < 32u && nslot >= 0 && nslot <= a.nTargets);
@@ -396,14 +403,17 @@ __device__ __forceinline__ int fan_first_pass(const PoolEnv& E, int qFirst, int 
                 const int nS0 = hN.y & 1023, nA0 = (hN.y >> 10) & 2047, nS1 = hB.y & 1023, nA1 = (hB.y >> 10) & 2047;
                 if (STATS) E.st[3] += 2;
                 bool blocked = false;
-                if (nA0 + nA1 > 0) {
-                    const int id = __ldg(nA0 > 0 ? E.f.entries + hN.x + nS0 : E.f.entries + hB.x + nS1);
+                const uint16_t* eN = E.f.entries + hN.x + nS0;
+                const uint16_t* eB = E.f.entries + hB.x + nS1 - nA0;
+                const int nFirst = min(nA0 + nA1, kFanFirstTests);
+                for (int t = 0; t < nFirst && !blocked; t++) {
+                    const int id = __ldg((t < nA0 ? eN : eB) + t);
                     ART_CHECK(a.counters, id < a.L.na);
                     if (STATS) E.st[1]++;
                     blocked = aabb_blocks(E.gv, id, no, ninv, nL);
                 }
                 if (!blocked) {
-                    const bool more = nA0 + nA1 > 1 || (nS0 | nS1 | (hN.y >> 21) | (hB.y >> 21)) != 0;
+                    const bool more = nA0 + nA1 > kFanFirstTests || (nS0 | nS1 | (hN.y >> 21) | (hB.y >> 21)) != 0;
                     if (more) survived = true;
                     else query_visible(E, nslot, nrec, nL);
                 }
@@ -423,7 +433,7 @@ __device__ __forceinline__ int fan_first_pass(const PoolEnv& E, int qFirst, int 
 // Pooled stages over the survivor list (read and, in stage 0, rewritten in place: a survivor is only ever written below
 // the entries already read). Queries are PREPARED 32 at a time by the whole warp -- including both list headers, so the
 // loads of 32 queries are in flight together -- and CONSUMED by whichever lanes are idle, a bounded slice per step.
-//   STAGE 0: the AABB lists (near list, then bin), skipping the first AABB (tested by fan_first_pass).
+//   STAGE 0: the AABB lists (near list, then bin), skipping the AABBs fan_first_pass has tested.
 //   STAGE 1: the sphere and OBB lists.
 template <int STAGE, bool STATS>
 __device__ __forceinline__ int run_pool_fan(const PoolEnv& E, int count)
@@ -440,7 +450,8 @@ __device__ __forceinline__ int run_pool_fan(const PoolEnv& E, int count)
     uint32_t qpacked = 0;
     uint2 hdr = make_uint2(0, 0), hdr0 = make_uint2(0, 0), hdr1 = make_uint2(0, 0);
     int fPos = 2;                     // next of the two lists to open (2 = none left)
-    bool skipA = false, anySO = false;
+    int skipA = 0;                    // AABBs fan_first_pass has already tested
+    bool anySO = false;
     int kA = 0, kB = 0, kC = 0;       // cursors inside the current lists: AABB, sphere, OBB
     for (;;) {
         const uint32_t idle = __ballot_sync(kFull, !have);
@@ -486,7 +497,7 @@ __device__ __forceinline__ int run_pool_fan(const PoolEnv& E, int count)
                     const HitRec r = E.rec[qpacked >> 16];
                     qo = mk3(r.px, r.py, r.pz);
                     anySO = ((hdr0.y & 1023) | (hdr0.y >> 21) | (hdr1.y & 1023) | (hdr1.y >> 21)) != 0;
-                    fPos = 0; skipA = STAGE == 0; kA = kB = kC = 0; hdr = make_uint2(0, 0);
+                    fPos = 0; skipA = STAGE == 0 ? kFanFirstTests : 0; kA = kB = kC = 0; hdr = make_uint2(0, 0);
                     have = true;
                 }
                 bufNext = min(bufCount, bufNext + __popc(idle));
@@ -505,8 +516,8 @@ __device__ __forceinline__ int run_pool_fan(const PoolEnv& E, int count)
                 if (fPos >= 2) { walkDone = true; break; }
                 hdr = fPos == 0 ? hdr0 : hdr1;
                 fPos++;
-                kA = 0;
-                if (skipA && ((hdr.y >> 10) & 2047) != 0) { kA = 1; skipA = false; }   // fan_first_pass tested it
+                kA = min(skipA, (int)((hdr.y >> 10) & 2047));                       // fan_first_pass tested these
+                skipA -= kA;
             }
             bool blocked = false;
             if (!walkDone) {

@@ -181,14 +181,13 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
                             // lengths: three loops instead of nine), the next index is fetched while the current collider is tested
                             {   // ---- AABBs, PM:265-288 in the reference's operation order
                                 const int n01 = nA0 + nA1, n = n01 + nA2;
-                                const uint16_t* p0 = f.entries + h0.x + nS0;
-                                const uint16_t* p1 = f.entries + h1.x + nS1 - nA0;
-                                const uint16_t* p2 = f.entries + h2.x + nS2 - n01;
-                                int nxt = n > 0 ? (int)__ldg((0 < nA0 ? p0 : (0 < n01 ? p1 : p2))) : 0;
+                                // 32-bit entry offsets of the three lists, biased so that offset + k addresses entry k of the run
+                                const uint32_t o0 = h0.x + nS0, o1 = h1.x + nS1 - nA0, o2 = h2.x + nS2 - n01;
+                                int nxt = n > 0 ? (int)__ldg(f.entries + (0 < nA0 ? o0 : (0 < n01 ? o1 : o2))) : 0;
                                 for (int k = 0; k < n; k++) {
                                     const int id = nxt;
                                     const int k1 = k + 1;
-                                    if (k1 < n) nxt = (int)__ldg((k1 < nA0 ? p0 : (k1 < n01 ? p1 : p2)) + k1);
+                                    if (k1 < n) nxt = (int)__ldg(f.entries + ((k1 < nA0 ? o0 : (k1 < n01 ? o1 : o2)) + (uint32_t)k1));
                                     ART_CHECK(a.counters, id < a.L.na);
                                     const float tIn = k >= n01 ? tT : 0.0f, tOut = (k >= nA0 && k < n01) ? tT : inf;
                                     const float4 A = gv.aabbA[id];
@@ -202,11 +201,9 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
                             }
                             {   // ---- spheres, PM:303-328 (unit direction)
                                 const int n01 = nS0 + nS1, n = n01 + nS2;
-                                const uint16_t* p0 = f.entries + h0.x;
-                                const uint16_t* p1 = f.entries + h1.x - nS0;
-                                const uint16_t* p2 = f.entries + h2.x - n01;
+                                const uint32_t o0 = h0.x, o1 = h1.x - nS0, o2 = h2.x - n01;
                                 for (int k = 0; k < n; k++) {
-                                    const int id = (int)__ldg((k < nS0 ? p0 : (k < n01 ? p1 : p2)) + k);
+                                    const int id = (int)__ldg(f.entries + ((k < nS0 ? o0 : (k < n01 ? o1 : o2)) + (uint32_t)k));
                                     ART_CHECK(a.counters, id < a.L.ns);
                                     const float tIn = k >= n01 ? tT : 0.0f, tOut = (k >= nS0 && k < n01) ? tT : inf;
                                     const float4 sp = gv.sph[id];
@@ -221,14 +218,12 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
                             }
                             {   // ---- OBBs, PM:294-300 (stored rotation as is), cheap arithmetic about the point of closest approach
                                 const int n01 = nO0 + nO1, n = n01 + nO2;
-                                const uint16_t* p0 = f.entries + h0.x + nS0 + nA0;
-                                const uint16_t* p1 = f.entries + h1.x + nS1 + nA1 - nO0;
-                                const uint16_t* p2 = f.entries + h2.x + nS2 + nA2 - n01;
-                                int nxt = n > 0 ? (int)__ldg((0 < nO0 ? p0 : (0 < n01 ? p1 : p2))) : 0;
+                                const uint32_t o0 = h0.x + nS0 + nA0, o1 = h1.x + nS1 + nA1 - nO0, o2 = h2.x + nS2 + nA2 - n01;
+                                int nxt = n > 0 ? (int)__ldg(f.entries + (0 < nO0 ? o0 : (0 < n01 ? o1 : o2))) : 0;
                                 for (int k = 0; k < n; k++) {
                                     const int id = nxt;
                                     const int k1 = k + 1;
-                                    if (k1 < n) nxt = (int)__ldg((k1 < nO0 ? p0 : (k1 < n01 ? p1 : p2)) + k1);
+                                    if (k1 < n) nxt = (int)__ldg(f.entries + ((k1 < nO0 ? o0 : (k1 < n01 ? o1 : o2)) + (uint32_t)k1));
                                     ART_CHECK(a.counters, id < a.L.no);
                                     const float tIn = k >= n01 ? tT : 0.0f, tOut = (k >= nO0 && k < n01) ? tT : inf;
                                     const float4 c4 = gv.obbC[id];
