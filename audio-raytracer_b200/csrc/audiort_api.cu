@@ -186,6 +186,7 @@ struct ArtCtx {
     bool fansDisabled = false;                     // ART_DISABLE_FANS=1
     size_t fanEntriesPerPair = 64;                 // entry capacity = fans * colliders * this (grows after an overflow); ART_FAN_ENTRIES_PER_PAIR
     bool frameFans = false;                        // the frame in flight uses the fans
+    bool frameCopiedEarly = false;                 // per-ray outputs of the frame in flight travel on copyStream behind the trace job
     bool rerunning = false;                        // art_complete is re-running an overflowed frame without fans
     bool gridDisabled = false;                     // ART_DISABLE_GRID=1
     bool gridBuilt = false;                        // grid (or the decision that there is none) is current for the scene
@@ -953,6 +954,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     if (outputs) ctx->userOut = *outputs; else memset(&ctx->userOut, 0, sizeof ctx->userOut);
     ctx->map = map; ctx->frameH = H; ctx->frameNa = Na; ctx->frameT = T;
     ctx->frameFlags = prm->flags; ctx->frameJobs = prm->jobs;
+    ctx->frameCopiedEarly = copiedEarly;
     ctx->inFlight = true; ctx->frameDone = false;
     ctx->handle++;
     *outHandle = ctx->handle;
@@ -982,6 +984,22 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
     if (h != ctx->handle || h == 0) return fail(ctx, ART_E_STATE, "stale handle");
     if (!ctx->inFlight) return ctx->frameDone ? ART_OK : fail(ctx, ART_E_STATE, "no frame scheduled");
     cudaSetDevice(ctx->device);
+    // per-ray outputs reach pinned memory right after the trace job: hand them to the caller's arrays while the
+    // permeation job and the reduction are still running
+    bool perRayCopied = false;
+    auto copy_per_ray = [&]() {
+        const ArtOutputs& o = ctx->userOut;
+        const size_t nl = (size_t)ctx->map.nLocal, nh = nl * ctx->frameH;
+        const unsigned char* pb = ctx->pinAll.as<unsigned char>();
+        if (o.echoRayDistances) big_memcpy(o.echoRayDistances, pb + ctx->offEcho, nh * 2);
+        if (o.rayHitResults) big_memcpy(o.rayHitResults, pb + ctx->offHitPts, nh * 6);
+        if (o.rayHitResultCounts) big_memcpy(o.rayHitResultCounts, pb + ctx->offHitCnt, nl);
+        if (o.hitColliderIds) big_memcpy(o.hitColliderIds, pb + ctx->offHitIds, nh * 4);
+    };
+    if (ctx->frameCopiedEarly && ctx->haveUserOut && cudaEventSynchronize(ctx->evCopyDone) == cudaSuccess) {
+        copy_per_ray();
+        perRayCopied = true;
+    }
     cudaError_t e = cudaEventSynchronize(ctx->ev[5]);
     if (e != cudaSuccess) {
         ctx->poisoned = true; ctx->inFlight = false;
@@ -1010,9 +1028,9 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
         }
         ctx->inFlight = false;
         fanOverflow = true;
+        perRayCopied = false;
     }
-    const int Na = ctx->frameNa, T = ctx->frameT, H = ctx->frameH;
-    const size_t nLoc = (size_t)ctx->map.nLocal, NH = nLoc * H;
+    const int Na = ctx->frameNa, T = ctx->frameT;
     const BlobLayout bl = blob_layout(Na, T);
     BlobHeader* hh = ctx->pinPartials.as<BlobHeader>();
     hh->magic = kBlobMagic; hh->nTargets = Na; hh->batchCount = T; hh->shards = 1;
@@ -1057,15 +1075,8 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
     c.gridUsed = ctx->frameGridUsed | (fanOverflow ? 8u : 0u);
 
     // per-ray outputs: pinned staging -> caller arrays
-    const ArtOutputs& uo = ctx->userOut;
     const bool hostOut = !(ctx->frameFlags & ART_FRAME_NO_HOST_OUTPUTS);
-    if (hostOut && (ctx->frameJobs & ART_JOB_RAYTRACE) && ctx->haveUserOut) {
-        const unsigned char* pb = ctx->pinAll.as<unsigned char>();
-        if (uo.echoRayDistances) big_memcpy(uo.echoRayDistances, pb + ctx->offEcho, NH * 2);
-        if (uo.rayHitResults) big_memcpy(uo.rayHitResults, pb + ctx->offHitPts, NH * 6);
-        if (uo.rayHitResultCounts) big_memcpy(uo.rayHitResultCounts, pb + ctx->offHitCnt, nLoc);
-        if (uo.hitColliderIds) big_memcpy(uo.hitColliderIds, pb + ctx->offHitIds, NH * 4);
-    }
+    if (hostOut && (ctx->frameJobs & ART_JOB_RAYTRACE) && ctx->haveUserOut && !perRayCopied) copy_per_ray();
     ctx->lastBlob.assign(ctx->pinPartials.as<unsigned char>(), ctx->pinPartials.as<unsigned char>() + bl.bytes);
     ctx->frameDone = true;
     if (!(ctx->frameFlags & ART_FRAME_PARTIALS_ONLY) && ctx->haveUserOut) {

@@ -438,7 +438,7 @@ __device__ __forceinline__ int fan_first_pass(const PoolEnv& E, int qFirst, int 
 template <int STAGE, bool STATS>
 __device__ __forceinline__ int run_pool_fan(const PoolEnv& E, int count)
 {
-    const TraceArgs& a = E.a;
+    const TraceArgs& a = E.a; (void)a;       // (only the debug-bounds checks read it)
     const GeomView& gv = E.gv;
     const int lane = E.lane;
     const uint32_t ltMask = E.ltMask;
