@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(1024, 1) fan_order_kernel(const FanBuildArgs a
     for (int g = tid; g < nc; g += 1024) a.order[(size_t)fan * nc + g] = (uint32_t)(sKeys[g] & 0xFFFFFFFFull);
 }
 
-__global__ void __launch_bounds__(kFanCellsPerFace, 1) fan_build_kernel(const FanBuildArgs a)
+__global__ void __launch_bounds__(kFanCellsPerFace, 2) fan_build_kernel(const FanBuildArgs a)
 {
     static_assert(kFanCellsPerFace == 1024 && kFanBins == 32, "one thread per bin, one warp per bin row");
     __shared__ uint32_t sRect[1024];

@@ -213,18 +213,20 @@ def main():
         if world > 1:
             dist.barrier()
 
+    gather_out = torch.empty(world * blob_bytes, dtype=torch.uint8, device="cuda") if world > 1 else None
+
     def exchange(blob_np):
         """all-gather the per-source partial blobs (a few KB) over NCCL and merge; returns (merged, ms)."""
         if world == 1:
             return blob_np, 0.0
         mine = torch.from_numpy(blob_np).cuda()
-        out = [torch.empty_like(mine) for _ in range(world)]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        dist.all_gather(out, mine)
+        dist.all_gather_into_tensor(gather_out, mine)
         e1.record()
         torch.cuda.synchronize()
-        merged = native.merge_partials([o.cpu().numpy() for o in out])
+        allb = gather_out.cpu().numpy()
+        merged = native.merge_partials([allb[i * blob_bytes:(i + 1) * blob_bytes].copy() for i in range(world)])
         return merged, e0.elapsed_time(e1)
 
     partial_flag = native.FRAME_PARTIALS_ONLY if world > 1 else 0
