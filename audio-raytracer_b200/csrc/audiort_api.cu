@@ -1180,6 +1180,29 @@ ART_API int32_t art_grid_build_host(const ArtAABB* aabbs, int32_t nAABB, const A
     return ART_OK;
 }
 
+ART_API int32_t art_debug_get_fans(ArtCtx* ctx, ArtFanInfo* info, uint32_t* cells, int64_t cellsCapacity,
+                                   uint16_t* entries, int64_t entriesCapacity)
+{
+    if (!ctx || !info) return ART_E_ARG;
+    if (ctx->inFlight) return fail(ctx, ART_E_PENDING, "a frame is in flight");
+    if (!ctx->frameDone || !ctx->frameFans) return fail(ctx, ART_E_STATE, "the last frame did not use the target fans");
+    cudaSetDevice(ctx->device);
+    memset(info, 0, sizeof *info);
+    info->nFans = ctx->frameNa + 1; info->binsPerFace = kFanBins; info->cellsPerFan = kFanCells;
+    info->nearDist = 1e-3f * ctx->grid.d.errScale;
+    info->nCells = (int64_t)info->nFans * kFanCells;
+    info->nEntries = (int64_t)ctx->pinFanCtl.as<unsigned int>()[0];
+    if (cells) {
+        if (cellsCapacity < 2 * info->nCells) return fail(ctx, ART_E_ARG, "cells buffer too small");
+        CK(cudaMemcpy(cells, ctx->fanCells.p, (size_t)info->nCells * sizeof(uint2), cudaMemcpyDeviceToHost));
+    }
+    if (entries) {
+        if (entriesCapacity < info->nEntries) return fail(ctx, ART_E_ARG, "entries buffer too small");
+        CK(cudaMemcpy(entries, ctx->fanEntries.p, (size_t)info->nEntries * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    }
+    return ART_OK;
+}
+
 ART_API int32_t art_microbench(ArtCtx* ctx, int32_t kind, double* gops)
 {
     if (!ctx || !gops || kind < 0 || kind > 2) return ART_E_ARG;

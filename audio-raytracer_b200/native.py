@@ -28,13 +28,18 @@ EXPORTS = [
     "art_create", "art_destroy", "art_set_scene", "art_set_rays", "art_generate_fibonacci_rays", "art_get_rays",
     "art_set_ray_shard", "art_local_ray_count", "art_trace_schedule", "art_is_completed", "art_complete",
     "art_get_counters", "art_last_error", "art_partials_size", "art_get_partials", "art_partials_merge",
-    "art_finalize", "art_microbench", "art_grid_build_host",
+    "art_finalize", "art_microbench", "art_grid_build_host", "art_debug_get_fans",
 ]
 
 
 class ArtGridInfo(C.Structure):
     _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("g0", C.c_float * 3), ("g1", C.c_float * 3),
                 ("cellSize", C.c_float * 3), ("margin", C.c_float), ("nCells", C.c_int64), ("nEntries", C.c_int64)]
+
+
+class ArtFanInfo(C.Structure):
+    _fields_ = [("nFans", C.c_int32), ("binsPerFace", C.c_int32), ("cellsPerFan", C.c_int32), ("nearDist", C.c_float),
+                ("nCells", C.c_int64), ("nEntries", C.c_int64)]
 
 
 class ArtError(RuntimeError):
@@ -122,6 +127,8 @@ def load_library(path: Optional[str] = None):
     lib.art_last_error.argtypes = [vp]
     lib.art_grid_build_host.restype = i32
     lib.art_grid_build_host.argtypes = [vp, i32, vp, i32, vp, i32, C.c_float, C.POINTER(ArtGridInfo), vp, i64, vp, i64]
+    lib.art_debug_get_fans.restype = i32
+    lib.art_debug_get_fans.argtypes = [vp, C.POINTER(ArtFanInfo), vp, i64, vp, i64]
     lib.art_partials_size.restype = i64
     lib.art_partials_size.argtypes = [i32, i32]
     lib.art_get_partials.restype = i32
@@ -307,6 +314,15 @@ class Context:
         blob = np.zeros(size, np.uint8)
         self._check(self._lib.art_get_partials(self._ctx, self._handle.value, blob.ctypes.data, size))
         return blob
+
+    def get_fans(self):
+        """(info, cells uint32 [nFans, cellsPerFan, 2], entries uint16) of the target fans the last frame built."""
+        info = ArtFanInfo()
+        self._check(self._lib.art_debug_get_fans(self._ctx, C.byref(info), None, 0, None, 0))
+        cells = np.zeros(2 * info.nCells, dtype=np.uint32)
+        entries = np.zeros(max(1, info.nEntries), dtype=np.uint16)
+        self._check(self._lib.art_debug_get_fans(self._ctx, C.byref(info), cells.ctypes.data, cells.size, entries.ctypes.data, entries.size))
+        return info, cells.reshape(info.nFans, info.cellsPerFan, 2), entries
 
     def microbench(self, kind: int) -> float:
         g = C.c_double(0)

@@ -175,7 +175,9 @@ def workload_config(args, scene, world):
             "colliders": scene.n_colliders, "batch_count": scene.batch_count,
             "sharding": "none" if world == 1 else f"rays interleaved in chunks of {args.chunk} over {world} ranks",
             "l2": "flushed between steps (256 MiB write)", "reverb_reduction": "exact integer",
-            "path": "default: uniform-grid traversal, bit-identical to the brute-force scans (ART_FRAME_BRUTE_FORCE timed beside it)",
+            "path": "default: uniform-grid traversal for the bounce rays + per-frame target fans (direction-binned collider lists around the "
+                    "listener and every source) for the echo / muffle / permeation queries, fan build inside the timed region; "
+                    "bit-identical to the brute-force scans (ART_FRAME_BRUTE_FORCE timed beside it)",
             "rays_override": args.rays is not None}
 
 
@@ -331,11 +333,12 @@ def main():
         tfl = lambda flops, ms: (flops / (ms * 1e-3) / 1e12) if ms and ms > 0 else None
         if grid_used & 1:
             achieved = tfl(exec_trace_flops, trace_ms_avg)
-            kernel_name = "trace_grid_kernel (K1, default path: uniform-grid traversal)"
+            kernel_name = "trace_grid_kernel (K1, default path: uniform grid + target fans" + ("" if grid_used & 4 else " DISABLED") + ")"
             accounting = ("collider tests the kernel actually executed (ART_FRAME_GRID_STATS) x reference flops per test; "
-                          "the acceleration structure changes WHICH tests run, so the full-scan count is reported beside it "
-                          "(SURVEY 8f-4). The kernel is traversal/divergence bound, not FP32 bound: see profiles/ for issue-slot "
-                          "and lane utilisation.")
+                          "the acceleration structures change WHICH tests run (about 2.5 per occlusion query instead of the "
+                          "reference's scan), so the full-scan count is reported beside it (SURVEY 8f-4) and this fraction is "
+                          "LOW by design: the kernel's time goes into preparing 8e8 queries in exact FP32 (sqrt, 4 reciprocals "
+                          "each) and into latency, not into the tests. See profiles/ for issue-slot and lane utilisation.")
         else:
             achieved = tfl(trace_flops_local, trace_ms_avg)
             kernel_name = "trace_kernel (K1, brute force)"
@@ -365,7 +368,8 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, scene, world),
             "segments_per_step": total_segs / args.steps,
             "kernel_ms": {"trace": trace_ms_avg, "permeation": float(np.mean(perm_ms)), "reduce": float(np.mean(reduce_ms)),
-                          "partials_allgather": ex_ms_tot / args.steps},
+                          "partials_allgather": ex_ms_tot / args.steps,
+                          "note": "trace includes the per-frame fan build (fan_order_kernel + fan_build_kernel, profiles/*launches*)"},
             "wall_ms_per_step_device_mode": wall_dev_max / args.steps * 1e3,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -257,6 +257,21 @@ ART_API int32_t art_grid_build_host(const ArtAABB* aabbs, int32_t nAABB, const A
                                     const ArtSphere* spheres, int32_t nSphere, float cellScale, ArtGridInfo* info,
                                     uint32_t* cells, int64_t cellsCapacity, uint16_t* entries, int64_t entriesCapacity);
 
+/* Inspection of the target fans the last completed frame built on the device (csrc/fan_dev.cuh; tests, tooling):
+ * fan a < nTargets belongs to audio target a, fan nTargets to the listener. Per fan there are cellsPerFan cells:
+ * 6 cube faces x binsPerFace x binsPerFace direction bins (cell = face * B*B + ib * B + ia; face = 2*axis + (negative ? 1 : 0),
+ * ia / ib = tangent-plane coordinates of the other two axes in cyclic order, mapped from [-1,1] to [0,B)) followed by the
+ * near list. cells[2*i + {0,1}] = {first entry, nS | nA << 10 | nO << 21}, entries = collider indices per cell,
+ * spheres | AABBs | OBBs, each nearest to the goal first. cells / entries may be NULL to query the sizes first.
+ * Returns ART_E_STATE when the last frame did not use the fans. */
+typedef struct ArtFanInfo {
+    int32_t nFans, binsPerFace, cellsPerFan;
+    float   nearDist;           /* colliders whose bounds come this close to the goal are in its near list */
+    int64_t nCells, nEntries;   /* nEntries: entries in use (the lists are packed in no particular cell order) */
+} ArtFanInfo;
+ART_API int32_t art_debug_get_fans(ArtCtx* ctx, ArtFanInfo* info, uint32_t* cells, int64_t cellsCapacity,
+                                   uint16_t* entries, int64_t entriesCapacity);
+
 /* Device-side FP32 issue-rate microbenchmarks used for the roofline denominator (bench.py):
  * kind 0 = un-fused FADD/FMUL, 1 = FMNMX, 2 = FFMA. Returns achieved Gop/s (lane-ops). */
 ART_API int32_t art_microbench(ArtCtx* ctx, int32_t kind, double* gops);
