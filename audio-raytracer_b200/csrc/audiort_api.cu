@@ -180,7 +180,7 @@ struct ArtCtx {
     PinBuf pinScene;
     DevBuf rawScene, geom, attrs, owners, perm;    // perm: dens arrays + owned list
     HostGrid grid;                                 // uniform grid over the scene (grid_host.h)
-    DevBuf gridCells, gridEntries, gridRangeO, gridScratch;
+    DevBuf gridCells, gridEntries, gridRangeO, gridScratch, rotateLog;
     DevBuf fanBoxes, fanCells, fanEntries, fanCtl, fanOrder;  // target fans (fan_dev.cuh): collider bounds (per scene), lists (per frame)
     PinBuf pinFanCtl;
     bool fansDisabled = false;                     // ART_DISABLE_FANS=1
@@ -193,6 +193,7 @@ struct ArtCtx {
     float gridCellScale = 1.1f;                    // ART_GRID_CELL_SCALE
     int gridMinRays = -1;                          // ART_GRID_MIN_RAYS: smaller batches use the brute-force kernels (-1: heuristic)
     uint32_t frameGridUsed = 0;
+    float lastHitFill = 0.0f;        // previous trace frame: hits / (rays x MaxHitsPerRay); ~1 = rays live all their bounces (group rotation)
     GeomLayout L{};
     bool haveScene = false, sceneDirty = false;
     int permPreparedForTargets = -1;
@@ -443,7 +444,7 @@ ART_API void art_destroy(ArtCtx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->fanBoxes, &ctx->fanCells, &ctx->fanEntries, &ctx->fanCtl, &ctx->fanOrder, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
+    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->rotateLog, &ctx->fanBoxes, &ctx->fanCells, &ctx->fanEntries, &ctx->fanCtl, &ctx->fanOrder, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
                        &ctx->outAll, &ctx->firstHit, &ctx->partials, &ctx->queue })
         b->release();
     for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinAll, &ctx->pinPerm, &ctx->pinFanCtl })
@@ -868,10 +869,21 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             ta.anyOwned[sec] = owned > 0 ? 1 : 0;
         }
         ta.scratch = nullptr;
-        ta.raysPerWarp = trace_grid_rays_per_warp(map.nLocal, Na, ctx->numSms);
+        ta.migGroups = 0; ta.migSlots = 0; ta.migFlags = nullptr; ta.migState = nullptr;
+        trace_grid_plan(map.nLocal, Na, ctx->numSms, &ta.gridWarps, &ta.raysPerWarp);
         if (useGrid) {
             CK(ctx->gridScratch.ensure(trace_grid_scratch_bytes(ctx->numSms)));
             ta.scratch = ctx->gridScratch.as<uint32_t>();
+            // small batches (a shard of a ray-sharded frame): rotate the ray groups through the warps (k1_trace_grid.cu)
+            if (!(prm->flags & ART_FRAME_GRID_STATS)) ta.migGroups = trace_grid_rotation(map.nLocal, H, ctx->numSms, ta.gridWarps, ctx->lastHitFill >= 0.9f, &ta.migSlots);
+            if (ta.migGroups > 0) {
+                const size_t flagBytes = ((size_t)ta.migSlots * sizeof(unsigned int) + 255) & ~(size_t)255;
+                CK(ctx->rotateLog.ensure(flagBytes + (size_t)ta.migSlots * 64 * sizeof(float4)));
+                ta.migFlags = ctx->rotateLog.as<unsigned int>();
+                ta.migState = reinterpret_cast<float4*>(ctx->rotateLog.as<unsigned char>() + flagBytes);
+                CK(cudaMemsetAsync(ta.migFlags, 0, flagBytes, ctx->stream));
+                ctx->frameGridUsed |= 16u;
+            }
             const bool gInSmem = trace_grid_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
             CK(launch_trace_grid(ta, gd, useFans ? &fd : nullptr, ctx->numSms, gInSmem, (prm->flags & ART_FRAME_GRID_STATS) != 0, ctx->stream));
             ctx->frameGridUsed |= 1u;
@@ -1073,6 +1085,14 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
     cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); c.d2hMs = ms;
     c.kernelLaunches = ctx->kernelLaunches;
     c.gridUsed = ctx->frameGridUsed | (fanOverflow ? 8u : 0u);
+    if (ctx->frameJobs & ART_JOB_RAYTRACE) {
+        const double slotsTotal = (double)ctx->map.nLocal * (double)ctx->frameH;
+        ctx->lastHitFill = slotsTotal > 0 ? (float)((double)c.segmentHits / slotsTotal) : 0.0f;
+    }
+    if ((ctx->frameGridUsed & 16u) && c.debugViolations != 0) {
+        ctx->frameDone = false;
+        return fail(ctx, ART_E_CUDA, "trace job: a group-rotation wait timed out (%llu); outputs are incomplete", (unsigned long long)c.debugViolations);
+    }
 
     // per-ray outputs: pinned staging -> caller arrays
     const bool hostOut = !(ctx->frameFlags & ART_FRAME_NO_HOST_OUTPUTS);

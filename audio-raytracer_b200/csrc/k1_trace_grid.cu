@@ -13,6 +13,8 @@
 // the nearest hit is the lexicographic (t, sphere<AABB<OBB, index) minimum -- "strict <, first in
 // canonical order wins" (RT:244, 257, 270) -- and an occlusion query is an "any"; the grid only skips
 // colliders whose conservative bounds the ray does not come near (grid_host.h).
+#include <cstdlib>
+
 #include "device_util.cuh"
 #include "fan_dev.cuh"
 #include "grid_dev.cuh"
@@ -29,6 +31,7 @@ constexpr int kGridWarps = ART_GRID_WARPS;
 constexpr int kGridThreads = kGridWarps * 32;
 constexpr int kQueryWords = 16;          // per prepared query in the per-warp ring (3 x float4 + uint2, padded)
 constexpr uint32_t kNoHit = 0xFFFFFFFFu;
+constexpr int kRotateSlotBytes = 64 * sizeof(float4);   // one parked group: 32 lanes x 2 float4
 #ifndef ART_CAP_A
 #define ART_CAP_A 4
 #endif
@@ -346,6 +349,9 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
 #ifndef ART_FAN_FIRST_TESTS
 #define ART_FAN_FIRST_TESTS 2
 #endif
+#ifndef ART_FIRST_PASS_ROLLED
+#define ART_FIRST_PASS_ROLLED 1
+#endif
 constexpr int kFanFirstTests = ART_FAN_FIRST_TESTS;   // AABBs every query tests in the full-width first pass
 // Every echo / muffle query ends in the listener or an audio target, so instead of walking grid cells it tests the two
 // lists its goal's fan holds for it: the goal's near list and the direction bin of (hit point - goal), AABBs first,
@@ -406,6 +412,9 @@ __device__ __forceinline__ int fan_first_pass(const PoolEnv& E, int qFirst, int 
                 const uint16_t* eN = E.f.entries + hN.x + nS0;
                 const uint16_t* eB = E.f.entries + hB.x + nS1 - nA0;
                 const int nFirst = min(nA0 + nA1, kFanFirstTests);
+#if ART_FIRST_PASS_ROLLED
+#pragma unroll 1
+#endif
                 for (int t = 0; t < nFirst && !blocked; t++) {
                     const int id = __ldg((t < nA0 ? eN : eB) + t);
                     ART_CHECK(a.counters, id < a.L.na);
@@ -585,7 +594,8 @@ __device__ __forceinline__ int run_pool_fan(const PoolEnv& E, int count)
 
 // FAN: 0 = every occlusion query walks the grid; 1 = target fans, one-pass pool (few queries per hit point); 2 = target
 // fans, full-width first pass + pooled stages (many queries per hit point)
-template <bool SMEM, bool STATS, int FAN>
+// ROT: group rotation (TraceArgs::migGroups, trace_grid_rotation) instead of the per-lane ray queue
+template <bool SMEM, bool STATS, int FAN, bool ROT>
 __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const TraceArgs a, const GridDesc g, const FanDesc f)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -623,7 +633,59 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
     unsigned int nSegments = 0, nSegHits = 0;
     unsigned int st[4] = { 0, 0, 0, 0 };          // STATS: sphere / AABB / OBB tests, cells visited (this lane)
 
+    constexpr bool rotate = ROT;
     for (;;) {
+        if (rotate) {
+            // ================= group rotation: take the oldest waiting group (fresh groups first) =================
+            // nextRay[0] = pop tickets, [1] = push tickets, [2] = finished groups. Tickets below migGroups are the fresh
+            // groups; ticket migGroups + s is the s-th parked state of the log, valid once migFlags[s] is set.
+            unsigned int h = 0;
+            if (lane == 0) h = atomicAdd(&a.nextRay[0], 1u);
+            h = __shfl_sync(kFull, h, 0);
+            hasRay = false;
+            if (h < (unsigned)a.migGroups) {
+                j = (int)h * 32 + lane;
+                if (j < a.map.nLocal) {
+                    const int rayIndex = a.map.to_global(j);
+                    row = rayIndex / a.batchSize;                              // ART:161/191 batch k
+                    d = mk3(um_f16tof32(a.dirs[3 * (size_t)rayIndex]), um_f16tof32(a.dirs[3 * (size_t)rayIndex + 1]),
+                            um_f16tof32(a.dirs[3 * (size_t)rayIndex + 2]));    // RT:94
+                    o = RayOrigin;                                             // RT:95
+                    hits = 0;                                                  // RT:97
+                    life = a.maxRayLife;                                       // RT:99
+                    hasRay = true;
+                }
+            } else {
+                const unsigned int slot = h - (unsigned)a.migGroups;
+                int ok = slot < a.migSlots ? 1 : 0;
+                if (ok && lane == 0) {
+                    const volatile unsigned int* fl = a.migFlags + slot;
+                    const volatile unsigned int* fin = a.nextRay + 2;
+                    unsigned int spins = 0;
+                    while (*fl == 0u) {
+                        if (*fin >= (unsigned)a.migGroups) { ok = 0; break; }  // every group has finished: nothing will be parked any more
+                        __nanosleep(256);
+                        if (++spins > (1u << 22)) {                            // (seconds: cannot happen; never hang the device)
+                            atomicAdd(&a.counters[C_DEBUG_VIOLATIONS], 1ull);
+                            ok = 0;
+                            break;
+                        }
+                    }
+                    __threadfence();
+                }
+                ok = __shfl_sync(kFull, ok, 0);
+                if (!ok) break;
+                const float4* sp = a.migState + (size_t)slot * 64;
+                const float4 s0 = __ldcg(sp + lane), s1 = __ldcg(sp + 32 + lane);
+                const unsigned int packed = __float_as_uint(s1.w);
+                o = mk3(s0.x, s0.y, s0.z); life = s0.w;
+                d = mk3(s1.x, s1.y, s1.z);
+                hits = (int)(packed & 255u);
+                hasRay = ((packed >> 8) & 1u) != 0;
+                j = (int)(packed >> 9) * 32 + lane;
+                row = hasRay ? a.map.to_global(j) / a.batchSize : 0;
+            }
+        } else {
         // ================= refill dead lanes from the ray queue =================
         const uint32_t dead = __ballot_sync(kFull, !hasRay && lane < a.raysPerWarp);
         if (dead && !queueEmpty) {
@@ -646,7 +708,8 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
             }
             if (base + __popc(dead) >= a.map.nLocal) queueEmpty = true;
         }
-        if (!__any_sync(kFull, hasRay)) break;
+        }
+        if (!rotate && !__any_sync(kFull, hasRay)) break;
 
         // ================= ShootRayCast (RT:225-280), one lane = one ray =================
         float best = kFloatMax;
@@ -801,6 +864,25 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
                 hasRay = false;
             }
         }
+        if (rotate) {
+            // ================= park the group for whichever warp comes next, or retire it =================
+            if (__any_sync(kFull, hasRay)) {
+                unsigned int t = 0;
+                if (lane == 0) t = atomicAdd(&a.nextRay[1], 1u);
+                t = __shfl_sync(kFull, t, 0);
+                ART_CHECK(a.counters, t < a.migSlots);
+                float4* sp = a.migState + (size_t)t * 64;
+                const unsigned int packed = (unsigned)hits | (hasRay ? 256u : 0u) | ((unsigned)(j >> 5) << 9);
+                __stcg(sp + lane, make_float4(o.x, o.y, o.z, life));
+                __stcg(sp + 32 + lane, make_float4(d.x, d.y, d.z, __uint_as_float(packed)));
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) { __threadfence(); atomicExch(&a.migFlags[t], 1u); }
+            } else if (lane == 0) {
+                __threadfence();
+                atomicAdd(&a.nextRay[2], 1u);
+            }
+        }
     }
 
     // segment counters: warp sum -> one atomic per warp
@@ -822,17 +904,51 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
 }
 
 // ---- launcher -----------------------------------------------------------------------------------
-// Lanes per warp that own a ray. With R = 32 a batch of n rays takes k = ceil(n / (32 * warps)) rounds per lane and the
-// last round is mostly empty when n is small (one shard of a ray-sharded frame); R = ceil(n / (k * warps)) fills all k
-// rounds evenly instead. At least ~256 queries are kept in a round's pool.
-int trace_grid_rays_per_warp(int nLocal, int nTargets, int numCtas)
+// Launch shape of a batch of n local rays: warps per CTA and lanes per warp that own a ray. With R = 32 a batch takes
+// k = ceil(n / (32 * warps)) rounds per lane and the last round is mostly empty when n is small (one shard of a
+// ray-sharded frame); R = ceil(n / (k * warps)) fills all k rounds evenly instead. At least ~256 queries are kept in a
+// round's pool. The warp count is always the compiled maximum: the kernel is latency bound, and trading warps for fuller
+// lanes loses at every batch size (B200, C3 shard of 131,072 rays: 24 warps x 19 lanes 5.53 ms, 14 warps x 32 lanes
+// 6.27 ms; 1M rays: 24 warps 35.5 ms, 20 warps 38.4 ms, 16 warps 42.7 ms -- tools/exp_k1_warps.py). ART_K1_WARPS (read
+// per frame) forces a smaller count for that experiment.
+void trace_grid_plan(int nLocal, int nTargets, int numCtas, int* warpsOut, int* raysPerWarpOut)
 {
-    const long long warps = (long long)numCtas * kGridWarps;
+    const char* fv = getenv("ART_K1_WARPS");
+    const int forced = fv ? atoi(fv) : 0;
+    const int w = forced >= 1 && forced <= kGridWarps ? forced : kGridWarps;
+    const long long warps = (long long)numCtas * w;
     const long long k = (nLocal + warps * 32 - 1) / (warps * 32);
     long long r = k > 0 ? (nLocal + warps * k - 1) / (warps * k) : 32;
     const long long minPool = (256 + nTargets) / (nTargets + 1);
     if (r < minPool) r = minPool;
-    return (int)(r < 1 ? 1 : (r > 32 ? 32 : r));
+    *warpsOut = w;
+    *raysPerWarpOut = (int)(r < 1 ? 1 : (r > 32 ? 32 : r));
+}
+
+// Group rotation (TraceArgs::migGroups). Without it a warp keeps its rays for all H bounces, so 4,096 groups of 32 rays on
+// 3,552 warps take 2 x H rounds on the critical path (however the lanes are filled); rotating the groups through the
+// warps after every round takes 4,096 / 3,552 x H. That is what a shard of a ray-sharded frame looks like (B200, C3 / 8:
+// 5.55 -> 4.86 ms), and it still pays at full size (C3: 35.5 -> 35.1 ms) -- but a rotating group is never refilled, so
+// where many rays die early its lanes thin out while the ray queue would keep them busy. Hence: always for batches of at
+// most 4 groups per warp (where the queue's last rounds are badly filled anyway), and for larger ones only when the
+// caller saw rays living nearly all H bounces in the previous frame of the context (`fullLivedRays`).
+// Returns the number of groups (0 = off) and the capacity of the log of parked states (a group is parked at most H - 1
+// times; 1 KB each, capped at 1 GiB). ART_K1_ROTATE=0 disables it, ART_K1_ROTATE_MAX_K overrides the groups-per-warp
+// limit (read per frame: experiment knobs).
+int trace_grid_rotation(int nLocal, int H, int numCtas, int warpsPerCta, bool fullLivedRays, unsigned int* slotsOut)
+{
+    *slotsOut = 0;
+    const char* on = getenv("ART_K1_ROTATE");
+    if (on && atoi(on) == 0) return 0;
+    const char* mk = getenv("ART_K1_ROTATE_MAX_K");
+    const long long maxK = mk ? atoll(mk) : (fullLivedRays ? 1024 : 4);
+    const long long warps = (long long)numCtas * warpsPerCta;
+    const long long groups = ((long long)nLocal + 31) / 32;
+    if (H < 2 || H > 255 || groups <= warps || groups > maxK * warps) return 0;
+    const long long slots = groups * (H - 1);
+    if (slots * (long long)kRotateSlotBytes > (1ll << 30) || groups >= (1ll << 22)) return 0;
+    *slotsOut = (unsigned int)slots;
+    return (int)groups;
 }
 
 size_t trace_grid_scratch_bytes(int numCtas) { return (size_t)numCtas * kGridWarps * kChunkQ * sizeof(uint32_t); }
@@ -848,21 +964,24 @@ cudaError_t launch_trace_grid(const TraceArgs& a, const GridDesc& g, const FanDe
     const size_t smem = trace_grid_smem_bytes(a.L, geomInSmem);
     void (*k)(const TraceArgs, const GridDesc, const FanDesc) = nullptr;
     const int mode = !fans ? 0 : (a.nTargets + 1 >= kTwoStageSlots ? 2 : 1);
-    if (mode == 2) {
-        if (geomInSmem) k = stats ? trace_grid_kernel<true, true, 2> : trace_grid_kernel<true, false, 2>;
-        else k = stats ? trace_grid_kernel<false, true, 2> : trace_grid_kernel<false, false, 2>;
-    } else if (mode == 1) {
-        if (geomInSmem) k = stats ? trace_grid_kernel<true, true, 1> : trace_grid_kernel<true, false, 1>;
-        else k = stats ? trace_grid_kernel<false, true, 1> : trace_grid_kernel<false, false, 1>;
-    } else {
-        if (geomInSmem) k = stats ? trace_grid_kernel<true, true, 0> : trace_grid_kernel<true, false, 0>;
-        else k = stats ? trace_grid_kernel<false, true, 0> : trace_grid_kernel<false, false, 0>;
-    }
+    const bool rot = a.migGroups > 0;
+    if (stats && rot) return cudaErrorInvalidValue;          // (stats frames are planned without rotation)
+#define ART_PICK(FANMODE)                                                                                              \
+    do {                                                                                                               \
+        if (stats) k = geomInSmem ? trace_grid_kernel<true, true, FANMODE, false> : trace_grid_kernel<false, true, FANMODE, false>;   \
+        else if (rot) k = geomInSmem ? trace_grid_kernel<true, false, FANMODE, true> : trace_grid_kernel<false, false, FANMODE, true>; \
+        else k = geomInSmem ? trace_grid_kernel<true, false, FANMODE, false> : trace_grid_kernel<false, false, FANMODE, false>;        \
+    } while (0)
+    if (mode == 2) ART_PICK(2);
+    else if (mode == 1) ART_PICK(1);
+    else ART_PICK(0);
+#undef ART_PICK
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     FanDesc fd{};
     if (fans) fd = *fans;
-    k<<<numCtas, kGridThreads, smem, stream>>>(a, g, fd);
+    const int warps = a.gridWarps >= 1 && a.gridWarps <= kGridWarps ? a.gridWarps : kGridWarps;
+    k<<<numCtas, warps * 32, smem, stream>>>(a, g, fd);
     return cudaGetLastError();
 }
 

@@ -10,7 +10,8 @@ size_t trace_smem_bytes(const GeomLayout& L, int nTargets, bool geomInSmem, bool
 cudaError_t launch_trace(const TraceArgs& a, int numCtas, bool geomInSmem, bool count, cudaStream_t stream);
 size_t trace_grid_smem_bytes(const GeomLayout& L, bool geomInSmem);
 size_t trace_grid_scratch_bytes(int numCtas);
-int trace_grid_rays_per_warp(int nLocal, int nTargets, int numCtas);
+void trace_grid_plan(int nLocal, int nTargets, int numCtas, int* warps, int* raysPerWarp);
+int trace_grid_rotation(int nLocal, int H, int numCtas, int warpsPerCta, bool fullLivedRays, unsigned int* slots);
 int perm_grid_rays_per_warp(int nLocal, int nTargets, int numCtas);
 cudaError_t launch_trace_grid(const TraceArgs& a, const GridDesc& g, const FanDesc* fans, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream);
 cudaError_t launch_fan_build(const FanBuildArgs& a, cudaStream_t stream);

@@ -130,6 +130,13 @@ struct TraceArgs {
     unsigned int* nextRay;         // dynamic ray queue
     uint32_t* scratch;             // grid kernel: per-warp survivor lists (trace_grid_scratch_bytes)
     int raysPerWarp;               // grid kernel: lanes of a warp that own a ray (32 unless the batch is too small to fill the GPU)
+    int gridWarps;                 // grid kernel: warps per CTA of this launch (<= ART_GRID_WARPS, trace_grid_plan)
+    // grid kernel, group rotation (small batches, trace_grid_plan): rays are dealt in fixed groups of 32 and a group changes
+    // warps after every bounce round through a log of parked group states, so that all warps advance all groups evenly
+    int migGroups;                 // > 0: rotation on, number of groups = ceil(nLocal / 32)
+    unsigned int migSlots;         // capacity of the log: migGroups * (H - 1) parked states
+    unsigned int* migFlags;        // [migSlots] 0 = not yet published (zeroed per frame)
+    float4* migState;              // [migSlots][64]: per lane (o.xyz, life), (d.xyz, hits | alive << 8 | group << 9)
     int muffleInSmem;              // per-warp shared counters fit
     int anyOwned[3];               // does any sphere / AABB / OBB belong to a target < nTargets (RT:413/426/439)
 };

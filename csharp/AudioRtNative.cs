@@ -15,6 +15,7 @@ public static unsafe class AudioRtNative
 
     public const uint JOB_RAYTRACE = 1, JOB_PERMEATION = 2, JOB_PROCESS = 4, JOB_ALL = 7;
     public const uint FRAME_COUNTERS = 1, FRAME_REVERB_SEQ_FP32 = 2, FRAME_NO_HOST_OUTPUTS = 4, FRAME_PARTIALS_ONLY = 8;
+    public const uint FRAME_BRUTE_FORCE = 16, FRAME_GRID_STATS = 32, FRAME_FORCE_GRID = 64, FRAME_NO_FANS = 128;
 
     [StructLayout(LayoutKind.Sequential)]
     public struct ArtConfig { public int abiVersion; public int device; public uint flags; public fixed int reserved[5]; }

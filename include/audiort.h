@@ -179,7 +179,8 @@ typedef struct ArtCounters {
     uint32_t kernelLaunches;    /* kernels of this library launched for the frame */
     uint32_t gridUsed;          /* bit 0: trace job used the uniform grid, bit 1: permeation job did, bit 2: the frame's
                                    goal-directed queries used the target fans, bit 3: the fan build overflowed its entry
-                                   buffer and the frame was re-run on the grid walk (the buffer grows for the next frame) */
+                                   buffer and the frame was re-run on the grid walk (the buffer grows for the next frame), bit 4: the
+                                   trace job rotated its ray groups through the warps (small batches / shards) */
     /* ART_FRAME_GRID_STATS: collider tests the grid kernels actually executed ([3] = sphere, AABB, OBB) and grid
      * cells they visited; compare with traceTests + echoTests + muffleTests / permFirstTests / permLossTests, the
      * counts of the reference's full scans */
@@ -187,7 +188,8 @@ typedef struct ArtCounters {
     uint64_t gridPermFirstTests[3];
     uint64_t gridPermLossTests[3];
     uint64_t gridTraceCells, gridPermCells;
-    uint64_t debugViolations;   /* builds with -DART_DEBUG_BOUNDS: failed index checks in the grid kernels (0 otherwise) */
+    uint64_t debugViolations;   /* builds with -DART_DEBUG_BOUNDS: failed index checks in the grid kernels (0 otherwise);
+                                   any build: a group-rotation wait that timed out (art_complete then fails) */
 } ArtCounters;
 
 /* ≙ AudioRayTracer.Awake/InitializeAudioRaytraceSystem (ART:53-87): one context per AudioRayTracer. */

@@ -459,6 +459,11 @@ def test_c3_full_size_grid_equals_brute_force(gpu_ctx):
     np.testing.assert_array_equal(fast.permeation.view(np.uint32), slow.permeation.view(np.uint32))
     np.testing.assert_array_equal(fast.settings.view(np.uint8), slow.settings.view(np.uint8))
     np.testing.assert_allclose(fast.permeation_sum, slow.permeation_sum, rtol=1e-9, atol=1e-5 * s.n_rays * s.n_rays)
+    # the first frame showed rays living nearly all their 12 bounces, so the next one rotates its ray groups through
+    # the warps (gridUsed bit 4, k1_trace_grid.cu): same outputs
+    again = gpu_ctx.run_frame(s)
+    assert again.counters["gridUsed"] == 23
+    assert_same_frame(again, fast, "full-size C3, group rotation vs ray queue")
 
 
 @pytest.mark.parametrize("seed", range(16))
@@ -533,3 +538,30 @@ def test_fan_overflow_reruns_the_frame_on_the_grid_walk(oracle, monkeypatch):
             np.testing.assert_array_equal(g.muffle, o.muffle)
             np.testing.assert_array_equal(g.permeation.view(np.uint32), o.permeation.view(np.uint32))
         assert seen[0] & 8 and seen[-1] == 7, seen
+
+
+@pytest.mark.parametrize("name,n_rays,T,warps,life", [("c2", 65536, 1, 8, 1000.0), ("c3", 40000, 3, 4, 1000.0),
+                                                      ("c3", 30001, 2, 4, 70.0), ("c5", 60000, 1, 6, 150.0)])
+def test_group_rotation_is_bit_identical(monkeypatch, name, n_rays, T, warps, life):
+    """Small batches (one shard of a ray-sharded frame) rotate their groups of 32 rays through the warps after every
+    bounce round (k1_trace_grid.cu, gridUsed bit 4). Which warp traces a ray must not change any output: the rotated
+    frame equals the same frame without rotation and the brute-force scans, bit for bit -- including rays that die at
+    different bounces (short MaxRayLife) and a last group that is not full. ART_K1_WARPS shrinks the launch so that
+    test-sized batches give every warp between one and four groups."""
+    s = scenes.make_config(name, batch_count=T, n_rays=n_rays)
+    s.max_ray_life = life
+    monkeypatch.setenv("ART_K1_WARPS", str(warps))
+    with native.Context(0) as ctx:
+        native.upload(ctx, s)
+        slow = ctx.run_frame(s, flags=native.FRAME_BRUTE_FORCE)
+        rot = ctx.run_frame(s, flags=native.FRAME_FORCE_GRID)
+        rot2 = ctx.run_frame(s, flags=native.FRAME_FORCE_GRID)
+        monkeypatch.setenv("ART_K1_ROTATE", "0")
+        plain = ctx.run_frame(s, flags=native.FRAME_FORCE_GRID)
+    assert rot.counters["gridUsed"] & 16 and rot2.counters["gridUsed"] & 16, "rotation was not used"
+    assert not plain.counters["gridUsed"] & 16 and slow.counters["gridUsed"] == 0
+    assert 0 < rot.hit_counts.min() or life < 1000.0
+    if life < 1000.0:
+        assert len(np.unique(rot.hit_counts)) > 3, "rays should die at different bounces in this case"
+    for other, what in ((plain, "rotation vs no rotation"), (slow, "rotation vs brute force"), (rot2, "rotation twice")):
+        assert_same_frame(rot, other, what)

@@ -26,9 +26,11 @@ def main():
     ap.add_argument("--no-fans", action="store_true", help="grid kernels: every query walks the grid (no target fans)")
     ap.add_argument("--stats", action="store_true", help="ART_FRAME_GRID_STATS: tests / cells the grid kernels execute")
     ap.add_argument("--outputs", action="store_true", help="also produce hit points / ids / counts and copy everything back")
+    ap.add_argument("--shard", default=None, help="I/W: trace only shard I of a W-way ray-sharded frame (what one rank of a W-GPU run executes)")
     a = ap.parse_args()
     build.build()
-    s = scenes.make_config(a.workload, n_rays=a.rays)
+    shard = tuple(int(x) for x in a.shard.split("/")) if a.shard else None
+    s = scenes.make_config(a.workload, n_rays=a.rays, batch_count=shard[1] if shard else 1)
     if a.muffle_dist is not None:
         s.max_muffle_hit_distance = a.muffle_dist
     flags = (0 if a.outputs else native.FRAME_NO_HOST_OUTPUTS) | (native.FRAME_COUNTERS if a.counters else 0) | (native.FRAME_REVERB_SEQ_FP32 if a.seq else 0)
@@ -36,6 +38,9 @@ def main():
     flags |= (native.FRAME_NO_FANS if a.no_fans else 0) | (native.FRAME_GRID_STATS if a.stats else 0)
     with native.Context(0) as ctx:
         native.upload(ctx, s)
+        if shard:
+            ctx.set_ray_shard(shard[0], shard[1], 256)
+            flags |= native.FRAME_PARTIALS_ONLY
         for i in range(a.frames):
             r = ctx.run_frame(s, jobs=a.jobs, flags=flags, want=("echo", "hit_points", "hit_counts", "hit_ids") if a.outputs else ())
             c = r.counters
