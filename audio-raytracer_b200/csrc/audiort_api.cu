@@ -804,7 +804,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         const size_t cap = nFans * perFan + 4096;
         if (cap > ((size_t)1 << 30) || nFans * kFanCells > ((size_t)1 << 28)) useFans = false;   // > 2 GiB of lists: walk the grid instead
         else {
-            CK(ctx->fanCells.ensure(nFans * kFanCells * sizeof(uint2)));
+            CK(ctx->fanCells.ensure(nFans * kFanCells * (sizeof(uint2) + sizeof(uint32_t))));   // cells, then FanDesc::firstA
             CK(ctx->fanEntries.ensure(cap * sizeof(uint16_t)));
             CK(ctx->fanCtl.ensure(16));
             CK(ctx->pinFanCtl.ensure(16));
@@ -817,6 +817,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             fa.lx = prm->rayOrigin[0]; fa.ly = prm->rayOrigin[1]; fa.lz = prm->rayOrigin[2];
             fa.nearDist = 1e-3f * ctx->grid.d.errScale;
             fa.cells = ctx->fanCells.as<uint2>(); fa.entries = ctx->fanEntries.as<uint16_t>();
+            fa.firstA = reinterpret_cast<uint32_t*>(fa.cells + nFans * kFanCells);
             fa.capacity = (unsigned int)cap; fa.ctl = ctx->fanCtl.as<unsigned int>();
             fa.order = nullptr;
             if (nc <= 16384) {                       // the per-goal sort runs in one CTA's shared memory
@@ -826,7 +827,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             }
             CK(launch_fan_build(fa, ctx->stream));
             ctx->kernelLaunches++;
-            fd.nFans = (int)nFans; fd.cells = fa.cells; fd.entries = fa.entries; fd.nEntries = (int)cap;
+            fd.nFans = (int)nFans; fd.cells = fa.cells; fd.entries = fa.entries; fd.nEntries = (int)cap; fd.firstA = fa.firstA;
             ctx->frameGridUsed |= 4u;
         }
     }

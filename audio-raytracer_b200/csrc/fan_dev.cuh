@@ -37,6 +37,8 @@ struct FanDesc {
     const uint2* cells;        // [nFans * kFanCells]: x = first entry, y = nS | nA << 10 | nO << 21 (as GridDesc::cells)
     const uint16_t* entries;   // collider indices per cell: spheres, AABBs, OBBs, each nearest to the goal first
     int nEntries;              // capacity (bounds checks of debug builds)
+    const uint32_t* firstA;    // [nFans * kFanCells]: the cell's first two AABB entries, id0 | id1 << 16 (K1's first pass tests
+                               // exactly those: it reads them beside the header instead of chasing the entry list afterwards)
 };
 
 // fan_build_kernel arguments (k4_fan_build.cu)
@@ -50,6 +52,7 @@ struct FanBuildArgs {
     float lx, ly, lz;          // listener = goal of fan nTargets
     float nearDist;
     uint2* cells;              // [(nTargets + 1) * kFanCells]
+    uint32_t* firstA;          // [(nTargets + 1) * kFanCells], see FanDesc
     uint16_t* entries;
     unsigned int capacity;     // entries available
     unsigned int* ctl;         // [0] next free entry, [1] overflow flag (zeroed by the host before the launch)

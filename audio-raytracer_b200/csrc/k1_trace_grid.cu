@@ -359,7 +359,9 @@ constexpr int kFanFirstTests = ART_FAN_FIRST_TESTS;   // AABBs every query tests
 // owner checks fall away.
 //
 // Prepare query (slot, rec): 0 = gated out (RT:168), 1 = the goal is visible without any test, 2 = lists to test.
-__device__ __forceinline__ int fan_prepare(const PoolEnv& E, int nslot, int nrec, f3& no, f3& nd, f3& ninv, float& nL, uint2& hN, uint2& hB)
+template <bool FIRST>
+__device__ __forceinline__ int fan_prepare(const PoolEnv& E, int nslot, int nrec, f3& no, f3& nd, f3& ninv, float& nL, uint2& hN, uint2& hB,
+                                           uint32_t& fN, uint32_t& fB)
 {
     const TraceArgs& a = E.a;
     const HitRec r = E.rec[nrec];
@@ -378,6 +380,10 @@ __device__ __forceinline__ int fan_prepare(const PoolEnv& E, int nslot, int nrec
     const int fanBase = (nslot == 0 ? a.nTargets : nslot - 1) * kFanCells;
     hN = __ldg(&E.f.cells[fanBase + 6 * kFanCellsPerFace]);        // near list of the goal
     hB = __ldg(&E.f.cells[fanBase + bin]);
+    if (FIRST) {                                                   // the first two AABBs of either list, fetched beside the headers
+        fN = __ldg(&E.f.firstA[fanBase + 6 * kFanCellsPerFace]);
+        fB = __ldg(&E.f.firstA[fanBase + bin]);
+    }
     return 2;
 }
 
@@ -402,8 +408,8 @@ __device__ __forceinline__ int fan_first_pass(const PoolEnv& E, int qFirst, int 
             if (nslot > 0) nslot = a.targetOrder[nslot - 1] + 1;
             nrec = recOfOrd[ord];
             ART_CHECK(a.counters, (unsigned)nrec < 32u && nslot >= 0 && nslot <= a.nTargets);
-            f3 no, nd, ninv; float nL; uint2 hN, hB;
-            const int state = fan_prepare(E, nslot, nrec, no, nd, ninv, nL, hN, hB);
+            f3 no, nd, ninv; float nL; uint2 hN, hB; uint32_t fN = 0, fB = 0;
+            const int state = fan_prepare<kFanFirstTests <= 2>(E, nslot, nrec, no, nd, ninv, nL, hN, hB, fN, fB);
             if (state == 1) query_visible(E, nslot, nrec, nL);
             if (state == 2) {
                 const int nS0 = hN.y & 1023, nA0 = (hN.y >> 10) & 2047, nS1 = hB.y & 1023, nA1 = (hB.y >> 10) & 2047;
@@ -412,11 +418,13 @@ __device__ __forceinline__ int fan_first_pass(const PoolEnv& E, int qFirst, int 
                 const uint16_t* eN = E.f.entries + hN.x + nS0;
                 const uint16_t* eB = E.f.entries + hB.x + nS1 - nA0;
                 const int nFirst = min(nA0 + nA1, kFanFirstTests);
+                // the run "near list, then bin" starts with these ids (FanDesc::firstA): no dependent load of the entry lists here
+                const uint32_t ids = nA0 >= 2 ? fN : (nA0 == 1 ? (fN & 0xFFFFu) | (fB << 16) : fB);
 #if ART_FIRST_PASS_ROLLED
 #pragma unroll 1
 #endif
                 for (int t = 0; t < nFirst && !blocked; t++) {
-                    const int id = __ldg((t < nA0 ? eN : eB) + t);
+                    const int id = kFanFirstTests <= 2 ? (int)((ids >> (16 * t)) & 0xFFFFu) : (int)__ldg((t < nA0 ? eN : eB) + t);
                     ART_CHECK(a.counters, id < a.L.na);
                     if (STATS) E.st[1]++;
                     blocked = aabb_blocks(E.gv, id, no, ninv, nL);
@@ -478,7 +486,8 @@ __device__ __forceinline__ int run_pool_fan(const PoolEnv& E, int count)
                     packed = E.surv[qi];
                     const int nslot = (int)(packed & 0xFFFFu), nrec = (int)(packed >> 16);
                     ART_CHECK(a.counters, (unsigned)nrec < 32u && nslot >= 0 && nslot <= a.nTargets);
-                    const int state = fan_prepare(E, nslot, nrec, no, nd, ninv, nL, hN, hB);
+                    uint32_t fN, fB;
+                    const int state = fan_prepare<false>(E, nslot, nrec, no, nd, ninv, nL, hN, hB, fN, fB);
                     active = state == 2;
                     if (state == 1) query_visible(E, nslot, nrec, nL);
                 }

@@ -124,6 +124,8 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 2) fan_build_kernel(const Fa
 
     int cS = 0, cA = 0, cO = 0;
     unsigned int wpos = 0;                   // pass 1: next entry of this bin
+    unsigned int aPos = 0;                   // pass 1: where this bin's AABB entries start
+    uint32_t firstIds = 0;                   // pass 1: first two AABB entries of this bin, id0 | id1 << 16
     unsigned int blockTotal = 0;
     int nearTotal = 0;
     for (int pass = 0; pass < 2; pass++) {
@@ -177,14 +179,21 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 2) fan_build_kernel(const Fa
                     if (ia >= (rj & 255u) && ia <= ((rj >> 8) & 255u)) {
                         const uint32_t e = sIdT[c0 + j];
                         if (pass == 0) { const uint32_t t = e >> 16; cS += t == 0; cA += t == 1; cO += t == 2; }
-                        else a.entries[wpos++] = (uint16_t)(e & 0xFFFFu);
+                        else {
+                            if (wpos == aPos) firstIds = (e & 0xFFFFu) | (e << 16);          // (a single AABB is listed twice)
+                            else if (wpos == aPos + 1u) firstIds = (firstIds & 0xFFFFu) | (e << 16);
+                            a.entries[wpos++] = (uint16_t)(e & 0xFFFFu);
+                        }
                     }
                 }
             }
             __syncthreads();
             if (tid == 0) sNearCount += nM;
         }
-        if (pass == 1) break;
+        if (pass == 1) {
+            if (cA > 0) a.firstA[(size_t)fan * kFanCells + face * kFanCellsPerFace + tid] = firstIds;
+            break;
+        }
         // ---- reserve the CTA's span: block scan of the per-bin totals
         __syncthreads();
         nearTotal = nearCta ? sNearCount : 0;
@@ -219,11 +228,17 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 2) fan_build_kernel(const Fa
             return;
         }
         wpos = bs + binOff;
+        aPos = wpos + (unsigned)cS;
         cells[face * kFanCellsPerFace + tid] = make_uint2(wpos, (uint32_t)cS | ((uint32_t)cA << 10) | ((uint32_t)cO << 21));
         if (nearCta && tid == 0) {
-            uint32_t nS = 0, nA = 0, nO = 0;
-            for (int q = 0; q < nearTotal; q++) { const uint32_t t = sNear[q] >> 16; nS += t == 0; nA += t == 1; nO += t == 2; }
+            uint32_t nS = 0, nA = 0, nO = 0, ids = 0;
+            for (int q = 0; q < nearTotal; q++) {
+                const uint32_t t = sNear[q] >> 16;
+                if (t == 1) { if (nA == 0) ids = (sNear[q] & 0xFFFFu) | (sNear[q] << 16); else if (nA == 1) ids = (ids & 0xFFFFu) | (sNear[q] << 16); }
+                nS += t == 0; nA += t == 1; nO += t == 2;
+            }
             cells[6 * kFanCellsPerFace] = make_uint2(bs + blockTotal, nS | (nA << 10) | (nO << 21));
+            a.firstA[(size_t)fan * kFanCells + 6 * kFanCellsPerFace] = ids;
         }
         if (nearCta)
             for (int q = tid; q < nearTotal; q += 1024) a.entries[bs + blockTotal + q] = (uint16_t)(sNear[q] & 0xFFFFu);
