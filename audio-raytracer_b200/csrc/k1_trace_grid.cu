@@ -97,6 +97,8 @@ struct PoolEnv {
     int slots, lane;
     uint32_t ltMask;
     unsigned int* st;                    // STATS: per-lane counters {sphere, AABB, OBB tests, cells}
+    const float4* goalByPos;             // FAN 2, shared memory (or null): goal (xyz) and slot (w) of pool position p, [slots]
+    const float4* goalBySlot;            //   ... and goal (xyz) of slot s, [slots]; slot 0 = the listener (echo ray)
 };
 
 __device__ __forceinline__ void query_visible(const PoolEnv& E, int slot, int recIdx, float L)
@@ -367,7 +369,8 @@ __device__ __forceinline__ int fan_prepare(const PoolEnv& E, int nslot, int nrec
     const HitRec r = E.rec[nrec];
     no = mk3(r.px, r.py, r.pz);
     f3 T = E.RayOrigin;
-    if (nslot > 0) T = mk3(a.targets[3 * (nslot - 1)], a.targets[3 * (nslot - 1) + 1], a.targets[3 * (nslot - 1) + 2]);
+    if (E.goalBySlot) { const float4 gT = E.goalBySlot[nslot]; T = mk3(gT.x, gT.y, gT.z); }
+    else if (nslot > 0) T = mk3(a.targets[3 * (nslot - 1)], a.targets[3 * (nslot - 1) + 1], a.targets[3 * (nslot - 1) + 2]);
     const f3 v = sub3(T, no);                                      // RT:127 / RT:162
     const float len = sqrtr(dot3(v, v));
     nd = smul3(rcpr(len), v);                                      // normalize = rsqrt(dot) * v
@@ -405,7 +408,8 @@ __device__ __forceinline__ int fan_first_pass(const PoolEnv& E, int qFirst, int 
             nslot = q - ord * E.slots;
             if (nslot < 0) { ord--; nslot += E.slots; }
             else if (nslot >= E.slots) { ord++; nslot -= E.slots; }
-            if (nslot > 0) nslot = a.targetOrder[nslot - 1] + 1;
+            if (E.goalByPos) nslot = __float_as_int(E.goalByPos[nslot].w);
+            else if (nslot > 0) nslot = a.targetOrder[nslot - 1] + 1;
             nrec = recOfOrd[ord];
             ART_CHECK(a.counters, (unsigned)nrec < 32u && nslot >= 0 && nslot <= a.nTargets);
             f3 no, nd, ninv; float nL; uint2 hN, hB; uint32_t fN = 0, fB = 0;
@@ -629,6 +633,21 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
     float4* qbuf1 = qbase + (kGridWarps + warp) * 32;                 // (1/dir.xyz, tEnd)
     float4* qbuf2 = qbase + (2 * kGridWarps + warp) * 32;             // (tMax.xyz, cell | rec << 24)
     int* qbuf3 = reinterpret_cast<int*>(qbase + 3 * kGridWarps * 32) + warp * 32;   // slot
+    // FAN 2: the goals of the pool (listener + targets, in pool order and by slot) in shared memory, so that a query starts
+    // with one LDS instead of the dependent global loads targetOrder -> targets
+    const float4* goalByPos = nullptr; const float4* goalBySlot = nullptr;
+    if (FAN == 2 && a.goalsInSmem) {
+        float4* gp = reinterpret_cast<float4*>(smem + a.goalsSmemOffset);
+        for (int i = threadIdx.x; i < slots; i += blockDim.x) {
+            const int s = i == 0 ? 0 : a.targetOrder[i - 1] + 1;
+            gp[i] = s == 0 ? make_float4(a.ox, a.oy, a.oz, __int_as_float(0))
+                           : make_float4(a.targets[3 * (s - 1)], a.targets[3 * (s - 1) + 1], a.targets[3 * (s - 1) + 2], __int_as_float(s));
+            gp[slots + i] = i == 0 ? make_float4(a.ox, a.oy, a.oz, 0.0f)
+                                   : make_float4(a.targets[3 * (i - 1)], a.targets[3 * (i - 1) + 1], a.targets[3 * (i - 1) + 2], 0.0f);
+        }
+        __syncthreads();
+        goalByPos = gp; goalBySlot = gp + slots;
+    }
     const GeomView gv = make_view(geomBase, a.L);
     const f3 RayOrigin = mk3(a.ox, a.oy, a.oz);
     const uint32_t ltMask = (1u << lane) - 1u;
@@ -808,7 +827,7 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
         {
             const uint32_t hitMask = __ballot_sync(kFull, hit);
             const int total = __popc(hitMask) * slots;
-            const PoolEnv E = { a, g, f, gv, rec, qbuf0, qbuf1, qbuf2, qbuf3, surv, RayOrigin, hitMask, slots, lane, ltMask, st };
+            const PoolEnv E = { a, g, f, gv, rec, qbuf0, qbuf1, qbuf2, qbuf3, surv, RayOrigin, hitMask, slots, lane, ltMask, st, goalByPos, goalBySlot };
             const bool noSO = a.L.ns + a.L.no == 0;
             if (FAN == 1) {
                 for (int q0 = 0; q0 < total; q0 += kChunkQ) run_pool<2, STATS, true>(E, q0, min(kChunkQ, total - q0), noSO);
@@ -968,9 +987,21 @@ size_t trace_grid_smem_bytes(const GeomLayout& L, bool geomInSmem)
 }
 
 // fans == nullptr: the occlusion queries walk the grid cells along their segments instead of using the target fans
-cudaError_t launch_trace_grid(const TraceArgs& a, const GridDesc& g, const FanDesc* fans, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream)
+cudaError_t launch_trace_grid(const TraceArgs& a0, const GridDesc& g, const FanDesc* fans, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream)
 {
-    const size_t smem = trace_grid_smem_bytes(a.L, geomInSmem);
+    TraceArgs a = a0;
+    size_t smem = trace_grid_smem_bytes(a.L, geomInSmem);
+    a.goalsInSmem = 0; a.goalsSmemOffset = 0;
+    if (fans && a.nTargets + 1 >= kTwoStageSlots) {            // FAN 2: goal tables behind everything else, when they fit
+        static int maxOptin = -1;
+        if (maxOptin < 0) {
+            int dev = 0;
+            if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) maxOptin = 0;
+        }
+        const size_t off = (smem + 15) & ~(size_t)15;
+        const size_t need = off + 2 * (size_t)(a.nTargets + 1) * sizeof(float4);
+        if (need <= (size_t)maxOptin) { a.goalsInSmem = 1; a.goalsSmemOffset = (unsigned int)off; smem = need; }
+    }
     void (*k)(const TraceArgs, const GridDesc, const FanDesc) = nullptr;
     const int mode = !fans ? 0 : (a.nTargets + 1 >= kTwoStageSlots ? 2 : 1);
     const bool rot = a.migGroups > 0;

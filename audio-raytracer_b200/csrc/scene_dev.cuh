@@ -137,6 +137,8 @@ struct TraceArgs {
     unsigned int migSlots;         // capacity of the log: migGroups * (H - 1) parked states
     unsigned int* migFlags;        // [migSlots] 0 = not yet published (zeroed per frame)
     float4* migState;              // [migSlots][64]: per lane (o.xyz, life), (d.xyz, hits | alive << 8 | group << 9)
+    int goalsInSmem;               // grid kernel, FAN 2: listener + target positions staged in shared memory (launch_trace_grid)
+    unsigned int goalsSmemOffset;  //   byte offset of those tables in the dynamic shared memory
     int muffleInSmem;              // per-warp shared counters fit
     int anyOwned[3];               // does any sphere / AABB / OBB belong to a target < nTargets (RT:413/426/439)
 };
