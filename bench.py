@@ -60,7 +60,7 @@ def dist_env():
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons with NVML while the timed region runs."""
 
-    def __init__(self, device_index: int, period_s: float = 0.1):
+    def __init__(self, device_index: int, period_s: float = 0.02):
         super().__init__(daemon=True)
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._halt = threading.Event()
@@ -196,7 +196,10 @@ def main():
     from audio_raytracer_b200 import build, native
     build.build()
     torch.cuda.set_device(local)
-    os.environ["NCCL_DEBUG"] = os.environ.get("ART_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+    # keep stdout to the one JSON line: NCCL prints its version banner to stdout at WARN and above
+    if os.environ.get("ART_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = os.environ["ART_NCCL_DEBUG"]
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
