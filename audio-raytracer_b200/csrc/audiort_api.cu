@@ -877,6 +877,15 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             ta.scratch = ctx->gridScratch.as<uint32_t>();
             // small batches (a shard of a ray-sharded frame): rotate the ray groups through the warps (k1_trace_grid.cu)
             if (!(prm->flags & ART_FRAME_GRID_STATS)) ta.migGroups = trace_grid_rotation(map.nLocal, H, ctx->numSms, ta.gridWarps, ctx->lastHitFill >= 0.9f, &ta.migSlots);
+            {   // size the log for the case that a later frame of this batch size turns the rotation on (it depends on how long
+                // the previous frame's rays lived): the allocation then happens in the context's first frame, not in the middle
+                // of a running session
+                unsigned int potSlots = 0;
+                if (trace_grid_rotation(map.nLocal, H, ctx->numSms, ta.gridWarps, true, &potSlots) > 0) {
+                    const size_t fb = ((size_t)potSlots * sizeof(unsigned int) + 255) & ~(size_t)255;
+                    CK(ctx->rotateLog.ensure(fb + (size_t)potSlots * 64 * sizeof(float4)));
+                }
+            }
             if (ta.migGroups > 0) {
                 const size_t flagBytes = ((size_t)ta.migSlots * sizeof(unsigned int) + 255) & ~(size_t)255;
                 CK(ctx->rotateLog.ensure(flagBytes + (size_t)ta.migSlots * 64 * sizeof(float4)));

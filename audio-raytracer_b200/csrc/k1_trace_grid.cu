@@ -97,7 +97,7 @@ struct PoolEnv {
     int slots, lane;
     uint32_t ltMask;
     unsigned int* st;                    // STATS: per-lane counters {sphere, AABB, OBB tests, cells}
-    const float4* goalByPos;             // FAN 2, shared memory (or null): goal (xyz) and slot (w) of pool position p, [slots]
+    const float4* goalByPos;             // shared memory (or null): goal (xyz) and slot (w) of pool position p, [slots]
     const float4* goalBySlot;            //   ... and goal (xyz) of slot s, [slots]; slot 0 = the listener (echo ray)
 };
 
@@ -157,7 +157,8 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                         const int q = qFirst + qi;
                         const int ord = q / E.slots;
                         nslot = q - ord * E.slots;
-                        if (nslot > 0) nslot = a.targetOrder[nslot - 1] + 1;       // spatially sorted pool order
+                        if (E.goalByPos) nslot = __float_as_int(E.goalByPos[nslot].w);
+                        else if (nslot > 0) nslot = a.targetOrder[nslot - 1] + 1;  // spatially sorted pool order
                         nrec = __fns(E.hitMask, 0, ord + 1);
                     } else {
                         const uint32_t packed = E.surv[qi];   // STAGE 1
@@ -168,7 +169,8 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                     const HitRec r = E.rec[nrec];
                     const f3 no = mk3(r.px, r.py, r.pz);
                     f3 T = E.RayOrigin;
-                    if (nslot > 0) T = mk3(a.targets[3 * (nslot - 1)], a.targets[3 * (nslot - 1) + 1], a.targets[3 * (nslot - 1) + 2]);
+                    if (E.goalBySlot) { const float4 gT = E.goalBySlot[nslot]; T = mk3(gT.x, gT.y, gT.z); }
+                    else if (nslot > 0) T = mk3(a.targets[3 * (nslot - 1)], a.targets[3 * (nslot - 1) + 1], a.targets[3 * (nslot - 1) + 2]);
                     const f3 v = sub3(T, no);                                      // RT:127 / RT:162
                     const float len = sqrtr(dot3(v, v));
                     nd = smul3(rcpr(len), v);                                      // normalize = rsqrt(dot) * v
@@ -633,10 +635,10 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
     float4* qbuf1 = qbase + (kGridWarps + warp) * 32;                 // (1/dir.xyz, tEnd)
     float4* qbuf2 = qbase + (2 * kGridWarps + warp) * 32;             // (tMax.xyz, cell | rec << 24)
     int* qbuf3 = reinterpret_cast<int*>(qbase + 3 * kGridWarps * 32) + warp * 32;   // slot
-    // FAN 2: the goals of the pool (listener + targets, in pool order and by slot) in shared memory, so that a query starts
-    // with one LDS instead of the dependent global loads targetOrder -> targets
+    // the goals of the pool (listener + targets, in pool order and by slot) in shared memory, so that a query starts with
+    // one LDS instead of the dependent global loads targetOrder -> targets
     const float4* goalByPos = nullptr; const float4* goalBySlot = nullptr;
-    if (FAN == 2 && a.goalsInSmem) {
+    if (a.goalsInSmem) {
         float4* gp = reinterpret_cast<float4*>(smem + a.goalsSmemOffset);
         for (int i = threadIdx.x; i < slots; i += blockDim.x) {
             const int s = i == 0 ? 0 : a.targetOrder[i - 1] + 1;
@@ -992,7 +994,7 @@ cudaError_t launch_trace_grid(const TraceArgs& a0, const GridDesc& g, const FanD
     TraceArgs a = a0;
     size_t smem = trace_grid_smem_bytes(a.L, geomInSmem);
     a.goalsInSmem = 0; a.goalsSmemOffset = 0;
-    if (fans && a.nTargets + 1 >= kTwoStageSlots) {            // FAN 2: goal tables behind everything else, when they fit
+    {                                                          // goal tables behind everything else, when they fit
         static int maxOptin = -1;
         if (maxOptin < 0) {
             int dev = 0;
