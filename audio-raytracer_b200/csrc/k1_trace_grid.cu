@@ -374,21 +374,26 @@ __device__ __forceinline__ int fan_prepare(const PoolEnv& E, int nslot, int nrec
     if (E.goalBySlot) { const float4 gT = E.goalBySlot[nslot]; T = mk3(gT.x, gT.y, gT.z); }
     else if (nslot > 0) T = mk3(a.targets[3 * (nslot - 1)], a.targets[3 * (nslot - 1) + 1], a.targets[3 * (nslot - 1) + 2]);
     const f3 v = sub3(T, no);                                      // RT:127 / RT:162
+    // the list headers depend on the direction's bin only: their loads (L2) are issued first and complete while the exact
+    // square root and reciprocals below are computed
+    const int bin = fan_bin(-v.x, -v.y, -v.z);                     // direction goal -> hit point
+    hN = make_uint2(0, 0); hB = make_uint2(0, 0);
+    if (bin >= 0) {
+        const int fanBase = (nslot == 0 ? a.nTargets : nslot - 1) * kFanCells;
+        hN = __ldg(&E.f.cells[fanBase + 6 * kFanCellsPerFace]);    // near list of the goal
+        hB = __ldg(&E.f.cells[fanBase + bin]);
+        if (FIRST) {                                               // the first two AABBs of either list, fetched beside the headers
+            fN = __ldg(&E.f.firstA[fanBase + 6 * kFanCellsPerFace]);
+            fB = __ldg(&E.f.firstA[fanBase + bin]);
+        }
+    }
     const float len = sqrtr(dot3(v, v));
     nd = smul3(rcpr(len), v);                                      // normalize = rsqrt(dot) * v
-    ninv = mk3(0, 0, 0); hN = make_uint2(0, 0); hB = make_uint2(0, 0);
+    ninv = mk3(0, 0, 0);
     if (nslot == 0) nL = r.echoL;                                  // RT:130
     else { nL = len; if (!(nL < a.maxMuffle)) return 0; }          // RT:165, 168
-    const int bin = fan_bin(-v.x, -v.y, -v.z);                     // direction goal -> hit point
     if (bin < 0 || len != len) return 1;                           // degenerate (hit point == goal): no test can block
     ninv = mk3(rcpr(nd.x), rcpr(nd.y), rcpr(nd.z));
-    const int fanBase = (nslot == 0 ? a.nTargets : nslot - 1) * kFanCells;
-    hN = __ldg(&E.f.cells[fanBase + 6 * kFanCellsPerFace]);        // near list of the goal
-    hB = __ldg(&E.f.cells[fanBase + bin]);
-    if (FIRST) {                                                   // the first two AABBs of either list, fetched beside the headers
-        fN = __ldg(&E.f.firstA[fanBase + 6 * kFanCellsPerFace]);
-        fB = __ldg(&E.f.firstA[fanBase + bin]);
-    }
     return 2;
 }
 
