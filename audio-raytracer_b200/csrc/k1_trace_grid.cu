@@ -999,7 +999,8 @@ cudaError_t launch_trace_grid(const TraceArgs& a0, const GridDesc& g, const FanD
     TraceArgs a = a0;
     size_t smem = trace_grid_smem_bytes(a.L, geomInSmem);
     a.goalsInSmem = 0; a.goalsSmemOffset = 0;
-    {                                                          // goal tables behind everything else, when they fit
+    const char* noTab = getenv("ART_K1_NO_GOAL_TABLES");         // (read per launch: test knob for the global-memory fallback)
+    if (!(noTab && atoi(noTab) != 0)) {                          // goal tables behind everything else, when they fit
         static int maxOptin = -1;
         if (maxOptin < 0) {
             int dev = 0;

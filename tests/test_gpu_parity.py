@@ -540,6 +540,27 @@ def test_fan_overflow_reruns_the_frame_on_the_grid_walk(oracle, monkeypatch):
         assert seen[0] & 8 and seen[-1] == 7, seen
 
 
+@pytest.mark.parametrize("name,n_rays,flags", [("c3", 6000, 0), ("c3", 6000, native.FRAME_NO_FANS), ("c2", 20000, 0)])
+def test_goal_tables_in_shared_memory_do_not_change_results(monkeypatch, name, n_rays, flags):
+    """The grid kernels keep the listener + target positions of the query pool in shared memory when they fit
+    (k1_trace_grid.cu, launch_trace_grid); with very many targets they read targetOrder -> targets from global memory
+    instead. ART_K1_NO_GOAL_TABLES=1 forces that fallback: every output must stay the same, and equal the brute-force scans."""
+    s = scenes.make_config(name, n_rays=n_rays)
+    with native.Context(0) as ctx:
+        native.upload(ctx, s)
+        a = ctx.run_frame(s, flags=native.FRAME_FORCE_GRID | flags)
+        monkeypatch.setenv("ART_K1_NO_GOAL_TABLES", "1")
+        b = ctx.run_frame(s, flags=native.FRAME_FORCE_GRID | flags)
+        monkeypatch.delenv("ART_K1_NO_GOAL_TABLES")
+        c = ctx.run_frame(s, flags=native.FRAME_BRUTE_FORCE)
+    assert a.counters["gridUsed"] & 1 and b.counters["gridUsed"] & 1 and c.counters["gridUsed"] == 0
+    for x in (b, c):
+        for k in ("hit_counts", "hit_ids", "echo", "hit_points", "muffle", "muffle_totals"):
+            np.testing.assert_array_equal(getattr(a, k), getattr(x, k), err_msg=k)
+        np.testing.assert_array_equal(a.permeation.view(np.uint32), x.permeation.view(np.uint32))
+        np.testing.assert_array_equal(a.settings.view(np.uint8), x.settings.view(np.uint8))
+
+
 @pytest.mark.parametrize("name,n_rays,T,warps,life", [("c2", 65536, 1, 8, 1000.0), ("c3", 40000, 3, 4, 1000.0),
                                                       ("c3", 30001, 2, 4, 70.0), ("c5", 60000, 1, 6, 150.0)])
 def test_group_rotation_is_bit_identical(monkeypatch, name, n_rays, T, warps, life):
