@@ -181,6 +181,7 @@ struct ArtCtx {
     DevBuf rawScene, geom, attrs, owners, perm;    // perm: dens arrays + owned list
     HostGrid grid;                                 // uniform grid over the scene (grid_host.h)
     DevBuf gridCells, gridEntries, gridRangeO, gridScratch, rotateLog;
+    DevBuf permHitPts, permBinCnt, permPairs;       // binned loss lines (k2_permeation_binned.cu)
     DevBuf fanBoxes, fanCells, fanEntries, fanCtl, fanOrder;  // target fans (fan_dev.cuh): collider bounds (per scene), lists (per frame)
     PinBuf pinFanCtl;
     bool fansDisabled = false;                     // ART_DISABLE_FANS=1
@@ -444,7 +445,7 @@ ART_API void art_destroy(ArtCtx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->rotateLog, &ctx->fanBoxes, &ctx->fanCells, &ctx->fanEntries, &ctx->fanCtl, &ctx->fanOrder, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
+    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->rotateLog, &ctx->permHitPts, &ctx->permBinCnt, &ctx->permPairs, &ctx->fanBoxes, &ctx->fanCells, &ctx->fanEntries, &ctx->fanCtl, &ctx->fanOrder, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
                        &ctx->outAll, &ctx->firstHit, &ctx->partials, &ctx->queue })
         b->release();
     for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinAll, &ctx->pinPerm, &ctx->pinFanCtl })
@@ -942,7 +943,35 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         pa.counters = dh->counters;
         pa.nextRay = reinterpret_cast<unsigned int*>(ctx->partials.as<unsigned char>() + queueOff) + 8;
         pa.raysPerWarp = perm_grid_rays_per_warp(map.nLocal, Na, ctx->numSms);
-        if (useGrid) {
+        pa.hitPts = nullptr;
+        // Binned loss lines (k2_permeation_binned.cu): with the target fans and enough (ray, target) lines to fill the GPU, the
+        // lines are sorted by (target, direction bin) and evaluated 32 of one bin at a time. ART_K2_BINNED=0/1 forces it off/on.
+        bool binned = useGrid && useFans && !(prm->flags & ART_FRAME_GRID_STATS) && (size_t)map.nLocal * Na >= ((size_t)1 << 21);
+        if (const char* v = getenv("ART_K2_BINNED")) binned = useGrid && useFans && !(prm->flags & ART_FRAME_GRID_STATS) && atoi(v) != 0;
+        if (binned && (size_t)map.nLocal * Na > ((size_t)1 << 31)) binned = false;       // 32-bit offsets inside the pair list
+        if (useGrid && binned) {
+            PermBinArgs ba;
+            ba.slices = perm_binned_slices(map.nLocal, Na, ctx->numSms);
+            CK(ctx->permHitPts.ensure((size_t)nLoc * sizeof(float4)));
+            const size_t cntBytes = (perm_binned_cnt_bytes(Na, ba.slices) + 255) & ~(size_t)255;
+            const size_t startBytes = (perm_binned_start_bytes(Na) + 255) & ~(size_t)255;
+            CK(ctx->permBinCnt.ensure(cntBytes + startBytes + perm_binned_block_bytes(map.nLocal, Na)));
+            CK(ctx->permPairs.ensure((size_t)Na * nLoc * sizeof(uint32_t)));
+            pa.hitPts = ctx->permHitPts.as<float4>();
+            pa.raysPerWarp = 32;
+            ba.hitPts = pa.hitPts; ba.nLocal = map.nLocal; ba.targets = pa.targets; ba.nTargets = Na;
+            ba.cnt = ctx->permBinCnt.as<uint32_t>(); ba.pairRay = ctx->permPairs.as<uint32_t>();
+            ba.binStart = reinterpret_cast<uint32_t*>(ctx->permBinCnt.as<unsigned char>() + cntBytes);
+            ba.blockBin = reinterpret_cast<uint32_t*>(ctx->permBinCnt.as<unsigned char>() + cntBytes + startBytes);
+            ba.jobQueue = pa.nextRay + 1;
+            const bool g1 = perm_grid_smem_bytes(L, true, false) <= (size_t)ctx->maxSmemOptin;
+            CK(launch_permeation_grid(pa, gd, nullptr, ctx->numSms, g1, false, pmStream));          // first-hit distances + hit points
+            const bool g2 = perm_binned_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
+            CK(launch_permeation_binned(pa, ba, fd, ctx->numSms, g2, pmStream));
+            CK(launch_perm_last(pa, T, pmStream));
+            ctx->frameGridUsed |= 2u | 32u;
+            ctx->kernelLaunches += 5;
+        } else if (useGrid) {
             const bool gInSmem = perm_grid_smem_bytes(L, true, useFans) <= (size_t)ctx->maxSmemOptin;
             CK(launch_permeation_grid(pa, gd, useFans ? &fd : nullptr, ctx->numSms, gInSmem, (prm->flags & ART_FRAME_GRID_STATS) != 0, pmStream));
             CK(launch_perm_last(pa, T, pmStream));

@@ -140,6 +140,11 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
             rec[lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
         __syncwarp();
+        if (a.hitPts) {                 // binned mode: the loss lines are evaluated by perm_loss_binned_kernel
+            if (lane < a.raysPerWarp && j < a.map.nLocal) a.hitPts[j] = rec[lane];
+            __syncwarp();
+            continue;
+        }
 
         // ================= Phase 2: per-target loss rays (PM:67-86), one lane = one (ray, target) pair =================
         for (int tb = 0; tb * 32 < Na; tb++) {

@@ -20,6 +20,12 @@ cudaError_t launch_permeation(const PermArgs& a, int numCtas, bool geomInSmem, i
 cudaError_t launch_perm_last(const PermArgs& a, int T, cudaStream_t stream);
 size_t perm_grid_smem_bytes(const GeomLayout& L, bool geomInSmem, bool fans);
 cudaError_t launch_permeation_grid(const PermArgs& a, const GridDesc& g, const FanDesc* fans, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream);
+int perm_binned_slices(int nLocal, int nTargets, int numSms);
+size_t perm_binned_cnt_bytes(int nTargets, int slices);
+size_t perm_binned_start_bytes(int nTargets);
+size_t perm_binned_block_bytes(int nLocal, int nTargets);
+size_t perm_binned_smem_bytes(const GeomLayout& L, bool geomInSmem);
+cudaError_t launch_permeation_binned(const PermArgs& a, const PermBinArgs& ba, const FanDesc& fans, int numCtas, bool geomInSmem, cudaStream_t stream);
 cudaError_t launch_echo_stats(const uint16_t* echo, size_t n, EchoStats* out, bool sequential, int numSms, cudaStream_t stream);
 cudaError_t launch_fibonacci(uint16_t* dirs, int n, cudaStream_t stream);
 cudaError_t launch_microbench(int kind, int numSms, float* sink, long long* laneOps, cudaStream_t stream);

@@ -200,6 +200,22 @@ struct PermArgs {
     unsigned long long* counters;
     unsigned int* nextRay;
     int raysPerWarp;           // grid kernel: rays a warp takes from the queue at a time (<= 32)
+    float4* hitPts;            // grid kernel, binned mode (k2_permeation_binned.cu): [nLocal] (hit point - eps*d, hit flag) is
+                               // stored here and the loss lines are NOT evaluated by permeation_grid_kernel; null otherwise
+};
+
+// k2_permeation_binned.cu: the loss lines grouped by (target, direction bin of the target's fan)
+struct PermBinArgs {
+    const float4* hitPts;      // [nLocal] from permeation_grid_kernel
+    int nLocal;
+    const float* targets;      // float3 [nTargets]
+    int nTargets;
+    int slices;                // ray slices per target (one counting CTA each)
+    uint32_t* cnt;             // [nTargets][kBinBuckets][slices]: counts, then exclusive offsets into the target's region of pairRay
+    uint32_t* pairRay;         // [nTargets][nLocal]: local ray indices of the hitting rays, grouped by bin
+    uint32_t* binStart;        // [nTargets][kBinBuckets]: first line of every bucket (the last, always empty one = number of lines)
+    uint32_t* blockBin;        // [nTargets][ceil(nLocal / kBinBlock)]: bucket of the first line of every block of sorted lines
+    unsigned int* jobQueue;    // zeroed per frame
 };
 
 // K3 output (also part of the partial-result blob)
