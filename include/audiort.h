@@ -180,7 +180,9 @@ typedef struct ArtCounters {
     uint32_t gridUsed;          /* bit 0: trace job used the uniform grid, bit 1: permeation job did, bit 2: the frame's
                                    goal-directed queries used the target fans, bit 3: the fan build overflowed its entry
                                    buffer and the frame was re-run on the grid walk (the buffer grows for the next frame), bit 4: the
-                                   trace job rotated its ray groups through the warps (small batches / shards) */
+                                   trace job rotated its ray groups through the warps (small batches / shards), bit 5: the
+                                   permeation job evaluated its loss lines sorted by (target, direction bin) (large frames with
+                                   the target fans; ART_K2_BINNED=0/1 forces it off/on) */
     /* ART_FRAME_GRID_STATS: collider tests the grid kernels actually executed ([3] = sphere, AABB, OBB) and grid
      * cells they visited; compare with traceTests + echoTests + muffleTests / permFirstTests / permLossTests, the
      * counts of the reference's full scans */
