@@ -176,7 +176,8 @@ def workload_config(args, scene, world):
             "sharding": "none" if world == 1 else f"rays interleaved in chunks of {args.chunk} over {world} ranks",
             "l2": "flushed between steps (256 MiB write)", "reverb_reduction": "exact integer",
             "path": "default: uniform-grid traversal for the bounce rays + per-frame target fans (direction-binned collider lists around the "
-                    "listener and every source) for the echo / muffle / permeation queries, fan build inside the timed region; "
+                    "listener and every source) for the echo / muffle / permeation queries, fan build inside the timed region, "
+                    "permeation loss lines sorted by (source, direction bin) on the device every frame; "
                     "bit-identical to the brute-force scans (ART_FRAME_BRUTE_FORCE timed beside it)",
             "rays_override": args.rays is not None}
 
@@ -268,12 +269,14 @@ def main():
     barrier()
     wall0 = time.perf_counter()
     dev_ms, trace_ms, perm_ms, reduce_ms, ex_ms_tot, launches, segs = [], [], [], [], 0.0, 0, 0
+    timed_grid_used = 0
     for _ in range(args.steps):
         c, ex_ms = device_step()
         dev_ms.append(c["deviceMs"]); trace_ms.append(c["traceMs"]); perm_ms.append(c["permeationMs"]); reduce_ms.append(c["reduceMs"])
         ex_ms_tot += ex_ms
         launches += c["kernelLaunches"]
         segs += c["segments"]
+        timed_grid_used = int(c.get("gridUsed", 0))
     barrier()
     wall_dev = time.perf_counter() - wall0
     clocks = sampler.stop()
@@ -401,7 +404,9 @@ def main():
                              "frac": (tfl(trace_flops_local, bf["traceMs"]) or 0) / peak_tflops,
                              "step_ms": bf["deviceMs"], "segments_per_s": bf["segments"] / (bf["deviceMs"] * 1e-3) if bf["deviceMs"] else None},
                          "permeation_kernel": {
-                             "kernel": "permeation_grid_kernel (K2)" if grid_used & 2 else "permeation_kernel (K2, brute force)",
+                             "kernel": ("perm_loss_binned_kernel + permeation_grid_kernel (K2: first hits, then the loss lines counting-"
+                                        "sorted by (target, direction bin) and evaluated 32 of one bin at a time)" if timed_grid_used & 32
+                                        else "permeation_grid_kernel (K2)" if grid_used & 2 else "permeation_kernel (K2, brute force)"),
                              "achieved": tfl(exec_perm_flops if grid_used & 2 else perm_flops_local, perm_ms_avg),
                              "executed_flops_per_launch": exec_perm_flops if grid_used & 2 else perm_flops_local,
                              "algorithmic_flops_per_launch": perm_flops_local,
