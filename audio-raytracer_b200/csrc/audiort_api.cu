@@ -948,7 +948,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         // lines are sorted by (target, direction bin) and evaluated 32 of one bin at a time. ART_K2_BINNED=0/1 forces it off/on.
         bool binned = useGrid && useFans && !(prm->flags & ART_FRAME_GRID_STATS) && (size_t)map.nLocal * Na >= ((size_t)1 << 21);
         if (const char* v = getenv("ART_K2_BINNED")) binned = useGrid && useFans && !(prm->flags & ART_FRAME_GRID_STATS) && atoi(v) != 0;
-        if (binned && (size_t)map.nLocal * Na > ((size_t)1 << 31)) binned = false;       // 32-bit offsets inside the pair list
+        if (binned && ((size_t)map.nLocal * Na > ((size_t)1 << 31) || Na > 65535)) binned = false;   // 32-bit offsets inside the pair list; one grid row per target
         if (useGrid && binned) {
             PermBinArgs ba;
             ba.slices = perm_binned_slices(map.nLocal, Na, ctx->numSms);
