@@ -350,11 +350,13 @@ def main():
             kernel_name = "trace_kernel (K1, brute force)"
             accounting = "tests of the reference's full scans (early exits honoured) x reference flops per test"
         traffic = None
+        ncu_util = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             key = f"{args.workload}:{scene.n_rays}:{world}"
             if key in tr:
                 traffic = tr[key]
+            ncu_util = tr.get(key + ":ncu")       # issue-slot / lane utilisation of the two big kernels from the committed captures
         except Exception:
             pass
         micro = {}
@@ -388,6 +390,7 @@ def main():
                                         "MEASURED_PEAKS.json; parity forbids FMA contraction, SURVEY 8d); FMA peak = 2x; "
                                         "on-box microbenchmarks in 'measured_issue_rates'",
                          "peak_fma": 2 * peak_tflops,
+                         "ncu_utilisation": ncu_util,
                          "executed_flops_per_launch": exec_trace_flops if grid_used & 1 else trace_flops_local,
                          "flops_per_test": {"sphere": 38, "aabb": 35, "obb": 98},
                          "measured_issue_rates": micro,
