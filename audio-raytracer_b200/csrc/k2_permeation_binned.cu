@@ -172,123 +172,123 @@ __global__ void __launch_bounds__(kPBinThreads, 1) perm_loss_binned_kernel(const
         int bin = (int)ba.blockBin[job];
         long long accInt = 0, accFrac = 0;
         while (cur < blockEnd) {
-        // the bucket that holds line `cur`: the first b >= bin whose successor starts behind cur (32 candidates per step)
-        for (;;) {
-            const int cb = bin + lane;
-            const bool behind = cb + 1 < kBinBuckets && st[cb + 1] > cur;
-            const uint32_t m = __ballot_sync(kFull, behind);
-            if (m) { bin += __ffs(m) - 1; break; }
-            bin += 32;
-        }
-        const uint32_t start = cur, end = min(blockEnd, st[bin + 1]);
-        cur = end;
-        if (bin == kBucketNoDir) {
-            // no usable direction (hit point == target): no list to test, loss 0 (as permeation_grid_kernel)
-            if (lane == 0) {
-                const float v = subr(a.nTimesS, 0.0f);                             // PM:260
-                const float ip = truncf(v);
-                accInt += (long long)(end - start) * (long long)ip;
-                accFrac += (long long)(end - start) * (long long)(((double)v - (double)ip) * 68719476736.0);
+            // the bucket that holds line `cur`: the first b >= bin whose successor starts behind cur (32 candidates per step)
+            for (;;) {
+                const int cb = bin + lane;
+                const bool behind = cb + 1 < kBinBuckets && st[cb + 1] > cur;
+                const uint32_t m = __ballot_sync(kFull, behind);
+                if (m) { bin += __ffs(m) - 1; break; }
+                bin += 32;
             }
-        } else {
-            const f3 T = mk3(a.targets[3 * tgt], a.targets[3 * tgt + 1], a.targets[3 * tgt + 2]);
-            // cell 0: near list, whole line; 1: bin towards the hit point, t in [0, tT]; 2: opposite bin, t > tT
-            const int fanBase = tgt * kFanCells;
-            const int face = bin / kFanCellsPerFace, rb = bin - face * kFanCellsPerFace;
-            const uint2 h0 = __ldg(&f.cells[fanBase + 6 * kFanCellsPerFace]);
-            const uint2 h1 = __ldg(&f.cells[fanBase + bin]);
-            const uint2 h2 = __ldg(&f.cells[fanBase + (face ^ 1) * kFanCellsPerFace + (kFanCellsPerFace - 1 - rb)]);
-            const int nS0 = h0.y & 1023, nA0 = (h0.y >> 10) & 2047, nO0 = h0.y >> 21;
-            const int nS1 = h1.y & 1023, nA1 = (h1.y >> 10) & 2047, nO1 = h1.y >> 21;
-            const int nS2 = h2.y & 1023, nA2 = (h2.y >> 10) & 2047, nO2 = h2.y >> 21;
-            ART_CHECK(a.counters, h0.x + nS0 + nA0 + nO0 <= (unsigned)f.nEntries && h1.x + nS1 + nA1 + nO1 <= (unsigned)f.nEntries &&
-                                  h2.x + nS2 + nA2 + nO2 <= (unsigned)f.nEntries);
-            const uint32_t* rays = ba.pairRay + (size_t)tgt * ba.nLocal;
-            for (uint32_t i0 = start; i0 < end; i0 += 32) {
-                const bool on = i0 + lane < end;
-                float4 rr = make_float4(0, 0, 0, 0);
-                if (on) rr = ba.hitPts[rays[i0 + lane]];
-                const f3 Pp = mk3(rr.x, rr.y, rr.z);
-                const f3 toT = sub3(T, Pp);
-                // (an idle lane of the last chunk computes on zeros and is ignored)
-                const f3 dir = normalize3(toT);                                    // PM:76
-                const f3 inv = mk3(rcpr(dir.x), rcpr(dir.y), rcpr(dir.z));         // PM:270
-                const float tT = sqrt_fast(fmaf(toT.z, toT.z, fmaf(toT.y, toT.y, toT.x * toT.x)));   // line parameter of the target
-                float loss = 0.0f;
-                {   // ---- AABBs, PM:265-288 in the reference's operation order
-                    const int n01 = nA0 + nA1, n = n01 + nA2;
-                    const uint32_t o0 = h0.x + nS0, o1 = h1.x + nS1 - nA0, o2 = h2.x + nS2 - n01;
-                    int nxt = n > 0 ? (int)__ldg(f.entries + (0 < nA0 ? o0 : (0 < n01 ? o1 : o2))) : 0;
-                    for (int k = 0; k < n; k++) {
-                        const int id = nxt;
-                        const int k1 = k + 1;
-                        if (k1 < n) nxt = (int)__ldg(f.entries + ((k1 < nA0 ? o0 : (k1 < n01 ? o1 : o2)) + (uint32_t)k1));
-                        ART_CHECK(a.counters, id < a.L.na);
-                        const float tIn = k >= n01 ? tT : 0.0f, tOut = (k >= nA0 && k < n01) ? tT : inf;
-                        const float4 A = gv.aabbA[id];
-                        const float2 B = gv.aabbB[id];
-                        float tEnter, tExit;
-                        slab<8>(subr(A.x, Pp.x), subr(A.y, Pp.y), subr(A.z, Pp.z), subr(A.w, Pp.x), subr(B.x, Pp.y), subr(B.y, Pp.z),
-                                inv.x, inv.y, inv.z, tEnter, tExit);
-                        const float len = clip_len_b(tEnter, tExit, tIn, tOut);
-                        if (len > 0.0f) loss = fmaf(len, densA[id], loss);
-                    }
-                }
-                {   // ---- spheres, PM:303-328 (unit direction)
-                    const int n01 = nS0 + nS1, n = n01 + nS2;
-                    const uint32_t o0 = h0.x, o1 = h1.x - nS0, o2 = h2.x - n01;
-                    for (int k = 0; k < n; k++) {
-                        const int id = (int)__ldg(f.entries + ((k < nS0 ? o0 : (k < n01 ? o1 : o2)) + (uint32_t)k));
-                        ART_CHECK(a.counters, id < a.L.ns);
-                        const float tIn = k >= n01 ? tT : 0.0f, tOut = (k >= nS0 && k < n01) ? tT : inf;
-                        const float4 sp = gv.sph[id];
-                        const f3 oc = sub3(Pp, mk3(sp.x, sp.y, sp.z));
-                        const float cc = subr(dot3(oc, oc), sp.w);
-                        float b;
-                        if (sphere_loss_fast_miss(oc, cc, dir, b)) continue;       // disc < 0 (PM:311)
-                        const float sq = sqrtr(subr(mulr(b, b), cc));
-                        const float len = clip_len_b(subr(-b, sq), addr(-b, sq), tIn, tOut);
-                        if (len > 0.0f) loss = fmaf(len, densS[id], loss);
-                    }
-                }
-                {   // ---- OBBs, PM:294-300 (stored rotation as is), cheap arithmetic about the point of closest approach
-                    const int n01 = nO0 + nO1, n = n01 + nO2;
-                    const uint32_t o0 = h0.x + nS0 + nA0, o1 = h1.x + nS1 + nA1 - nO0, o2 = h2.x + nS2 + nA2 - n01;
-                    int nxt = n > 0 ? (int)__ldg(f.entries + (0 < nO0 ? o0 : (0 < n01 ? o1 : o2))) : 0;
-                    for (int k = 0; k < n; k++) {
-                        const int id = nxt;
-                        const int k1 = k + 1;
-                        if (k1 < n) nxt = (int)__ldg(f.entries + ((k1 < nO0 ? o0 : (k1 < n01 ? o1 : o2)) + (uint32_t)k1));
-                        ART_CHECK(a.counters, id < a.L.no);
-                        const float tIn = k >= n01 ? tT : 0.0f, tOut = (k >= nO0 && k < n01) ? tT : inf;
-                        const float4 c4 = gv.obbC[id];
-                        const float2 h2o = gv.obbH[id];
-                        const f3 pc = mk3(Pp.x - c4.x, Pp.y - c4.y, Pp.z - c4.z);
-                        const float bq = fmaf(pc.z, dir.z, fmaf(pc.y, dir.y, pc.x * dir.x));
-                        const float pp = fmaf(pc.z, pc.z, fmaf(pc.y, pc.y, pc.x * pc.x));
-                        const float r2 = fmaf(h2o.y, h2o.y, fmaf(h2o.x, h2o.x, c4.w * c4.w));
-                        if (pp - bq * bq > r2 * 1.001f + 1e-4f) continue;         // the line passes the bounding sphere
-                        const float4 q4 = gv.obbQ[id];
-                        const f3 pn = mk3(fmaf(dir.x, -bq, pc.x), fmaf(dir.y, -bq, pc.y), fmaf(dir.z, -bq, pc.z));
-                        const f3 lo = qrot_fast(q4, pn), ld = qrot_fast(q4, dir);
-                        const float rx = rcp_fast(ld.x), ry = rcp_fast(ld.y), rz = rcp_fast(ld.z);
-                        const float ax = (-c4.w - lo.x) * rx, bx = (c4.w - lo.x) * rx;
-                        const float ay = (-h2o.x - lo.y) * ry, by = (h2o.x - lo.y) * ry;
-                        const float az = (-h2o.y - lo.z) * rz, bz = (h2o.y - lo.z) * rz;
-                        const float tEnter = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)) - bq;
-                        const float tExit = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) - bq;
-                        const float len = clip_len_b(tEnter, tExit, tIn, tOut);
-                        if (len > 0.0f) loss = fmaf(len, densO[id], loss);
-                    }
-                }
-                if (on) {
-                    const float v = subr(a.nTimesS, loss);                         // PM:260
+            const uint32_t start = cur, end = min(blockEnd, st[bin + 1]);
+            cur = end;
+            if (bin == kBucketNoDir) {
+                // no usable direction (hit point == target): no list to test, loss 0 (as permeation_grid_kernel)
+                if (lane == 0) {
+                    const float v = subr(a.nTimesS, 0.0f);                             // PM:260
                     const float ip = truncf(v);
-                    accInt += (long long)ip;
-                    accFrac += (long long)(((double)v - (double)ip) * 68719476736.0);
+                    accInt += (long long)(end - start) * (long long)ip;
+                    accFrac += (long long)(end - start) * (long long)(((double)v - (double)ip) * 68719476736.0);
+                }
+            } else {
+                const f3 T = mk3(a.targets[3 * tgt], a.targets[3 * tgt + 1], a.targets[3 * tgt + 2]);
+                // cell 0: near list, whole line; 1: bin towards the hit point, t in [0, tT]; 2: opposite bin, t > tT
+                const int fanBase = tgt * kFanCells;
+                const int face = bin / kFanCellsPerFace, rb = bin - face * kFanCellsPerFace;
+                const uint2 h0 = __ldg(&f.cells[fanBase + 6 * kFanCellsPerFace]);
+                const uint2 h1 = __ldg(&f.cells[fanBase + bin]);
+                const uint2 h2 = __ldg(&f.cells[fanBase + (face ^ 1) * kFanCellsPerFace + (kFanCellsPerFace - 1 - rb)]);
+                const int nS0 = h0.y & 1023, nA0 = (h0.y >> 10) & 2047, nO0 = h0.y >> 21;
+                const int nS1 = h1.y & 1023, nA1 = (h1.y >> 10) & 2047, nO1 = h1.y >> 21;
+                const int nS2 = h2.y & 1023, nA2 = (h2.y >> 10) & 2047, nO2 = h2.y >> 21;
+                ART_CHECK(a.counters, h0.x + nS0 + nA0 + nO0 <= (unsigned)f.nEntries && h1.x + nS1 + nA1 + nO1 <= (unsigned)f.nEntries &&
+                                      h2.x + nS2 + nA2 + nO2 <= (unsigned)f.nEntries);
+                const uint32_t* rays = ba.pairRay + (size_t)tgt * ba.nLocal;
+                for (uint32_t i0 = start; i0 < end; i0 += 32) {
+                    const bool on = i0 + lane < end;
+                    float4 rr = make_float4(0, 0, 0, 0);
+                    if (on) rr = ba.hitPts[rays[i0 + lane]];
+                    const f3 Pp = mk3(rr.x, rr.y, rr.z);
+                    const f3 toT = sub3(T, Pp);
+                    // (an idle lane of the last chunk computes on zeros and is ignored)
+                    const f3 dir = normalize3(toT);                                    // PM:76
+                    const f3 inv = mk3(rcpr(dir.x), rcpr(dir.y), rcpr(dir.z));         // PM:270
+                    const float tT = sqrt_fast(fmaf(toT.z, toT.z, fmaf(toT.y, toT.y, toT.x * toT.x)));   // line parameter of the target
+                    float loss = 0.0f;
+                    {   // ---- AABBs, PM:265-288 in the reference's operation order
+                        const int n01 = nA0 + nA1, n = n01 + nA2;
+                        const uint32_t o0 = h0.x + nS0, o1 = h1.x + nS1 - nA0, o2 = h2.x + nS2 - n01;
+                        int nxt = n > 0 ? (int)__ldg(f.entries + (0 < nA0 ? o0 : (0 < n01 ? o1 : o2))) : 0;
+                        for (int k = 0; k < n; k++) {
+                            const int id = nxt;
+                            const int k1 = k + 1;
+                            if (k1 < n) nxt = (int)__ldg(f.entries + ((k1 < nA0 ? o0 : (k1 < n01 ? o1 : o2)) + (uint32_t)k1));
+                            ART_CHECK(a.counters, id < a.L.na);
+                            const float tIn = k >= n01 ? tT : 0.0f, tOut = (k >= nA0 && k < n01) ? tT : inf;
+                            const float4 A = gv.aabbA[id];
+                            const float2 B = gv.aabbB[id];
+                            float tEnter, tExit;
+                            slab<8>(subr(A.x, Pp.x), subr(A.y, Pp.y), subr(A.z, Pp.z), subr(A.w, Pp.x), subr(B.x, Pp.y), subr(B.y, Pp.z),
+                                    inv.x, inv.y, inv.z, tEnter, tExit);
+                            const float len = clip_len_b(tEnter, tExit, tIn, tOut);
+                            if (len > 0.0f) loss = fmaf(len, densA[id], loss);
+                        }
+                    }
+                    {   // ---- spheres, PM:303-328 (unit direction)
+                        const int n01 = nS0 + nS1, n = n01 + nS2;
+                        const uint32_t o0 = h0.x, o1 = h1.x - nS0, o2 = h2.x - n01;
+                        for (int k = 0; k < n; k++) {
+                            const int id = (int)__ldg(f.entries + ((k < nS0 ? o0 : (k < n01 ? o1 : o2)) + (uint32_t)k));
+                            ART_CHECK(a.counters, id < a.L.ns);
+                            const float tIn = k >= n01 ? tT : 0.0f, tOut = (k >= nS0 && k < n01) ? tT : inf;
+                            const float4 sp = gv.sph[id];
+                            const f3 oc = sub3(Pp, mk3(sp.x, sp.y, sp.z));
+                            const float cc = subr(dot3(oc, oc), sp.w);
+                            float b;
+                            if (sphere_loss_fast_miss(oc, cc, dir, b)) continue;       // disc < 0 (PM:311)
+                            const float sq = sqrtr(subr(mulr(b, b), cc));
+                            const float len = clip_len_b(subr(-b, sq), addr(-b, sq), tIn, tOut);
+                            if (len > 0.0f) loss = fmaf(len, densS[id], loss);
+                        }
+                    }
+                    {   // ---- OBBs, PM:294-300 (stored rotation as is), cheap arithmetic about the point of closest approach
+                        const int n01 = nO0 + nO1, n = n01 + nO2;
+                        const uint32_t o0 = h0.x + nS0 + nA0, o1 = h1.x + nS1 + nA1 - nO0, o2 = h2.x + nS2 + nA2 - n01;
+                        int nxt = n > 0 ? (int)__ldg(f.entries + (0 < nO0 ? o0 : (0 < n01 ? o1 : o2))) : 0;
+                        for (int k = 0; k < n; k++) {
+                            const int id = nxt;
+                            const int k1 = k + 1;
+                            if (k1 < n) nxt = (int)__ldg(f.entries + ((k1 < nO0 ? o0 : (k1 < n01 ? o1 : o2)) + (uint32_t)k1));
+                            ART_CHECK(a.counters, id < a.L.no);
+                            const float tIn = k >= n01 ? tT : 0.0f, tOut = (k >= nO0 && k < n01) ? tT : inf;
+                            const float4 c4 = gv.obbC[id];
+                            const float2 h2o = gv.obbH[id];
+                            const f3 pc = mk3(Pp.x - c4.x, Pp.y - c4.y, Pp.z - c4.z);
+                            const float bq = fmaf(pc.z, dir.z, fmaf(pc.y, dir.y, pc.x * dir.x));
+                            const float pp = fmaf(pc.z, pc.z, fmaf(pc.y, pc.y, pc.x * pc.x));
+                            const float r2 = fmaf(h2o.y, h2o.y, fmaf(h2o.x, h2o.x, c4.w * c4.w));
+                            if (pp - bq * bq > r2 * 1.001f + 1e-4f) continue;         // the line passes the bounding sphere
+                            const float4 q4 = gv.obbQ[id];
+                            const f3 pn = mk3(fmaf(dir.x, -bq, pc.x), fmaf(dir.y, -bq, pc.y), fmaf(dir.z, -bq, pc.z));
+                            const f3 lo = qrot_fast(q4, pn), ld = qrot_fast(q4, dir);
+                            const float rx = rcp_fast(ld.x), ry = rcp_fast(ld.y), rz = rcp_fast(ld.z);
+                            const float ax = (-c4.w - lo.x) * rx, bx = (c4.w - lo.x) * rx;
+                            const float ay = (-h2o.x - lo.y) * ry, by = (h2o.x - lo.y) * ry;
+                            const float az = (-h2o.y - lo.z) * rz, bz = (h2o.y - lo.z) * rz;
+                            const float tEnter = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)) - bq;
+                            const float tExit = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) - bq;
+                            const float len = clip_len_b(tEnter, tExit, tIn, tOut);
+                            if (len > 0.0f) loss = fmaf(len, densO[id], loss);
+                        }
+                    }
+                    if (on) {
+                        const float v = subr(a.nTimesS, loss);                         // PM:260
+                        const float ip = truncf(v);
+                        accInt += (long long)ip;
+                        accFrac += (long long)(((double)v - (double)ip) * 68719476736.0);
+                    }
                 }
             }
-        }
         }   // next bin segment of the block
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) {
