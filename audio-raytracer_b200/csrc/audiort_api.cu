@@ -181,6 +181,7 @@ struct ArtCtx {
     DevBuf rawScene, geom, attrs, owners, perm;    // perm: dens arrays + owned list
     HostGrid grid;                                 // uniform grid over the scene (grid_host.h)
     DevBuf gridCells, gridEntries, gridRangeO, gridScratch, rotateLog;
+    DevBuf hitRecs, queryScratch;                  // bounce-only trace job: hit records + survivor lists of query_fan_kernel
     DevBuf permHitPts, permBinCnt, permPairs;       // binned loss lines (k2_permeation_binned.cu)
     DevBuf fanBoxes, fanCells, fanEntries, fanCtl, fanOrder;  // target fans (fan_dev.cuh): collider bounds (per scene), lists (per frame)
     PinBuf pinFanCtl;
@@ -445,7 +446,7 @@ ART_API void art_destroy(ArtCtx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->rotateLog, &ctx->permHitPts, &ctx->permBinCnt, &ctx->permPairs, &ctx->fanBoxes, &ctx->fanCells, &ctx->fanEntries, &ctx->fanCtl, &ctx->fanOrder, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
+    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->rotateLog, &ctx->hitRecs, &ctx->queryScratch, &ctx->permHitPts, &ctx->permBinCnt, &ctx->permPairs, &ctx->fanBoxes, &ctx->fanCells, &ctx->fanEntries, &ctx->fanCtl, &ctx->fanOrder, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
                        &ctx->outAll, &ctx->firstHit, &ctx->partials, &ctx->queue })
         b->release();
     for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinAll, &ctx->pinPerm, &ctx->pinFanCtl })
@@ -805,7 +806,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         const size_t cap = nFans * perFan + 4096;
         if (cap > ((size_t)1 << 30) || nFans * kFanCells > ((size_t)1 << 28)) useFans = false;   // > 2 GiB of lists: walk the grid instead
         else {
-            CK(ctx->fanCells.ensure(nFans * kFanCells * (sizeof(uint2) + sizeof(uint32_t))));   // cells, then FanDesc::firstA
+            CK(ctx->fanCells.ensure(nFans * kFanCells * (sizeof(uint4) + sizeof(uint2) + sizeof(uint32_t))));   // FanDesc::cells4, cells, firstA
             CK(ctx->fanEntries.ensure(cap * sizeof(uint16_t)));
             CK(ctx->fanCtl.ensure(16));
             CK(ctx->pinFanCtl.ensure(16));
@@ -817,7 +818,8 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             fa.targets = ctx->targets.as<float>(); fa.nTargets = Na;
             fa.lx = prm->rayOrigin[0]; fa.ly = prm->rayOrigin[1]; fa.lz = prm->rayOrigin[2];
             fa.nearDist = 1e-3f * ctx->grid.d.errScale;
-            fa.cells = ctx->fanCells.as<uint2>(); fa.entries = ctx->fanEntries.as<uint16_t>();
+            fa.cells4 = ctx->fanCells.as<uint4>();
+            fa.cells = reinterpret_cast<uint2*>(fa.cells4 + nFans * kFanCells); fa.entries = ctx->fanEntries.as<uint16_t>();
             fa.firstA = reinterpret_cast<uint32_t*>(fa.cells + nFans * kFanCells);
             fa.capacity = (unsigned int)cap; fa.ctl = ctx->fanCtl.as<unsigned int>();
             fa.order = nullptr;
@@ -828,7 +830,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             }
             CK(launch_fan_build(fa, ctx->stream));
             ctx->kernelLaunches++;
-            fd.nFans = (int)nFans; fd.cells = fa.cells; fd.entries = fa.entries; fd.nEntries = (int)cap; fd.firstA = fa.firstA;
+            fd.nFans = (int)nFans; fd.cells = fa.cells; fd.entries = fa.entries; fd.nEntries = (int)cap; fd.firstA = fa.firstA; fd.cells4 = fa.cells4;
             ctx->frameGridUsed |= 4u;
         }
     }
@@ -873,7 +875,33 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         ta.scratch = nullptr;
         ta.migGroups = 0; ta.migSlots = 0; ta.migFlags = nullptr; ta.migState = nullptr;
         trace_grid_plan(map.nLocal, Na, ctx->numSms, &ta.gridWarps, &ta.raysPerWarp);
-        if (useGrid) {
+        ta.recA = nullptr; ta.recB = nullptr; ta.recCount = nullptr;
+        if (useGrid && useFans) {
+            // Bounce-only tracer + one query kernel over all hit points (k1_query_fan.cu): RT:124-173 only writes
+            // EchoRayDistances / MuffleRayHits, nothing there feeds the bounce loop.
+            const bool stats = (prm->flags & ART_FRAME_GRID_STATS) != 0;
+            const size_t recBytesA = (NH * sizeof(float4) + 255) & ~(size_t)255;
+            CK(ctx->hitRecs.ensure(recBytesA + NH * sizeof(float2) + 16));
+            CK(ctx->queryScratch.ensure(query_fan_scratch_bytes(ctx->numSms)));
+            ta.recA = ctx->hitRecs.as<float4>();
+            ta.recB = reinterpret_cast<float2*>(ctx->hitRecs.as<unsigned char>() + recBytesA);
+            ta.recCount = ta.nextRay + 4;                        // (zeroed with the queue counters)
+            const bool gInSmem = trace_grid_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
+            CK(launch_trace_grid(ta, gd, true, ctx->numSms, gInSmem, stats, ctx->stream));
+            QueryArgs qa;
+            qa.geom = ta.geom; qa.L = L; qa.recA = ta.recA; qa.recB = ta.recB; qa.recCount = ta.recCount;
+            qa.map = map; qa.H = H; qa.batchSize = b;
+            qa.ox = ta.ox; qa.oy = ta.oy; qa.oz = ta.oz; qa.targets = ta.targets; qa.nTargets = Na;
+            qa.maxMuffle = ta.maxMuffle; qa.errScale = gd.errScale;
+            qa.echo = ta.echo; qa.muffleCounts = ta.muffleCounts; qa.muffleRows = T; qa.counters = ta.counters;
+            qa.queue = ta.nextRay + 5;
+            qa.scratch = ctx->queryScratch.as<float4>();
+            qa.tablesInSmem = 0; qa.muffleInSmem = 0;
+            const bool qInSmem = query_fan_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
+            CK(launch_query_fan(qa, fd, ctx->numSms, qInSmem, stats, ctx->maxSmemOptin, ctx->stream));
+            ctx->kernelLaunches++;
+            ctx->frameGridUsed |= 1u;
+        } else if (useGrid) {
             CK(ctx->gridScratch.ensure(trace_grid_scratch_bytes(ctx->numSms)));
             ta.scratch = ctx->gridScratch.as<uint32_t>();
             // small batches (a shard of a ray-sharded frame): rotate the ray groups through the warps (k1_trace_grid.cu)
@@ -896,7 +924,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
                 ctx->frameGridUsed |= 16u;
             }
             const bool gInSmem = trace_grid_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
-            CK(launch_trace_grid(ta, gd, useFans ? &fd : nullptr, ctx->numSms, gInSmem, (prm->flags & ART_FRAME_GRID_STATS) != 0, ctx->stream));
+            CK(launch_trace_grid(ta, gd, false, ctx->numSms, gInSmem, (prm->flags & ART_FRAME_GRID_STATS) != 0, ctx->stream));
             ctx->frameGridUsed |= 1u;
         } else {
             CK(launch_trace(ta, ctx->numSms, geomInSmem, count, ctx->stream));
@@ -1253,7 +1281,8 @@ ART_API int32_t art_debug_get_fans(ArtCtx* ctx, ArtFanInfo* info, uint32_t* cell
     info->nEntries = (int64_t)ctx->pinFanCtl.as<unsigned int>()[0];
     if (cells) {
         if (cellsCapacity < 2 * info->nCells) return fail(ctx, ART_E_ARG, "cells buffer too small");
-        CK(cudaMemcpy(cells, ctx->fanCells.p, (size_t)info->nCells * sizeof(uint2), cudaMemcpyDeviceToHost));
+        // (the buffer holds FanDesc::cells4, then cells, then firstA)
+        CK(cudaMemcpy(cells, ctx->fanCells.as<unsigned char>() + (size_t)info->nCells * sizeof(uint4), (size_t)info->nCells * sizeof(uint2), cudaMemcpyDeviceToHost));
     }
     if (entries) {
         if (entriesCapacity < info->nEntries) return fail(ctx, ART_E_ARG, "entries buffer too small");

@@ -39,6 +39,8 @@ struct FanDesc {
     int nEntries;              // capacity (bounds checks of debug builds)
     const uint32_t* firstA;    // [nFans * kFanCells]: the cell's first two AABB entries, id0 | id1 << 16 (K1's first pass tests
                                // exactly those: it reads them beside the header instead of chasing the entry list afterwards)
+    const uint4* cells4;       // [nFans * kFanCells]: (cells[i].x, cells[i].y, AABB ids 0 | 1 << 16, AABB ids 2 | 3 << 16) -- header and
+                               // first ids in ONE 16-byte load (query_fan_kernel: one divergent L2 access per query)
 };
 
 // fan_build_kernel arguments (k4_fan_build.cu)
@@ -53,6 +55,7 @@ struct FanBuildArgs {
     float nearDist;
     uint2* cells;              // [(nTargets + 1) * kFanCells]
     uint32_t* firstA;          // [(nTargets + 1) * kFanCells], see FanDesc
+    uint4* cells4;             // [(nTargets + 1) * kFanCells], see FanDesc
     uint16_t* entries;
     unsigned int capacity;     // entries available
     unsigned int* ctl;         // [0] next free entry, [1] overflow flag (zeroed by the host before the launch)

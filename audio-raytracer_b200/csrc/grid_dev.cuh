@@ -123,4 +123,18 @@ __device__ __forceinline__ float obb_dist_nearest_q(const GeomView& gv, float4 q
     return obb_dist_exact(q4.x, q4.y, q4.z, q4.w, pc.x, pc.y, pc.z, h.x, h.y, h.z, d.x, d.y, d.z);
 }
 
+// any-hit: does the exact test report a distance < limit (RT:390 / RT:441)?
+__device__ __forceinline__ bool obb_blocks(const GeomView& gv, int id, f3 o, f3 d, float dd, float errScale, float limit)
+{
+    const float4 c4 = gv.obbC[id];
+    const float2 h2 = gv.obbH[id];
+    const f3 h = mk3(c4.w, h2.x, h2.y);
+    const f3 pc = sub3(o, mk3(c4.x, c4.y, c4.z));
+    if (obb_sure_miss(pc, obb_cull_c(pc, h), d, dd)) return false;
+    const float4 q4 = gv.obbQ[id];
+    const int cls = obb_classify(q4, pc, h, d, errScale, limit);
+    if (cls != 2) return cls == 1;
+    return obb_dist_exact(q4.x, q4.y, q4.z, q4.w, pc.x, pc.y, pc.z, h.x, h.y, h.z, d.x, d.y, d.z) < limit;
+}
+
 }  // namespace art

@@ -16,7 +16,6 @@
 #include <cstdlib>
 
 #include "device_util.cuh"
-#include "fan_dev.cuh"
 #include "grid_dev.cuh"
 #include "intersect.cuh"
 #include "scene_dev.cuh"
@@ -55,20 +54,6 @@ __device__ __forceinline__ float obb_dist_nearest(const GeomView& gv, int id, f3
     if (!obb_maybe_nearer(q4, pc, h, d, errScale, best)) return quiet_nan();
     return obb_dist_exact(q4.x, q4.y, q4.z, q4.w, pc.x, pc.y, pc.z, h.x, h.y, h.z, d.x, d.y, d.z);
 }
-// any-hit: does the exact test report a distance < limit (RT:390 / RT:441)?
-__device__ __forceinline__ bool obb_blocks(const GeomView& gv, int id, f3 o, f3 d, float dd, float errScale, float limit)
-{
-    const float4 c4 = gv.obbC[id];
-    const float2 h2 = gv.obbH[id];
-    const f3 h = mk3(c4.w, h2.x, h2.y);
-    const f3 pc = sub3(o, mk3(c4.x, c4.y, c4.z));
-    if (obb_sure_miss(pc, obb_cull_c(pc, h), d, dd)) return false;
-    const float4 q4 = gv.obbQ[id];
-    const int cls = obb_classify(q4, pc, h, d, errScale, limit);
-    if (cls != 2) return cls == 1;
-    return obb_dist_exact(q4.x, q4.y, q4.z, q4.w, pc.x, pc.y, pc.z, h.x, h.y, h.z, d.x, d.y, d.z) < limit;
-}
-
 struct HitRec {            // per hit point, shared memory (one per lane)
     float px, py, pz;      // Pp = hit - eps*d   (RT:124 == RT:158)
     float echoL;           // distance(RayOrigin, hit)  (RT:130)
@@ -87,7 +72,6 @@ constexpr int kTwoStageSlots = 16;       // queries per hit point from which the
 struct PoolEnv {
     const TraceArgs& a;
     const GridDesc& g;
-    const FanDesc& f;                    // target fans (FAN variants): the pool's queries all end in the listener or a target
     const GeomView& gv;
     const HitRec* rec;                   // per-warp hit records (shared memory)
     float4* qbuf0; float4* qbuf1; float4* qbuf2; int* qbuf3;   // per-warp ring of prepared queries (shared memory)
@@ -116,10 +100,7 @@ __device__ __forceinline__ void query_visible(const PoolEnv& E, int slot, int re
 //   STAGE 1: the survivors, against the sphere and OBB lists. A query that survives this too sees its goal.
 //   STAGE 2: (few queries per hit point) all three lists in one pass.
 // An occlusion query is an "any" over all colliders (RT:365-449), so the order of the tests is free.
-// FAN: instead of walking the grid cells along the segment, a query tests the two lists its goal's fan holds for
-// it (fan_dev.cuh): the goal's near list and the direction bin of (hit point - goal). Colliders owned by the goal's
-// target are not in its fan, so the owner checks fall away.
-template <int STAGE, bool STATS, bool FAN>
+template <int STAGE, bool STATS>
 __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count, bool noSO)
 {
     const TraceArgs& a = E.a;
@@ -127,8 +108,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
     const GeomView& gv = E.gv;
     const int lane = E.lane;
     const uint32_t ltMask = E.ltMask;
-    const uint16_t* const ebase = FAN ? E.f.entries : g.entries;
-    int fCell0 = 0, fCell1 = 0, fPos = 2;   // FAN: near cell, bin cell, next of the two to fetch (2 = none left)
+    const uint16_t* const ebase = g.entries;
     int nextQ = 0, bufNext = 0, bufCount = 0, survCount = 0;
     bool have = false;
     f3 qo = mk3(0, 0, 0), qd = mk3(0, 0, 0), qinv = mk3(0, 0, 0);
@@ -179,15 +159,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                     else { nL = len; gate = nL < a.maxMuffle; }                    // RT:165, 168
                     if (gate) {
                         ninv = mk3(rcpr(nd.x), rcpr(nd.y), rcpr(nd.z));
-                        if (FAN) {
-                            const int bin = fan_bin(-v.x, -v.y, -v.z);             // direction goal -> hit point
-                            const int fanBase = (nslot == 0 ? a.nTargets : nslot - 1) * kFanCells;
-                            nw.ix = fanBase + 6 * kFanCellsPerFace;                // near list of the goal
-                            nw.iy = fanBase + bin;
-                            active = bin >= 0 && len == len;                       // degenerate (hit point == goal): no test can block
-                        } else {
-                            active = dda_init(g, no, nd, ninv, nL, nw);
-                        }
+                        active = dda_init(g, no, nd, ninv, nL, nw);
                         if (!active) query_visible(E, nslot, nrec, nL);            // nothing near the segment
                     }
                 }
@@ -196,9 +168,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                     const int pos = __popc(act & ltMask);
                     E.qbuf0[pos] = make_float4(nd.x, nd.y, nd.z, nL);
                     E.qbuf1[pos] = make_float4(ninv.x, ninv.y, ninv.z, nw.tEnd);
-                    if (FAN) E.qbuf2[pos] = make_float4(__int_as_float(nw.ix), __int_as_float(nw.iy), 0.0f, __int_as_float(nrec << 24));
-                    else E.qbuf2[pos] = make_float4(nw.tmx, nw.tmy, nw.tmz,
-                                                    __int_as_float(nw.ix | (nw.iy << 8) | (nw.iz << 16) | (nrec << 24)));
+                    E.qbuf2[pos] = make_float4(nw.tmx, nw.tmy, nw.tmz, __int_as_float(nw.ix | (nw.iy << 8) | (nw.iz << 16) | (nrec << 24)));
                     E.qbuf3[pos] = nslot;
                 }
                 bufNext = 0;
@@ -215,13 +185,9 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                     qinv = mk3(v1.x, v1.y, v1.z); w.tEnd = v1.w;
                     const int packed = __float_as_int(v2.w);
                     qrec = (packed >> 24) & 31;
-                    if (FAN) {
-                        fCell0 = __float_as_int(v2.x); fCell1 = __float_as_int(v2.y); fPos = 0;
-                    } else {
-                        w.tmx = v2.x; w.tmy = v2.y; w.tmz = v2.z;
-                        w.ix = packed & 255; w.iy = (packed >> 8) & 255; w.iz = (packed >> 16) & 255;
-                        w.tdx = fabsf(g.csx * qinv.x); w.tdy = fabsf(g.csy * qinv.y); w.tdz = fabsf(g.csz * qinv.z);
-                    }
+                    w.tmx = v2.x; w.tmy = v2.y; w.tmz = v2.z;
+                    w.ix = packed & 255; w.iy = (packed >> 8) & 255; w.iz = (packed >> 16) & 255;
+                    w.tdx = fabsf(g.csx * qinv.x); w.tdy = fabsf(g.csy * qinv.y); w.tdz = fabsf(g.csz * qinv.z);
                     qdd = dot3(qd, qd);
                     const HitRec r = E.rec[qrec];
                     qo = mk3(r.px, r.py, r.pz);
@@ -242,18 +208,12 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
             bool walkDone = false;
             for (int s = 0; s < kSkipCells; s++) {
                 if (kA < (int)((hdr.y >> 10) & 2047)) break;
-                if (FAN) {
-                    if (fPos >= 2) { walkDone = true; break; }
-                    hdr = __ldg(&E.f.cells[fPos == 0 ? fCell0 : fCell1]);
-                    fPos++;
-                } else {
-                    if (!fresh) {
-                        const float tNext = dda_next_t(w);
-                        if (tNext > w.tEnd || !dda_step(g, qd, w)) { walkDone = true; break; }
-                    }
-                    fresh = false;
-                    hdr = dda_cell(g, w);
+                if (!fresh) {
+                    const float tNext = dda_next_t(w);
+                    if (tNext > w.tEnd || !dda_step(g, qd, w)) { walkDone = true; break; }
                 }
+                fresh = false;
+                hdr = dda_cell(g, w);
                 if (STATS) E.st[3]++;
                 kA = 0;
             }
@@ -264,10 +224,10 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                 const int ownerId = qslot - 1;         // -1 for the echo ray: never equals a valid owner below
                 for (int c = 0; c < kCapA && kA < nA && !blocked; c++, kA++) {
                     const int id = __ldg(e + kA);
-                    ART_CHECK(a.counters, id < a.L.na && hdr.x + nS + nA <= (unsigned)(FAN ? E.f.nEntries : g.nEntries));
+                    ART_CHECK(a.counters, id < a.L.na && hdr.x + nS + nA <= (unsigned)g.nEntries);
                     if (STATS) E.st[1]++;
                     if (aabb_blocks(gv, id, qo, qinv, qL))
-                        blocked = FAN || !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
+                        blocked = !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
                 }
             }
             if (blocked) {
@@ -285,18 +245,12 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                 const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
                 const bool pending = kB < nS || kC < nO || (STAGE == 2 && kA < nA);
                 if (pending) break;
-                if (FAN) {
-                    if (fPos >= 2) { walkDone = true; break; }
-                    hdr = __ldg(&E.f.cells[fPos == 0 ? fCell0 : fCell1]);
-                    fPos++;
-                } else {
-                    if (!fresh) {
-                        const float tNext = dda_next_t(w);
-                        if (tNext > w.tEnd || !dda_step(g, qd, w)) { walkDone = true; break; }
-                    }
-                    fresh = false;
-                    hdr = dda_cell(g, w);
+                if (!fresh) {
+                    const float tNext = dda_next_t(w);
+                    if (tNext > w.tEnd || !dda_step(g, qd, w)) { walkDone = true; break; }
                 }
+                fresh = false;
+                hdr = dda_cell(g, w);
                 if (STATS) E.st[3]++;
                 kA = kB = kC = 0;
             }
@@ -311,7 +265,7 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                         ART_CHECK(a.counters, id < a.L.na);
                         if (STATS) E.st[1]++;
                         if (aabb_blocks(gv, id, qo, qinv, qL))
-                            blocked = FAN || !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
+                            blocked = !(qslot > 0 && a.anyOwned[1] && (int)a.at.ownA[id] == ownerId);   // RT:426
                     }
                 }
                 for (int c = 0; c < kCapS && kB < nS && !blocked; c++, kB++) {
@@ -319,14 +273,14 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
                     ART_CHECK(a.counters, id < a.L.ns);
                     if (STATS) E.st[0]++;
                     if (sphere_dist(gv, id, qo, qd, qdd) < qL)
-                        blocked = FAN || !(qslot > 0 && a.anyOwned[0] && (int)a.at.ownS[id] == ownerId);       // RT:413
+                        blocked = !(qslot > 0 && a.anyOwned[0] && (int)a.at.ownS[id] == ownerId);       // RT:413
                 }
                 for (int c = 0; c < kCapO && kC < nO && !blocked; c++, kC++) {
                     const int id = __ldg(e + nS + nA + kC);
-                    ART_CHECK(a.counters, id < a.L.no && hdr.x + nS + nA + nO <= (unsigned)(FAN ? E.f.nEntries : g.nEntries));
+                    ART_CHECK(a.counters, id < a.L.no && hdr.x + nS + nA + nO <= (unsigned)g.nEntries);
                     if (STATS) E.st[2]++;
                     if (obb_blocks(gv, id, qo, qd, qdd, g.errScale, qL))
-                        blocked = FAN || !(qslot > 0 && a.anyOwned[2] && (int)a.at.ownO[id] == ownerId);       // RT:439
+                        blocked = !(qslot > 0 && a.anyOwned[2] && (int)a.at.ownO[id] == ownerId);       // RT:439
                 }
             }
             if (blocked) {
@@ -349,274 +303,13 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
     return survCount;
 }
 
-// ---- target-fan occlusion queries (FAN kernels, fan_dev.cuh) ---------------------------------------------
-#ifndef ART_FAN_FIRST_TESTS
-#define ART_FAN_FIRST_TESTS 2
-#endif
-#ifndef ART_FIRST_PASS_ROLLED
-#define ART_FIRST_PASS_ROLLED 1
-#endif
-constexpr int kFanFirstTests = ART_FAN_FIRST_TESTS;   // AABBs every query tests in the full-width first pass
-// Every echo / muffle query ends in the listener or an audio target, so instead of walking grid cells it tests the two
-// lists its goal's fan holds for it: the goal's near list and the direction bin of (hit point - goal), AABBs first,
-// nearest to the goal first. Colliders owned by the goal's target are not in its fan (RT:413/426/439 skip them), so the
-// owner checks fall away.
-//
-// Prepare query (slot, rec): 0 = gated out (RT:168), 1 = the goal is visible without any test, 2 = lists to test.
-template <bool FIRST>
-__device__ __forceinline__ int fan_prepare(const PoolEnv& E, int nslot, int nrec, f3& no, f3& nd, f3& ninv, float& nL, uint2& hN, uint2& hB,
-                                           uint32_t& fN, uint32_t& fB)
-{
-    const TraceArgs& a = E.a;
-    const HitRec r = E.rec[nrec];
-    no = mk3(r.px, r.py, r.pz);
-    f3 T = E.RayOrigin;
-    if (E.goalBySlot) { const float4 gT = E.goalBySlot[nslot]; T = mk3(gT.x, gT.y, gT.z); }
-    else if (nslot > 0) T = mk3(a.targets[3 * (nslot - 1)], a.targets[3 * (nslot - 1) + 1], a.targets[3 * (nslot - 1) + 2]);
-    const f3 v = sub3(T, no);                                      // RT:127 / RT:162
-    // the list headers depend on the direction's bin only: their loads (L2) are issued first and complete while the exact
-    // square root and reciprocals below are computed
-    const int bin = fan_bin(-v.x, -v.y, -v.z);                     // direction goal -> hit point
-    hN = make_uint2(0, 0); hB = make_uint2(0, 0);
-    if (bin >= 0) {
-        const int fanBase = (nslot == 0 ? a.nTargets : nslot - 1) * kFanCells;
-        hN = __ldg(&E.f.cells[fanBase + 6 * kFanCellsPerFace]);    // near list of the goal
-        hB = __ldg(&E.f.cells[fanBase + bin]);
-        if (FIRST) {                                               // the first two AABBs of either list, fetched beside the headers
-            fN = __ldg(&E.f.firstA[fanBase + 6 * kFanCellsPerFace]);
-            fB = __ldg(&E.f.firstA[fanBase + bin]);
-        }
-    }
-    const float len = sqrtr(dot3(v, v));
-    nd = smul3(rcpr(len), v);                                      // normalize = rsqrt(dot) * v
-    ninv = mk3(0, 0, 0);
-    if (nslot == 0) nL = r.echoL;                                  // RT:130
-    else { nL = len; if (!(nL < a.maxMuffle)) return 0; }          // RT:165, 168
-    if (bin < 0 || len != len) return 1;                           // degenerate (hit point == goal): no test can block
-    ninv = mk3(rcpr(nd.x), rcpr(nd.y), rcpr(nd.z));
-    return 2;
-}
-
-// First pass, full width: every (hit point, slot) query of the round is prepared by its own lane and tested against
-// the first kFanFirstTests AABBs of its lists -- with nearest-first lists that alone blocks most queries. The others go to the
-// survivor list (slot | rec << 16) for the pooled stages below. recOfOrd: lane of the n-th hit point of the round.
-template <bool STATS>
-__device__ __forceinline__ int fan_first_pass(const PoolEnv& E, int qFirst, int count, const int* recOfOrd)
-{
-    const TraceArgs& a = E.a;
-    const float invSlots = 1.0f / (float)E.slots;
-    int survCount = 0;
-    for (int q0 = 0; q0 < count; q0 += 32) {
-        const int q = qFirst + q0 + E.lane;
-        bool survived = false;
-        int nslot = 0, nrec = 0;
-        if (q0 + E.lane < count) {
-            int ord = (int)((float)q * invSlots);                  // q < 2^24: the product is within one of q / slots
-            nslot = q - ord * E.slots;
-            if (nslot < 0) { ord--; nslot += E.slots; }
-            else if (nslot >= E.slots) { ord++; nslot -= E.slots; }
-            if (E.goalByPos) nslot = __float_as_int(E.goalByPos[nslot].w);
-            else if (nslot > 0) nslot = a.targetOrder[nslot - 1] + 1;
-            nrec = recOfOrd[ord];
-            ART_CHECK(a.counters, (unsigned)nrec < 32u && nslot >= 0 && nslot <= a.nTargets);
-            f3 no, nd, ninv; float nL; uint2 hN, hB; uint32_t fN = 0, fB = 0;
-            const int state = fan_prepare<kFanFirstTests <= 2>(E, nslot, nrec, no, nd, ninv, nL, hN, hB, fN, fB);
-            if (state == 1) query_visible(E, nslot, nrec, nL);
-            if (state == 2) {
-                const int nS0 = hN.y & 1023, nA0 = (hN.y >> 10) & 2047, nS1 = hB.y & 1023, nA1 = (hB.y >> 10) & 2047;
-                if (STATS) E.st[3] += 2;
-                bool blocked = false;
-                const uint16_t* eN = E.f.entries + hN.x + nS0;
-                const uint16_t* eB = E.f.entries + hB.x + nS1 - nA0;
-                const int nFirst = min(nA0 + nA1, kFanFirstTests);
-                // the run "near list, then bin" starts with these ids (FanDesc::firstA): no dependent load of the entry lists here
-                const uint32_t ids = nA0 >= 2 ? fN : (nA0 == 1 ? (fN & 0xFFFFu) | (fB << 16) : fB);
-#if ART_FIRST_PASS_ROLLED
-#pragma unroll 1
-#endif
-                for (int t = 0; t < nFirst && !blocked; t++) {
-                    const int id = kFanFirstTests <= 2 ? (int)((ids >> (16 * t)) & 0xFFFFu) : (int)__ldg((t < nA0 ? eN : eB) + t);
-                    ART_CHECK(a.counters, id < a.L.na);
-                    if (STATS) E.st[1]++;
-                    blocked = aabb_blocks(E.gv, id, no, ninv, nL);
-                }
-                if (!blocked) {
-                    const bool more = nA0 + nA1 > kFanFirstTests || (nS0 | nS1 | (hN.y >> 21) | (hB.y >> 21)) != 0;
-                    if (more) survived = true;
-                    else query_visible(E, nslot, nrec, nL);
-                }
-            }
-        }
-        const uint32_t push = __ballot_sync(kFull, survived);
-        if (push) {
-            ART_CHECK(a.counters, survCount + __popc(push) <= kChunkQ);
-            if (survived) E.surv[survCount + __popc(push & E.ltMask)] = (uint32_t)nslot | ((uint32_t)nrec << 16);
-            survCount += __popc(push);
-        }
-    }
-    __syncwarp();
-    return survCount;
-}
-
-// Pooled stages over the survivor list (read and, in stage 0, rewritten in place: a survivor is only ever written below
-// the entries already read). Queries are PREPARED 32 at a time by the whole warp -- including both list headers, so the
-// loads of 32 queries are in flight together -- and CONSUMED by whichever lanes are idle, a bounded slice per step.
-//   STAGE 0: the AABB lists (near list, then bin), skipping the AABBs fan_first_pass has tested.
-//   STAGE 1: the sphere and OBB lists.
-template <int STAGE, bool STATS>
-__device__ __forceinline__ int run_pool_fan(const PoolEnv& E, int count)
-{
-    const TraceArgs& a = E.a; (void)a;       // (only the debug-bounds checks read it)
-    const GeomView& gv = E.gv;
-    const int lane = E.lane;
-    const uint32_t ltMask = E.ltMask;
-    const uint16_t* const ebase = E.f.entries;
-    int nextQ = 0, bufNext = 0, bufCount = 0, survCount = 0;
-    bool have = false;
-    f3 qo = mk3(0, 0, 0), qd = mk3(0, 0, 0), qinv = mk3(0, 0, 0);
-    float qL = 0.0f, qdd = 0.0f;
-    uint32_t qpacked = 0;
-    uint2 hdr = make_uint2(0, 0), hdr0 = make_uint2(0, 0), hdr1 = make_uint2(0, 0);
-    int fPos = 2;                     // next of the two lists to open (2 = none left)
-    int skipA = 0;                    // AABBs fan_first_pass has already tested
-    bool anySO = false;
-    int kA = 0, kB = 0, kC = 0;       // cursors inside the current lists: AABB, sphere, OBB
-    for (;;) {
-        const uint32_t idle = __ballot_sync(kFull, !have);
-        if (idle) {
-            if (bufNext == bufCount && nextQ < count) {
-                // ---- prepare the next 32 queries (all lanes)
-                const int qi = nextQ + lane;
-                nextQ += 32;
-                bool active = false;
-                f3 no, nd = mk3(0, 0, 0), ninv = mk3(0, 0, 0);
-                float nL = 0.0f;
-                uint2 hN = make_uint2(0, 0), hB = make_uint2(0, 0);
-                uint32_t packed = 0;
-                if (qi < count) {
-                    packed = E.surv[qi];
-                    const int nslot = (int)(packed & 0xFFFFu), nrec = (int)(packed >> 16);
-                    ART_CHECK(a.counters, (unsigned)nrec < 32u && nslot >= 0 && nslot <= a.nTargets);
-                    uint32_t fN, fB;
-                    const int state = fan_prepare<false>(E, nslot, nrec, no, nd, ninv, nL, hN, hB, fN, fB);
-                    active = state == 2;
-                    if (state == 1) query_visible(E, nslot, nrec, nL);
-                }
-                const uint32_t act = __ballot_sync(kFull, active);
-                if (active) {
-                    const int pos = __popc(act & ltMask);
-                    E.qbuf0[pos] = make_float4(nd.x, nd.y, nd.z, nL);
-                    E.qbuf1[pos] = make_float4(ninv.x, ninv.y, ninv.z, __uint_as_float(packed));
-                    E.qbuf2[pos] = make_float4(__uint_as_float(hN.x), __uint_as_float(hN.y), __uint_as_float(hB.x), __uint_as_float(hB.y));
-                }
-                bufNext = 0;
-                bufCount = __popc(act);
-                __syncwarp();
-            }
-            if (bufNext < bufCount) {
-                // ---- idle lanes take prepared queries
-                const int pos = bufNext + __popc(idle & ltMask);
-                if (!have && pos < bufCount) {
-                    const float4 v0 = E.qbuf0[pos], v1 = E.qbuf1[pos], v2 = E.qbuf2[pos];
-                    qd = mk3(v0.x, v0.y, v0.z); qL = v0.w;
-                    qinv = mk3(v1.x, v1.y, v1.z); qpacked = __float_as_uint(v1.w);
-                    hdr0 = make_uint2(__float_as_uint(v2.x), __float_as_uint(v2.y));
-                    hdr1 = make_uint2(__float_as_uint(v2.z), __float_as_uint(v2.w));
-                    qdd = dot3(qd, qd);
-                    const HitRec r = E.rec[qpacked >> 16];
-                    qo = mk3(r.px, r.py, r.pz);
-                    anySO = ((hdr0.y & 1023) | (hdr0.y >> 21) | (hdr1.y & 1023) | (hdr1.y >> 21)) != 0;
-                    fPos = 0; skipA = STAGE == 0 ? kFanFirstTests : 0; kA = kB = kC = 0; hdr = make_uint2(0, 0);
-                    have = true;
-                }
-                bufNext = min(bufCount, bufNext + __popc(idle));
-                __syncwarp();
-            }
-        }
-        if (!__any_sync(kFull, have)) {
-            if (bufNext == bufCount && nextQ >= count) break;
-            continue;
-        }
-        bool survived = false;
-        if (have && STAGE == 0) {
-            bool walkDone = false;
-            for (int s = 0; s < 3; s++) {
-                if (kA < (int)((hdr.y >> 10) & 2047)) break;
-                if (fPos >= 2) { walkDone = true; break; }
-                hdr = fPos == 0 ? hdr0 : hdr1;
-                fPos++;
-                kA = min(skipA, (int)((hdr.y >> 10) & 2047));                       // fan_first_pass tested these
-                skipA -= kA;
-            }
-            bool blocked = false;
-            if (!walkDone) {
-                const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047;
-                const uint16_t* e = ebase + hdr.x + nS;
-                for (int c = 0; c < kCapA && kA < nA && !blocked; c++, kA++) {
-                    const int id = __ldg(e + kA);
-                    ART_CHECK(a.counters, id < a.L.na && hdr.x + nS + nA <= (unsigned)E.f.nEntries);
-                    if (STATS) E.st[1]++;
-                    blocked = aabb_blocks(gv, id, qo, qinv, qL);
-                }
-            }
-            if (blocked) {
-                have = false;
-            } else if (walkDone) {
-                have = false;
-                if (anySO) survived = true;
-                else query_visible(E, (int)(qpacked & 0xFFFFu), (int)(qpacked >> 16), qL);
-            }
-        }
-        if (have && STAGE == 1) {
-            bool walkDone = false;
-            for (int s = 0; s < 3; s++) {
-                if (kB < (int)(hdr.y & 1023) || kC < (int)(hdr.y >> 21)) break;
-                if (fPos >= 2) { walkDone = true; break; }
-                hdr = fPos == 0 ? hdr0 : hdr1;
-                fPos++;
-                kB = kC = 0;
-            }
-            bool blocked = false;
-            if (!walkDone) {
-                const uint16_t* e = ebase + hdr.x;
-                const int nS = hdr.y & 1023, nA = (hdr.y >> 10) & 2047, nO = hdr.y >> 21;
-                for (int c = 0; c < kCapS && kB < nS && !blocked; c++, kB++) {
-                    const int id = __ldg(e + kB);
-                    ART_CHECK(a.counters, id < a.L.ns);
-                    if (STATS) E.st[0]++;
-                    blocked = sphere_dist(gv, id, qo, qd, qdd) < qL;
-                }
-                for (int c = 0; c < kCapO && kC < nO && !blocked; c++, kC++) {
-                    const int id = __ldg(e + nS + nA + kC);
-                    ART_CHECK(a.counters, id < a.L.no && hdr.x + nS + nA + nO <= (unsigned)E.f.nEntries);
-                    if (STATS) E.st[2]++;
-                    blocked = obb_blocks(gv, id, qo, qd, qdd, E.g.errScale, qL);
-                }
-            }
-            if (blocked) {
-                have = false;
-            } else if (walkDone) {
-                have = false;
-                query_visible(E, (int)(qpacked & 0xFFFFu), (int)(qpacked >> 16), qL);   // every list tested: the ray sees its goal
-            }
-        }
-        if (STAGE == 0) {
-            const uint32_t push = __ballot_sync(kFull, survived);
-            if (push) {
-                if (survived) E.surv[survCount + __popc(push & ltMask)] = qpacked;
-                survCount += __popc(push);
-            }
-        }
-    }
-    __syncwarp();
-    return survCount;
-}
-
-// FAN: 0 = every occlusion query walks the grid; 1 = target fans, one-pass pool (few queries per hit point); 2 = target
-// fans, full-width first pass + pooled stages (many queries per hit point)
+// REC: bounce-only mode -- the echo / muffle queries of a hit point do not feed the bounce loop (RT:124-173 only write
+//      EchoRayDistances / MuffleRayHits), so the tracer appends one record per hit point (TraceArgs::recA / recB) and
+//      query_fan_kernel (k1_query_fan.cu) evaluates all of them afterwards against the target fans. Without REC every
+//      occlusion query walks the grid inside the bounce loop (the pools above).
 // ROT: group rotation (TraceArgs::migGroups, trace_grid_rotation) instead of the per-lane ray queue
-template <bool SMEM, bool STATS, int FAN, bool ROT>
-__global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const TraceArgs a, const GridDesc g, const FanDesc f)
+template <bool SMEM, bool STATS, bool REC, bool ROT>
+__global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const TraceArgs a, const GridDesc g)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -792,6 +485,8 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
             }
         }
         const bool hit = hasRay && bkey != kNoHit;
+        HitRec recOut;
+        recOut.px = recOut.py = recOut.pz = recOut.echoL = recOut.echoMul = 0.0f; recOut.resultId = 0;
         int hitType = 0, hitIdx = 0;
         float4 attr = make_float4(0, 0, 0, 0);
         if (hasRay && !hit) {                                                  // RT:201-207 ray left the scene
@@ -826,38 +521,42 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
             r.resultId = (int)rayResultId;
             r.row = row;
             r.pad = 0;
-            rec[lane] = r;
+            if (!REC) rec[lane] = r;
+            recOut = r;
         }
         __syncwarp();
 
         // ================= echo + muffle queries of all hit points (RT:121-175) =================
-        {
+        if (REC) {
+            // bounce-only mode: one record per hit point, appended in whatever order the warps get here (the queries'
+            // results -- echo halves indexed by rayResultId, integer muffle counts -- do not depend on it)
             const uint32_t hitMask = __ballot_sync(kFull, hit);
-            const int total = __popc(hitMask) * slots;
-            const PoolEnv E = { a, g, f, gv, rec, qbuf0, qbuf1, qbuf2, qbuf3, surv, RayOrigin, hitMask, slots, lane, ltMask, st, goalByPos, goalBySlot };
-            const bool noSO = a.L.ns + a.L.no == 0;
-            if (FAN == 1) {
-                for (int q0 = 0; q0 < total; q0 += kChunkQ) run_pool<2, STATS, true>(E, q0, min(kChunkQ, total - q0), noSO);
-            } else if (FAN == 2) {
-                if (hit) qbuf3[__popc(hitMask & ltMask)] = lane;       // lane of the n-th hit point of the round
-                __syncwarp();
-                for (int q0 = 0; q0 < total; q0 += kChunkQ) {          // (the survivor list holds kChunkQ queries)
-                    const int n0 = fan_first_pass<STATS>(E, q0, min(kChunkQ, total - q0), qbuf3);
-                    const int n1 = n0 > 0 ? run_pool_fan<0, STATS>(E, n0) : 0;
-                    if (n1 > 0) run_pool_fan<1, STATS>(E, n1);
-                }
-            } else {
-                for (int q0 = 0; q0 < total; q0 += kChunkQ) {
-                    if (slots >= kTwoStageSlots) {
-                        const int nSurv = run_pool<0, STATS, false>(E, q0, min(kChunkQ, total - q0), noSO);
-                        if (nSurv > 0) run_pool<1, STATS, false>(E, 0, nSurv, noSO);
-                    } else {
-                        run_pool<2, STATS, false>(E, q0, min(kChunkQ, total - q0), noSO);   // few queries per hit point: one pass over all types
-                    }
+            if (hitMask) {
+                unsigned int base = 0;
+                if (lane == 0) base = atomicAdd(a.recCount, (unsigned)__popc(hitMask));
+                base = __shfl_sync(kFull, base, 0);
+                if (hit) {
+                    const unsigned int idx = base + (unsigned)__popc(hitMask & ltMask);
+                    a.recA[idx] = make_float4(recOut.px, recOut.py, recOut.pz, recOut.echoL);
+                    a.recB[idx] = make_float2(recOut.echoMul, __int_as_float(recOut.resultId));
                 }
             }
         }
-        __syncwarp();
+        if (!REC) {
+            const uint32_t hitMask = __ballot_sync(kFull, hit);
+            const int total = __popc(hitMask) * slots;
+            const PoolEnv E = { a, g, gv, rec, qbuf0, qbuf1, qbuf2, qbuf3, surv, RayOrigin, hitMask, slots, lane, ltMask, st, goalByPos, goalBySlot };
+            const bool noSO = a.L.ns + a.L.no == 0;
+            for (int q0 = 0; q0 < total; q0 += kChunkQ) {
+                if (slots >= kTwoStageSlots) {
+                    const int nSurv = run_pool<0, STATS>(E, q0, min(kChunkQ, total - q0), noSO);
+                    if (nSurv > 0) run_pool<1, STATS>(E, 0, nSurv, noSO);
+                } else {
+                    run_pool<2, STATS>(E, q0, min(kChunkQ, total - q0), noSO);   // few queries per hit point: one pass over all types
+                }
+            }
+            __syncwarp();
+        }
 
         // ================= termination / reflection (RT:178-193) =================
         if (hit) {
@@ -993,14 +692,15 @@ size_t trace_grid_smem_bytes(const GeomLayout& L, bool geomInSmem)
     return (geomInSmem ? L.bytes : 0) + (size_t)kGridWarps * 32 * (sizeof(HitRec) + kQueryWords * 4);
 }
 
-// fans == nullptr: the occlusion queries walk the grid cells along their segments instead of using the target fans
-cudaError_t launch_trace_grid(const TraceArgs& a0, const GridDesc& g, const FanDesc* fans, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream)
+// records: bounce-only mode (TraceArgs::recA / recB / recCount set; the queries run in query_fan_kernel afterwards);
+// otherwise the occlusion queries walk the grid cells along their segments inside the bounce loop
+cudaError_t launch_trace_grid(const TraceArgs& a0, const GridDesc& g, bool records, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream)
 {
     TraceArgs a = a0;
     size_t smem = trace_grid_smem_bytes(a.L, geomInSmem);
     a.goalsInSmem = 0; a.goalsSmemOffset = 0;
     const char* noTab = getenv("ART_K1_NO_GOAL_TABLES");         // (read per launch: test knob for the global-memory fallback)
-    if (!(noTab && atoi(noTab) != 0)) {                          // goal tables behind everything else, when they fit
+    if (!records && !(noTab && atoi(noTab) != 0)) {              // goal tables behind everything else, when they fit
         static int maxOptin = -1;
         if (maxOptin < 0) {
             int dev = 0;
@@ -1010,26 +710,20 @@ cudaError_t launch_trace_grid(const TraceArgs& a0, const GridDesc& g, const FanD
         const size_t need = off + 2 * (size_t)(a.nTargets + 1) * sizeof(float4);
         if (need <= (size_t)maxOptin) { a.goalsInSmem = 1; a.goalsSmemOffset = (unsigned int)off; smem = need; }
     }
-    void (*k)(const TraceArgs, const GridDesc, const FanDesc) = nullptr;
-    const int mode = !fans ? 0 : (a.nTargets + 1 >= kTwoStageSlots ? 2 : 1);
+    void (*k)(const TraceArgs, const GridDesc) = nullptr;
     const bool rot = a.migGroups > 0;
     if (stats && rot) return cudaErrorInvalidValue;          // (stats frames are planned without rotation)
-#define ART_PICK(FANMODE)                                                                                              \
-    do {                                                                                                               \
-        if (stats) k = geomInSmem ? trace_grid_kernel<true, true, FANMODE, false> : trace_grid_kernel<false, true, FANMODE, false>;   \
-        else if (rot) k = geomInSmem ? trace_grid_kernel<true, false, FANMODE, true> : trace_grid_kernel<false, false, FANMODE, true>; \
-        else k = geomInSmem ? trace_grid_kernel<true, false, FANMODE, false> : trace_grid_kernel<false, false, FANMODE, false>;        \
-    } while (0)
-    if (mode == 2) ART_PICK(2);
-    else if (mode == 1) ART_PICK(1);
-    else ART_PICK(0);
-#undef ART_PICK
+    if (records && (rot || !a.recA || !a.recB || !a.recCount)) return cudaErrorInvalidValue;
+    if (records) {
+        if (stats) k = geomInSmem ? trace_grid_kernel<true, true, true, false> : trace_grid_kernel<false, true, true, false>;
+        else k = geomInSmem ? trace_grid_kernel<true, false, true, false> : trace_grid_kernel<false, false, true, false>;
+    } else if (stats) k = geomInSmem ? trace_grid_kernel<true, true, false, false> : trace_grid_kernel<false, true, false, false>;
+    else if (rot) k = geomInSmem ? trace_grid_kernel<true, false, false, true> : trace_grid_kernel<false, false, false, true>;
+    else k = geomInSmem ? trace_grid_kernel<true, false, false, false> : trace_grid_kernel<false, false, false, false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    FanDesc fd{};
-    if (fans) fd = *fans;
     const int warps = a.gridWarps >= 1 && a.gridWarps <= kGridWarps ? a.gridWarps : kGridWarps;
-    k<<<numCtas, warps * 32, smem, stream>>>(a, g, fd);
+    k<<<numCtas, warps * 32, smem, stream>>>(a, g);
     return cudaGetLastError();
 }
 

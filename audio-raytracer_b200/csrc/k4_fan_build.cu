@@ -126,6 +126,8 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 2) fan_build_kernel(const Fa
     unsigned int wpos = 0;                   // pass 1: next entry of this bin
     unsigned int aPos = 0;                   // pass 1: where this bin's AABB entries start
     uint32_t firstIds = 0;                   // pass 1: first two AABB entries of this bin, id0 | id1 << 16
+    uint32_t nextIds = 0;                    // pass 1: AABB entries 2 and 3, id2 | id3 << 16
+    uint2 myCell = make_uint2(0u, 0u);       // this bin's header (written in pass 0, repeated in cells4 after pass 1)
     unsigned int blockTotal = 0;
     int nearTotal = 0;
     for (int pass = 0; pass < 2; pass++) {
@@ -182,6 +184,8 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 2) fan_build_kernel(const Fa
                         else {
                             if (wpos == aPos) firstIds = (e & 0xFFFFu) | (e << 16);          // (a single AABB is listed twice)
                             else if (wpos == aPos + 1u) firstIds = (firstIds & 0xFFFFu) | (e << 16);
+                            else if (wpos == aPos + 2u) nextIds = (e & 0xFFFFu) | (e << 16);
+                            else if (wpos == aPos + 3u) nextIds = (nextIds & 0xFFFFu) | (e << 16);
                             a.entries[wpos++] = (uint16_t)(e & 0xFFFFu);
                         }
                     }
@@ -192,6 +196,7 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 2) fan_build_kernel(const Fa
         }
         if (pass == 1) {
             if (cA > 0) a.firstA[(size_t)fan * kFanCells + face * kFanCellsPerFace + tid] = firstIds;
+            a.cells4[(size_t)fan * kFanCells + face * kFanCellsPerFace + tid] = make_uint4(myCell.x, myCell.y, firstIds, nextIds);
             break;
         }
         // ---- reserve the CTA's span: block scan of the per-bin totals
@@ -224,21 +229,33 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 2) fan_build_kernel(const Fa
         uint2* cells = a.cells + (size_t)fan * kFanCells;
         if (bs == 0xFFFFFFFFu) {
             cells[face * kFanCellsPerFace + tid] = make_uint2(0u, 0u);
-            if (nearCta && tid == 0) cells[6 * kFanCellsPerFace] = make_uint2(0u, 0u);
+            a.cells4[(size_t)fan * kFanCells + face * kFanCellsPerFace + tid] = make_uint4(0u, 0u, 0u, 0u);
+            if (nearCta && tid == 0) {
+                cells[6 * kFanCellsPerFace] = make_uint2(0u, 0u);
+                a.cells4[(size_t)fan * kFanCells + 6 * kFanCellsPerFace] = make_uint4(0u, 0u, 0u, 0u);
+            }
             return;
         }
         wpos = bs + binOff;
         aPos = wpos + (unsigned)cS;
-        cells[face * kFanCellsPerFace + tid] = make_uint2(wpos, (uint32_t)cS | ((uint32_t)cA << 10) | ((uint32_t)cO << 21));
+        myCell = make_uint2(wpos, (uint32_t)cS | ((uint32_t)cA << 10) | ((uint32_t)cO << 21));
+        cells[face * kFanCellsPerFace + tid] = myCell;
         if (nearCta && tid == 0) {
-            uint32_t nS = 0, nA = 0, nO = 0, ids = 0;
+            uint32_t nS = 0, nA = 0, nO = 0, ids = 0, ids2 = 0;
             for (int q = 0; q < nearTotal; q++) {
                 const uint32_t t = sNear[q] >> 16;
-                if (t == 1) { if (nA == 0) ids = (sNear[q] & 0xFFFFu) | (sNear[q] << 16); else if (nA == 1) ids = (ids & 0xFFFFu) | (sNear[q] << 16); }
+                if (t == 1) {
+                    if (nA == 0) ids = (sNear[q] & 0xFFFFu) | (sNear[q] << 16);
+                    else if (nA == 1) ids = (ids & 0xFFFFu) | (sNear[q] << 16);
+                    else if (nA == 2) ids2 = (sNear[q] & 0xFFFFu) | (sNear[q] << 16);
+                    else if (nA == 3) ids2 = (ids2 & 0xFFFFu) | (sNear[q] << 16);
+                }
                 nS += t == 0; nA += t == 1; nO += t == 2;
             }
-            cells[6 * kFanCellsPerFace] = make_uint2(bs + blockTotal, nS | (nA << 10) | (nO << 21));
+            const uint2 nc2 = make_uint2(bs + blockTotal, nS | (nA << 10) | (nO << 21));
+            cells[6 * kFanCellsPerFace] = nc2;
             a.firstA[(size_t)fan * kFanCells + 6 * kFanCellsPerFace] = ids;
+            a.cells4[(size_t)fan * kFanCells + 6 * kFanCellsPerFace] = make_uint4(nc2.x, nc2.y, ids, ids2);
         }
         if (nearCta)
             for (int q = tid; q < nearTotal; q += 1024) a.entries[bs + blockTotal + q] = (uint16_t)(sNear[q] & 0xFFFFu);

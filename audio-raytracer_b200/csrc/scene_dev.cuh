@@ -141,6 +141,35 @@ struct TraceArgs {
     unsigned int goalsSmemOffset;  //   byte offset of those tables in the dynamic shared memory
     int muffleInSmem;              // per-warp shared counters fit
     int anyOwned[3];               // does any sphere / AABB / OBB belong to a target < nTargets (RT:413/426/439)
+    // grid kernel, bounce-only mode (target fans in use): the echo / muffle queries of a hit point do not feed the bounce
+    // loop (RT:124-173 only WRITE EchoRayDistances / MuffleRayHits), so the tracer just appends one record per hit point
+    // and query_fan_kernel (k1_query_fan.cu) evaluates all of them afterwards
+    float4* recA;                  // [nLocal*H] (hit - eps*d).xyz (RT:124 == RT:158), distance(RayOrigin, hit) (RT:130)
+    float2* recB;                  // [nLocal*H] material Echo of the hit collider (RT:135-141), rayResultId (RT:115) as int bits
+    unsigned int* recCount;        // records appended so far (zeroed per frame)
+};
+
+// k1_query_fan.cu: the echo-return ray (RT:124-145) and the Na muffle rays (RT:153-173) of every hit point the bounce
+// tracer recorded, evaluated against the target fans (fan_dev.cuh)
+struct QueryArgs {
+    const unsigned char* geom;     // geometry blob (global)
+    GeomLayout L;
+    const float4* recA; const float2* recB; const unsigned int* recCount;   // hit records (TraceArgs)
+    ShardMap map;
+    int H, batchSize;
+    float ox, oy, oz;              // RayOrigin = goal of slot 0 (echo ray)
+    const float* targets;          // float3 [nTargets] = goals of slots 1..Na (muffle rays)
+    int nTargets;
+    float maxMuffle;               // MaxMuffleHitDistance (RT:168)
+    float errScale;                // GridDesc::errScale (conservative OBB pre-tests)
+    uint16_t* echo;                // half [nLocal*H]
+    uint32_t* muffleCounts;        // u32 [T*Na], row = batch index of the ray
+    int muffleRows;                // T
+    unsigned long long* counters;  // [C_COUNT]
+    unsigned int* queue;           // next block of 32 records (zeroed per frame)
+    float4* scratch;               // per-warp survivor lists (query_fan_scratch_bytes)
+    int tablesInSmem;              // goal positions + near-list headers of all slots staged in shared memory
+    int muffleInSmem;              // per-CTA muffle counters [T*Na] in shared memory
 };
 
 // Uniform grid over the collider scene (acceleration structure). Built on the host at

@@ -460,11 +460,15 @@ def test_c3_full_size_grid_equals_brute_force(gpu_ctx):
     np.testing.assert_array_equal(fast.permeation.view(np.uint32), slow.permeation.view(np.uint32))
     np.testing.assert_array_equal(fast.settings.view(np.uint8), slow.settings.view(np.uint8))
     np.testing.assert_allclose(fast.permeation_sum, slow.permeation_sum, rtol=1e-9, atol=1e-5 * s.n_rays * s.n_rays)
-    # the first frame showed rays living nearly all their 12 bounces, so the next one rotates its ray groups through
-    # the warps (gridUsed bit 4, k1_trace_grid.cu): same outputs
+    # a second frame of the same context (buffers reused, fans rebuilt): same outputs
     again = gpu_ctx.run_frame(s)
-    assert again.counters["gridUsed"] == 55
-    assert_same_frame(again, fast, "full-size C3, group rotation vs ray queue")
+    assert again.counters["gridUsed"] == 39
+    assert_same_frame(again, fast, "full-size C3, second frame")
+    # the grid walk (no fans): the previous frames showed rays living nearly all their 12 bounces, so it rotates its ray
+    # groups through the warps (gridUsed bit 4, k1_trace_grid.cu): same outputs
+    walk = gpu_ctx.run_frame(s, flags=native.FRAME_NO_FANS)
+    assert walk.counters["gridUsed"] == 19
+    assert_same_frame(walk, fast, "full-size C3, grid walk with group rotation vs fans")
 
 
 @pytest.mark.parametrize("seed", range(16))
@@ -576,14 +580,17 @@ def test_group_rotation_is_bit_identical(monkeypatch, name, n_rays, T, warps, li
     with native.Context(0) as ctx:
         native.upload(ctx, s)
         slow = ctx.run_frame(s, flags=native.FRAME_BRUTE_FORCE)
-        rot = ctx.run_frame(s, flags=native.FRAME_FORCE_GRID)
-        rot2 = ctx.run_frame(s, flags=native.FRAME_FORCE_GRID)
+        # (the rotation belongs to the grid walk; with the target fans the queries run in their own kernel, k1_query_fan.cu)
+        rot = ctx.run_frame(s, flags=native.FRAME_FORCE_GRID | native.FRAME_NO_FANS)
+        rot2 = ctx.run_frame(s, flags=native.FRAME_FORCE_GRID | native.FRAME_NO_FANS)
         monkeypatch.setenv("ART_K1_ROTATE", "0")
-        plain = ctx.run_frame(s, flags=native.FRAME_FORCE_GRID)
+        plain = ctx.run_frame(s, flags=native.FRAME_FORCE_GRID | native.FRAME_NO_FANS)
+        fans = ctx.run_frame(s, flags=native.FRAME_FORCE_GRID)
     assert rot.counters["gridUsed"] & 16 and rot2.counters["gridUsed"] & 16, "rotation was not used"
     assert not plain.counters["gridUsed"] & 16 and slow.counters["gridUsed"] == 0
     assert 0 < rot.hit_counts.min() or life < 1000.0
     if life < 1000.0:
         assert len(np.unique(rot.hit_counts)) > 3, "rays should die at different bounces in this case"
-    for other, what in ((plain, "rotation vs no rotation"), (slow, "rotation vs brute force"), (rot2, "rotation twice")):
+    assert fans.counters["gridUsed"] & 4 and not fans.counters["gridUsed"] & 16
+    for other, what in ((plain, "rotation vs no rotation"), (slow, "rotation vs brute force"), (rot2, "rotation twice"), (fans, "rotation vs fans")):
         assert_same_frame(rot, other, what)
