@@ -15,12 +15,12 @@
 // first AABB ids come with ONE 16-byte load (FanDesc::cells4):
 //   pass 0   every (hit point, goal) query is prepared (exact sqrt, four exact reciprocals) and tested against the first two
 //            AABBs of its lists -- with nearest-first lists that blocks most queries;
-//   rounds   the others go, WITH their prepared state (1/dir, limit, bin header: 32 B), to a per-warp survivor list in
-//            global scratch (L2 resident) and are taken up again 32 at a time, one lane per survivor, for the next
-//            4, 8, 16, ... AABBs; the list is compacted in place after every round, so the lanes stay full while the
-//            population decays geometrically;
-//   S/O      a query no AABB blocks is tested against the sphere and OBB lists; if nothing blocks it sees its goal.
-// Goals are processed in chunks of at most 32 (<= 1,024 queries per warp in flight) so that the lists stay small.
+//   AABBs    the others are queued WITH their prepared state (64 B, self-contained) in a per-warp list in global scratch
+//            (L2 resident). Whenever enough have gathered, every lane takes one into registers and tests one AABB per step;
+//            a lane whose query is blocked takes the next one at once, so the lanes stay full whatever the list lengths.
+//            When the queue runs dry the few queries still in flight are written back (with their cursor) and wait for the
+//            next run -- no warp ever idles through the long lists of a few unobstructed queries;
+//   S/O      a query no AABB blocks is queued the same way for the sphere and OBB lists; if nothing blocks, it sees its goal.
 #include <cstdlib>
 
 #include "device_util.cuh"
@@ -36,23 +36,28 @@ namespace art {
 #ifndef ART_Q_WARPS
 #define ART_Q_WARPS 32
 #endif
-#ifndef ART_Q_FIRST_SPAN
-#define ART_Q_FIRST_SPAN 4
+#ifndef ART_Q_RUN
+#define ART_Q_RUN 192
+#endif
+#ifndef ART_Q_MIN_LANES
+#define ART_Q_MIN_LANES 20
 #endif
 constexpr int kQWarps = ART_Q_WARPS;
 constexpr int kQThreads = kQWarps * 32;
-constexpr int kQGoalChunk = 32;                      // goals per pass
-constexpr int kQListCap = kQGoalChunk * 32;          // survivors a warp can hold per list
-constexpr int kQFirstTests = 2;                      // AABBs of pass 0 (their ids come with the headers, FanDesc::cells4)
-constexpr int kQFirstSpan = ART_Q_FIRST_SPAN;        // AABBs of the first survivor round (doubles every round)
+constexpr int kQFirstTests = 2;                      // AABBs of pass 0 at most (their ids come with the headers, FanDesc::cells4)
+constexpr int kQRun = ART_Q_RUN;                     // queued queries from which a refill loop runs
+constexpr int kQMinLanes = ART_Q_MIN_LANES;          // a loop whose queue is dry stops (and writes its queries back) below this many busy lanes
+constexpr int kQCapA = kQRun + 64;                   // AABB queue: < kQRun before a goal step, <= 32 more per step, <= 32 written back
+constexpr int kQCapSO = 2 * kQRun + 128;             // sphere / OBB queue: additionally everything one AABB run passes on
+constexpr int kQEntry = 4;                           // float4 per queued query
 constexpr int kQMuffleSmemMax = 4096;                // per-CTA muffle counters [T * Na] kept in shared memory up to this size
 
+// A queued query, 64 B:  e0 = (1/dir.xyz, limit L)   e1 = (P.xyz, |goal - P|)   e2 = (bin header x, y, slot | cursor << 16, batch row)
+//                        e3 = (material Echo, rayResultId, -, -)
 struct QEnv {
     const QueryArgs& a;
     const FanDesc& f;
     const GeomView& gv;
-    const float4* recP;          // per-warp records, shared memory: (px, py, pz, echoL)
-    const float4* recQ;          //   (echoMul, rayResultId bits, batch row bits, -)
     const float4* goalTab;       // shared memory (or null): goal position of slot s
     const uint4* nearTab;        // shared memory (or null): near-list header + first ids of slot s
     uint32_t* sMuffle;           // shared memory (or null): per-CTA muffle counters
@@ -84,119 +89,163 @@ __device__ __forceinline__ void q_visible(const QEnv& E, int slot, float L, floa
     }
 }
 
-// One round over the survivor list: AABB entries [kBeg, kEnd) of (near list, then bin). Survivors with more AABBs left are
-// written back in place (a survivor is only ever written below the entries already read), the ones whose AABB lists are
-// exhausted go to the sphere / OBB list or see their goal.
+// The AABB lists of the queued queries, entries [cursor, nA0 + nA1) of the run "near list, then bin". Every lane holds ONE
+// query in registers and tests one AABB per step; a lane whose query is blocked (or has run through its lists) takes the
+// next one from the queue at once. A query no AABB blocks goes to the sphere / OBB queue or sees its goal. With `drain`
+// the loop runs until every query is resolved; otherwise it stops once the queue is empty and fewer than kQMinLanes lanes
+// are busy, writes the queries in flight back to the front of the queue and returns their number.
 template <bool STATS>
-__device__ __forceinline__ int q_round_aabb(const QEnv& E, float4* listA, int nIn, int kBeg, int kEnd, float4* listSO, int& nSO)
+__device__ __forceinline__ int q_loop_aabb(const QEnv& E, float4* listA, int nIn, bool drain, float4* listSO, int& nSO)
 {
     const QueryArgs& a = E.a; (void)a;
-    int w = 0;
-    for (int i0 = 0; i0 < nIn; i0 += 32) {
-        const int i = i0 + E.lane;
-        const bool on = i < nIn;
-        float4 q0 = make_float4(0, 0, 0, 0), q1 = make_float4(0, 0, 0, 0);
-        if (on) { q0 = listA[2 * i]; q1 = listA[2 * i + 1]; }
-        __syncwarp();                                    // every entry of this step is read before any is overwritten
-        bool keep = false, toSO = false;
-        if (on) {
-            const uint32_t packed = __float_as_uint(q1.z);
-            const int slot = (int)(packed & 0xFFFFu), rc = (int)(packed >> 16);
-            ART_CHECK(a.counters, rc < 32 && slot <= a.nTargets);
-            const float4 rp = E.recP[rc];
-            const f3 P = mk3(rp.x, rp.y, rp.z), inv = mk3(q0.x, q0.y, q0.z);
-            const float L = q0.w;
-            const uint4 n4 = q_near(E, slot);
-            const uint32_t hBx = __float_as_uint(q1.x), hBy = __float_as_uint(q1.y);
-            const int nS0 = n4.y & 1023, nA0 = (n4.y >> 10) & 2047, nS1 = hBy & 1023, nA1 = (hBy >> 10) & 2047;
-            const int nAll = nA0 + nA1, kLast = min(kEnd, nAll);
-            const uint16_t* eN = E.f.entries + n4.x + nS0;
-            const uint16_t* eB = E.f.entries + hBx + nS1 - nA0;
-            ART_CHECK(a.counters, kBeg < nAll && n4.x + nS0 + nA0 <= (unsigned)E.f.nEntries && hBx + nS1 + nA1 <= (unsigned)E.f.nEntries);
-            bool blocked = false;
-            int nxt = (int)__ldg((kBeg < nA0 ? eN : eB) + kBeg);
-            for (int k = kBeg; k < kLast && !blocked; k++) {
-                const int id = nxt;
-                if (k + 1 < kLast) nxt = (int)__ldg((k + 1 < nA0 ? eN : eB) + k + 1);
-                ART_CHECK(a.counters, id < a.L.na);
-                if (STATS) E.st[1]++;
-                blocked = aabb_blocks(E.gv, id, P, inv, L);
+    int next = 0;
+    bool have = false, anySO = false;
+    float4 e0 = make_float4(0, 0, 0, 0), e1 = e0, e2 = e0, e3 = e0;
+    uint32_t oN = 0, oB = 0;
+    int nA0 = 0, nAll = 0, k = 0, idNext = 0;           // idNext: entry k, fetched one step ahead (the lists live in L2)
+    for (;;) {
+        const uint32_t need = __ballot_sync(kFull, !have);
+        if (need && next < nIn) {
+            const int idx = next + __popc(need & E.ltMask);
+            if (!have && idx < nIn) {
+                const float4* src = listA + (size_t)kQEntry * idx;
+                e0 = src[0]; e1 = src[1]; e2 = src[2]; e3 = src[3];
+                const uint32_t packed = __float_as_uint(e2.z);
+                const int slot = (int)(packed & 0xFFFFu);
+                ART_CHECK(a.counters, slot <= a.nTargets);
+                const uint4 n4 = q_near(E, slot);
+                const uint32_t hBx = __float_as_uint(e2.x), hBy = __float_as_uint(e2.y);
+                const int nS0 = n4.y & 1023, nS1 = hBy & 1023, nA1 = (hBy >> 10) & 2047;
+                nA0 = (n4.y >> 10) & 2047; nAll = nA0 + nA1;
+                oN = n4.x + nS0; oB = hBx + nS1 - nA0;               // entry k: k < nA0 ? oN + k : oB + k
+                k = (int)(packed >> 16);
+                ART_CHECK(a.counters, k < nAll && n4.x + nS0 + nA0 <= (unsigned)E.f.nEntries && hBx + nS1 + nA1 <= (unsigned)E.f.nEntries);
+                anySO = (((n4.y | hBy) & 1023u) | ((n4.y | hBy) >> 21)) != 0;
+                idNext = (int)__ldg(E.f.entries + (k < nA0 ? oN : oB) + k);
+                have = true;
             }
-            if (!blocked) {
-                if (nAll > kEnd) keep = true;
-                else if (((n4.y | hBy) & 1023u) | ((n4.y | hBy) >> 21)) toSO = true;
-                else {
-                    const float4 rq = E.recQ[rc];
-                    q_visible(E, slot, L, rq.x, __float_as_int(rq.y), __float_as_int(rq.z));
-                }
+            next = min(nIn, next + __popc(need));
+        }
+        const uint32_t busy = __ballot_sync(kFull, have);
+        if (!busy) break;                                // the queue is exhausted and every query has been resolved
+        if (!drain && next >= nIn && __popc(busy) < kQMinLanes) break;
+        bool toSO = false;
+        if (have) {
+            const int id = idNext;
+            k++;
+            if (k < nAll) idNext = (int)__ldg(E.f.entries + (k < nA0 ? oN : oB) + k);
+            ART_CHECK(a.counters, id < a.L.na);
+            if (STATS) E.st[1]++;
+            if (aabb_blocks(E.gv, id, mk3(e1.x, e1.y, e1.z), mk3(e0.x, e0.y, e0.z), e0.w)) have = false;
+            else if (k >= nAll) {
+                have = false;
+                if (anySO) toSO = true;
+                else q_visible(E, (int)(__float_as_uint(e2.z) & 0xFFFFu), e0.w, e3.x, __float_as_int(e3.y), __float_as_int(e2.w));
             }
         }
-        const uint32_t km = __ballot_sync(kFull, keep), sm = __ballot_sync(kFull, toSO);
-        if (keep) { const int pos = w + __popc(km & E.ltMask); listA[2 * pos] = q0; listA[2 * pos + 1] = q1; }
-        if (toSO) {
-            const int pos = nSO + __popc(sm & E.ltMask);
-            ART_CHECK(a.counters, pos < kQListCap);
-            listSO[2 * pos] = q0; listSO[2 * pos + 1] = q1;
+        const uint32_t sm = __ballot_sync(kFull, toSO);
+        if (sm) {
+            if (toSO) {
+                const int pos = nSO + __popc(sm & E.ltMask);
+                ART_CHECK(a.counters, pos < kQCapSO);
+                float4* dst = listSO + (size_t)kQEntry * pos;
+                dst[0] = e0; dst[1] = e1;
+                dst[2] = make_float4(e2.x, e2.y, __uint_as_float(__float_as_uint(e2.z) & 0xFFFFu), e2.w);   // cursor 0
+                dst[3] = e3;
+            }
+            nSO += __popc(sm);
         }
-        w += __popc(km);
-        nSO += __popc(sm);
+    }
+    // (only reached with queries in flight when !drain: the queue is empty, so they go to its front)
+    const uint32_t busy = __ballot_sync(kFull, have);
+    if (have) {
+        float4* dst = listA + (size_t)kQEntry * __popc(busy & E.ltMask);
+        dst[0] = e0; dst[1] = e1;
+        dst[2] = make_float4(e2.x, e2.y, __uint_as_float((__float_as_uint(e2.z) & 0xFFFFu) | ((uint32_t)k << 16)), e2.w);
+        dst[3] = e3;
     }
     __syncwarp();
-    return w;
+    return __popc(busy);
 }
 
-// The queries no AABB blocks: sphere lists, then OBB lists (near list, then bin). One lane per query.
+// The queries no AABB blocks: sphere lists, then OBB lists (near list, then bin), one test per lane and step with the same
+// refill scheme; the cursor runs over the spheres first, then the OBBs.
 template <bool STATS>
-__device__ __forceinline__ void q_pass_so(const QEnv& E, const float4* listSO, int nIn)
+__device__ __forceinline__ int q_loop_so(const QEnv& E, float4* listSO, int nIn, bool drain)
 {
     const QueryArgs& a = E.a;
-    for (int i0 = 0; i0 < nIn; i0 += 32) {
-        const int i = i0 + E.lane;
-        if (i >= nIn) continue;
-        const float4 q0 = listSO[2 * i], q1 = listSO[2 * i + 1];
-        const uint32_t packed = __float_as_uint(q1.z);
-        const int slot = (int)(packed & 0xFFFFu), rc = (int)(packed >> 16);
-        ART_CHECK(a.counters, rc < 32 && slot <= a.nTargets);
-        const float4 rp = E.recP[rc];
-        const f3 P = mk3(rp.x, rp.y, rp.z);
-        const float L = q0.w, len = q1.w;
-        const f3 v = sub3(q_goal(E, slot), P);                           // RT:127 / RT:162
-        const f3 d = smul3(rcpr(len), v);                                // normalize = rsqrt(dot) * v, len from pass 0
-        const float dd = dot3(d, d);
-        const uint4 n4 = q_near(E, slot);
-        const uint32_t hBx = __float_as_uint(q1.x), hBy = __float_as_uint(q1.y);
-        const int nS0 = n4.y & 1023, nA0 = (n4.y >> 10) & 2047, nO0 = n4.y >> 21;
-        const int nS1 = hBy & 1023, nA1 = (hBy >> 10) & 2047, nO1 = hBy >> 21;
-        ART_CHECK(a.counters, n4.x + nS0 + nA0 + nO0 <= (unsigned)E.f.nEntries && hBx + nS1 + nA1 + nO1 <= (unsigned)E.f.nEntries);
-        bool blocked = false;
-        {
-            const uint16_t* eN = E.f.entries + n4.x;
-            const uint16_t* eB = E.f.entries + hBx - nS0;
-            const int n = nS0 + nS1;
-            for (int k = 0; k < n && !blocked; k++) {
-                const int id = (int)__ldg((k < nS0 ? eN : eB) + k);
+    int next = 0;
+    bool have = false;
+    float4 e1 = make_float4(0, 0, 0, 0), e2 = e1, e3 = e1;
+    f3 d = mk3(0, 0, 0);
+    float L = 0.0f, dd = 0.0f, i0x = 0.0f, i0y = 0.0f, i0z = 0.0f;
+    uint32_t oSN = 0, oSB = 0, oON = 0, oOB = 0;
+    int nS0 = 0, nS = 0, nO0 = 0, nTot = 0, k = 0, idNext = 0;
+    for (;;) {
+        const uint32_t need = __ballot_sync(kFull, !have);
+        if (need && next < nIn) {
+            const int idx = next + __popc(need & E.ltMask);
+            if (!have && idx < nIn) {
+                const float4* src = listSO + (size_t)kQEntry * idx;
+                const float4 e0 = src[0];
+                e1 = src[1]; e2 = src[2]; e3 = src[3];
+                i0x = e0.x; i0y = e0.y; i0z = e0.z; L = e0.w;
+                const uint32_t packed = __float_as_uint(e2.z);
+                const int slot = (int)(packed & 0xFFFFu);
+                ART_CHECK(a.counters, slot <= a.nTargets);
+                const f3 v = sub3(q_goal(E, slot), mk3(e1.x, e1.y, e1.z));   // RT:127 / RT:162
+                d = smul3(rcpr(e1.w), v);                                    // normalize = rsqrt(dot) * v, |v| from pass 0
+                dd = dot3(d, d);
+                const uint4 n4 = q_near(E, slot);
+                const uint32_t hBx = __float_as_uint(e2.x), hBy = __float_as_uint(e2.y);
+                const int nA0 = (n4.y >> 10) & 2047, nS1 = hBy & 1023, nA1 = (hBy >> 10) & 2047, nO1 = hBy >> 21;
+                nS0 = n4.y & 1023; nO0 = n4.y >> 21;
+                ART_CHECK(a.counters, n4.x + nS0 + nA0 + nO0 <= (unsigned)E.f.nEntries && hBx + nS1 + nA1 + nO1 <= (unsigned)E.f.nEntries);
+                nS = nS0 + nS1; nTot = nS + nO0 + nO1;
+                oSN = n4.x; oSB = hBx - nS0;                             // sphere k: k < nS0 ? oSN + k : oSB + k
+                oON = n4.x + nS0 + nA0; oOB = hBx + nS1 + nA1 - nO0;     // OBB j = k - nS: j < nO0 ? oON + j : oOB + j
+                k = (int)(packed >> 16);
+                ART_CHECK(a.counters, k < nTot);
+                idNext = (int)__ldg(E.f.entries + (k < nS ? (k < nS0 ? oSN : oSB) + k : (k - nS < nO0 ? oON : oOB) + (k - nS)));
+                have = true;
+            }
+            next = min(nIn, next + __popc(need));
+        }
+        const uint32_t busy = __ballot_sync(kFull, have);
+        if (!busy) break;
+        if (!drain && next >= nIn && __popc(busy) < kQMinLanes) break;
+        if (have) {
+            const f3 P = mk3(e1.x, e1.y, e1.z);
+            const int id = idNext;
+            const bool isSphere = k < nS;
+            k++;
+            if (k < nTot) idNext = (int)__ldg(E.f.entries + (k < nS ? (k < nS0 ? oSN : oSB) + k : (k - nS < nO0 ? oON : oOB) + (k - nS)));
+            bool blocked;
+            if (isSphere) {
                 ART_CHECK(a.counters, id < a.L.ns);
                 if (STATS) E.st[0]++;
                 blocked = sphere_dist(E.gv, id, P, d, dd) < L;           // RT:370-377 / RT:410-419
-            }
-        }
-        if (!blocked) {
-            const uint16_t* eN = E.f.entries + n4.x + nS0 + nA0;
-            const uint16_t* eB = E.f.entries + hBx + nS1 + nA1 - nO0;
-            const int n = nO0 + nO1;
-            for (int k = 0; k < n && !blocked; k++) {
-                const int id = (int)__ldg((k < nO0 ? eN : eB) + k);
+            } else {
                 ART_CHECK(a.counters, id < a.L.no);
                 if (STATS) E.st[2]++;
                 blocked = obb_blocks(E.gv, id, P, d, dd, a.errScale, L); // RT:388-394 / RT:436-445
             }
-        }
-        if (!blocked) {
-            const float4 rq = E.recQ[rc];
-            q_visible(E, slot, L, rq.x, __float_as_int(rq.y), __float_as_int(rq.z));
+            if (blocked) have = false;
+            else if (k >= nTot) {
+                have = false;
+                q_visible(E, (int)(__float_as_uint(e2.z) & 0xFFFFu), L, e3.x, __float_as_int(e3.y), __float_as_int(e2.w));
+            }
         }
     }
+    const uint32_t busy = __ballot_sync(kFull, have);
+    if (have) {
+        float4* dst = listSO + (size_t)kQEntry * __popc(busy & E.ltMask);
+        dst[0] = make_float4(i0x, i0y, i0z, L); dst[1] = e1;
+        dst[2] = make_float4(e2.x, e2.y, __uint_as_float((__float_as_uint(e2.z) & 0xFFFFu) | ((uint32_t)k << 16)), e2.w);
+        dst[3] = e3;
+    }
     __syncwarp();
+    return __popc(busy);
 }
 
 template <bool SMEM, bool STATS>
@@ -217,9 +266,6 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
         geomBase = p;
         p += a.L.bytes;
     }
-    float4* recP = reinterpret_cast<float4*>(p) + warp * 32;
-    float4* recQ = reinterpret_cast<float4*>(p) + (kQWarps + warp) * 32;
-    p += (size_t)2 * kQWarps * 32 * sizeof(float4);
     float4* goalTab = nullptr; uint4* nearTab = nullptr; uint32_t* sMuffle = nullptr;
     if (a.tablesInSmem) {
         goalTab = reinterpret_cast<float4*>(p); p += (size_t)slots * sizeof(float4);
@@ -238,12 +284,11 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
     const GeomView gv = make_view(geomBase, a.L);
     const uint32_t ltMask = (1u << lane) - 1u;
     unsigned int st[4] = { 0, 0, 0, 0 };
-    const QEnv E = { a, f, gv, recP, recQ, goalTab, nearTab, sMuffle, lane, ltMask, st };
-    float4* listA = a.scratch + ((size_t)blockIdx.x * kQWarps + warp) * (size_t)(4 * kQListCap);
-    float4* listSO = listA + 2 * kQListCap;
+    const QEnv E = { a, f, gv, goalTab, nearTab, sMuffle, lane, ltMask, st };
+    float4* listA = a.scratch + ((size_t)blockIdx.x * kQWarps + warp) * (size_t)(kQEntry * (kQCapA + kQCapSO));
+    float4* listSO = listA + kQEntry * kQCapA;
+    int nA = 0, nSO = 0;                             // queued queries (kept across goals and record blocks)
     const unsigned int nRec = *a.recCount;           // the bounce tracer has finished (stream order)
-    const int nChunks = (slots + kQGoalChunk - 1) / kQGoalChunk;
-    const int chunk = (slots + nChunks - 1) / nChunks;
 
     for (;;) {
         unsigned int blk = 0;
@@ -263,76 +308,73 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
             ART_CHECK(a.counters, resultId >= 0 && resultId / a.H < a.map.nLocal);
             row = a.map.to_global(resultId / a.H) / a.batchSize;         // ART:161/191 batch of the ray
         }
-        __syncwarp();                                                    // (the previous block's rounds have read their records)
-        recP[lane] = make_float4(P.x, P.y, P.z, echoL);
-        recQ[lane] = make_float4(echoMul, __int_as_float(resultId), __int_as_float(row), 0.0f);
-        __syncwarp();
-
-        for (int s0 = 0; s0 < slots; s0 += chunk) {
-            const int s1 = min(slots, s0 + chunk);
-            int nA = 0, nSO = 0;
-            // ---- pass 0: lane = hit point, all lanes walk the goals together
-            for (int s = s0; s < s1; s++) {
-                bool pushA = false, pushSO = false;
-                float4 q0 = make_float4(0, 0, 0, 0), q1 = make_float4(0, 0, 0, 0);
-                const uint4 n4 = q_near(E, s);
-                if (valid) {
-                    const f3 v = sub3(q_goal(E, s), P);                            // RT:127 / RT:162
-                    // the bin header depends on the direction's bin only: its load (L2) is issued first and completes
-                    // while the exact square root and reciprocals below are computed
-                    const int bin = fan_bin(-v.x, -v.y, -v.z);                     // direction goal -> hit point
-                    uint4 c4 = make_uint4(0u, 0u, 0u, 0u);
-                    if (bin >= 0) c4 = __ldg(&f.cells4[(size_t)q_fan_of(a, s) * kFanCells + bin]);
-                    const float len = sqrtr(dot3(v, v));
-                    float L = echoL;                                               // RT:130
-                    bool gate = true;
-                    if (s > 0) { L = len; gate = L < a.maxMuffle; }                // RT:165, 168
-                    if (gate) {
-                        if (bin < 0 || len != len) {
-                            q_visible(E, s, L, echoMul, resultId, row);            // degenerate (hit point == goal): no test can block
-                        } else {
-                            const f3 nd = smul3(rcpr(len), v);                     // normalize = rsqrt(dot) * v
-                            const f3 inv = mk3(rcpr(nd.x), rcpr(nd.y), rcpr(nd.z));
-                            const int nA0 = (n4.y >> 10) & 2047, nA1 = (c4.y >> 10) & 2047, nAll = nA0 + nA1;
-                            if (STATS) st[3] += 2;
-                            // the run "near list, then bin" starts with these ids: no dependent load of the entry lists here
-                            const uint32_t ids = nA0 >= 2 ? n4.z : (nA0 == 1 ? (n4.z & 0xFFFFu) | (c4.z << 16) : c4.z);
-                            const int nFirst = min(nAll, kQFirstTests);
-                            bool blocked = false;
+        // ---- pass 0: lane = hit point, all lanes walk the goals together
+        for (int s = 0; s < slots; s++) {
+            int push = 0;                                                // 1: AABB queue, 2: sphere / OBB queue
+            float4 e0 = make_float4(0, 0, 0, 0), e2 = e0;
+            float len = 0.0f;
+            const uint4 n4 = q_near(E, s);
+            if (valid) {
+                const f3 v = sub3(q_goal(E, s), P);                                // RT:127 / RT:162
+                // the bin header depends on the direction's bin only: its load (L2) is issued first and completes
+                // while the exact square root and reciprocals below are computed
+                const int bin = fan_bin(-v.x, -v.y, -v.z);                         // direction goal -> hit point
+                uint4 c4 = make_uint4(0u, 0u, 0u, 0u);
+                if (bin >= 0) c4 = __ldg(&f.cells4[(size_t)q_fan_of(a, s) * kFanCells + bin]);
+                len = sqrtr(dot3(v, v));
+                float L = echoL;                                                   // RT:130
+                bool gate = true;
+                if (s > 0) { L = len; gate = L < a.maxMuffle; }                    // RT:165, 168
+                if (gate) {
+                    if (bin < 0 || len != len) {
+                        q_visible(E, s, L, echoMul, resultId, row);                // degenerate (hit point == goal): no test can block
+                    } else {
+                        const f3 nd = smul3(rcpr(len), v);                         // normalize = rsqrt(dot) * v
+                        const f3 inv = mk3(rcpr(nd.x), rcpr(nd.y), rcpr(nd.z));
+                        const int nA0 = (n4.y >> 10) & 2047, nA1 = (c4.y >> 10) & 2047, nAll = nA0 + nA1;
+                        if (STATS) st[3] += 2;
+                        // the run "near list, then bin" starts with these ids: no dependent load of the entry lists here
+                        const uint32_t ids = nA0 >= 2 ? n4.z : (nA0 == 1 ? (n4.z & 0xFFFFu) | (c4.z << 16) : c4.z);
+                        const int nFirst = min(nAll, a.firstTests);
+                        bool blocked = false;
 #pragma unroll 1
-                            for (int t = 0; t < nFirst && !blocked; t++) {
-                                const int id = (int)((ids >> (16 * t)) & 0xFFFFu);
-                                ART_CHECK(a.counters, id < a.L.na);
-                                if (STATS) st[1]++;
-                                blocked = aabb_blocks(gv, id, P, inv, L);
-                            }
-                            if (!blocked) {
-                                if (nAll > kQFirstTests) pushA = true;
-                                else if (((n4.y | c4.y) & 1023u) | ((n4.y | c4.y) >> 21)) pushSO = true;
-                                else q_visible(E, s, L, echoMul, resultId, row);
-                                q0 = make_float4(inv.x, inv.y, inv.z, L);
-                                q1 = make_float4(__uint_as_float(c4.x), __uint_as_float(c4.y), __uint_as_float((uint32_t)s | ((uint32_t)lane << 16)), len);
-                            }
+                        for (int t = 0; t < nFirst && !blocked; t++) {
+                            const int id = (int)((ids >> (16 * t)) & 0xFFFFu);
+                            ART_CHECK(a.counters, id < a.L.na);
+                            if (STATS) st[1]++;
+                            blocked = aabb_blocks(gv, id, P, inv, L);
+                        }
+                        if (!blocked) {
+                            if (nAll > nFirst) push = 1;
+                            else if (((n4.y | c4.y) & 1023u) | ((n4.y | c4.y) >> 21)) push = 2;
+                            else q_visible(E, s, L, echoMul, resultId, row);
+                            e0 = make_float4(inv.x, inv.y, inv.z, L);
+                            e2 = make_float4(__uint_as_float(c4.x), __uint_as_float(c4.y),
+                                             __uint_as_float((uint32_t)s | (push == 1 ? (uint32_t)nFirst << 16 : 0u)), __int_as_float(row));
                         }
                     }
                 }
-                const uint32_t am = __ballot_sync(kFull, pushA), sm = __ballot_sync(kFull, pushSO);
-                if (pushA) { const int pos = nA + __popc(am & ltMask); listA[2 * pos] = q0; listA[2 * pos + 1] = q1; }
-                if (pushSO) { const int pos = nSO + __popc(sm & ltMask); listSO[2 * pos] = q0; listSO[2 * pos + 1] = q1; }
-                nA += __popc(am);
-                nSO += __popc(sm);
             }
-            __syncwarp();
-            // ---- survivor rounds: the next 4, 8, 16, ... AABBs
-            int kBeg = kQFirstTests, span = kQFirstSpan;
-            while (nA > 0) {
-                nA = q_round_aabb<STATS>(E, listA, nA, kBeg, kBeg + span, listSO, nSO);
-                kBeg += span;
-                if (span < 1024) span *= 2;
+            const uint32_t am = __ballot_sync(kFull, push == 1), sm = __ballot_sync(kFull, push == 2);
+            if (push) {
+                const int pos = push == 1 ? nA + __popc(am & ltMask) : nSO + __popc(sm & ltMask);
+                ART_CHECK(a.counters, pos < (push == 1 ? kQCapA : kQCapSO));
+                float4* dst = (push == 1 ? listA : listSO) + (size_t)kQEntry * pos;
+                dst[0] = e0;
+                dst[1] = make_float4(P.x, P.y, P.z, len);
+                dst[2] = e2;
+                dst[3] = make_float4(echoMul, __int_as_float(resultId), 0.0f, 0.0f);
             }
-            if (nSO > 0) q_pass_so<STATS>(E, listSO, nSO);
+            nA += __popc(am);
+            nSO += __popc(sm);
+            // ---- the queued queries' remaining AABBs / sphere and OBB lists, whenever enough have gathered to fill the lanes
+            if (nA >= kQRun) { __syncwarp(); nA = q_loop_aabb<STATS>(E, listA, nA, false, listSO, nSO); }
+            if (nSO >= kQRun) { __syncwarp(); nSO = q_loop_so<STATS>(E, listSO, nSO, false); }
         }
     }
+    __syncwarp();
+    if (nA > 0) q_loop_aabb<STATS>(E, listA, nA, true, listSO, nSO);
+    if (nSO > 0) q_loop_so<STATS>(E, listSO, nSO, true);
 
     if (sMuffle) {
         __syncthreads();
@@ -350,8 +392,8 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
 }
 
 // ---- launcher -----------------------------------------------------------------------------------
-size_t query_fan_smem_bytes(const GeomLayout& L, bool geomInSmem) { return (geomInSmem ? L.bytes : 0) + (size_t)2 * kQWarps * 32 * sizeof(float4); }
-size_t query_fan_scratch_bytes(int numCtas) { return (size_t)numCtas * kQWarps * 4 * kQListCap * sizeof(float4); }
+size_t query_fan_smem_bytes(const GeomLayout& L, bool geomInSmem) { return geomInSmem ? L.bytes : 0; }
+size_t query_fan_scratch_bytes(int numCtas) { return (size_t)numCtas * kQWarps * kQEntry * (kQCapA + kQCapSO) * sizeof(float4); }
 
 cudaError_t launch_query_fan(const QueryArgs& a0, const FanDesc& fans, int numCtas, bool geomInSmem, bool stats, int maxSmemOptin, cudaStream_t stream)
 {
@@ -361,6 +403,9 @@ cudaError_t launch_query_fan(const QueryArgs& a0, const FanDesc& fans, int numCt
     a.tablesInSmem = 0; a.muffleInSmem = 0;
     const char* noTab = getenv("ART_K1_NO_GOAL_TABLES");         // (read per launch: test knob for the global-memory fallbacks)
     const bool tabs = !(noTab && atoi(noTab) != 0);
+    // experiment knob (read per launch): AABBs tested in pass 0 (1 or 2)
+    a.firstTests = kQFirstTests;
+    if (const char* v = getenv("ART_Q_FIRST_TESTS")) { const int n = atoi(v); if (n >= 1 && n <= kQFirstTests) a.firstTests = n; }
     if (tabs && smem + tables <= (size_t)maxSmemOptin) { a.tablesInSmem = 1; smem += tables; }
     const size_t cnt = (size_t)a.muffleRows * a.nTargets;
     if (tabs && cnt <= (size_t)kQMuffleSmemMax && smem + cnt * sizeof(uint32_t) <= (size_t)maxSmemOptin) { a.muffleInSmem = 1; smem += cnt * sizeof(uint32_t); }

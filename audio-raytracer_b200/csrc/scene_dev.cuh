@@ -170,6 +170,7 @@ struct QueryArgs {
     float4* scratch;               // per-warp survivor lists (query_fan_scratch_bytes)
     int tablesInSmem;              // goal positions + near-list headers of all slots staged in shared memory
     int muffleInSmem;              // per-CTA muffle counters [T*Na] in shared memory
+    int firstTests;                // AABBs every query tests in pass 0 (1 or 2)
 };
 
 // Uniform grid over the collider scene (acceleration structure). Built on the host at
