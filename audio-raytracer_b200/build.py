@@ -75,7 +75,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
         sys.stderr.write("\n".join(log))
         raise RuntimeError("nvcc failed, see audio-raytracer_b200/build/nvcc.log")
     target = out or LIB
-    link = [nvcc] + ARCH + ["-shared", "-o", target] + objs + ["-lcudart"]
+    link = [nvcc] + ARCH + ["-shared", "-o", target] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(link)
     if verbose:
         sys.stdout.write("\n".join(log))

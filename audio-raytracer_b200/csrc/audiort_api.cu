@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <new>
 #include <string>
 #include <thread>
@@ -148,6 +149,41 @@ struct PinBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// ---- NCCL, loaded on first use (art_comm_*): single-GPU hosts need no libnccl ------------------------------------------
+struct NcclUniqueId { char internal[128]; };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool tried = false;
+    bool ok() const { return lib && GetUniqueId && CommInitRank && AllGather && CommDestroy && GetErrorString; }
+};
+NcclApi& nccl_api()
+{
+    static NcclApi api;
+    if (!api.tried) {
+        api.tried = true;
+        const char* names[] = { getenv("ART_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
+        for (const char* n : names) {
+            if (!n || !*n) continue;
+            api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (api.lib) {
+            api.GetUniqueId = reinterpret_cast<int (*)(NcclUniqueId*)>(dlsym(api.lib, "ncclGetUniqueId"));
+            api.CommInitRank = reinterpret_cast<int (*)(void**, int, NcclUniqueId, int)>(dlsym(api.lib, "ncclCommInitRank"));
+            api.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(api.lib, "ncclAllGather"));
+            api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(api.lib, "ncclCommDestroy"));
+            api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(api.lib, "ncclGetErrorString"));
+        }
+    }
+    return api;
+}
+constexpr int kNcclChar = 0;   // ncclInt8 / ncclChar
+
 inline float h2f(uint16_t h)   // IEEE binary16 -> binary32 (== math.f16tof32), host copy for scene prep
 {
     uint32_t sign = ((uint32_t)h & 0x8000u) << 16, mag = h & 0x7FFFu, bits;
@@ -224,6 +260,22 @@ struct ArtCtx {
     ArtCounters counters{};
     std::vector<unsigned char> lastBlob;
     std::vector<int> frameOwnedCount;
+    cudaEvent_t evFan = nullptr, evBounce = nullptr, evX0 = nullptr, evX1 = nullptr;   // sub-times of the trace job, blob exchange
+    bool frameIsRerun = false;                     // the frame in flight is the second pass of a frame whose fan build overflowed
+    bool frameSplit = false;                       // the frame in flight ran the bounce-only tracer + query kernel
+    bool rayHostValid = false;                     // pinRays holds the whole batch (art_set_rays); false for device-generated rays
+    bool dirsLocal = false;                        // the device direction array holds only this context's shard, in local order
+
+    // multi-device context (ArtConfig.nDevices > 1): this object owns no CUDA state itself, only one child per device
+    std::vector<ArtCtx*> children;
+    bool scatterGlobal = false;                    // child: per-ray outputs go to the caller's arrays at GLOBAL ray positions
+    std::vector<float> parentTargets;              // parent: library-owned copy of the frame's target positions
+
+    // multi-process communicator (art_comm_init)
+    void* comm = nullptr;
+    int commRank = 0, commWorld = 1;
+    DevBuf gathered; PinBuf pinGathered;
+    bool frameComm = false;                        // the frame in flight all-gathers the ranks' partial blobs on the device
 };
 
 namespace {
@@ -393,6 +445,33 @@ int32_t finalize_blob(const unsigned char* blob, size_t bytes, const ArtParams* 
 // =================================================================================================
 extern "C" {
 
+// frees everything a (possibly half-constructed) device context owns; used by art_destroy and by every failure path of
+// art_create
+static void release_ctx(ArtCtx* ctx)
+{
+    if (!ctx) return;
+    for (ArtCtx* c : ctx->children) release_ctx(c);
+    ctx->children.clear();
+    if (ctx->stream || ctx->copyStream || ctx->stream2) cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+    if (ctx->copyStream) cudaStreamSynchronize(ctx->copyStream);
+    if (ctx->comm && nccl_api().ok()) nccl_api().CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->rotateLog, &ctx->hitRecs, &ctx->queryScratch, &ctx->permHitPts, &ctx->permBinCnt, &ctx->permPairs, &ctx->fanBoxes, &ctx->fanCells, &ctx->fanEntries, &ctx->fanCtl, &ctx->fanOrder, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
+                       &ctx->outAll, &ctx->firstHit, &ctx->partials, &ctx->queue, &ctx->gathered })
+        b->release();
+    for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinAll, &ctx->pinPerm, &ctx->pinFanCtl, &ctx->pinGathered })
+        b->release();
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t evx : { ctx->evReady, ctx->evP0, ctx->evP1, ctx->evTraceDone, ctx->evCopyDone, ctx->evFan, ctx->evBounce, ctx->evX0, ctx->evX1 })
+        if (evx) cudaEventDestroy(evx);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
 ART_API int32_t art_create(const ArtConfig* cfg, ArtCtx** out)
 {
     if (!cfg || !out) return fail(nullptr, ART_E_ARG, "art_create: null argument");
@@ -405,21 +484,45 @@ ART_API int32_t art_create(const ArtConfig* cfg, ArtCtx** out)
         return fail(nullptr, ART_E_NO_DEVICE, "art_create: no CUDA device (%s); libaudiort_cuda has no CPU fallback",
                     e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
     }
+    if (cfg->nDevices > 1) {
+        // ---- one context over several GPUs: a parent that owns one ordinary device context per entry of devices[]
+        if (cfg->nDevices > ART_MAX_DEVICES) return fail(nullptr, ART_E_ARG, "art_create: nDevices %d > %d", cfg->nDevices, ART_MAX_DEVICES);
+        if (cfg->shardChunkRays < 0) return fail(nullptr, ART_E_ARG, "art_create: shardChunkRays < 0");
+        ArtCtx* parent = new (std::nothrow) ArtCtx();
+        if (!parent) return fail(nullptr, ART_E_NOMEM, "art_create: out of memory");
+        parent->device = cfg->devices[0];
+        for (int i = 0; i < cfg->nDevices; i++) {
+            ArtConfig c1 = *cfg;
+            c1.nDevices = 0; c1.device = cfg->devices[i];
+            ArtCtx* child = nullptr;
+            const int32_t rc = art_create(&c1, &child);
+            if (rc != ART_OK) { release_ctx(parent); return rc; }      // (g_createError holds the child's message)
+            child->shardIndex = i; child->shardCount = cfg->nDevices;
+            child->chunkRays = cfg->shardChunkRays > 0 ? cfg->shardChunkRays : 256;
+            child->scatterGlobal = true;
+            parent->children.push_back(child);
+        }
+        *out = parent;
+        return ART_OK;
+    }
     if (cfg->device < 0 || cfg->device >= nDev) return fail(nullptr, ART_E_ARG, "art_create: device %d out of range [0,%d)", cfg->device, nDev);
     ArtCtx* ctx = new (std::nothrow) ArtCtx();
     if (!ctx) return fail(nullptr, ART_E_NOMEM, "art_create: out of memory");
     ctx->device = cfg->device;
     auto bail = [&](cudaError_t ee, const char* what) {
         int32_t rc = fail(nullptr, ART_E_CUDA, "art_create: %s: %s", what, cudaGetErrorString(ee));
-        delete ctx;
+        release_ctx(ctx);
         return rc;
     };
     if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) return bail(e, "cudaSetDevice");
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, ctx->device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
-    if (prop.major < 10) {
-        delete ctx;
-        return fail(nullptr, ART_E_NO_DEVICE, "art_create: device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+    // the library carries one arch-specific cubin (sm_100a, no PTX): it runs on compute capability 10.0 only
+    cudaFuncAttributes fattr;
+    if (prop.major != 10 || prop.minor != 0 || cudaFuncGetAttributes(&fattr, art::fibonacci_kernel) != cudaSuccess) {
+        cudaGetLastError();
+        release_ctx(ctx);
+        return fail(nullptr, ART_E_NO_DEVICE, "art_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device, prop.major, prop.minor);
     }
     ctx->numSms = prop.multiProcessorCount;
     ctx->maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
@@ -428,6 +531,8 @@ ART_API int32_t art_create(const ArtConfig* cfg, ArtCtx** out)
     if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaEventCreateWithFlags(&ctx->evReady, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->evP0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evP1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&ctx->evFan)) != cudaSuccess || (e = cudaEventCreate(&ctx->evBounce)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&ctx->evX0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evX1)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&ctx->evTraceDone, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&ctx->evCopyDone, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     for (auto& ev : ctx->ev)
@@ -441,25 +546,7 @@ ART_API int32_t art_create(const ArtConfig* cfg, ArtCtx** out)
     return ART_OK;
 }
 
-ART_API void art_destroy(ArtCtx* ctx)
-{
-    if (!ctx) return;
-    cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->rotateLog, &ctx->hitRecs, &ctx->queryScratch, &ctx->permHitPts, &ctx->permBinCnt, &ctx->permPairs, &ctx->fanBoxes, &ctx->fanCells, &ctx->fanEntries, &ctx->fanCtl, &ctx->fanOrder, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
-                       &ctx->outAll, &ctx->firstHit, &ctx->partials, &ctx->queue })
-        b->release();
-    for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinAll, &ctx->pinPerm, &ctx->pinFanCtl })
-        b->release();
-    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
-    for (cudaEvent_t evx : { ctx->evReady, ctx->evP0, ctx->evP1 }) if (evx) cudaEventDestroy(evx);
-    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
-    if (ctx->evTraceDone) cudaEventDestroy(ctx->evTraceDone);
-    if (ctx->evCopyDone) cudaEventDestroy(ctx->evCopyDone);
-    if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    delete ctx;
-}
+ART_API void art_destroy(ArtCtx* ctx) { release_ctx(ctx); }
 
 ART_API const char* art_last_error(ArtCtx* ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
 
@@ -468,6 +555,14 @@ ART_API int32_t art_set_scene(ArtCtx* ctx, const ArtAABB* aabbs, int32_t nAABB, 
 {
     if (!ctx) return ART_E_ARG;
     if (ctx->inFlight) return fail(ctx, ART_E_PENDING, "art_set_scene: a frame is in flight");
+    if (!ctx->children.empty()) {
+        for (ArtCtx* c : ctx->children) {
+            const int32_t rc = art_set_scene(c, aabbs, nAABB, obbs, nOBB, spheres, nSphere);
+            if (rc != ART_OK) return fail(ctx, rc, "%s", c->err.c_str());
+        }
+        ctx->haveScene = true;
+        return ART_OK;
+    }
     if (nAABB < 0 || nOBB < 0 || nSphere < 0 || (nAABB && !aabbs) || (nOBB && !obbs) || (nSphere && !spheres))
         return fail(ctx, ART_E_ARG, "art_set_scene: bad counts/pointers");
     if (nAABB >= (1 << 24) || nOBB >= (1 << 24) || nSphere >= (1 << 24)) return fail(ctx, ART_E_ARG, "art_set_scene: too many colliders");
@@ -499,12 +594,21 @@ ART_API int32_t art_set_rays(ArtCtx* ctx, const uint16_t* dirs, int32_t rayCount
     if (!ctx) return ART_E_ARG;
     if (ctx->inFlight) return fail(ctx, ART_E_PENDING, "art_set_rays: a frame is in flight");
     if (!dirs || rayCount <= 0) return fail(ctx, ART_E_ARG, "art_set_rays: bad arguments");
+    if (!ctx->children.empty()) {
+        for (ArtCtx* c : ctx->children) {
+            const int32_t rc = art_set_rays(c, dirs, rayCount);
+            if (rc != ART_OK) return fail(ctx, rc, "%s", c->err.c_str());
+        }
+        ctx->nGlobal = rayCount; ctx->haveRays = true;
+        return ART_OK;
+    }
     cudaSetDevice(ctx->device);
     CK(ctx->pinRays.ensure(6 * (size_t)rayCount));
     memcpy(ctx->pinRays.p, dirs, 6 * (size_t)rayCount);
     ctx->nGlobal = rayCount;
     ctx->haveRays = true;
     ctx->raysDirty = true;
+    ctx->rayHostValid = true;
     return ART_OK;
 }
 
@@ -513,6 +617,14 @@ ART_API int32_t art_generate_fibonacci_rays(ArtCtx* ctx, int32_t rayCount)
     if (!ctx) return ART_E_ARG;
     if (ctx->inFlight) return fail(ctx, ART_E_PENDING, "art_generate_fibonacci_rays: a frame is in flight");
     if (rayCount <= 0) return fail(ctx, ART_E_ARG, "art_generate_fibonacci_rays: bad ray count");
+    if (!ctx->children.empty()) {
+        for (ArtCtx* c : ctx->children) {
+            const int32_t rc = art_generate_fibonacci_rays(c, rayCount);
+            if (rc != ART_OK) return fail(ctx, rc, "%s", c->err.c_str());
+        }
+        ctx->nGlobal = rayCount; ctx->haveRays = true;
+        return ART_OK;
+    }
     cudaSetDevice(ctx->device);
     CK(ctx->dirs.ensure(6 * (size_t)rayCount));
     CK(launch_fibonacci(ctx->dirs.as<uint16_t>(), rayCount, ctx->stream));
@@ -520,6 +632,8 @@ ART_API int32_t art_generate_fibonacci_rays(ArtCtx* ctx, int32_t rayCount)
     ctx->nGlobal = rayCount;
     ctx->haveRays = true;
     ctx->raysDirty = false;
+    ctx->rayHostValid = false;
+    ctx->dirsLocal = false;                        // the whole batch lives on the device
     return ART_OK;
 }
 
@@ -527,9 +641,10 @@ ART_API int32_t art_get_rays(ArtCtx* ctx, uint16_t* dirs, int32_t capacityRays)
 {
     if (!ctx || !dirs) return ART_E_ARG;
     if (!ctx->haveRays) return fail(ctx, ART_E_STATE, "art_get_rays: no rays set");
+    if (!ctx->children.empty()) return art_get_rays(ctx->children[0], dirs, capacityRays);
     if (capacityRays < ctx->nGlobal) return fail(ctx, ART_E_ARG, "art_get_rays: capacity %d < %d", capacityRays, ctx->nGlobal);
     cudaSetDevice(ctx->device);
-    if (ctx->raysDirty) { memcpy(dirs, ctx->pinRays.p, 6 * (size_t)ctx->nGlobal); return ART_OK; }
+    if (ctx->rayHostValid) { memcpy(dirs, ctx->pinRays.p, 6 * (size_t)ctx->nGlobal); return ART_OK; }
     CK(cudaMemcpyAsync(dirs, ctx->dirs.p, 6 * (size_t)ctx->nGlobal, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return ART_OK;
@@ -541,6 +656,11 @@ ART_API int32_t art_set_ray_shard(ArtCtx* ctx, int32_t shardIndex, int32_t shard
     if (ctx->inFlight) return fail(ctx, ART_E_PENDING, "art_set_ray_shard: a frame is in flight");
     if (shardCount < 1 || shardIndex < 0 || shardIndex >= shardCount || chunkRays < 0)
         return fail(ctx, ART_E_ARG, "art_set_ray_shard: bad shard %d/%d chunk %d", shardIndex, shardCount, chunkRays);
+    if (!ctx->children.empty() || ctx->scatterGlobal) return fail(ctx, ART_E_STATE, "art_set_ray_shard: a multi-device context owns its shard map");
+    if (ctx->comm) return fail(ctx, ART_E_STATE, "art_set_ray_shard: the communicator owns the shard map (art_comm_init)");
+    if (shardIndex != ctx->shardIndex || shardCount != ctx->shardCount || chunkRays != ctx->chunkRays) {
+        if (ctx->rayHostValid) ctx->raysDirty = true;   // the device holds only the shard's directions: upload the new shard
+    }
     ctx->shardIndex = shardIndex; ctx->shardCount = shardCount; ctx->chunkRays = chunkRays;
     return ART_OK;
 }
@@ -549,12 +669,102 @@ ART_API int32_t art_local_ray_count(ArtCtx* ctx)
 {
     if (!ctx) return ART_E_ARG;
     if (!ctx->haveRays) return fail(ctx, ART_E_STATE, "art_local_ray_count: no rays set");
+    if (!ctx->children.empty()) return ctx->nGlobal;    // every ray is local to a multi-device context
     return local_ray_count(ctx->nGlobal, ctx->shardIndex, ctx->shardCount, effective_chunk(ctx));
+}
+
+// ---- multi-device context: fan the frame out over the children, merge their partial results -------------------------
+static int32_t multi_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtOutputs* outputs, ArtHandle* outHandle)
+{
+    if (ctx->inFlight) return fail(ctx, ART_E_PENDING, "art_trace_schedule: a frame is already in flight");
+    if (!ctx->haveScene || !ctx->haveRays) return fail(ctx, ART_E_STATE, "art_trace_schedule: scene or rays not set");
+    if (prm->totalAudioTargets <= 0 || !prm->audioTargetPositions) return fail(ctx, ART_E_ARG, "totalAudioTargets must be >= 1 and audioTargetPositions non-null");
+    if (prm->flags & ART_FRAME_REVERB_SEQ_FP32) return fail(ctx, ART_E_ARG, "ART_FRAME_REVERB_SEQ_FP32 needs the whole echo array on one device");
+    ArtParams p = *prm;
+    p.flags |= ART_FRAME_PARTIALS_ONLY;               // the children export partial blobs; this context merges and finalises
+    const size_t n = ctx->children.size();
+    std::vector<int32_t> rcs(n, ART_OK);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < n; i++)
+        th.emplace_back([&, i] { ArtHandle h = 0; rcs[i] = art_trace_schedule(ctx->children[i], &p, outputs, &h); });
+    for (auto& t : th) t.join();
+    for (size_t i = 0; i < n; i++)
+        if (rcs[i] != ART_OK) {
+            for (size_t k = 0; k < n; k++)
+                if (rcs[k] == ART_OK) art_complete(ctx->children[k], ctx->children[k]->handle);   // do not leave frames in flight
+            return fail(ctx, rcs[i], "device %d: %s", ctx->children[i]->device, ctx->children[i]->err.c_str());
+        }
+    ctx->parentTargets.assign(prm->audioTargetPositions, prm->audioTargetPositions + 3 * (size_t)prm->totalAudioTargets);
+    ctx->params = *prm;
+    ctx->params.audioTargetPositions = ctx->parentTargets.data();
+    ctx->haveUserOut = outputs != nullptr;
+    if (outputs) ctx->userOut = *outputs; else memset(&ctx->userOut, 0, sizeof ctx->userOut);
+    ctx->frameFlags = prm->flags; ctx->frameJobs = prm->jobs;
+    ctx->frameNa = prm->totalAudioTargets; ctx->frameT = prm->batchCount; ctx->frameH = prm->maxHitsPerRay;
+    ctx->inFlight = true; ctx->frameDone = false;
+    ctx->handle++;
+    *outHandle = ctx->handle;
+    return ART_OK;
+}
+
+static int32_t multi_is_completed(ArtCtx* ctx)
+{
+    for (ArtCtx* c : ctx->children) {
+        const int32_t rc = art_is_completed(c, c->handle);
+        if (rc < 0) return fail(ctx, rc, "device %d: %s", c->device, c->err.c_str());
+        if (rc == 0) return 0;
+    }
+    return 1;
+}
+
+static int32_t multi_complete(ArtCtx* ctx)
+{
+    const size_t n = ctx->children.size();
+    std::vector<int32_t> rcs(n, ART_OK);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < n; i++)
+        th.emplace_back([&, i] { rcs[i] = art_complete(ctx->children[i], ctx->children[i]->handle); });   // (scatters its per-ray outputs)
+    for (auto& t : th) t.join();
+    ctx->inFlight = false;
+    for (size_t i = 0; i < n; i++)
+        if (rcs[i] != ART_OK) return fail(ctx, rcs[i], "device %d: %s", ctx->children[i]->device, ctx->children[i]->err.c_str());
+    // exact, order-independent merge of the per-source partials (integer sums + max-by-ray-index select)
+    ctx->lastBlob = ctx->children[0]->lastBlob;
+    for (size_t i = 1; i < n; i++) {
+        const int32_t rc = art_partials_merge(ctx->lastBlob.data(), ctx->children[i]->lastBlob.data(), (int64_t)ctx->lastBlob.size());
+        if (rc != ART_OK) return fail(ctx, rc, "merging the partial results of device %d failed", ctx->children[i]->device);
+    }
+    ArtCounters& c = ctx->counters;
+    c = ArtCounters{};
+    for (size_t i = 0; i < n; i++) {
+        const ArtCounters& k = ctx->children[i]->counters;
+        const uint64_t* src = &k.segments; uint64_t* dst = &c.segments;
+        for (int w = 0; w < 22; w++) dst[w] += src[w];              // segments .. permLossTests: 22 consecutive u64 counters
+        for (int w = 0; w < 3; w++) { c.gridTraceTests[w] += k.gridTraceTests[w]; c.gridPermFirstTests[w] += k.gridPermFirstTests[w]; c.gridPermLossTests[w] += k.gridPermLossTests[w]; }
+        c.gridTraceCells += k.gridTraceCells; c.gridPermCells += k.gridPermCells; c.debugViolations += k.debugViolations;
+        for (int w = 0; w < 3; w++) c.gridQueryTests[w] += k.gridQueryTests[w];
+        c.gridQueryLists += k.gridQueryLists;
+        c.traceMs = std::max(c.traceMs, k.traceMs); c.permeationMs = std::max(c.permeationMs, k.permeationMs);
+        c.reduceMs = std::max(c.reduceMs, k.reduceMs); c.deviceMs = std::max(c.deviceMs, k.deviceMs);
+        c.h2dMs = std::max(c.h2dMs, k.h2dMs); c.d2hMs = std::max(c.d2hMs, k.d2hMs);
+        c.fanBuildMs = std::max(c.fanBuildMs, k.fanBuildMs); c.bounceMs = std::max(c.bounceMs, k.bounceMs); c.queryMs = std::max(c.queryMs, k.queryMs);
+        c.kernelLaunches += k.kernelLaunches;
+        c.gridUsed |= k.gridUsed;
+    }
+    c.devicesUsed = (uint32_t)n;
+    ctx->frameDone = true;
+    if (!(ctx->frameFlags & ART_FRAME_PARTIALS_ONLY) && ctx->haveUserOut) {
+        std::string err;
+        const int32_t rc = finalize_blob(ctx->lastBlob.data(), ctx->lastBlob.size(), &ctx->params, ctx->nGlobal, &ctx->userOut, &err);
+        if (rc != ART_OK) return fail(ctx, rc, "finalize: %s", err.c_str());
+    }
+    return ART_OK;
 }
 
 ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtOutputs* outputs, ArtHandle* outHandle)
 {
     if (!ctx || !prm || !outHandle) return ART_E_ARG;
+    if (!ctx->children.empty()) return multi_schedule(ctx, prm, outputs, outHandle);
     if (ctx->poisoned) return fail(ctx, ART_E_CUDA, "context poisoned by an earlier CUDA error");
     if (ctx->inFlight) return fail(ctx, ART_E_PENDING, "art_trace_schedule: a frame is already in flight");
     if (!ctx->haveScene || !ctx->haveRays) return fail(ctx, ART_E_STATE, "art_trace_schedule: scene or rays not set");
@@ -585,6 +795,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     cudaSetDevice(ctx->device);
     ctx->kernelLaunches = 0;
     ctx->frameGridUsed = 0;
+    if (!ctx->rerunning) ctx->frameIsRerun = false;
 
     const int chunk = effective_chunk(ctx);
     ShardMap map;
@@ -631,10 +842,33 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         ctx->sceneDirty = false;
     }
     if (ctx->raysDirty) {
-        CK(ctx->dirs.ensure(6 * (size_t)N));
-        CK(cudaMemcpyAsync(ctx->dirs.p, ctx->pinRays.p, 6 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+        if (ctx->shardCount > 1) {
+            // a shard needs only its own directions: pack the chunks it owns (local order) behind the batch in pinned memory
+            const size_t all = (6 * (size_t)N + 63) & ~(size_t)63;
+            if (ctx->pinRays.cap < all + 6 * nLoc) {
+                PinBuf bigger;
+                CK(bigger.ensure(all + 6 * nLoc));
+                memcpy(bigger.p, ctx->pinRays.p, 6 * (size_t)N);
+                ctx->pinRays.release();
+                ctx->pinRays = bigger;
+            }
+            const unsigned char* src = ctx->pinRays.as<unsigned char>();
+            unsigned char* dst = ctx->pinRays.as<unsigned char>() + all;
+            for (size_t j0 = 0; j0 < nLoc; j0 += (size_t)chunk) {
+                const size_t cnt = std::min((size_t)chunk, nLoc - j0);
+                memcpy(dst + 6 * j0, src + 6 * (size_t)map.to_global((int)j0), 6 * cnt);
+            }
+            CK(ctx->dirs.ensure(6 * nLoc + 16));
+            CK(cudaMemcpyAsync(ctx->dirs.p, dst, 6 * nLoc, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->dirsLocal = true;
+        } else {
+            CK(ctx->dirs.ensure(6 * (size_t)N));
+            CK(cudaMemcpyAsync(ctx->dirs.p, ctx->pinRays.p, 6 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->dirsLocal = false;
+        }
         ctx->raysDirty = false;
     }
+    map.dirsLocal = ctx->dirsLocal ? 1 : 0;
     CK(ctx->pinTargets.ensure(16 * (size_t)Na));
     CK(ctx->targets.ensure(16 * (size_t)Na));
     memmove(ctx->pinTargets.p, prm->audioTargetPositions, 12 * (size_t)Na);   // (a re-run passes the library-owned copy back in)
@@ -835,6 +1069,8 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         }
     }
     ctx->frameFans = useFans;
+    CK(cudaEventRecord(ctx->evFan, ctx->stream));
+    ctx->frameSplit = false;
 
     // Small frames (brute-force kernels, GPU far from full): run the permeation job on a second stream beside the trace
     // job, as the reference schedules them (ART:191, 213). Large frames stay serial so that each kernel is timed alone.
@@ -888,6 +1124,8 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             ta.recCount = ta.nextRay + 4;                        // (zeroed with the queue counters)
             const bool gInSmem = trace_grid_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
             CK(launch_trace_grid(ta, gd, true, ctx->numSms, gInSmem, stats, ctx->stream));
+            CK(cudaEventRecord(ctx->evBounce, ctx->stream));
+            ctx->frameSplit = true;
             QueryArgs qa;
             qa.geom = ta.geom; qa.L = L; qa.recA = ta.recA; qa.recB = ta.recB; qa.recCount = ta.recCount;
             qa.map = map; qa.H = H; qa.batchSize = b;
@@ -1021,6 +1259,17 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     if (overlapJobs) CK(cudaStreamWaitEvent(ctx->stream, ctx->evP1, 0));      // join the permeation job
     CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+    // ---------------- multi-process frames: all-gather the ranks' partial blobs on the device ----------------
+    ctx->frameComm = ctx->comm != nullptr && ctx->commWorld > 1 && !(prm->flags & ART_FRAME_PARTIALS_ONLY) && !ctx->rerunning;
+    if (ctx->frameComm) {
+        CK(ctx->gathered.ensure(bl.bytes * (size_t)ctx->commWorld));
+        CK(ctx->pinGathered.ensure(bl.bytes * (size_t)ctx->commWorld));
+        CK(cudaEventRecord(ctx->evX0, ctx->stream));
+        const int nrc = nccl_api().AllGather(ctx->partials.p, ctx->gathered.p, bl.bytes, kNcclChar, ctx->comm, ctx->stream);
+        if (nrc != 0) { ctx->poisoned = true; return fail(ctx, ART_E_CUDA, "ncclAllGather: %s", nccl_api().GetErrorString(nrc)); }
+        CK(cudaEventRecord(ctx->evX1, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->pinGathered.p, ctx->gathered.p, bl.bytes * (size_t)ctx->commWorld, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     // ---------------- read back ----------------
     CK(cudaMemcpyAsync(ctx->pinPartials.p, ctx->partials.p, bl.bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (useFans) CK(cudaMemcpyAsync(ctx->pinFanCtl.p, ctx->fanCtl.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1044,17 +1293,45 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     return ART_OK;
 }
 
+// The fan lists of the frame in flight did not fit their buffer (or a list exceeded its length limit): its results are
+// incomplete. Schedule it again on the grid walk (under the same handle) and give the next frame a larger buffer.
+static bool needs_rerun(const ArtCtx* ctx) { return ctx->frameFans && !ctx->frameIsRerun && ctx->pinFanCtl.as<unsigned int>()[1] != 0; }
+static int32_t start_rerun(ArtCtx* ctx)
+{
+    if (ctx->fanEntriesPerPair < 4096) ctx->fanEntriesPerPair *= 4;
+    ArtParams prm = ctx->params;
+    ArtOutputs uo = ctx->userOut;
+    const bool hadOut = ctx->haveUserOut;
+    const ArtHandle keep = ctx->handle;
+    ctx->inFlight = false;
+    ctx->rerunning = true;
+    ArtHandle h2 = 0;
+    const int32_t rc = art_trace_schedule(ctx, &prm, hadOut ? &uo : nullptr, &h2);
+    ctx->rerunning = false;
+    ctx->handle = keep;
+    ctx->frameIsRerun = true;
+    return rc;
+}
+
 ART_API int32_t art_is_completed(ArtCtx* ctx, ArtHandle h)
 {
     if (!ctx) return ART_E_ARG;
     if (h != ctx->handle || h == 0) return fail(ctx, ART_E_STATE, "stale handle");
     if (!ctx->inFlight) return 1;
+    if (!ctx->children.empty()) return multi_is_completed(ctx);
     cudaSetDevice(ctx->device);
     cudaError_t e = cudaEventQuery(ctx->ev[5]);
-    if (e == cudaSuccess) return 1;
     if (e == cudaErrorNotReady) { cudaGetLastError(); return 0; }
-    ctx->poisoned = true;
-    return fail(ctx, ART_E_CUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        ctx->poisoned = true;
+        return fail(ctx, ART_E_CUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
+    }
+    if (needs_rerun(ctx)) {
+        // keep polling callers (ART:95) from ever blocking in art_complete: the second pass starts here, asynchronously
+        const int32_t rc = start_rerun(ctx);
+        return rc != ART_OK ? rc : 0;
+    }
+    return 1;
 }
 
 ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
@@ -1062,18 +1339,32 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
     if (!ctx) return ART_E_ARG;
     if (h != ctx->handle || h == 0) return fail(ctx, ART_E_STATE, "stale handle");
     if (!ctx->inFlight) return ctx->frameDone ? ART_OK : fail(ctx, ART_E_STATE, "no frame scheduled");
+    if (!ctx->children.empty()) return multi_complete(ctx);
     cudaSetDevice(ctx->device);
     // per-ray outputs reach pinned memory right after the trace job: hand them to the caller's arrays while the
     // permeation job and the reduction are still running
     bool perRayCopied = false;
     auto copy_per_ray = [&]() {
         const ArtOutputs& o = ctx->userOut;
-        const size_t nl = (size_t)ctx->map.nLocal, nh = nl * ctx->frameH;
+        const size_t nl = (size_t)ctx->map.nLocal, H = (size_t)ctx->frameH, nh = nl * H;
         const unsigned char* pb = ctx->pinAll.as<unsigned char>();
-        if (o.echoRayDistances) big_memcpy(o.echoRayDistances, pb + ctx->offEcho, nh * 2);
-        if (o.rayHitResults) big_memcpy(o.rayHitResults, pb + ctx->offHitPts, nh * 6);
-        if (o.rayHitResultCounts) big_memcpy(o.rayHitResultCounts, pb + ctx->offHitCnt, nl);
-        if (o.hitColliderIds) big_memcpy(o.hitColliderIds, pb + ctx->offHitIds, nh * 4);
+        if (!ctx->scatterGlobal || ctx->map.shardCount <= 1) {
+            if (o.echoRayDistances) big_memcpy(o.echoRayDistances, pb + ctx->offEcho, nh * 2);
+            if (o.rayHitResults) big_memcpy(o.rayHitResults, pb + ctx->offHitPts, nh * 6);
+            if (o.rayHitResultCounts) big_memcpy(o.rayHitResultCounts, pb + ctx->offHitCnt, nl);
+            if (o.hitColliderIds) big_memcpy(o.hitColliderIds, pb + ctx->offHitIds, nh * 4);
+            return;
+        }
+        // child of a multi-device context: the caller's arrays are indexed by GLOBAL ray, this context owns every
+        // shardCount-th chunk of them
+        const size_t chunk = (size_t)ctx->map.chunk;
+        for (size_t j0 = 0; j0 < nl; j0 += chunk) {
+            const size_t cnt = std::min(chunk, nl - j0), g0 = (size_t)ctx->map.to_global((int)j0);
+            if (o.echoRayDistances) memcpy(o.echoRayDistances + g0 * H, pb + ctx->offEcho + j0 * H * 2, cnt * H * 2);
+            if (o.rayHitResults) memcpy(o.rayHitResults + g0 * H * 3, pb + ctx->offHitPts + j0 * H * 6, cnt * H * 6);
+            if (o.rayHitResultCounts) memcpy(o.rayHitResultCounts + g0, pb + ctx->offHitCnt + j0, cnt);
+            if (o.hitColliderIds) memcpy(o.hitColliderIds + g0 * H, pb + ctx->offHitIds + j0 * H * 4, cnt * H * 4);
+        }
     };
     if (ctx->frameCopiedEarly && ctx->haveUserOut && cudaEventSynchronize(ctx->evCopyDone) == cudaSuccess) {
         copy_per_ray();
@@ -1084,31 +1375,20 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
         ctx->poisoned = true; ctx->inFlight = false;
         return fail(ctx, ART_E_CUDA, "frame failed: %s", cudaGetErrorString(e));
     }
-    ctx->inFlight = false;
-    bool fanOverflow = false;
-    if (ctx->frameFans && ctx->pinFanCtl.as<unsigned int>()[1] != 0) {
-        // the fan lists did not fit their buffer (or a list exceeded its length limit): the frame's results are incomplete.
-        // Run it again on the grid walk and give the next frame a larger buffer.
-        if (ctx->fanEntriesPerPair < 4096) ctx->fanEntriesPerPair *= 4;
-        ArtParams prm = ctx->params;
-        ArtOutputs uo = ctx->userOut;
-        const bool hadOut = ctx->haveUserOut;
-        const ArtHandle keep = ctx->handle;
-        ctx->rerunning = true;
-        ArtHandle h2 = 0;
-        int32_t rc = art_trace_schedule(ctx, &prm, hadOut ? &uo : nullptr, &h2);
-        ctx->rerunning = false;
-        ctx->handle = keep;
+    if (needs_rerun(ctx)) {
+        const int32_t rc = start_rerun(ctx);
         if (rc != ART_OK) { ctx->inFlight = false; return rc; }
         e = cudaEventSynchronize(ctx->ev[5]);
         if (e != cudaSuccess) {
             ctx->poisoned = true; ctx->inFlight = false;
             return fail(ctx, ART_E_CUDA, "frame failed: %s", cudaGetErrorString(e));
         }
-        ctx->inFlight = false;
-        fanOverflow = true;
         perRayCopied = false;
+    } else if (ctx->frameIsRerun) {
+        perRayCopied = false;                      // (the second pass was started by art_is_completed)
     }
+    ctx->inFlight = false;
+    const bool fanOverflow = ctx->frameIsRerun;
     const int Na = ctx->frameNa, T = ctx->frameT;
     const BlobLayout bl = blob_layout(Na, T);
     BlobHeader* hh = ctx->pinPartials.as<BlobHeader>();
@@ -1124,7 +1404,9 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
     for (int k = 0; k < 3; k++) {
         c.gridTraceTests[k] = dc[C_GRID_RT_S + k]; c.gridPermFirstTests[k] = dc[C_GRID_PF_S + k]; c.gridPermLossTests[k] = dc[C_GRID_PL_S + k];
     }
-    c.gridTraceCells = dc[C_GRID_RT_CELLS]; c.gridPermCells = dc[C_GRID_PM_CELLS];
+    c.gridTraceCells = dc[C_GRID_RT_CELLS] + dc[C_GRID_Q_LISTS]; c.gridPermCells = dc[C_GRID_PM_CELLS];
+    for (int k = 0; k < 3; k++) { c.gridQueryTests[k] = dc[C_GRID_Q_S + k]; c.gridTraceTests[k] += c.gridQueryTests[k]; }
+    c.gridQueryLists = dc[C_GRID_Q_LISTS];
     c.debugViolations = dc[C_DEBUG_VIOLATIONS];
     {
         const int* ownedCount = ctx->frameOwnedCount.data();
@@ -1150,6 +1432,16 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
     cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[6]); c.deviceMs = ms;
     if (ctx->frameOverlap) { cudaEventElapsedTime(&ms, ctx->evP0, ctx->evP1); c.permeationMs = ms; }
     cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); c.d2hMs = ms;
+    c.fanBuildMs = c.bounceMs = c.queryMs = c.exchangeMs = 0.0f;
+    if (ctx->frameJobs & ART_JOB_RAYTRACE) {
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->evFan); c.fanBuildMs = ms;
+        if (ctx->frameSplit) {
+            cudaEventElapsedTime(&ms, ctx->evFan, ctx->evBounce); c.bounceMs = ms;
+            cudaEventElapsedTime(&ms, ctx->evBounce, ctx->ev[2]); c.queryMs = ms;
+        } else {
+            cudaEventElapsedTime(&ms, ctx->evFan, ctx->ev[2]); c.bounceMs = ms;   // bounce rays and queries in one kernel
+        }
+    }
     c.kernelLaunches = ctx->kernelLaunches;
     c.gridUsed = ctx->frameGridUsed | (fanOverflow ? 8u : 0u);
     if (ctx->frameJobs & ART_JOB_RAYTRACE) {
@@ -1165,6 +1457,30 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
     const bool hostOut = !(ctx->frameFlags & ART_FRAME_NO_HOST_OUTPUTS);
     if (hostOut && (ctx->frameJobs & ART_JOB_RAYTRACE) && ctx->haveUserOut && !perRayCopied) copy_per_ray();
     ctx->lastBlob.assign(ctx->pinPartials.as<unsigned char>(), ctx->pinPartials.as<unsigned char>() + bl.bytes);
+    c.devicesUsed = 1;
+    if (ctx->frameComm) {
+        // multi-process frame: every rank holds all ranks' blobs (gathered on the device); merge them exactly. The header
+        // fields and the derived permeation counters are functions of each blob's own device counters and the shared scene.
+        cudaEventElapsedTime(&ms, ctx->evX0, ctx->evX1); c.exchangeMs = ms;
+        unsigned char* all = ctx->pinGathered.as<unsigned char>();
+        for (int r = 0; r < ctx->commWorld; r++) {
+            BlobHeader* hr = reinterpret_cast<BlobHeader*>(all + (size_t)r * bl.bytes);
+            hr->magic = kBlobMagic; hr->nTargets = Na; hr->batchCount = T; hr->shards = 1;
+            const uint64_t rays = hr->counters[C_PERM_RAYS], hit = hr->counters[C_PERM_HIT_RAYS];
+            const uint64_t nSec[3] = { (uint64_t)ctx->L.ns, (uint64_t)ctx->L.na, (uint64_t)ctx->L.no };
+            for (int sct = 0; sct < 3; sct++) {
+                uint64_t owned = 0;
+                for (int a = 0; a < Na; a++) owned += (uint64_t)ctx->frameOwnedCount[(size_t)sct * Na + a];
+                hr->counters[C_PERM_FIRST_S + sct] = rays * nSec[sct];
+                hr->counters[C_PERM_LOSS_S + sct] = hit * (nSec[sct] * (uint64_t)Na - owned);
+            }
+            hr->counters[C_PERM_PAIRS] = hit * (uint64_t)Na;
+            if (r == 0) ctx->lastBlob.assign(all, all + bl.bytes);
+            else if (art_partials_merge(ctx->lastBlob.data(), all + (size_t)r * bl.bytes, (int64_t)bl.bytes) != ART_OK)
+                return fail(ctx, ART_E_ARG, "merging the partial results of rank %d failed", r);
+        }
+        c.devicesUsed = (uint32_t)ctx->commWorld;
+    }
     ctx->frameDone = true;
     if (!(ctx->frameFlags & ART_FRAME_PARTIALS_ONLY) && ctx->haveUserOut) {
         std::string err;
@@ -1234,7 +1550,46 @@ ART_API int32_t art_partials_merge(void* accumBlob, const void* otherBlob, int64
 ART_API int32_t art_finalize(const void* blob, int64_t blobBytes, const ArtParams* params, int32_t rayCount, const ArtOutputs* outputs)
 {
     if (!blob || !params || !outputs || rayCount <= 0) return ART_E_ARG;
+    // the same range checks art_trace_schedule applies (PA:34-35 divide by these; RT:115 / ATM:112 index with their products)
+    if (params->totalAudioTargets < 1 || params->totalAudioTargets > 32767 || params->batchCount < 1 || params->maxHitsPerRay < 1) return ART_E_ARG;
+    if ((long long)rayCount * params->maxHitsPerRay > 0x7FFFFFFFLL || (long long)params->batchCount * params->totalAudioTargets > 0x7FFFFFFFLL) return ART_E_ARG;
     return finalize_blob(static_cast<const unsigned char*>(blob), (size_t)blobBytes, params, rayCount, outputs, nullptr);
+}
+
+ART_API int32_t art_comm_unique_id(void* uniqueId128)
+{
+    if (!uniqueId128) return ART_E_ARG;
+    NcclApi& n = nccl_api();
+    if (!n.ok()) return fail(nullptr, ART_E_STATE, "art_comm_unique_id: libnccl.so.2 could not be loaded (set ART_NCCL_LIB)");
+    NcclUniqueId id;
+    const int rc = n.GetUniqueId(&id);
+    if (rc != 0) return fail(nullptr, ART_E_CUDA, "ncclGetUniqueId: %s", n.GetErrorString(rc));
+    memcpy(uniqueId128, &id, sizeof id);
+    return ART_OK;
+}
+
+ART_API int32_t art_comm_init(ArtCtx* ctx, const void* uniqueId128, int32_t rank, int32_t world, int32_t chunkRays)
+{
+    if (!ctx || !uniqueId128) return ART_E_ARG;
+    if (!ctx->children.empty() || ctx->scatterGlobal) return fail(ctx, ART_E_STATE, "art_comm_init: not available on a multi-device context");
+    if (ctx->inFlight) return fail(ctx, ART_E_PENDING, "art_comm_init: a frame is in flight");
+    if (world < 1 || rank < 0 || rank >= world || chunkRays < 0) return fail(ctx, ART_E_ARG, "art_comm_init: bad rank %d / world %d / chunk %d", rank, world, chunkRays);
+    if (ctx->comm) return fail(ctx, ART_E_STATE, "art_comm_init: the context already has a communicator");
+    NcclApi& n = nccl_api();
+    if (!n.ok()) return fail(ctx, ART_E_STATE, "art_comm_init: libnccl.so.2 could not be loaded (set ART_NCCL_LIB)");
+    cudaSetDevice(ctx->device);
+    NcclUniqueId id;
+    memcpy(&id, uniqueId128, sizeof id);
+    void* comm = nullptr;
+    const int rc = n.CommInitRank(&comm, world, id, rank);
+    if (rc != 0) return fail(ctx, ART_E_CUDA, "ncclCommInitRank: %s", n.GetErrorString(rc));
+    ctx->comm = comm; ctx->commRank = rank; ctx->commWorld = world;
+    const int chunk = chunkRays > 0 ? chunkRays : 256;
+    if (rank != ctx->shardIndex || world != ctx->shardCount || chunk != ctx->chunkRays) {
+        if (ctx->rayHostValid) ctx->raysDirty = true;
+    }
+    ctx->shardIndex = rank; ctx->shardCount = world; ctx->chunkRays = chunk;
+    return ART_OK;
 }
 
 ART_API int32_t art_grid_build_host(const ArtAABB* aabbs, int32_t nAABB, const ArtOBB* obbs, int32_t nOBB,
@@ -1272,6 +1627,7 @@ ART_API int32_t art_debug_get_fans(ArtCtx* ctx, ArtFanInfo* info, uint32_t* cell
 {
     if (!ctx || !info) return ART_E_ARG;
     if (ctx->inFlight) return fail(ctx, ART_E_PENDING, "a frame is in flight");
+    if (!ctx->children.empty()) return art_debug_get_fans(ctx->children[0], info, cells, cellsCapacity, entries, entriesCapacity);
     if (!ctx->frameDone || !ctx->frameFans) return fail(ctx, ART_E_STATE, "the last frame did not use the target fans");
     cudaSetDevice(ctx->device);
     memset(info, 0, sizeof *info);
@@ -1295,6 +1651,7 @@ ART_API int32_t art_microbench(ArtCtx* ctx, int32_t kind, double* gops)
 {
     if (!ctx || !gops || kind < 0 || kind > 2) return ART_E_ARG;
     if (ctx->inFlight) return fail(ctx, ART_E_PENDING, "a frame is in flight");
+    if (!ctx->children.empty()) return art_microbench(ctx->children[0], kind, gops);
     cudaSetDevice(ctx->device);
     CK(ctx->queue.ensure(64));
     cudaEvent_t e0, e1;

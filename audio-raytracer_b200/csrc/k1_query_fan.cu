@@ -290,11 +290,23 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
     int nA = 0, nSO = 0;                             // queued queries (kept across goals and record blocks)
     const unsigned int nRec = *a.recCount;           // the bounce tracer has finished (stream order)
 
+    // Work unit = (block of 32 records, group of goals). With few records (a small batch against many targets) the goals of
+    // a block are split over several warps so that the whole GPU is busy; otherwise a unit covers all goals of its block.
+    const unsigned int nBlocks = (nRec + 31u) / 32u;
+    const unsigned int totalWarps = gridDim.x * (unsigned)kQWarps;
+    unsigned int nGroups = 1;
+    if (nBlocks > 0 && nBlocks < 2u * totalWarps) nGroups = min((unsigned)slots, (2u * totalWarps + nBlocks - 1u) / nBlocks);
+    const int perGroup = (slots + (int)nGroups - 1) / (int)nGroups;
+    nGroups = (unsigned)((slots + perGroup - 1) / perGroup);
+    const unsigned long long nUnits = (unsigned long long)nBlocks * nGroups;
+
     for (;;) {
-        unsigned int blk = 0;
-        if (lane == 0) blk = atomicAdd(a.queue, 1u);
-        blk = __shfl_sync(kFull, blk, 0);
-        if ((unsigned long long)blk * 32ull >= (unsigned long long)nRec) break;
+        unsigned int unit = 0;
+        if (lane == 0) unit = atomicAdd(a.queue, 1u);
+        unit = __shfl_sync(kFull, unit, 0);
+        if ((unsigned long long)unit >= nUnits) break;
+        const unsigned int blk = unit / nGroups;
+        const int sBeg = (int)(unit - blk * nGroups) * perGroup, sEnd = min(slots, sBeg + perGroup);
         const unsigned int ri = blk * 32u + (unsigned)lane;
         const bool valid = ri < nRec;
         f3 P = mk3(0, 0, 0);
@@ -309,7 +321,7 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
             row = a.map.to_global(resultId / a.H) / a.batchSize;         // ART:161/191 batch of the ray
         }
         // ---- pass 0: lane = hit point, all lanes walk the goals together
-        for (int s = 0; s < slots; s++) {
+        for (int s = sBeg; s < sEnd; s++) {
             int push = 0;                                                // 1: AABB queue, 2: sphere / OBB queue
             float4 e0 = make_float4(0, 0, 0, 0), e2 = e0;
             float len = 0.0f;
@@ -384,10 +396,10 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
         }
     }
     if (STATS) {
-        atomicAdd(&a.counters[C_GRID_RT_S], (unsigned long long)st[0]);
-        atomicAdd(&a.counters[C_GRID_RT_A], (unsigned long long)st[1]);
-        atomicAdd(&a.counters[C_GRID_RT_O], (unsigned long long)st[2]);
-        atomicAdd(&a.counters[C_GRID_RT_CELLS], (unsigned long long)st[3]);
+        atomicAdd(&a.counters[C_GRID_Q_S], (unsigned long long)st[0]);
+        atomicAdd(&a.counters[C_GRID_Q_A], (unsigned long long)st[1]);
+        atomicAdd(&a.counters[C_GRID_Q_O], (unsigned long long)st[2]);
+        atomicAdd(&a.counters[C_GRID_Q_LISTS], (unsigned long long)st[3]);
     }
 }
 

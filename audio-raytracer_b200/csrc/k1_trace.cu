@@ -120,8 +120,8 @@ __global__ void __launch_bounds__(kThreads, 1) trace_kernel(const TraceArgs a)
         const int row = rayIndex / a.batchSize;   // batch k of ART:161/191; slot row (RT:63-64) applied at finalisation
         if (row != curRow) { flush_muffle(curRow); curRow = row; }
 
-        f3 d = mk3(um_f16tof32(a.dirs[3 * (size_t)rayIndex]), um_f16tof32(a.dirs[3 * (size_t)rayIndex + 1]),
-                   um_f16tof32(a.dirs[3 * (size_t)rayIndex + 2]));   // RT:94
+        f3 d = mk3(um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex)]), um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex) + 1]),
+                   um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex) + 2]));   // RT:94
         f3 o = RayOrigin;                                            // RT:95
         int hits = 0;                                                // RT:97 (byte; H <= 255)
         float life = a.maxRayLife;                                   // RT:99

@@ -376,8 +376,8 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
                 if (j < a.map.nLocal) {
                     const int rayIndex = a.map.to_global(j);
                     row = rayIndex / a.batchSize;                              // ART:161/191 batch k
-                    d = mk3(um_f16tof32(a.dirs[3 * (size_t)rayIndex]), um_f16tof32(a.dirs[3 * (size_t)rayIndex + 1]),
-                            um_f16tof32(a.dirs[3 * (size_t)rayIndex + 2]));    // RT:94
+                    d = mk3(um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex)]), um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex) + 1]),
+                            um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex) + 2]));    // RT:94
                     o = RayOrigin;                                             // RT:95
                     hits = 0;                                                  // RT:97
                     life = a.maxRayLife;                                       // RT:99
@@ -426,8 +426,8 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
                     j = jj;
                     const int rayIndex = a.map.to_global(j);
                     row = rayIndex / a.batchSize;                              // ART:161/191 batch k
-                    d = mk3(um_f16tof32(a.dirs[3 * (size_t)rayIndex]), um_f16tof32(a.dirs[3 * (size_t)rayIndex + 1]),
-                            um_f16tof32(a.dirs[3 * (size_t)rayIndex + 2]));    // RT:94
+                    d = mk3(um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex)]), um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex) + 1]),
+                            um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex) + 2]));    // RT:94
                     o = RayOrigin;                                             // RT:95
                     hits = 0;                                                  // RT:97
                     life = a.maxRayLife;                                       // RT:99

@@ -60,8 +60,8 @@ __global__ void __launch_bounds__(kThreads, 1) permeation_kernel(const PermArgs 
         if (j >= a.map.nLocal) break;
         const int rayIndex = a.map.to_global(j);
         nRays++;
-        const f3 d = mk3(um_f16tof32(a.dirs[3 * (size_t)rayIndex]), um_f16tof32(a.dirs[3 * (size_t)rayIndex + 1]),
-                         um_f16tof32(a.dirs[3 * (size_t)rayIndex + 2]));                  // PM:53
+        const f3 d = mk3(um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex)]), um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex) + 1]),
+                         um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex) + 2]));                  // PM:53
         const f3 o = RayOrigin;
 
         // ================= ShootRayCast, distance only (PM:101-141) =================
@@ -305,8 +305,8 @@ __global__ void __launch_bounds__(128) perm_last_kernel(const PermArgs a, int T)
     int j = rayIndex;
     if (a.map.shardCount > 1) j = ((rayIndex / a.map.chunk) / a.map.shardCount) * a.map.chunk + rayIndex % a.map.chunk;
     const GeomView gv = make_view(a.geom, a.L);
-    const f3 d = mk3(um_f16tof32(a.dirs[3 * (size_t)rayIndex]), um_f16tof32(a.dirs[3 * (size_t)rayIndex + 1]),
-                     um_f16tof32(a.dirs[3 * (size_t)rayIndex + 2]));
+    const f3 d = mk3(um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex)]), um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex) + 1]),
+                     um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex) + 2]));
     const f3 o = mk3(a.ox, a.oy, a.oz);
     const float t = a.firstHitDist[j];
     const f3 P = add3(o, mul3s(d, t));

@@ -92,8 +92,8 @@ __global__ void __launch_bounds__(kPGridThreads, 1) permeation_grid_kernel(const
         if (hasRay) {
             nRays++;
             const int rayIndex = a.map.to_global(j);
-            const f3 d = mk3(um_f16tof32(a.dirs[3 * (size_t)rayIndex]), um_f16tof32(a.dirs[3 * (size_t)rayIndex + 1]),
-                             um_f16tof32(a.dirs[3 * (size_t)rayIndex + 2]));   // PM:53
+            const f3 d = mk3(um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex)]), um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex) + 1]),
+                             um_f16tof32(a.dirs[3 * a.map.dir_index(j, rayIndex) + 2]));   // PM:53
             const f3 o = RayOrigin;
             const float dd = dot3(d, d);
             const f3 inv = mk3(rcpr(d.x), rcpr(d.y), rcpr(d.z));

@@ -90,6 +90,7 @@ enum CounterIdx {
     C_GRID_PF_S, C_GRID_PF_A, C_GRID_PF_O,
     C_GRID_PL_S, C_GRID_PL_A, C_GRID_PL_O,
     C_GRID_RT_CELLS, C_GRID_PM_CELLS,
+    C_GRID_Q_S, C_GRID_Q_A, C_GRID_Q_O, C_GRID_Q_LISTS,   // ... by query_fan_kernel (echo / muffle queries against the target fans)
     C_DEBUG_VIOLATIONS,        // -DART_DEBUG_BOUNDS builds: index checks that failed in the grid kernels (must stay 0)
     C_COUNT
 };
@@ -99,6 +100,8 @@ struct ShardMap {
     int nGlobal;      // RayDirections.Length
     int nLocal;       // rays traced by this context
     int shardIndex, shardCount, chunk;
+    int dirsLocal;    // the device direction array holds only this context's rays, in local order (else all nGlobal rays)
+    __host__ __device__ inline size_t dir_index(int j, int rayIndex) const { return (size_t)(dirsLocal ? j : rayIndex); }
     __host__ __device__ inline int to_global(int j) const
     {
         if (shardCount <= 1) return j;

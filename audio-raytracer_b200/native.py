@@ -18,7 +18,8 @@ from .layouts import AABB_DT, OBB_DT, SPHERE_DT, SETTINGS_DT
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AUDIORT_LIB") or os.path.join(_HERE, "libaudiort_cuda.so")
 
-ART_ABI_VERSION = 2
+ART_ABI_VERSION = 3
+ART_MAX_DEVICES = 16
 ART_OK, ART_E_ARG, ART_E_CUDA, ART_E_PENDING, ART_E_NO_DEVICE, ART_E_STATE, ART_E_NOMEM = 0, -1, -2, -3, -4, -5, -6
 JOB_RAYTRACE, JOB_PERMEATION, JOB_PROCESS, JOB_ALL = 1, 2, 4, 7
 FRAME_COUNTERS, FRAME_REVERB_SEQ_FP32, FRAME_NO_HOST_OUTPUTS, FRAME_PARTIALS_ONLY, FRAME_BRUTE_FORCE, FRAME_GRID_STATS, FRAME_FORCE_GRID = 1, 2, 4, 8, 16, 32, 64
@@ -28,7 +29,7 @@ EXPORTS = [
     "art_create", "art_destroy", "art_set_scene", "art_set_rays", "art_generate_fibonacci_rays", "art_get_rays",
     "art_set_ray_shard", "art_local_ray_count", "art_trace_schedule", "art_is_completed", "art_complete",
     "art_get_counters", "art_last_error", "art_partials_size", "art_get_partials", "art_partials_merge",
-    "art_finalize", "art_microbench", "art_grid_build_host", "art_debug_get_fans",
+    "art_finalize", "art_microbench", "art_grid_build_host", "art_debug_get_fans", "art_comm_unique_id", "art_comm_init",
 ]
 
 
@@ -49,7 +50,8 @@ class ArtError(RuntimeError):
 
 
 class ArtConfig(C.Structure):
-    _fields_ = [("abiVersion", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32), ("reserved", C.c_int32 * 5)]
+    _fields_ = [("abiVersion", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32), ("nDevices", C.c_int32),
+                ("devices", C.c_int32 * ART_MAX_DEVICES), ("shardChunkRays", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class ArtParams(C.Structure):
@@ -75,7 +77,9 @@ class ArtCounters(C.Structure):
                 ("traceMs", C.c_float), ("permeationMs", C.c_float), ("reduceMs", C.c_float), ("deviceMs", C.c_float),
                 ("h2dMs", C.c_float), ("d2hMs", C.c_float), ("kernelLaunches", C.c_uint32), ("gridUsed", C.c_uint32),
                 ("gridTraceTests", C.c_uint64 * 3), ("gridPermFirstTests", C.c_uint64 * 3), ("gridPermLossTests", C.c_uint64 * 3),
-                ("gridTraceCells", C.c_uint64), ("gridPermCells", C.c_uint64), ("debugViolations", C.c_uint64)]
+                ("gridTraceCells", C.c_uint64), ("gridPermCells", C.c_uint64), ("debugViolations", C.c_uint64),
+                ("fanBuildMs", C.c_float), ("bounceMs", C.c_float), ("queryMs", C.c_float), ("exchangeMs", C.c_float),
+                ("devicesUsed", C.c_uint32), ("reserved0", C.c_uint32), ("gridQueryTests", C.c_uint64 * 3), ("gridQueryLists", C.c_uint64)]
 
     def as_dict(self) -> dict:
         out = {}
@@ -139,6 +143,10 @@ def load_library(path: Optional[str] = None):
     lib.art_finalize.argtypes = [vp, i64, C.POINTER(ArtParams), i32, C.POINTER(ArtOutputs)]
     lib.art_microbench.restype = i32
     lib.art_microbench.argtypes = [vp, i32, C.POINTER(C.c_double)]
+    lib.art_comm_unique_id.restype = i32
+    lib.art_comm_unique_id.argtypes = [vp]
+    lib.art_comm_init.restype = i32
+    lib.art_comm_init.argtypes = [vp, vp, i32, i32, i32]
     if path is None:
         _lib = lib
     return lib
@@ -162,10 +170,16 @@ class FrameResult:
 class Context:
     """One ArtCtx: the plugin-side state of one AudioRayTracer (ART:53-87, 241-254)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, devices=None, shard_chunk_rays: int = 0):
+        """devices: several CUDA ordinals -> ONE context over those GPUs (ArtConfig.nDevices / devices[])."""
         self._lib = load_library()
         self._ctx = C.c_void_p()
         cfg = ArtConfig(abiVersion=ART_ABI_VERSION, device=device, flags=0)
+        if devices is not None:
+            cfg.nDevices = len(devices)
+            for i, d in enumerate(devices):
+                cfg.devices[i] = int(d)
+            cfg.shardChunkRays = shard_chunk_rays
         rc = self._lib.art_create(C.byref(cfg), C.byref(self._ctx))
         if rc != ART_OK:
             raise ArtError(rc, (self._lib.art_last_error(None) or b"").decode())
@@ -225,6 +239,11 @@ class Context:
 
     def local_ray_count(self) -> int:
         return self._check(self._lib.art_local_ray_count(self._ctx))
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int, chunk_rays: int = 0):
+        """Join a multi-process communicator (one rank per GPU); frames are then merged inside the library."""
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id)[:128].ljust(128, b"\0"))
+        self._check(self._lib.art_comm_init(self._ctx, buf, rank, world, chunk_rays))
 
     # -- frames -----------------------------------------------------------------------------
     @staticmethod
@@ -328,6 +347,16 @@ class Context:
         g = C.c_double(0)
         self._check(self._lib.art_microbench(self._ctx, kind, C.byref(g)))
         return float(g.value)
+
+
+def comm_unique_id() -> bytes:
+    """128-byte communicator id (rank 0 creates it, the caller distributes it to all ranks)."""
+    lib = load_library()
+    buf = (C.c_ubyte * 128)()
+    rc = lib.art_comm_unique_id(buf)
+    if rc != ART_OK:
+        raise ArtError(rc, "art_comm_unique_id: libnccl.so.2 not available")
+    return bytes(buf)
 
 
 def merge_partials(blobs) -> np.ndarray:

@@ -45,7 +45,6 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=None, help="override the ray count (debug only; marks the line)")
     ap.add_argument("--chunk", type=int, default=256, help="rays per interleaved shard chunk (N > 1)")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -118,30 +117,37 @@ def flops_of(counters: dict):
     return trace, perm
 
 
-def cpu_reference_sample(scene, seconds: float, threads: int):
-    """The reference algorithm on the host cores (oracle port, RT + PM) over a bounded, spread-out sample of
-    the workload's rays. Returns (segments/s, description, threads, seconds, segments)."""
-    from oracle import oracle as orc
+# rays per window of the CPU sample (4 windows at 10/35/60/85 % of the Fibonacci index), fixed per workload so that the
+# `cpu_baseline` leg of this arm and `--impl reference` time exactly the same work (about 2-4 s on 16 host threads)
+CPU_SAMPLE_WINDOW = {"c1": None, "c1_1src": None, "c2": None, "c3": 512, "c4": 256, "c5": 384}
+
+
+def cpu_sample_windows(workload: str, scene):
     N = scene.n_rays
-    # calibrate on a few rays, then size 4 windows spread over the sphere
-    ncal = min(N, max(32, 8 * threads))
-    t0 = time.perf_counter()
-    c = orc.trace_range(scene, N // 2, ncal, threads=threads, with_outputs=False)
-    orc.permeation_range(scene, N // 2, ncal, threads=threads)
-    dt = max(time.perf_counter() - t0, 1e-4)
-    per_ray = dt / ncal
-    total = int(max(64, min(N, seconds / per_ray)))
-    win = max(16, total // 4)
+    win = CPU_SAMPLE_WINDOW.get(workload)
+    if win is None or 4 * win >= N:
+        return [(0, N)], f"all {N} rays, RT+PM jobs, full scene and targets"
     starts = [int(f * (N - win)) for f in (0.1, 0.35, 0.6, 0.85)]
+    return [(s0, win) for s0 in starts], (f"{4 * win} of {N} rays (4 windows of {win} at 10/35/60/85% of the Fibonacci index), "
+                                           "RT+PM jobs, full scene and targets")
+
+
+def cpu_reference_sample(scene, workload: str, threads: int, shrink: int = 1):
+    """The reference algorithm on the host cores (oracle port, RT + PM) over the workload's fixed ray sample (`shrink`:
+    only every shrink-th part of each window, for the single-thread figure). Returns (segments/s, description, seconds)."""
+    from oracle import oracle as orc
+    windows, desc = cpu_sample_windows(workload, scene)
     seg, t = 0, 0.0
-    for s0 in starts:
+    for s0, cnt in windows:
+        cnt = max(1, cnt // shrink)
         t0 = time.perf_counter()
-        c = orc.trace_range(scene, s0, win, threads=threads, with_outputs=False)
-        orc.permeation_range(scene, s0, win, threads=threads)
+        c = orc.trace_range(scene, s0, cnt, threads=threads, with_outputs=False)
+        orc.permeation_range(scene, s0, cnt, threads=threads)
         t += time.perf_counter() - t0
         seg += c["segments"]
-    desc = f"{4 * win} of {N} rays (4 windows of {win} at 10/35/60/85% of the Fibonacci index), RT+PM jobs, full scene and targets"
-    return seg / t, desc, threads, t, seg
+    if shrink > 1:
+        desc = f"the first 1/{shrink} of each window of: " + desc
+    return seg / t, desc, t
 
 
 def run_reference(args, scene, rank, world):
@@ -151,7 +157,7 @@ def run_reference(args, scene, rank, world):
     vals = []
     desc = ""
     for i in range(args.warmup + args.steps):
-        v, desc, th, t, seg = cpu_reference_sample(scene, max(2.0, args.cpu_seconds / max(1, args.steps)), threads)
+        v, desc, t = cpu_reference_sample(scene, args.workload, threads)
         if i >= args.warmup:
             vals.append((v, t))
     value = float(np.mean([v for v, _ in vals]))
@@ -160,10 +166,12 @@ def run_reference(args, scene, rank, world):
         "warmup": args.warmup, "ms_per_step": float(np.mean([t for _, t in vals]) * 1e3), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, scene, world),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
+                         "values_per_step": [v for v, _ in vals]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference is C#/Unity and cannot run here (no .NET toolchain); this is the C restatement "
-                "oracle/audiort_oracle.c of its Execute() bodies on all host threads",
+        "note": "the reference is C#/Unity and cannot run here or on the GPU box (no dotnet / mono: profiles/r02_dotnet_probe.txt); "
+                "this is the C restatement oracle/audiort_oracle.c of its Execute() bodies (brute-force scans, as the reference "
+                "loops do) on all host threads, one step = the workload's fixed ray sample",
     }
     print(json.dumps(line), flush=True)
 
@@ -173,11 +181,12 @@ def workload_config(args, scene, world):
                         f"{len(scene.aabbs)} AABB + {len(scene.obbs)} OBB + {len(scene.spheres)} spheres",
             "rays": scene.n_rays, "max_hits_per_ray": scene.max_hits_per_ray, "targets": scene.n_targets,
             "colliders": scene.n_colliders, "batch_count": scene.batch_count,
-            "sharding": "none" if world == 1 else f"rays interleaved in chunks of {args.chunk} over {world} ranks",
+            "sharding": "none" if world == 1 else f"rays interleaved in chunks of {args.chunk} over {world} ranks; per-source partials "
+                                                  "all-gathered on the device inside the library (ncclAllGather), merged and finalised on every rank",
             "l2": "flushed between steps (256 MiB write)", "reverb_reduction": "exact integer",
-            "path": "default: uniform-grid traversal for the bounce rays + per-frame target fans (direction-binned collider lists around the "
-                    "listener and every source) for the echo / muffle / permeation queries, fan build inside the timed region, "
-                    "permeation loss lines sorted by (source, direction bin) on the device every frame; "
+            "path": "default: bounce-only tracer on the uniform grid, then one query kernel over all hit points using per-frame target "
+                    "fans (direction-binned collider lists around the listener and every source; fan build inside the timed region "
+                    "every step), permeation loss lines sorted by (source, direction bin) on the device every frame; "
                     "bit-identical to the brute-force scans (ART_FRAME_BRUTE_FORCE timed beside it)",
             "rays_override": args.rays is not None}
 
@@ -195,7 +204,15 @@ def main():
     import torch
     import torch.distributed as dist
     from audio_raytracer_b200 import build, native
-    build.build()
+    # one rank builds (a stale library would otherwise be rebuilt by N processes into the same files), the others wait
+    lock = os.path.join(ROOT, "audio-raytracer_b200", ".build.lock")
+    import fcntl
+    with open(lock, "w") as lf:
+        fcntl.flock(lf, fcntl.LOCK_EX)
+        try:
+            build.build()
+        finally:
+            fcntl.flock(lf, fcntl.LOCK_UN)
     torch.cuda.set_device(local)
     # keep stdout to the one JSON line: NCCL prints its version banner to stdout at WARN and above
     if os.environ.get("ART_NCCL_DEBUG"):
@@ -206,9 +223,15 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
 
     ctx = native.Context(device=local)
-    native.upload(ctx, scene)
     if world > 1:
-        ctx.set_ray_shard(rank, world, args.chunk)
+        # the library exchanges the per-source partial blobs itself (device-resident ncclAllGather on its own stream) and
+        # finalises on every rank; torch.distributed only carries the 128-byte communicator id and the timing reductions
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(native.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(uid, 0)
+        ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world, args.chunk)
+    native.upload(ctx, scene)
     n_local = ctx.local_ray_count()
     H, Na, T = scene.max_hits_per_ray, scene.n_targets, scene.batch_count
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -219,42 +242,21 @@ def main():
         if world > 1:
             dist.barrier()
 
-    gather_out = torch.empty(world * blob_bytes, dtype=torch.uint8, device="cuda") if world > 1 else None
-
-    def exchange(blob_np):
-        """all-gather the per-source partial blobs (a few KB) over NCCL and merge; returns (merged, ms)."""
-        if world == 1:
-            return blob_np, 0.0
-        mine = torch.from_numpy(blob_np).cuda()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dist.all_gather_into_tensor(gather_out, mine)
-        e1.record()
-        torch.cuda.synchronize()
-        allb = gather_out.cpu().numpy()
-        merged = native.merge_partials([allb[i * blob_bytes:(i + 1) * blob_bytes].copy() for i in range(world)])
-        return merged, e0.elapsed_time(e1)
-
-    partial_flag = native.FRAME_PARTIALS_ONLY if world > 1 else 0
-
     def device_step(flags=0):
         flush.zero_()
         torch.cuda.synchronize()
-        r = ctx.run_frame(scene, flags=flags | native.FRAME_NO_HOST_OUTPUTS | partial_flag, want=())
-        blob, ex_ms = exchange(ctx.get_partials(Na, T))
-        if world > 1:
-            native.finalize(blob, scene, scene.n_rays)
-        return r.counters, ex_ms
+        r = ctx.run_frame(scene, flags=flags | native.FRAME_NO_HOST_OUTPUTS, want=())
+        return r.counters
 
     # ---- untimed passes: (1) oracle-equivalent test counts of the reference's full scans -> reference-formulation flops
     #      of a step; (2) the brute-force kernels without counters -> their own roofline; (3) the tests the default
     #      (uniform-grid) kernels actually execute
     barrier()
-    cnt, _ = device_step(native.FRAME_COUNTERS)
+    cnt = device_step(native.FRAME_COUNTERS)
     trace_flops_local, perm_flops_local = flops_of(cnt)
     device_step(native.FRAME_BRUTE_FORCE)
-    bf, _ = device_step(native.FRAME_BRUTE_FORCE)
-    gst, _ = device_step(native.FRAME_GRID_STATS)
+    bf = device_step(native.FRAME_BRUTE_FORCE)
+    gst = device_step(native.FRAME_GRID_STATS)
     grid_used = int(gst.get("gridUsed", 0))
     exec_trace_flops = sum(f * n for f, n in zip(FLOPS_TRACE, gst["gridTraceTests"]))
     exec_perm_flops = sum(f * n for f, n in zip(FLOPS_PERM_FIRST, gst["gridPermFirstTests"])) + \
@@ -269,11 +271,13 @@ def main():
     barrier()
     wall0 = time.perf_counter()
     dev_ms, trace_ms, perm_ms, reduce_ms, ex_ms_tot, launches, segs = [], [], [], [], 0.0, 0, 0
+    fan_ms, bounce_ms, query_ms = [], [], []
     timed_grid_used = 0
     for _ in range(args.steps):
-        c, ex_ms = device_step()
+        c = device_step()
         dev_ms.append(c["deviceMs"]); trace_ms.append(c["traceMs"]); perm_ms.append(c["permeationMs"]); reduce_ms.append(c["reduceMs"])
-        ex_ms_tot += ex_ms
+        fan_ms.append(c["fanBuildMs"]); bounce_ms.append(c["bounceMs"]); query_ms.append(c["queryMs"])
+        ex_ms_tot += c["exchangeMs"]
         launches += c["kernelLaunches"]
         segs += c["segments"]
         timed_grid_used = int(c.get("gridUsed", 0))
@@ -285,20 +289,17 @@ def main():
     out = native.FrameResult()
     for _ in range(max(1, min(args.warmup, 2))):
         native.upload(ctx, scene)
-        ctx.run_frame(scene, flags=partial_flag, result=out, want=("echo", "hit_points", "hit_counts"))
+        ctx.run_frame(scene, result=out, want=("echo", "hit_points", "hit_counts"))
     barrier()
     t0 = time.perf_counter()
     e2e_segs = 0
     for _ in range(args.steps):
         native.upload(ctx, scene)                                  # H2D: scene structs + ray directions (+ targets)
-        r = ctx.run_frame(scene, flags=partial_flag, result=out, want=("echo", "hit_points", "hit_counts"))
-        blob, _ = exchange(ctx.get_partials(Na, T))
-        if world > 1:
-            native.finalize(blob, scene, scene.n_rays)
+        r = ctx.run_frame(scene, result=out, want=("echo", "hit_points", "hit_counts"))   # (world > 1: merged + finalised in the library)
         e2e_segs += r.counters["segments"]
     barrier()
     e2e_s = time.perf_counter() - t0
-    h2d = scene.n_rays * 6 + len(scene.aabbs) * 20 + len(scene.obbs) * 26 + len(scene.spheres) * 16 + Na * 12
+    h2d = n_local * 6 + len(scene.aabbs) * 20 + len(scene.obbs) * 26 + len(scene.spheres) * 16 + Na * 12
     d2h = n_local * H * (2 + 6) + n_local + blob_bytes
 
     # ---- reduce over ranks
@@ -337,26 +338,44 @@ def main():
         peak_tflops = n_sms * 128 * sm_max * 1e6 / 1e12          # FP32 instruction issue, no FMA
         perm_ms_avg = float(np.mean(perm_ms))
         tfl = lambda flops, ms: (flops / (ms * 1e-3) / 1e12) if ms and ms > 0 else None
-        if grid_used & 1:
+        fan_ms_avg, bounce_ms_avg, query_ms_avg = float(np.mean(fan_ms)), float(np.mean(bounce_ms)), float(np.mean(query_ms))
+        q_tests = [int(x) for x in gst.get("gridQueryTests", [0, 0, 0])]
+        b_tests = [int(t) - q for t, q in zip(gst["gridTraceTests"], q_tests)]
+        q_flops = sum(f * n for f, n in zip(FLOPS_TRACE, q_tests))
+        b_flops = sum(f * n for f, n in zip(FLOPS_TRACE, b_tests))
+        split = query_ms_avg > 0
+        if grid_used & 1 and split:
+            # the dominant kernel of the step: the echo / muffle queries of all hit points (k1_query_fan.cu)
+            achieved = tfl(q_flops, query_ms_avg)
+            kernel_name = "query_fan_kernel (K1b: echo + muffle queries of every hit point against the target fans)"
+            accounting = ("collider tests the kernel actually executed (ART_FRAME_GRID_STATS) x reference flops per test; the "
+                          "acceleration structures change WHICH tests run (about 2.6 per occlusion query instead of the reference's "
+                          "scan), so the full-scan count is reported beside it (SURVEY 8f-4). The fraction is low by design: a "
+                          "query costs an exact sqrt + four exact reciprocals and a direction-bin lookup before its first test; "
+                          "profiles/ holds issue-slot and lane utilisation. 'kernels' lists the bounce tracer and K2 as well.")
+        elif grid_used & 1:
             achieved = tfl(exec_trace_flops, trace_ms_avg)
-            kernel_name = "trace_grid_kernel (K1, default path: uniform grid + target fans" + ("" if grid_used & 4 else " DISABLED") + ")"
-            accounting = ("collider tests the kernel actually executed (ART_FRAME_GRID_STATS) x reference flops per test; "
-                          "the acceleration structures change WHICH tests run (about 2.5 per occlusion query instead of the "
-                          "reference's scan), so the full-scan count is reported beside it (SURVEY 8f-4) and this fraction is "
-                          "LOW by design: the kernel's time goes into preparing 8e8 queries in exact FP32 (sqrt, 4 reciprocals "
-                          "each) and into latency, not into the tests. See profiles/ for issue-slot and lane utilisation.")
+            kernel_name = "trace_grid_kernel (K1, grid walk: bounce rays and occlusion queries in one kernel)"
+            accounting = "collider tests the kernel actually executed (ART_FRAME_GRID_STATS) x reference flops per test"
         else:
             achieved = tfl(trace_flops_local, trace_ms_avg)
             kernel_name = "trace_kernel (K1, brute force)"
             accounting = "tests of the reference's full scans (early exits honoured) x reference flops per test"
-        traffic = None
-        ncu_util = None
+        # dram bytes per launch and issue-slot / lane utilisation come from ONE committed ncu --set full capture; they are only
+        # reported when that capture was taken from exactly these kernel sources
+        traffic, ncu_util, traffic_note = None, None, None
         try:
+            import hashlib
+            h = hashlib.sha1()
+            cs = os.path.join(ROOT, "audio-raytracer_b200", "csrc")
+            for f in sorted(os.listdir(cs)):
+                h.update(open(os.path.join(cs, f), "rb").read())
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            key = f"{args.workload}:{scene.n_rays}:{world}"
-            if key in tr:
-                traffic = tr[key]
-            ncu_util = tr.get(key + ":ncu")       # issue-slot / lane utilisation of the two big kernels from the committed captures
+            ent = tr.get(f"{args.workload}:{scene.n_rays}:{world}")
+            if ent and ent.get("csrc_sha1") == h.hexdigest():
+                traffic, ncu_util = ent.get("traffic"), ent.get("ncu")
+            elif ent:
+                traffic_note = f"profiles/traffic.json was captured from other kernel sources ({ent.get('csrc_sha1', '?')[:10]} != {h.hexdigest()[:10]}): not reported"
         except Exception:
             pass
         micro = {}
@@ -368,16 +387,25 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, desc, th, t, seg = cpu_reference_sample(scene, args.cpu_seconds, threads)
-            cpu = {"value": v, "unit": UNIT, "cores": th, "kind": "port", "sample": desc, "seconds": t}
+            cpu_reference_sample(scene, args.workload, threads, shrink=8)          # warm-up (page in the scene, spin up the cores)
+            v, desc, t = cpu_reference_sample(scene, args.workload, threads)
+            v1, desc1, t1 = cpu_reference_sample(scene, args.workload, 1, shrink=8)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc, "seconds": t,
+                   "single_thread": {"value": v1, "sample": desc1, "seconds": t1},
+                   "gpu_brute_force_over_cpu": (bf["segments"] / (bf["deviceMs"] * 1e-3) / v) if bf["deviceMs"] else None,
+                   "gpu_default_over_cpu": value / v,
+                   "note": "C port of the reference's brute-force loops. gpu_brute_force_over_cpu compares like with like (same "
+                           "tests executed); the rest of gpu_default_over_cpu is algorithmic (grid + target fans)."}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, scene, world),
             "segments_per_step": total_segs / args.steps,
-            "kernel_ms": {"trace": trace_ms_avg, "permeation": float(np.mean(perm_ms)), "reduce": float(np.mean(reduce_ms)),
+            "kernel_ms": {"trace": trace_ms_avg, "trace_fan_build": fan_ms_avg, "trace_bounce": bounce_ms_avg, "trace_queries": query_ms_avg,
+                          "permeation": float(np.mean(perm_ms)), "reduce": float(np.mean(reduce_ms)),
                           "partials_allgather": ex_ms_tot / args.steps,
-                          "note": "trace includes the per-frame fan build (fan_order_kernel + fan_build_kernel, profiles/*launches*)"},
+                          "note": "trace = per-frame fan build (fan_order_kernel + fan_build_kernel) + bounce tracer (trace_grid_kernel, "
+                                  "bounce-only) + query_fan_kernel; partials_allgather = ncclAllGather of the per-source blobs inside the library"},
             "wall_ms_per_step_device_mode": wall_dev_max / args.steps * 1e3,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -385,13 +413,21 @@ def main():
             "gpu_launches": launches_all,
             "roofline": {"bound": "fp32", "kernel": kernel_name, "achieved": achieved, "peak": peak_tflops,
                          "unit": "TFLOP/s", "frac": (achieved / peak_tflops) if achieved else None, "traffic": traffic,
+                         "traffic_note": traffic_note,
                          "accounting": accounting,
+                         "kernels": {
+                             "query_fan_kernel": {"ms": query_ms_avg, "tests_executed": q_tests, "executed_flops": q_flops,
+                                                  "achieved": tfl(q_flops, query_ms_avg), "frac": (tfl(q_flops, query_ms_avg) or 0) / peak_tflops},
+                             "trace_grid_kernel_bounce_only": {"ms": bounce_ms_avg, "tests_executed": b_tests, "executed_flops": b_flops,
+                                                               "achieved": tfl(b_flops, bounce_ms_avg), "frac": (tfl(b_flops, bounce_ms_avg) or 0) / peak_tflops},
+                             "permeation (K2)": {"ms": perm_ms_avg, "executed_flops": exec_perm_flops,
+                                                 "achieved": tfl(exec_perm_flops, perm_ms_avg), "frac": (tfl(exec_perm_flops, perm_ms_avg) or 0) / peak_tflops}},
                          "peak_source": f"148 SM x 128 FP32 lanes x {sm_max:.0f} MHz, un-fused issue rate (no FP32 figure in "
                                         "MEASURED_PEAKS.json; parity forbids FMA contraction, SURVEY 8d); FMA peak = 2x; "
                                         "on-box microbenchmarks in 'measured_issue_rates'",
                          "peak_fma": 2 * peak_tflops,
                          "ncu_utilisation": ncu_util,
-                         "executed_flops_per_launch": exec_trace_flops if grid_used & 1 else trace_flops_local,
+                         "executed_flops_per_launch": (q_flops if split else exec_trace_flops) if grid_used & 1 else trace_flops_local,
                          "flops_per_test": {"sphere": 38, "aabb": 35, "obb": 98},
                          "measured_issue_rates": micro,
                          "reference_formulation": {

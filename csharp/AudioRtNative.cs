@@ -11,14 +11,22 @@ using Unity.Mathematics;
 public static unsafe class AudioRtNative
 {
     const string Lib = "audiort_cuda";
-    public const int ART_ABI_VERSION = 2;
+    public const int ART_ABI_VERSION = 3;
+    public const int ART_MAX_DEVICES = 16;
 
     public const uint JOB_RAYTRACE = 1, JOB_PERMEATION = 2, JOB_PROCESS = 4, JOB_ALL = 7;
     public const uint FRAME_COUNTERS = 1, FRAME_REVERB_SEQ_FP32 = 2, FRAME_NO_HOST_OUTPUTS = 4, FRAME_PARTIALS_ONLY = 8;
     public const uint FRAME_BRUTE_FORCE = 16, FRAME_GRID_STATS = 32, FRAME_FORCE_GRID = 64, FRAME_NO_FANS = 128;
 
     [StructLayout(LayoutKind.Sequential)]
-    public struct ArtConfig { public int abiVersion; public int device; public uint flags; public fixed int reserved[5]; }
+    public struct ArtConfig
+    {
+        public int abiVersion; public int device; public uint flags;
+        public int nDevices;                       // > 1: one context over devices[0..nDevices) (the library shards the rays and merges)
+        public fixed int devices[ART_MAX_DEVICES];
+        public int shardChunkRays;
+        public fixed int reserved[3];
+    }
 
     [StructLayout(LayoutKind.Sequential)]
     public struct ArtParams

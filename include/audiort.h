@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ART_ABI_VERSION 2
+#define ART_ABI_VERSION 3
 
 typedef enum ArtStatus {
     ART_OK          =  0,
@@ -89,11 +89,21 @@ typedef int32_t ArtHandle;   /* frame ticket, stands in for Unity's JobHandle (A
 /* art_create flags */
 #define ART_CREATE_DEFAULT        0u
 
+#define ART_MAX_DEVICES 16
+
 typedef struct ArtConfig {
     int32_t  abiVersion;     /* must be ART_ABI_VERSION */
-    int32_t  device;         /* CUDA device ordinal */
+    int32_t  device;         /* CUDA device ordinal (used when nDevices <= 1) */
     uint32_t flags;
-    int32_t  reserved[5];
+    /* nDevices > 1: ONE context over several GPUs of this process. The library owns one device context per entry of
+     * devices[], the ray shard map (interleaved chunks of shardChunkRays rays, 0 = 256), the exchange and exact merge of the
+     * per-source partial results and the scatter of the per-ray outputs into the caller's arrays; every entry point keeps
+     * its single-device meaning and art_trace_schedule stays one call (ART:161-237). Results are bit-identical with a
+     * one-device context. */
+    int32_t  nDevices;
+    int32_t  devices[ART_MAX_DEVICES];
+    int32_t  shardChunkRays;
+    int32_t  reserved[3];
 } ArtConfig;
 
 /* Which jobs a frame runs (ART:191, 213, 237). */
@@ -192,6 +202,16 @@ typedef struct ArtCounters {
     uint64_t gridTraceCells, gridPermCells;
     uint64_t debugViolations;   /* builds with -DART_DEBUG_BOUNDS: failed index checks in the grid kernels (0 otherwise);
                                    any build: a group-rotation wait that timed out (art_complete then fails) */
+    /* parts of traceMs (default path): per-frame target-fan build, bounce tracer (trace_grid_kernel, bounce-only mode),
+     * echo / muffle query kernel (query_fan_kernel); 0 where a part did not run */
+    float    fanBuildMs, bounceMs, queryMs;
+    float    exchangeMs;        /* multi-process frames (art_comm_init): device time of the all-gather of the partial blobs */
+    uint32_t devicesUsed;       /* GPUs that worked on this frame (multi-device context: nDevices) */
+    uint32_t reserved0;
+    /* ART_FRAME_GRID_STATS, default path: the part of gridTraceTests / gridTraceCells executed by query_fan_kernel (echo and
+     * muffle queries against the target fans; "cells" = lists opened); the rest belongs to the bounce tracer's grid walk */
+    uint64_t gridQueryTests[3];
+    uint64_t gridQueryLists;
 } ArtCounters;
 
 /* ≙ AudioRayTracer.Awake/InitializeAudioRaytraceSystem (ART:53-87): one context per AudioRayTracer. */
@@ -245,6 +265,16 @@ ART_API int32_t art_get_partials(ArtCtx* ctx, ArtHandle h, void* blob, int64_t b
 ART_API int32_t art_partials_merge(void* accumBlob, const void* otherBlob, int64_t blobBytes);
 ART_API int32_t art_finalize(const void* blob, int64_t blobBytes, const ArtParams* params, int32_t rayCount,
                              const ArtOutputs* outputs /* only the per-target arrays are used */);
+
+/* ---- multi-process sharding (one rank per GPU, e.g. under torchrun / mpirun) -----------------------------------------
+ * art_comm_init joins the context to a communicator of `world` ranks (NCCL, loaded with dlopen("libnccl.so.2") on first
+ * use -- single-GPU hosts need no NCCL) and makes it trace shard `rank` of the batch (interleaved chunks of chunkRays rays,
+ * 0 = 256). From then on a frame scheduled WITHOUT ART_FRAME_PARTIALS_ONLY all-gathers the ranks' partial blobs on the
+ * device (one ncclAllGather of a few KB on the context's stream, no host round trip), merges them exactly and finalises on
+ * every rank: art_complete returns the same per-source outputs everywhere. Per-ray outputs stay local (local ray indexing).
+ * uniqueId: 128 bytes from art_comm_unique_id on one rank, distributed by the caller (MPI_Bcast, torch.distributed ...). */
+ART_API int32_t art_comm_unique_id(void* uniqueId128);
+ART_API int32_t art_comm_init(ArtCtx* ctx, const void* uniqueId128, int32_t rank, int32_t world, int32_t chunkRays);
 
 /* Host-only inspection of the acceleration structure art_set_scene builds (a uniform grid over the colliders;
  * csrc/grid_host.h): cell (x,y,z) = cells[2*((z*ny + y)*nx + x) + {0,1}] = {first entry, nS | nA << 10 | nO << 21},

@@ -662,7 +662,8 @@ typedef struct {
 
 /* kind 0: RT batches (item = batch k of size itemSize starting at first + k*itemSize);
  * kind 1: RT arbitrary sub-ranges for bounded samples (muffle u16 table not touched);
- * kind 2: PM arbitrary sub-ranges, work/counters only (no slot writes: Q5 is order dependent). */
+ * kind 2: PM arbitrary sub-ranges, work/counters only (no slot writes: Q5 is order dependent);
+ * kind 3: as 2 but the per-target sums over rays (permeationSum extension) are accumulated -- single thread only. */
 static void* worker(void* p)
 {
     Work* w = (Work*)p;
@@ -673,8 +674,9 @@ static void* worker(void* p)
         int32_t count = w->end - start < w->itemSize ? w->end - start : w->itemSize;
         if (w->kind == 0) {
             or_rt_execute(w->s, w->o, start, count, 0, w->c);
-        } else if (w->kind == 2) {
-            OrOutputs o2 = *w->o; o2.permeationPowerRemains = NULL; o2.permeationSum = NULL;
+        } else if (w->kind == 2 || w->kind == 3) {
+            OrOutputs o2 = *w->o; o2.permeationPowerRemains = NULL;
+            if (w->kind == 2) o2.permeationSum = NULL;
             or_pm_execute(w->s, &o2, start, count, w->c);
         } else {
             OrOutputs o2 = *w->o; o2.muffleRayHits = NULL;
@@ -745,6 +747,7 @@ int or_permeation_range(const OrScene* s, const OrOutputs* o, int32_t first, int
 {
     if (check_scene(s) || !o || first < 0 || count < 0 || first + count > s->rayCount) return -1;
     OrCounters dummy; if (!c) { c = &dummy; } memset(c, 0, sizeof *c);
-    run_items(s, o, c, 2, first, first + count, 16, nThreads);
+    /* one thread: the caller's permeationSum (zeroed by the caller) receives the window's per-target sums */
+    run_items(s, o, c, nThreads <= 1 && o->permeationSum ? 3 : 2, first, first + count, 16, nThreads);
     return 0;
 }

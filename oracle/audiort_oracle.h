@@ -164,7 +164,8 @@ int or_trace_range(const OrScene* s, const OrOutputs* o, int32_t first, int32_t 
                    int nThreads, OrCounters* c);
 
 /* Permeation work only (first hit + per-target loss rays) for rays
- * [first, first+count): counters, no slot writes. CPU-baseline timing helper. */
+ * [first, first+count): counters, no slot writes. CPU-baseline timing helper. With nThreads <= 1 and
+ * o->permeationSum set (zeroed by the caller) the window's per-target sums over rays are accumulated there. */
 int or_permeation_range(const OrScene* s, const OrOutputs* o, int32_t first, int32_t count,
                         int nThreads, OrCounters* c);
 

@@ -219,10 +219,17 @@ def trace_range(scene, first: int, count: int, threads: int = 1, with_outputs: b
     return fr
 
 
-def permeation_range(scene, first: int, count: int, threads: int = 1) -> dict:
+def permeation_range(scene, first: int, count: int, threads: int = 1, sums: Optional[np.ndarray] = None) -> dict:
+    """PM work over rays [first, first+count). ``sums`` (float64 [Na], single thread only): receives the window's per-target
+    sums of the PM:260 values (the permeationSum extension)."""
     keep = []
     s = _scene_struct(scene, keep)
     o = OrOutputs()
+    if sums is not None:
+        if threads > 1:
+            raise ValueError("permeation sums need threads=1 (order-dependent double accumulation)")
+        sums[:] = 0
+        o.permeationSum = sums.ctypes.data
     c = OrCounters()
     if lib().or_permeation_range(C.byref(s), C.byref(o), first, count, threads, C.byref(c)) != 0:
         raise ValueError("oracle: invalid arguments")

@@ -70,7 +70,7 @@ def load_golden(name):
     return s, out
 
 
-N_COUNTERS = 34          # scene_dev.cuh CounterIdx::C_COUNT
+N_COUNTERS = 38          # scene_dev.cuh CounterIdx::C_COUNT
 BLOB_MAGIC = 0x41525442  # "ARTB"
 
 

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(art_lib):
 def test_wire_struct_sizes():
     from audio_raytracer_b200.layouts import AABB_DT, OBB_DT, SPHERE_DT, SETTINGS_DT
     assert (AABB_DT.itemsize, OBB_DT.itemsize, SPHERE_DT.itemsize, SETTINGS_DT.itemsize) == (20, 26, 16, 24)
-    assert C.sizeof(native.ArtConfig) == 32
+    assert C.sizeof(native.ArtConfig) == 4 * (4 + native.ART_MAX_DEVICES + 1 + 3)
     assert C.sizeof(native.ArtOutputs) == 9 * C.sizeof(C.c_void_p)
 
 
