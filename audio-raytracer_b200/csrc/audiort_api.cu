@@ -216,7 +216,13 @@ struct ArtCtx {
     PinBuf pinScene;
     DevBuf rawScene, geom, attrs, owners, perm;    // perm: dens arrays + owned list
     HostGrid grid;                                 // uniform grid over the scene (grid_host.h)
-    DevBuf gridCells, gridEntries, gridRangeO, gridScratch, rotateLog;
+    DevBuf gridCells, gridEntries, gridRangeO, gridScratch, rotateLog, gridCnt, gridCtl;
+    PinBuf pinGrid, pinGridCtl;
+    size_t gridEntriesPerCollider = 64;            // entry capacity of the device-built grid (grows after an overflow)
+    bool frameGridBuilt = false;                   // the frame in flight uses cell lists built for it (overflow flag to check)
+    bool rerunNoGrid = false;                      // second pass of a frame whose grid build overflowed: brute-force kernels
+    int dirtyLo[3] = { 0, 0, 0 }, dirtyHi[3] = { 0, 0, 0 };   // per type (S, A, O): struct range changed since the last upload
+    bool sceneLayoutChanged = true;                // counts changed: everything is uploaded
     DevBuf hitRecs, queryScratch;                  // bounce-only trace job: hit records + survivor lists of query_fan_kernel
     DevBuf permHitPts, permBinCnt, permPairs;       // binned loss lines (k2_permeation_binned.cu)
     DevBuf fanBoxes, fanCells, fanEntries, fanCtl, fanOrder;  // target fans (fan_dev.cuh): collider bounds (per scene), lists (per frame)
@@ -458,10 +464,10 @@ static void release_ctx(ArtCtx* ctx)
     if (ctx->copyStream) cudaStreamSynchronize(ctx->copyStream);
     if (ctx->comm && nccl_api().ok()) nccl_api().CommDestroy(ctx->comm);
     ctx->comm = nullptr;
-    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->rotateLog, &ctx->hitRecs, &ctx->queryScratch, &ctx->permHitPts, &ctx->permBinCnt, &ctx->permPairs, &ctx->fanBoxes, &ctx->fanCells, &ctx->fanEntries, &ctx->fanCtl, &ctx->fanOrder, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
+    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->rotateLog, &ctx->gridCnt, &ctx->gridCtl, &ctx->hitRecs, &ctx->queryScratch, &ctx->permHitPts, &ctx->permBinCnt, &ctx->permPairs, &ctx->fanBoxes, &ctx->fanCells, &ctx->fanEntries, &ctx->fanCtl, &ctx->fanOrder, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
                        &ctx->outAll, &ctx->firstHit, &ctx->partials, &ctx->queue, &ctx->gathered })
         b->release();
-    for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinAll, &ctx->pinPerm, &ctx->pinFanCtl, &ctx->pinGathered })
+    for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinAll, &ctx->pinPerm, &ctx->pinFanCtl, &ctx->pinGathered, &ctx->pinGrid, &ctx->pinGridCtl })
         b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t evx : { ctx->evReady, ctx->evP0, ctx->evP1, ctx->evTraceDone, ctx->evCopyDone, ctx->evFan, ctx->evBounce, ctx->evX0, ctx->evX1 })
@@ -541,6 +547,7 @@ ART_API int32_t art_create(const ArtConfig* cfg, ArtCtx** out)
     if (const char* v = getenv("ART_GRID_MIN_RAYS")) ctx->gridMinRays = atoi(v);
     if (const char* v = getenv("ART_DISABLE_FANS")) ctx->fansDisabled = atoi(v) != 0;
     if (const char* v = getenv("ART_FAN_ENTRIES_PER_PAIR")) { const long n = atol(v); if (n >= 1 && n <= 65536) ctx->fanEntriesPerPair = (size_t)n; }
+    if (const char* v = getenv("ART_GRID_ENTRIES_PER_COLLIDER")) { const long n = atol(v); if (n >= 0 && n <= 16384) ctx->gridEntriesPerCollider = (size_t)n; }
     if (const char* v = getenv("ART_GRID_CELL_SCALE")) { const float f = (float)atof(v); if (f > 0.05f && f < 50.0f) ctx->gridCellScale = f; }
     *out = ctx;
     return ART_OK;
@@ -567,9 +574,40 @@ ART_API int32_t art_set_scene(ArtCtx* ctx, const ArtAABB* aabbs, int32_t nAABB, 
         return fail(ctx, ART_E_ARG, "art_set_scene: bad counts/pointers");
     if (nAABB >= (1 << 24) || nOBB >= (1 << 24) || nSphere >= (1 << 24)) return fail(ctx, ART_E_ARG, "art_set_scene: too many colliders");
     static_assert(sizeof(ArtAABB) == 20 && sizeof(ArtOBB) == 26 && sizeof(ArtSphere) == 16, "wire layout");
-    ctx->hostS.assign(reinterpret_cast<const uint16_t*>(spheres), reinterpret_cast<const uint16_t*>(spheres) + 8 * (size_t)nSphere);
-    ctx->hostA.assign(reinterpret_cast<const uint16_t*>(aabbs), reinterpret_cast<const uint16_t*>(aabbs) + 10 * (size_t)nAABB);
-    ctx->hostO.assign(reinterpret_cast<const uint16_t*>(obbs), reinterpret_cast<const uint16_t*>(obbs) + 13 * (size_t)nOBB);
+    // The reference double-buffers its collider arrays (DataTypes/NativeJobBatch.cs:36-50) and re-bakes only the dynamic
+    // colliders per frame (ACM:115-122): diff the new payload against the previous one and remember, per type, the range of
+    // structs that changed -- only that range is uploaded by the next frame (nothing at all when the scene is unchanged).
+    {
+        const uint16_t* src[3] = { reinterpret_cast<const uint16_t*>(spheres), reinterpret_cast<const uint16_t*>(aabbs), reinterpret_cast<const uint16_t*>(obbs) };
+        std::vector<uint16_t>* dst[3] = { &ctx->hostS, &ctx->hostA, &ctx->hostO };
+        const int words[3] = { 8, 10, 13 }, cnt[3] = { nSphere, nAABB, nOBB };
+        const bool sameLayout = ctx->haveScene && ctx->hostS.size() == 8 * (size_t)nSphere && ctx->hostA.size() == 10 * (size_t)nAABB &&
+                                ctx->hostO.size() == 13 * (size_t)nOBB;
+        bool any = !sameLayout;
+        for (int t = 0; t < 3; t++) {
+            int lo = cnt[t], hi = 0;
+            if (sameLayout) {
+                const uint16_t* old = dst[t]->data();
+                const size_t rowBytes = 2 * (size_t)words[t];
+                for (int i = 0; i < cnt[t]; i++)
+                    if (memcmp(old + (size_t)i * words[t], src[t] + (size_t)i * words[t], rowBytes) != 0) { lo = i; break; }
+                for (int i = cnt[t] - 1; i >= lo && lo < cnt[t]; i--)
+                    if (memcmp(old + (size_t)i * words[t], src[t] + (size_t)i * words[t], rowBytes) != 0) { hi = i + 1; break; }
+                if (lo < hi) {
+                    any = true;
+                    memcpy(dst[t]->data() + (size_t)lo * words[t], src[t] + (size_t)lo * words[t], rowBytes * (size_t)(hi - lo));
+                }
+            } else {
+                lo = 0; hi = cnt[t];
+                dst[t]->assign(src[t], src[t] + (size_t)words[t] * cnt[t]);
+            }
+            // (ranges of frames that were never scheduled accumulate)
+            if (ctx->sceneDirty && sameLayout) { ctx->dirtyLo[t] = std::min(ctx->dirtyLo[t], lo); ctx->dirtyHi[t] = std::max(ctx->dirtyHi[t], hi); }
+            else { ctx->dirtyLo[t] = lo; ctx->dirtyHi[t] = hi; }
+        }
+        if (!sameLayout) ctx->sceneLayoutChanged = true;
+        if (!any) return ART_OK;                       // identical scene: packed geometry, grid and owner tables stay valid
+    }
     GeomLayout& L = ctx->L;
     L.ns = nSphere; L.na = nAABB; L.no = nOBB;
     L.nsPad = (nSphere + SC_S - 1) / SC_S * SC_S;
@@ -809,13 +847,27 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     if (ctx->sceneDirty) {
         const size_t bS = ctx->hostS.size() * 2, bA = ctx->hostA.size() * 2, bO = ctx->hostO.size() * 2;
         const size_t offA = (bS + 15) & ~(size_t)15, offO = (offA + bA + 15) & ~(size_t)15, tot = offO + bO + 16;
+        const bool fullUpload = ctx->sceneLayoutChanged || ctx->pinScene.cap < tot || ctx->rawScene.cap < tot;
         CK(ctx->pinScene.ensure(tot));
         CK(ctx->rawScene.ensure(tot));
         unsigned char* hp = ctx->pinScene.as<unsigned char>();
-        if (bS) memcpy(hp, ctx->hostS.data(), bS);
-        if (bA) memcpy(hp + offA, ctx->hostA.data(), bA);
-        if (bO) memcpy(hp + offO, ctx->hostO.data(), bO);
-        CK(cudaMemcpyAsync(ctx->rawScene.p, hp, tot, cudaMemcpyHostToDevice, ctx->stream));
+        if (fullUpload) {
+            if (bS) memcpy(hp, ctx->hostS.data(), bS);
+            if (bA) memcpy(hp + offA, ctx->hostA.data(), bA);
+            if (bO) memcpy(hp + offO, ctx->hostO.data(), bO);
+            CK(cudaMemcpyAsync(ctx->rawScene.p, hp, tot, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            // only the structs that changed since the last upload (art_set_scene diffed the payloads)
+            const size_t offs[3] = { 0, offA, offO }, row[3] = { 16, 20, 26 };
+            const std::vector<uint16_t>* srcv[3] = { &ctx->hostS, &ctx->hostA, &ctx->hostO };
+            for (int t = 0; t < 3; t++) {
+                if (ctx->dirtyLo[t] >= ctx->dirtyHi[t]) continue;
+                const size_t b0 = row[t] * (size_t)ctx->dirtyLo[t], nb = row[t] * (size_t)(ctx->dirtyHi[t] - ctx->dirtyLo[t]);
+                memcpy(hp + offs[t] + b0, reinterpret_cast<const unsigned char*>(srcv[t]->data()) + b0, nb);
+                CK(cudaMemcpyAsync(ctx->rawScene.as<unsigned char>() + offs[t] + b0, hp + offs[t] + b0, nb, cudaMemcpyHostToDevice, ctx->stream));
+            }
+        }
+        ctx->sceneLayoutChanged = false;
         CK(ctx->geom.ensure(L.bytes + 16));
         const size_t nAttr4 = (size_t)L.nsPad + 3 * (size_t)L.naPad + 3 * (size_t)L.noPad;
         CK(ctx->attrs.ensure(nAttr4 * sizeof(float4) + 16));
@@ -1003,21 +1055,49 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         }
         if (map.nLocal < minRays) useGrid = false;
     }
+    if (ctx->rerunNoGrid) useGrid = false;            // second pass of a frame whose grid build overflowed
+    ctx->frameGridBuilt = false;
     if (useGrid && !ctx->gridBuilt) {
-        // uniform grid over the current scene (host build, two small uploads)
-        build_grid(ctx->hostS, ctx->hostA, ctx->hostO, ctx->gridCellScale, ctx->grid);
+        // Uniform grid over the current scene. The host works out what is O(colliders) -- bounds, dimensions, margins -- and
+        // stages the conservative boxes in pinned memory; the cell lists are filled on the device (k5_grid_build.cu). No
+        // cell walk and no stream synchronisation on the host: a scene that changes every frame costs a few tens of us here.
+        grid_params(ctx->hostS, ctx->hostA, ctx->hostO, ctx->gridCellScale, ctx->grid);
         if (ctx->grid.ok) {
-            CK(ctx->gridCells.ensure(ctx->grid.cells.size() * sizeof(uint2)));
-            CK(ctx->gridEntries.ensure(ctx->grid.entries.size() * sizeof(uint16_t)));
-            CK(ctx->gridRangeO.ensure(ctx->grid.rangeO.size() * sizeof(uint2)));
-            CK(cudaMemcpyAsync(ctx->gridRangeO.p, ctx->grid.rangeO.data(), ctx->grid.rangeO.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemcpyAsync(ctx->gridCells.p, ctx->grid.cells.data(), ctx->grid.cells.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemcpyAsync(ctx->gridEntries.p, ctx->grid.entries.data(), ctx->grid.entries.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+            const size_t nCells = (size_t)ctx->grid.d.nx * ctx->grid.d.ny * ctx->grid.d.nz;
+            const size_t nc = (size_t)L.ns + L.na + L.no;
+            // (ART_GRID_ENTRIES_PER_COLLIDER=0, a test knob, leaves room for 16 entries only: the build overflows, the frame is
+            // re-run on the brute-force kernels and the next build gets a larger buffer)
+            const size_t cap = ctx->gridEntriesPerCollider == 0 ? 16
+                             : std::min<size_t>((size_t)1 << 28, ctx->gridEntriesPerCollider * nc + 8 * nCells + 1024);
             const size_t boxBytes = ctx->grid.boxLo.size() * sizeof(float);
+            const size_t rangeBytes = ctx->grid.rangeO.size() * sizeof(uint2);
+            const size_t rangeOff = (2 * boxBytes + 15) & ~(size_t)15;
+            CK(ctx->pinGrid.ensure(rangeOff + rangeBytes + 16));
+            CK(ctx->pinGridCtl.ensure(16));
             CK(ctx->fanBoxes.ensure(2 * boxBytes + 32));
-            CK(cudaMemcpyAsync(ctx->fanBoxes.p, ctx->grid.boxLo.data(), boxBytes, cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemcpyAsync(ctx->fanBoxes.as<unsigned char>() + boxBytes, ctx->grid.boxHi.data(), boxBytes, cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));   // pageable host vectors
+            CK(ctx->gridRangeO.ensure(rangeBytes + 16));
+            CK(ctx->gridCells.ensure(nCells * sizeof(uint2)));
+            CK(ctx->gridEntries.ensure(cap * sizeof(uint16_t) + 16));
+            CK(ctx->gridCnt.ensure(nCells * 3 * sizeof(unsigned int)));
+            CK(ctx->gridCtl.ensure(16));
+            unsigned char* hp = ctx->pinGrid.as<unsigned char>();
+            memcpy(hp, ctx->grid.boxLo.data(), boxBytes);
+            memcpy(hp + boxBytes, ctx->grid.boxHi.data(), boxBytes);
+            memcpy(hp + rangeOff, ctx->grid.rangeO.data(), rangeBytes);
+            CK(cudaMemcpyAsync(ctx->fanBoxes.p, hp, 2 * boxBytes, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->gridRangeO.p, hp + rangeOff, rangeBytes, cudaMemcpyHostToDevice, ctx->stream));
+            GridBuildArgs ga;
+            ga.boxLo = ctx->fanBoxes.as<float4>(); ga.boxHi = ga.boxLo + nc;
+            ga.ns = L.ns; ga.na = L.na; ga.no = L.no;
+            ga.g0x = ctx->grid.d.g0x; ga.g0y = ctx->grid.d.g0y; ga.g0z = ctx->grid.d.g0z;
+            ga.csx = ctx->grid.d.csx; ga.csy = ctx->grid.d.csy; ga.csz = ctx->grid.d.csz;
+            ga.nx = ctx->grid.d.nx; ga.ny = ctx->grid.d.ny; ga.nz = ctx->grid.d.nz;
+            ga.cnt = ctx->gridCnt.as<unsigned int>(); ga.cells = ctx->gridCells.as<uint2>(); ga.entries = ctx->gridEntries.as<uint16_t>();
+            ga.capacity = (unsigned int)cap; ga.ctl = ctx->gridCtl.as<unsigned int>();
+            CK(launch_grid_build(ga, ctx->stream));
+            ctx->kernelLaunches += 4;
+            ctx->grid.d.nEntries = (int)cap;
+            ctx->frameGridBuilt = true;
         }
         ctx->gridBuilt = true;
     }
@@ -1273,6 +1353,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     // ---------------- read back ----------------
     CK(cudaMemcpyAsync(ctx->pinPartials.p, ctx->partials.p, bl.bytes, cudaMemcpyDeviceToHost, ctx->stream));
     if (useFans) CK(cudaMemcpyAsync(ctx->pinFanCtl.p, ctx->fanCtl.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->frameGridBuilt) CK(cudaMemcpyAsync(ctx->pinGridCtl.p, ctx->gridCtl.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
     if (copiedEarly) CK(cudaStreamWaitEvent(ctx->stream, ctx->evCopyDone, 0));
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
 
@@ -1295,10 +1376,26 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
 
 // The fan lists of the frame in flight did not fit their buffer (or a list exceeded its length limit): its results are
 // incomplete. Schedule it again on the grid walk (under the same handle) and give the next frame a larger buffer.
-static bool needs_rerun(const ArtCtx* ctx) { return ctx->frameFans && !ctx->frameIsRerun && ctx->pinFanCtl.as<unsigned int>()[1] != 0; }
+// Likewise when the device-built grid overflowed its entry buffer or a cell list outgrew the header format: second pass on
+// the brute-force kernels, larger buffer for the next scene upload.
+static bool grid_overflowed(const ArtCtx* ctx) { return ctx->frameGridBuilt && ctx->pinGridCtl.as<unsigned int>()[1] != 0; }
+static bool needs_rerun(const ArtCtx* ctx)
+{
+    if (ctx->frameIsRerun) return false;
+    return grid_overflowed(ctx) || (ctx->frameFans && ctx->pinFanCtl.as<unsigned int>()[1] != 0);
+}
 static int32_t start_rerun(ArtCtx* ctx)
 {
-    if (ctx->fanEntriesPerPair < 4096) ctx->fanEntriesPerPair *= 4;
+    if (getenv("ART_DEBUG_LOG"))
+        fprintf(stderr, "[audiort] frame re-run: grid ctl {%u, %u} (built %d), fan ctl {%u, %u} (fans %d)\n",
+                ctx->pinGridCtl.p ? ctx->pinGridCtl.as<unsigned int>()[0] : 0u, ctx->pinGridCtl.p ? ctx->pinGridCtl.as<unsigned int>()[1] : 0u,
+                (int)ctx->frameGridBuilt, ctx->pinFanCtl.p ? ctx->pinFanCtl.as<unsigned int>()[0] : 0u,
+                ctx->pinFanCtl.p ? ctx->pinFanCtl.as<unsigned int>()[1] : 0u, (int)ctx->frameFans);
+    if (grid_overflowed(ctx)) {
+        if (ctx->gridEntriesPerCollider < 16384) ctx->gridEntriesPerCollider = std::max<size_t>(64, ctx->gridEntriesPerCollider * 4);
+        ctx->rerunNoGrid = true;
+        ctx->gridBuilt = false;                        // the next frame builds the lists again, into the larger buffer
+    } else if (ctx->fanEntriesPerPair < 4096) ctx->fanEntriesPerPair *= 4;
     ArtParams prm = ctx->params;
     ArtOutputs uo = ctx->userOut;
     const bool hadOut = ctx->haveUserOut;
@@ -1308,6 +1405,7 @@ static int32_t start_rerun(ArtCtx* ctx)
     ArtHandle h2 = 0;
     const int32_t rc = art_trace_schedule(ctx, &prm, hadOut ? &uo : nullptr, &h2);
     ctx->rerunning = false;
+    ctx->rerunNoGrid = false;
     ctx->handle = keep;
     ctx->frameIsRerun = true;
     return rc;

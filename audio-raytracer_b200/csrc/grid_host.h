@@ -23,8 +23,13 @@
 
 namespace art {
 
+namespace gridimpl {
+struct Box { float lo[3], hi[3]; float r; };   // r: sphere radius (spheres only)
+}  // namespace gridimpl
+
 struct HostGrid {
     GridDesc d{};                       // device pointers left null
+    std::vector<gridimpl::Box> bS, bA, bO;   // un-inflated bounds per collider (grid_params)
     std::vector<uint2> cells;
     std::vector<uint16_t> entries;
     std::vector<uint2> rangeO;          // per OBB: the cell range it is listed in (packed 8 bits per axis)
@@ -50,21 +55,22 @@ inline float h2f(uint16_t h)
     float out; memcpy(&out, &bits, 4); return out;
 }
 
-struct Box { float lo[3], hi[3]; float r; };   // r: sphere radius (spheres only)
-
 }  // namespace gridimpl
 
-// cellScale: cell edge = cellScale * cbrt(volume / colliders)
-inline void build_grid(const std::vector<uint16_t>& rawS, const std::vector<uint16_t>& rawA, const std::vector<uint16_t>& rawO,
-                       float cellScale, HostGrid& g)
+// Part 1 (cheap, O(colliders)): collider bounds, grid dimensions, margins, the inflated boxes (input of the target fans and of
+// the device-side cell fill, k5_grid_build.cu) and the OBB cell ranges. cellScale: cell edge = cellScale * cbrt(volume / colliders).
+// g.ok is set when the scene can be gridded; the cell lists are NOT built here.
+inline void grid_params(const std::vector<uint16_t>& rawS, const std::vector<uint16_t>& rawA, const std::vector<uint16_t>& rawO,
+                        float cellScale, HostGrid& g)
 {
     using namespace gridimpl;
     g.ok = false; g.cells.clear(); g.entries.clear(); g.rangeO.clear(); g.boxLo.clear(); g.boxHi.clear();
+    std::vector<Box>& bS = g.bS; std::vector<Box>& bA = g.bA; std::vector<Box>& bO = g.bO;
     const size_t ns = rawS.size() / 8, na = rawA.size() / 10, no = rawO.size() / 13;
     if (ns + na + no == 0) { g.why = "empty scene"; return; }
     if (ns > 65535 || na > 65535 || no > 65535) { g.why = "more than 65535 colliders of one type"; return; }
 
-    std::vector<Box> bS(ns), bA(na), bO(no);
+    bS.assign(ns, Box{}); bA.assign(na, Box{}); bO.assign(no, Box{});
     float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
     auto grow = [&](const Box& b) {
         for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], b.lo[k]); hi[k] = std::max(hi[k], b.hi[k]); }
@@ -154,8 +160,47 @@ inline void build_grid(const std::vector<uint16_t>& rawS, const std::vector<uint
     d.nx = dim[0]; d.ny = dim[1]; d.nz = dim[2];
     d.errScale = D;
     d.cells = nullptr; d.entries = nullptr; d.rangeO = nullptr;
-    const size_t nCells = (size_t)dim[0] * dim[1] * dim[2];
+    auto range = [&](const Box& b, float extra, int i0[3], int i1[3]) {
+        for (int k = 0; k < 3; k++) {
+            const float a = (b.lo[k] - (m + extra) - lo[k]) / csz[k], z = (b.hi[k] + (m + extra) - lo[k]) / csz[k];
+            i0[k] = std::max(0, std::min(dim[k] - 1, (int)std::floor(a)));
+            i1[k] = std::max(0, std::min(dim[k] - 1, (int)std::floor(z)));
+        }
+    };
+    auto sphereExtra = [&](const Box& b) { return std::min(D, 1e-6f * D * D / std::max(b.r, 1e-3f)); };
+    g.boxLo.reserve(4 * nc + 4); g.boxHi.reserve(4 * nc + 4);
+    auto pushBoxes = [&](const std::vector<Box>& bs, int type) {
+        for (const Box& b : bs) {
+            const float infl = m + (type == 0 ? sphereExtra(b) : 0.0f);
+            for (int k = 0; k < 3; k++) { g.boxLo.push_back(b.lo[k] - infl); g.boxHi.push_back(b.hi[k] + infl); }
+            g.boxLo.push_back(0.0f); g.boxHi.push_back(0.0f);
+        }
+    };
+    pushBoxes(bS, 0); pushBoxes(bA, 1); pushBoxes(bO, 2);
+    g.rangeO.resize(no + 1);
+    for (size_t i = 0; i < no; i++) {
+        int i0[3], i1[3];
+        range(bO[i], 0.0f, i0, i1);
+        g.rangeO[i] = make_uint2((uint32_t)(i0[0] | (i0[1] << 8) | (i0[2] << 16)), (uint32_t)(i1[0] | (i1[1] << 8) | (i1[2] << 16)));
+    }
+    g.ok = true;
+    g.why = "";
+}
 
+// Part 2, host version (art_grid_build_host: inspection, tests): the cell lists. The library itself fills them on the device.
+inline void build_grid(const std::vector<uint16_t>& rawS, const std::vector<uint16_t>& rawA, const std::vector<uint16_t>& rawO,
+                       float cellScale, HostGrid& g)
+{
+    using namespace gridimpl;
+    grid_params(rawS, rawA, rawO, cellScale, g);
+    if (!g.ok) return;
+    g.ok = false;
+    const std::vector<Box>& bS = g.bS; const std::vector<Box>& bA = g.bA; const std::vector<Box>& bO = g.bO;
+    GridDesc& d = g.d;
+    const int dim[3] = { d.nx, d.ny, d.nz };
+    const float lo[3] = { d.g0x, d.g0y, d.g0z }, csz[3] = { d.csx, d.csy, d.csz };
+    const float m = g.margin, D = d.errScale;
+    const size_t nCells = (size_t)dim[0] * dim[1] * dim[2];
     auto range = [&](const Box& b, float extra, int i0[3], int i1[3]) {
         for (int k = 0; k < 3; k++) {
             const float a = (b.lo[k] - (m + extra) - lo[k]) / csz[k], z = (b.hi[k] + (m + extra) - lo[k]) / csz[k];
@@ -194,21 +239,6 @@ inline void build_grid(const std::vector<uint16_t>& rawS, const std::vector<uint
     d.nEntries = (int)off;
     auto fill = [&](size_t cell, int type, uint16_t id) { g.entries[cursor[cell * 3 + type]++] = id; };
     visit(bS, 0, fill); visit(bA, 1, fill); visit(bO, 2, fill);   // ascending canonical index inside each list
-    g.boxLo.reserve(4 * nc + 4); g.boxHi.reserve(4 * nc + 4);
-    auto pushBoxes = [&](const std::vector<Box>& bs, int type) {
-        for (const Box& b : bs) {
-            const float infl = m + (type == 0 ? sphereExtra(b) : 0.0f);
-            for (int k = 0; k < 3; k++) { g.boxLo.push_back(b.lo[k] - infl); g.boxHi.push_back(b.hi[k] + infl); }
-            g.boxLo.push_back(0.0f); g.boxHi.push_back(0.0f);
-        }
-    };
-    pushBoxes(bS, 0); pushBoxes(bA, 1); pushBoxes(bO, 2);
-    g.rangeO.resize(no + 1);
-    for (size_t i = 0; i < no; i++) {
-        int i0[3], i1[3];
-        range(bO[i], 0.0f, i0, i1);
-        g.rangeO[i] = make_uint2((uint32_t)(i0[0] | (i0[1] << 8) | (i0[2] << 16)), (uint32_t)(i1[0] | (i1[1] << 8) | (i1[2] << 16)));
-    }
     g.ok = true;
     g.why = "";
 }

@@ -21,6 +21,7 @@
 //            When the queue runs dry the few queries still in flight are written back (with their cursor) and wait for the
 //            next run -- no warp ever idles through the long lists of a few unobstructed queries;
 //   S/O      a query no AABB blocks is queued the same way for the sphere and OBB lists; if nothing blocks, it sees its goal.
+#include <algorithm>
 #include <cstdlib>
 
 #include "device_util.cuh"
@@ -290,23 +291,23 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
     int nA = 0, nSO = 0;                             // queued queries (kept across goals and record blocks)
     const unsigned int nRec = *a.recCount;           // the bounce tracer has finished (stream order)
 
-    // Work unit = (block of 32 records, group of goals). With few records (a small batch against many targets) the goals of
-    // a block are split over several warps so that the whole GPU is busy; otherwise a unit covers all goals of its block.
+    // Work unit = (block of 32 records, group of goals). With few records (a small batch against many targets) the launcher
+    // splits the goals of a block over several warps so that the whole GPU is busy (QueryArgs::goalGroups); otherwise a unit
+    // covers all goals of its block.
     const unsigned int nBlocks = (nRec + 31u) / 32u;
-    const unsigned int totalWarps = gridDim.x * (unsigned)kQWarps;
-    unsigned int nGroups = 1;
-    if (nBlocks > 0 && nBlocks < 2u * totalWarps) nGroups = min((unsigned)slots, (2u * totalWarps + nBlocks - 1u) / nBlocks);
-    const int perGroup = (slots + (int)nGroups - 1) / (int)nGroups;
-    nGroups = (unsigned)((slots + perGroup - 1) / perGroup);
-    const unsigned long long nUnits = (unsigned long long)nBlocks * nGroups;
 
     for (;;) {
         unsigned int unit = 0;
         if (lane == 0) unit = atomicAdd(a.queue, 1u);
         unit = __shfl_sync(kFull, unit, 0);
-        if ((unsigned long long)unit >= nUnits) break;
-        const unsigned int blk = unit / nGroups;
-        const int sBeg = (int)(unit - blk * nGroups) * perGroup, sEnd = min(slots, sBeg + perGroup);
+        unsigned int blk = unit;
+        int sBeg = 0, sEnd = slots;
+        if (a.goalGroups > 1) {
+            blk = unit / (unsigned)a.goalGroups;
+            sBeg = (int)(unit - blk * (unsigned)a.goalGroups) * a.goalsPerGroup;
+            sEnd = min(slots, sBeg + a.goalsPerGroup);
+        }
+        if (blk >= nBlocks) break;
         const unsigned int ri = blk * 32u + (unsigned)lane;
         const bool valid = ri < nRec;
         f3 P = mk3(0, 0, 0);
@@ -415,6 +416,15 @@ cudaError_t launch_query_fan(const QueryArgs& a0, const FanDesc& fans, int numCt
     a.tablesInSmem = 0; a.muffleInSmem = 0;
     const char* noTab = getenv("ART_K1_NO_GOAL_TABLES");         // (read per launch: test knob for the global-memory fallbacks)
     const bool tabs = !(noTab && atoi(noTab) != 0);
+    // few records (upper bound: local rays x MaxHitsPerRay): split every block's goals over several warps
+    {
+        const long long maxBlocks = ((long long)a.map.nLocal * a.H + 31) / 32, warps = (long long)numCtas * kQWarps;
+        const int slots = a.nTargets + 1;
+        long long g = 1;
+        if (maxBlocks > 0 && maxBlocks < 2 * warps) g = std::min<long long>(slots, (2 * warps + maxBlocks - 1) / maxBlocks);
+        a.goalsPerGroup = (int)((slots + g - 1) / g);
+        a.goalGroups = (slots + a.goalsPerGroup - 1) / a.goalsPerGroup;
+    }
     // experiment knob (read per launch): AABBs tested in pass 0 (1 or 2)
     a.firstTests = kQFirstTests;
     if (const char* v = getenv("ART_Q_FIRST_TESTS")) { const int n = atoi(v); if (n >= 1 && n <= kQFirstTests) a.firstTests = n; }

@@ -17,6 +17,7 @@ cudaError_t launch_trace_grid(const TraceArgs& a, const GridDesc& g, bool record
 size_t query_fan_scratch_bytes(int numCtas);
 size_t query_fan_smem_bytes(const GeomLayout& L, bool geomInSmem);
 cudaError_t launch_query_fan(const QueryArgs& a, const FanDesc& fans, int numCtas, bool geomInSmem, bool stats, int maxSmemOptin, cudaStream_t stream);
+cudaError_t launch_grid_build(const GridBuildArgs& a, cudaStream_t stream);
 cudaError_t launch_fan_build(const FanBuildArgs& a, cudaStream_t stream);
 size_t perm_smem_bytes(const GeomLayout& L, bool geomInSmem);
 cudaError_t launch_permeation(const PermArgs& a, int numCtas, bool geomInSmem, int T, cudaStream_t stream);

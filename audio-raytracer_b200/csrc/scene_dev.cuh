@@ -60,20 +60,29 @@ struct AttrArrays {
     const int*    ownedCount;// [3][nTargetsCap] colliders of each type owned by target a (counters only)
 };
 
-struct GeomView {
-    const float4* sph; const float4* aabbA; const float2* aabbB;
-    const float4* obbQ; const float4* obbC; const float2* obbH;
+// One plane of the blob: base pointer + byte offset. Every plane of a view shares the base, and the offsets are kernel
+// parameters (constant bank), so a view costs the kernels one address register pair instead of six.
+template <class T>
+struct PlaneRef {
+    const unsigned char* base;
+    uint32_t off;
+    __host__ __device__ __forceinline__ const T& operator[](int i) const { return reinterpret_cast<const T*>(base + off)[i]; }
 };
 
-__host__ __device__ inline GeomView make_view(const unsigned char* base, const GeomLayout& L)
+struct GeomView {
+    PlaneRef<float4> sph; PlaneRef<float4> aabbA; PlaneRef<float2> aabbB;
+    PlaneRef<float4> obbQ; PlaneRef<float4> obbC; PlaneRef<float2> obbH;
+};
+
+__host__ __device__ __forceinline__ GeomView make_view(const unsigned char* base, const GeomLayout& L)
 {
     GeomView v;
-    v.sph = reinterpret_cast<const float4*>(base + L.offSph);
-    v.aabbA = reinterpret_cast<const float4*>(base + L.offAabbA);
-    v.aabbB = reinterpret_cast<const float2*>(base + L.offAabbB);
-    v.obbQ = reinterpret_cast<const float4*>(base + L.offObbQ);
-    v.obbC = reinterpret_cast<const float4*>(base + L.offObbC);
-    v.obbH = reinterpret_cast<const float2*>(base + L.offObbH);
+    v.sph = { base, L.offSph };
+    v.aabbA = { base, L.offAabbA };
+    v.aabbB = { base, L.offAabbB };
+    v.obbQ = { base, L.offObbQ };
+    v.obbC = { base, L.offObbC };
+    v.obbH = { base, L.offObbH };
     return v;
 }
 
@@ -174,6 +183,7 @@ struct QueryArgs {
     int tablesInSmem;              // goal positions + near-list headers of all slots staged in shared memory
     int muffleInSmem;              // per-CTA muffle counters [T*Na] in shared memory
     int firstTests;                // AABBs every query tests in pass 0 (1 or 2)
+    int goalGroups, goalsPerGroup; // > 1 group: the goals of a record block are split over several warps (small batches)
 };
 
 // Uniform grid over the collider scene (acceleration structure). Built on the host at
@@ -195,6 +205,21 @@ struct GridDesc {
     const uint2* rangeO;          // per OBB: cell range it is listed in, x = ix0 | iy0 << 8 | iz0 << 16, y = ix1 | iy1 << 8 | iz1 << 16
 };
 constexpr int kGridMaxS = 1023, kGridMaxA = 2047, kGridMaxO = 2047;
+
+// k5_grid_build.cu: the grid's cell lists, filled on the device from the colliders' conservative boxes
+struct GridBuildArgs {
+    const float4* boxLo;          // [ns + na + no] conservative bounds, canonical order S | A | O (grid_host.h: grid_params)
+    const float4* boxHi;
+    int ns, na, no;
+    float g0x, g0y, g0z;          // grid min corner
+    float csx, csy, csz;          // cell size
+    int nx, ny, nz;
+    unsigned int* cnt;            // [nx*ny*nz * 3] scratch: counts, then write cursors
+    uint2* cells;                 // [nx*ny*nz]
+    uint16_t* entries;
+    unsigned int capacity;        // entries available
+    unsigned int* ctl;            // [0] entries used, [1] overflow flag (cell list too long for the header format / buffer too small)
+};
 
 // K0 arguments
 struct PackArgs {

@@ -194,6 +194,11 @@ def workload_config(args, scene, world):
 def main():
     args = parse_args()
     rank, world, local = dist_env()
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner to fd 1) write to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     from audio_raytracer_b200 import scenes
     scene = scenes.make_config(args.workload, batch_count=max(1, args.gpus), n_rays=args.rays)
 
