@@ -19,7 +19,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libaudiort_cuda.so")
-SOURCES = ["audiort_api.cu", "k0_pack.cu", "k1_trace.cu", "k1_trace_grid.cu", "k1_query_fan.cu", "k2_permeation.cu", "k2_permeation_grid.cu", "k2_permeation_binned.cu", "k3_reduce.cu", "k4_fan_build.cu", "k5_grid_build.cu"]
+SOURCES = ["audiort_api.cu", "k0_pack.cu", "k1_trace.cu", "k1_trace_grid.cu", "k1_bounce.cu", "k1_query_fan.cu", "k2_permeation.cu", "k2_permeation_grid.cu", "k2_permeation_binned.cu", "k3_reduce.cu", "k4_fan_build.cu", "k5_grid_build.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-O2", "-Xptxas", "-v"]

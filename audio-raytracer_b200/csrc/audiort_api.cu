@@ -248,6 +248,7 @@ struct ArtCtx {
     PinBuf pinRays; DevBuf dirs;
     bool haveRays = false, raysDirty = false;
     int shardIndex = 0, shardCount = 1, chunkRays = 0;
+    bool chunkAuto = false;                        // chunk size derived from the batch size (library-owned shard maps)
 
     // frame
     DevBuf targets, ownedCount, outAll, firstHit, partials, queue;   // outAll: echo | hit ids | hit points | hit counts, one memset, one copy
@@ -267,6 +268,8 @@ struct ArtCtx {
     std::vector<unsigned char> lastBlob;
     std::vector<int> frameOwnedCount;
     cudaEvent_t evFan = nullptr, evBounce = nullptr, evX0 = nullptr, evX1 = nullptr;   // sub-times of the trace job, blob exchange
+    cudaEvent_t evF0 = nullptr;                    // start of a fan build that runs on stream2 beside the bounce tracer
+    bool frameFanBeside = false;
     bool frameIsRerun = false;                     // the frame in flight is the second pass of a frame whose fan build overflowed
     bool frameSplit = false;                       // the frame in flight ran the bounce-only tracer + query kernel
     bool rayHostValid = false;                     // pinRays holds the whole batch (art_set_rays); false for device-generated rays
@@ -338,6 +341,15 @@ int local_ray_count(int nGlobal, int shardIndex, int shardCount, int chunk)
 int effective_chunk(const ArtCtx* c)
 {
     if (c->shardCount <= 1) return c->nGlobal > 0 ? c->nGlobal : 1;
+    if (c->chunkAuto) {
+        // Library-owned shard maps: 8 interleaved chunks per shard. Few, long chunks keep a shard's first-hit points (one
+        // latitude band of the Fibonacci sphere per chunk) together, so the permeation job's (source, direction bin) groups
+        // stay long enough to fill warps; 8 of them still balance the bands' different geometry over the shards (B200, C3 / 8:
+        // chunks of 256 rays 5.47 ms per rank, 16,384 rays 5.18 ms, one contiguous slice 4.7 .. 5.5 ms depending on the rank).
+        long long ch = ((long long)c->nGlobal + 8LL * c->shardCount - 1) / (8LL * c->shardCount);
+        ch = (ch + 255) / 256 * 256;
+        return (int)(ch < 256 ? 256 : ch);
+    }
     if (c->chunkRays > 0) return c->chunkRays;
     return (c->nGlobal + c->shardCount - 1) / c->shardCount;   // contiguous slices
 }
@@ -470,7 +482,7 @@ static void release_ctx(ArtCtx* ctx)
     for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinAll, &ctx->pinPerm, &ctx->pinFanCtl, &ctx->pinGathered, &ctx->pinGrid, &ctx->pinGridCtl })
         b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
-    for (cudaEvent_t evx : { ctx->evReady, ctx->evP0, ctx->evP1, ctx->evTraceDone, ctx->evCopyDone, ctx->evFan, ctx->evBounce, ctx->evX0, ctx->evX1 })
+    for (cudaEvent_t evx : { ctx->evReady, ctx->evP0, ctx->evP1, ctx->evTraceDone, ctx->evCopyDone, ctx->evFan, ctx->evBounce, ctx->evX0, ctx->evX1, ctx->evF0 })
         if (evx) cudaEventDestroy(evx);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
@@ -504,7 +516,7 @@ ART_API int32_t art_create(const ArtConfig* cfg, ArtCtx** out)
             const int32_t rc = art_create(&c1, &child);
             if (rc != ART_OK) { release_ctx(parent); return rc; }      // (g_createError holds the child's message)
             child->shardIndex = i; child->shardCount = cfg->nDevices;
-            child->chunkRays = cfg->shardChunkRays > 0 ? cfg->shardChunkRays : 256;
+            child->chunkRays = cfg->shardChunkRays; child->chunkAuto = cfg->shardChunkRays == 0;
             child->scatterGlobal = true;
             parent->children.push_back(child);
         }
@@ -539,6 +551,7 @@ ART_API int32_t art_create(const ArtConfig* cfg, ArtCtx** out)
     if ((e = cudaEventCreate(&ctx->evP0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evP1)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->evFan)) != cudaSuccess || (e = cudaEventCreate(&ctx->evBounce)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->evX0)) != cudaSuccess || (e = cudaEventCreate(&ctx->evX1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&ctx->evF0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&ctx->evTraceDone, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreateWithFlags(&ctx->evCopyDone, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
     for (auto& ev : ctx->ev)
@@ -699,7 +712,7 @@ ART_API int32_t art_set_ray_shard(ArtCtx* ctx, int32_t shardIndex, int32_t shard
     if (shardIndex != ctx->shardIndex || shardCount != ctx->shardCount || chunkRays != ctx->chunkRays) {
         if (ctx->rayHostValid) ctx->raysDirty = true;   // the device holds only the shard's directions: upload the new shard
     }
-    ctx->shardIndex = shardIndex; ctx->shardCount = shardCount; ctx->chunkRays = chunkRays;
+    ctx->shardIndex = shardIndex; ctx->shardCount = shardCount; ctx->chunkRays = chunkRays; ctx->chunkAuto = false;
     return ART_OK;
 }
 
@@ -1112,6 +1125,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
     // Target fans (fan_dev.cuh): every echo / muffle / permeation query ends in the listener or an audio target, so the
     // colliders are binned by direction around those few goals, on the device, every frame (the goals move).
     FanDesc fd{};
+    bool fanBeside = false;
     bool useFans = useGrid && !ctx->fansDisabled && !ctx->rerunning && !(prm->flags & ART_FRAME_NO_FANS);
     if (useFans) {
         const size_t nFans = (size_t)Na + 1, nc = (size_t)L.ns + L.na + L.no;
@@ -1124,7 +1138,11 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             CK(ctx->fanEntries.ensure(cap * sizeof(uint16_t)));
             CK(ctx->fanCtl.ensure(16));
             CK(ctx->pinFanCtl.ensure(16));
-            CK(cudaMemsetAsync(ctx->fanCtl.p, 0, 16, ctx->stream));
+            // (Building the fans on the second stream beside the bounce tracer was measured and dropped: the two kernels'
+            // CTAs do not fit one SM's register file together, so the build only ran in the tracer's tail -- C3 / 8 shard
+            // 3.26 -> 3.20 ms, but C4's 257 fans 1.55 -> 1.80 ms.)
+            cudaStream_t fanStream = ctx->stream;
+            CK(cudaMemsetAsync(ctx->fanCtl.p, 0, 16, fanStream));
             FanBuildArgs fa;
             fa.boxLo = ctx->fanBoxes.as<float4>(); fa.boxHi = fa.boxLo + nc;
             fa.ns = L.ns; fa.na = L.na; fa.no = L.no;
@@ -1142,14 +1160,16 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
                 fa.order = ctx->fanOrder.as<uint32_t>();
                 ctx->kernelLaunches++;
             }
-            CK(launch_fan_build(fa, ctx->stream));
+            CK(launch_fan_build(fa, fanStream));
+            if (fanBeside) CK(cudaEventRecord(ctx->evFan, ctx->stream2));
             ctx->kernelLaunches++;
             fd.nFans = (int)nFans; fd.cells = fa.cells; fd.entries = fa.entries; fd.nEntries = (int)cap; fd.firstA = fa.firstA; fd.cells4 = fa.cells4;
             ctx->frameGridUsed |= 4u;
         }
     }
     ctx->frameFans = useFans;
-    CK(cudaEventRecord(ctx->evFan, ctx->stream));
+    ctx->frameFanBeside = fanBeside;
+    if (!fanBeside) CK(cudaEventRecord(ctx->evFan, ctx->stream));
     ctx->frameSplit = false;
 
     // Small frames (brute-force kernels, GPU far from full): run the permeation job on a second stream beside the trace
@@ -1202,9 +1222,10 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             ta.recA = ctx->hitRecs.as<float4>();
             ta.recB = reinterpret_cast<float2*>(ctx->hitRecs.as<unsigned char>() + recBytesA);
             ta.recCount = ta.nextRay + 4;                        // (zeroed with the queue counters)
-            const bool gInSmem = trace_grid_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
-            CK(launch_trace_grid(ta, gd, true, ctx->numSms, gInSmem, stats, ctx->stream));
+            const bool gInSmem = bounce_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
+            CK(launch_bounce(ta, gd, ctx->numSms, gInSmem, stats, ctx->stream));
             CK(cudaEventRecord(ctx->evBounce, ctx->stream));
+            if (fanBeside) CK(cudaStreamWaitEvent(ctx->stream, ctx->evFan, 0));      // the queries need the fans
             ctx->frameSplit = true;
             QueryArgs qa;
             qa.geom = ta.geom; qa.L = L; qa.recA = ta.recA; qa.recB = ta.recB; qa.recCount = ta.recCount;
@@ -1242,7 +1263,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
                 ctx->frameGridUsed |= 16u;
             }
             const bool gInSmem = trace_grid_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
-            CK(launch_trace_grid(ta, gd, false, ctx->numSms, gInSmem, (prm->flags & ART_FRAME_GRID_STATS) != 0, ctx->stream));
+            CK(launch_trace_grid(ta, gd, ctx->numSms, gInSmem, (prm->flags & ART_FRAME_GRID_STATS) != 0, ctx->stream));
             ctx->frameGridUsed |= 1u;
         } else {
             CK(launch_trace(ta, ctx->numSms, geomInSmem, count, ctx->stream));
@@ -1266,6 +1287,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         copiedEarly = true;
     }
     // ---------------- K2 ----------------
+    bool joinPermLast = false;
     if (wantPM) {
         CK(ctx->firstHit.ensure(nLoc * 4 + 16));
         PermArgs pa;
@@ -1312,9 +1334,15 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             ba.jobQueue = pa.nextRay + 1;
             const bool g1 = perm_grid_smem_bytes(L, true, false) <= (size_t)ctx->maxSmemOptin;
             CK(launch_permeation_grid(pa, gd, nullptr, ctx->numSms, g1, false, pmStream));          // first-hit distances + hit points
+            // the canonical last-writer slots (PM:85, quirk Q5) need only the first hits: a few hundred warps of serial FP32
+            // sums (0.1 ms whatever the batch size) run beside the loss lines on the second stream
+            CK(cudaEventRecord(ctx->evReady, pmStream));
+            CK(cudaStreamWaitEvent(ctx->stream2, ctx->evReady, 0));
+            CK(launch_perm_last(pa, T, ctx->stream2));
+            CK(cudaEventRecord(ctx->evP1, ctx->stream2));
+            joinPermLast = true;
             const bool g2 = perm_binned_smem_bytes(L, true) <= (size_t)ctx->maxSmemOptin;
             CK(launch_permeation_binned(pa, ba, fd, ctx->numSms, g2, pmStream));
-            CK(launch_perm_last(pa, T, pmStream));
             ctx->frameGridUsed |= 2u | 32u;
             ctx->kernelLaunches += 5;
         } else if (useGrid) {
@@ -1337,7 +1365,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         ctx->kernelLaunches += (prm->flags & ART_FRAME_REVERB_SEQ_FP32) ? 2 : 1;
     }
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
-    if (overlapJobs) CK(cudaStreamWaitEvent(ctx->stream, ctx->evP1, 0));      // join the permeation job
+    if (overlapJobs || joinPermLast) CK(cudaStreamWaitEvent(ctx->stream, ctx->evP1, 0));      // join the permeation job / its last-writer kernel
     CK(cudaEventRecord(ctx->ev[6], ctx->stream));
     // ---------------- multi-process frames: all-gather the ranks' partial blobs on the device ----------------
     ctx->frameComm = ctx->comm != nullptr && ctx->commWorld > 1 && !(prm->flags & ART_FRAME_PARTIALS_ONLY) && !ctx->rerunning;
@@ -1532,9 +1560,10 @@ ART_API int32_t art_complete(ArtCtx* ctx, ArtHandle h)
     cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); c.d2hMs = ms;
     c.fanBuildMs = c.bounceMs = c.queryMs = c.exchangeMs = 0.0f;
     if (ctx->frameJobs & ART_JOB_RAYTRACE) {
-        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->evFan); c.fanBuildMs = ms;
+        cudaEventElapsedTime(&ms, ctx->frameFanBeside ? ctx->evF0 : ctx->ev[1], ctx->evFan); c.fanBuildMs = ms;
         if (ctx->frameSplit) {
-            cudaEventElapsedTime(&ms, ctx->evFan, ctx->evBounce); c.bounceMs = ms;
+            // (a fan build beside the bounce tracer: the two intervals overlap; queryMs starts when both have finished)
+            cudaEventElapsedTime(&ms, ctx->frameFanBeside ? ctx->ev[1] : ctx->evFan, ctx->evBounce); c.bounceMs = ms;
             cudaEventElapsedTime(&ms, ctx->evBounce, ctx->ev[2]); c.queryMs = ms;
         } else {
             cudaEventElapsedTime(&ms, ctx->evFan, ctx->ev[2]); c.bounceMs = ms;   // bounce rays and queries in one kernel
@@ -1682,11 +1711,8 @@ ART_API int32_t art_comm_init(ArtCtx* ctx, const void* uniqueId128, int32_t rank
     const int rc = n.CommInitRank(&comm, world, id, rank);
     if (rc != 0) return fail(ctx, ART_E_CUDA, "ncclCommInitRank: %s", n.GetErrorString(rc));
     ctx->comm = comm; ctx->commRank = rank; ctx->commWorld = world;
-    const int chunk = chunkRays > 0 ? chunkRays : 256;
-    if (rank != ctx->shardIndex || world != ctx->shardCount || chunk != ctx->chunkRays) {
-        if (ctx->rayHostValid) ctx->raysDirty = true;
-    }
-    ctx->shardIndex = rank; ctx->shardCount = world; ctx->chunkRays = chunk;
+    if (ctx->rayHostValid) ctx->raysDirty = true;      // the device holds only the shard's directions
+    ctx->shardIndex = rank; ctx->shardCount = world; ctx->chunkRays = chunkRays; ctx->chunkAuto = chunkRays == 0;
     return ART_OK;
 }
 

@@ -303,12 +303,10 @@ __device__ __forceinline__ int run_pool(const PoolEnv& E, int qFirst, int count,
     return survCount;
 }
 
-// REC: bounce-only mode -- the echo / muffle queries of a hit point do not feed the bounce loop (RT:124-173 only write
-//      EchoRayDistances / MuffleRayHits), so the tracer appends one record per hit point (TraceArgs::recA / recB) and
-//      query_fan_kernel (k1_query_fan.cu) evaluates all of them afterwards against the target fans. Without REC every
-//      occlusion query walks the grid inside the bounce loop (the pools above).
+// This kernel runs bounce rays AND occlusion queries, all on the grid walk; it is the path of frames without target fans
+// (ART_FRAME_NO_FANS, fan overflow re-runs). With fans the frame runs bounce_kernel (k1_bounce.cu) + query_fan_kernel instead.
 // ROT: group rotation (TraceArgs::migGroups, trace_grid_rotation) instead of the per-lane ray queue
-template <bool SMEM, bool STATS, bool REC, bool ROT>
+template <bool SMEM, bool STATS, bool ROT>
 __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const TraceArgs a, const GridDesc g)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -485,8 +483,6 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
             }
         }
         const bool hit = hasRay && bkey != kNoHit;
-        HitRec recOut;
-        recOut.px = recOut.py = recOut.pz = recOut.echoL = recOut.echoMul = 0.0f; recOut.resultId = 0;
         int hitType = 0, hitIdx = 0;
         float4 attr = make_float4(0, 0, 0, 0);
         if (hasRay && !hit) {                                                  // RT:201-207 ray left the scene
@@ -521,28 +517,12 @@ __global__ void __launch_bounds__(kGridThreads, 1) trace_grid_kernel(const Trace
             r.resultId = (int)rayResultId;
             r.row = row;
             r.pad = 0;
-            if (!REC) rec[lane] = r;
-            recOut = r;
+            rec[lane] = r;
         }
         __syncwarp();
 
         // ================= echo + muffle queries of all hit points (RT:121-175) =================
-        if (REC) {
-            // bounce-only mode: one record per hit point, appended in whatever order the warps get here (the queries'
-            // results -- echo halves indexed by rayResultId, integer muffle counts -- do not depend on it)
-            const uint32_t hitMask = __ballot_sync(kFull, hit);
-            if (hitMask) {
-                unsigned int base = 0;
-                if (lane == 0) base = atomicAdd(a.recCount, (unsigned)__popc(hitMask));
-                base = __shfl_sync(kFull, base, 0);
-                if (hit) {
-                    const unsigned int idx = base + (unsigned)__popc(hitMask & ltMask);
-                    a.recA[idx] = make_float4(recOut.px, recOut.py, recOut.pz, recOut.echoL);
-                    a.recB[idx] = make_float2(recOut.echoMul, __int_as_float(recOut.resultId));
-                }
-            }
-        }
-        if (!REC) {
+        {
             const uint32_t hitMask = __ballot_sync(kFull, hit);
             const int total = __popc(hitMask) * slots;
             const PoolEnv E = { a, g, gv, rec, qbuf0, qbuf1, qbuf2, qbuf3, surv, RayOrigin, hitMask, slots, lane, ltMask, st, goalByPos, goalBySlot };
@@ -692,15 +672,14 @@ size_t trace_grid_smem_bytes(const GeomLayout& L, bool geomInSmem)
     return (geomInSmem ? L.bytes : 0) + (size_t)kGridWarps * 32 * (sizeof(HitRec) + kQueryWords * 4);
 }
 
-// records: bounce-only mode (TraceArgs::recA / recB / recCount set; the queries run in query_fan_kernel afterwards);
-// otherwise the occlusion queries walk the grid cells along their segments inside the bounce loop
-cudaError_t launch_trace_grid(const TraceArgs& a0, const GridDesc& g, bool records, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream)
+// The occlusion queries walk the grid cells along their segments inside the bounce loop.
+cudaError_t launch_trace_grid(const TraceArgs& a0, const GridDesc& g, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream)
 {
     TraceArgs a = a0;
     size_t smem = trace_grid_smem_bytes(a.L, geomInSmem);
     a.goalsInSmem = 0; a.goalsSmemOffset = 0;
     const char* noTab = getenv("ART_K1_NO_GOAL_TABLES");         // (read per launch: test knob for the global-memory fallback)
-    if (!records && !(noTab && atoi(noTab) != 0)) {              // goal tables behind everything else, when they fit
+    if (!(noTab && atoi(noTab) != 0)) {                          // goal tables behind everything else, when they fit
         static int maxOptin = -1;
         if (maxOptin < 0) {
             int dev = 0;
@@ -713,13 +692,9 @@ cudaError_t launch_trace_grid(const TraceArgs& a0, const GridDesc& g, bool recor
     void (*k)(const TraceArgs, const GridDesc) = nullptr;
     const bool rot = a.migGroups > 0;
     if (stats && rot) return cudaErrorInvalidValue;          // (stats frames are planned without rotation)
-    if (records && (rot || !a.recA || !a.recB || !a.recCount)) return cudaErrorInvalidValue;
-    if (records) {
-        if (stats) k = geomInSmem ? trace_grid_kernel<true, true, true, false> : trace_grid_kernel<false, true, true, false>;
-        else k = geomInSmem ? trace_grid_kernel<true, false, true, false> : trace_grid_kernel<false, false, true, false>;
-    } else if (stats) k = geomInSmem ? trace_grid_kernel<true, true, false, false> : trace_grid_kernel<false, true, false, false>;
-    else if (rot) k = geomInSmem ? trace_grid_kernel<true, false, false, true> : trace_grid_kernel<false, false, false, true>;
-    else k = geomInSmem ? trace_grid_kernel<true, false, false, false> : trace_grid_kernel<false, false, false, false>;
+    if (stats) k = geomInSmem ? trace_grid_kernel<true, true, false> : trace_grid_kernel<false, true, false>;
+    else if (rot) k = geomInSmem ? trace_grid_kernel<true, false, true> : trace_grid_kernel<false, false, true>;
+    else k = geomInSmem ? trace_grid_kernel<true, false, false> : trace_grid_kernel<false, false, false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int warps = a.gridWarps >= 1 && a.gridWarps <= kGridWarps ? a.gridWarps : kGridWarps;

@@ -98,19 +98,30 @@ __global__ void __launch_bounds__(1024, 1) fan_order_kernel(const FanBuildArgs a
     for (int g = tid; g < nc; g += 1024) a.order[(size_t)fan * nc + g] = (uint32_t)(sKeys[g] & 0xFFFFFFFFull);
 }
 
-__global__ void __launch_bounds__(kFanCellsPerFace, 2) fan_build_kernel(const FanBuildArgs a)
+// ROWS bin rows (= warps) per CTA: a face can be cut into 32 / ROWS strips. Measured on B200 (C3, 65 fans x 4,096 colliders):
+// whole faces (390 CTAs, two waves of which the second is one third full) 396 us, strips of 8 rows (1,560 CTAs) 505 us --
+// every strip sweeps and projects all colliders itself, which costs more than the shorter last wave saves.
+#ifndef ART_FAN_ROWS
+#define ART_FAN_ROWS 32
+#endif
+constexpr int kFanRows = ART_FAN_ROWS;
+constexpr int kFanThreads = kFanRows * 32;
+constexpr int kFanParts = kFanBins / kFanRows;
+
+__global__ void __launch_bounds__(kFanThreads, 2048 / kFanThreads) fan_build_kernel(const FanBuildArgs a)
 {
-    static_assert(kFanCellsPerFace == 1024 && kFanBins == 32, "one thread per bin, one warp per bin row");
-    __shared__ uint32_t sRect[1024];
-    __shared__ uint32_t sIdT[1024];          // local collider index | type << 16
+    static_assert(kFanCellsPerFace == 1024 && kFanBins == 32 && kFanBins % kFanRows == 0, "one thread per bin, one warp per bin row");
+    __shared__ uint32_t sRect[kFanThreads];
+    __shared__ uint32_t sIdT[kFanThreads];   // local collider index | type << 16
     __shared__ uint32_t sNear[kFanMaxNear];
     __shared__ int sWarpCnt[32], sWarpNear[32], sWarpTot[32];
     __shared__ int sNearCount;
     __shared__ unsigned int sBase;
 
-    const int face = blockIdx.x, fan = blockIdx.y;
+    const int face = blockIdx.x / kFanParts, part = blockIdx.x % kFanParts, fan = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t ia = (uint32_t)lane, ib = (uint32_t)warp;
+    const uint32_t ia = (uint32_t)lane, ib = (uint32_t)(part * kFanRows + warp);
+    const int cellOfThread = face * kFanCellsPerFace + (int)ib * kFanBins + lane;
     const uint32_t ltMask = (1u << lane) - 1u;
     const int nc = a.ns + a.na + a.no;
     float T[3];
@@ -118,7 +129,7 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 2) fan_build_kernel(const Fa
     else { T[0] = a.lx; T[1] = a.ly; T[2] = a.lz; }
     const int k = face >> 1;
     const bool neg = face & 1;
-    const bool nearCta = face == 0;
+    const bool nearCta = face == 0 && part == 0;
     if (tid == 0) sNearCount = 0;
     __syncthreads();
 
@@ -131,7 +142,7 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 2) fan_build_kernel(const Fa
     unsigned int blockTotal = 0;
     int nearTotal = 0;
     for (int pass = 0; pass < 2; pass++) {
-        for (int base = 0; base < nc; base += 1024) {
+        for (int base = 0; base < nc; base += kFanThreads) {
             uint32_t rect = kRectEmpty, idT = 0;
             bool near = false;
             if (base + tid < nc) {
@@ -151,7 +162,7 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 2) fan_build_kernel(const Fa
             const uint32_t nbal = __ballot_sync(kFull, near && nearCta && pass == 0);
             if (lane == 0) { sWarpCnt[warp] = __popc(bal); sWarpNear[warp] = __popc(nbal); }
             __syncthreads();
-            int incl = sWarpCnt[lane], nincl = sWarpNear[lane];
+            int incl = lane < kFanRows ? sWarpCnt[lane] : 0, nincl = lane < kFanRows ? sWarpNear[lane] : 0;
 #pragma unroll
             for (int s = 1; s < 32; s <<= 1) {
                 const int v = __shfl_up_sync(kFull, incl, s), nv = __shfl_up_sync(kFull, nincl, s);
@@ -195,8 +206,8 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 2) fan_build_kernel(const Fa
             if (tid == 0) sNearCount += nM;
         }
         if (pass == 1) {
-            if (cA > 0) a.firstA[(size_t)fan * kFanCells + face * kFanCellsPerFace + tid] = firstIds;
-            a.cells4[(size_t)fan * kFanCells + face * kFanCellsPerFace + tid] = make_uint4(myCell.x, myCell.y, firstIds, nextIds);
+            if (cA > 0) a.firstA[(size_t)fan * kFanCells + cellOfThread] = firstIds;
+            a.cells4[(size_t)fan * kFanCells + cellOfThread] = make_uint4(myCell.x, myCell.y, firstIds, nextIds);
             break;
         }
         // ---- reserve the CTA's span: block scan of the per-bin totals
@@ -209,7 +220,7 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 2) fan_build_kernel(const Fa
         for (int s = 1; s < 32; s <<= 1) { const int v = __shfl_up_sync(kFull, incl, s); if (lane >= s) incl += v; }
         if (lane == 31) sWarpTot[warp] = incl;
         __syncthreads();
-        int wincl = sWarpTot[lane];
+        int wincl = lane < kFanRows ? sWarpTot[lane] : 0;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) { const int v = __shfl_up_sync(kFull, wincl, s); if (lane >= s) wincl += v; }
         blockTotal = (unsigned)__shfl_sync(kFull, wincl, 31);
@@ -228,8 +239,8 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 2) fan_build_kernel(const Fa
         const unsigned int bs = sBase;
         uint2* cells = a.cells + (size_t)fan * kFanCells;
         if (bs == 0xFFFFFFFFu) {
-            cells[face * kFanCellsPerFace + tid] = make_uint2(0u, 0u);
-            a.cells4[(size_t)fan * kFanCells + face * kFanCellsPerFace + tid] = make_uint4(0u, 0u, 0u, 0u);
+            cells[cellOfThread] = make_uint2(0u, 0u);
+            a.cells4[(size_t)fan * kFanCells + cellOfThread] = make_uint4(0u, 0u, 0u, 0u);
             if (nearCta && tid == 0) {
                 cells[6 * kFanCellsPerFace] = make_uint2(0u, 0u);
                 a.cells4[(size_t)fan * kFanCells + 6 * kFanCellsPerFace] = make_uint4(0u, 0u, 0u, 0u);
@@ -239,7 +250,7 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 2) fan_build_kernel(const Fa
         wpos = bs + binOff;
         aPos = wpos + (unsigned)cS;
         myCell = make_uint2(wpos, (uint32_t)cS | ((uint32_t)cA << 10) | ((uint32_t)cO << 21));
-        cells[face * kFanCellsPerFace + tid] = myCell;
+        cells[cellOfThread] = myCell;
         if (nearCta && tid == 0) {
             uint32_t nS = 0, nA = 0, nO = 0, ids = 0, ids2 = 0;
             for (int q = 0; q < nearTotal; q++) {
@@ -258,7 +269,7 @@ __global__ void __launch_bounds__(kFanCellsPerFace, 2) fan_build_kernel(const Fa
             a.cells4[(size_t)fan * kFanCells + 6 * kFanCellsPerFace] = make_uint4(nc2.x, nc2.y, ids, ids2);
         }
         if (nearCta)
-            for (int q = tid; q < nearTotal; q += 1024) a.entries[bs + blockTotal + q] = (uint16_t)(sNear[q] & 0xFFFFu);
+            for (int q = tid; q < nearTotal; q += kFanThreads) a.entries[bs + blockTotal + q] = (uint16_t)(sNear[q] & 0xFFFFu);
     }
 }
 
@@ -276,7 +287,7 @@ cudaError_t launch_fan_build(const FanBuildArgs& a, cudaStream_t stream)
         fan_order_kernel<<<nFans, 1024, smem, stream>>>(a, nPow2);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    fan_build_kernel<<<dim3(6, nFans), kFanCellsPerFace, 0, stream>>>(a);
+    fan_build_kernel<<<dim3(6 * kFanParts, nFans), kFanThreads, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -80,16 +80,19 @@ __global__ void __launch_bounds__(1024, 1) grid_scan_kernel(const GridBuildArgs 
     for (int s = 1; s < 32; s <<= 1) { const unsigned int v = __shfl_up_sync(kFull, w, s); if (lane >= s) w += v; }
     unsigned int off = (warp == 0 ? 0u : __shfl_sync(kFull, w, warp - 1)) + incl - sum;
     const unsigned int total = __shfl_sync(kFull, w, 31);
+    // a cell list too long for the header format, or more entries than the buffer holds: every cell is left EMPTY (the
+    // kernels of this frame then walk an empty grid -- harmless, their results are discarded by the re-run)
+    const bool overflow = __syncthreads_or(bad) || total > a.capacity;
     for (int c = c0; c < c1; c++) {
         const unsigned int s = a.cnt[(size_t)c * 3], aa = a.cnt[(size_t)c * 3 + 1], o = a.cnt[(size_t)c * 3 + 2];
-        a.cells[c] = make_uint2(off, s | (aa << 10) | (o << 21));
+        a.cells[c] = overflow ? make_uint2(0u, 0u) : make_uint2(off, s | (aa << 10) | (o << 21));
         a.cnt[(size_t)c * 3] = off; a.cnt[(size_t)c * 3 + 1] = off + s; a.cnt[(size_t)c * 3 + 2] = off + s + aa;
         off += s + aa + o;
     }
-    if (__syncthreads_or(bad) || total > a.capacity) {
-        if (threadIdx.x == 0) atomicExch(&a.ctl[1], 1u);
+    if (threadIdx.x == 0) {
+        if (overflow) atomicExch(&a.ctl[1], 1u);
+        a.ctl[0] = total;
     }
-    if (threadIdx.x == 0) a.ctl[0] = total;
 }
 
 __global__ void __launch_bounds__(256) grid_sort_kernel(const GridBuildArgs a)

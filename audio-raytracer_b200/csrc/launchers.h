@@ -13,7 +13,9 @@ size_t trace_grid_scratch_bytes(int numCtas);
 void trace_grid_plan(int nLocal, int nTargets, int numCtas, int* warps, int* raysPerWarp);
 int trace_grid_rotation(int nLocal, int H, int numCtas, int warpsPerCta, bool fullLivedRays, unsigned int* slots);
 int perm_grid_rays_per_warp(int nLocal, int nTargets, int numCtas);
-cudaError_t launch_trace_grid(const TraceArgs& a, const GridDesc& g, bool records, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream);
+cudaError_t launch_trace_grid(const TraceArgs& a, const GridDesc& g, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream);
+size_t bounce_smem_bytes(const GeomLayout& L, bool geomInSmem);
+cudaError_t launch_bounce(const TraceArgs& a, const GridDesc& g, int numCtas, bool geomInSmem, bool stats, cudaStream_t stream);
 size_t query_fan_scratch_bytes(int numCtas);
 size_t query_fan_smem_bytes(const GeomLayout& L, bool geomInSmem);
 cudaError_t launch_query_fan(const QueryArgs& a, const FanDesc& fans, int numCtas, bool geomInSmem, bool stats, int maxSmemOptin, cudaStream_t stream);

@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--workload", default="c3", choices=["c1", "c1_1src", "c2", "c3", "c4", "c5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=None, help="override the ray count (debug only; marks the line)")
-    ap.add_argument("--chunk", type=int, default=256, help="rays per interleaved shard chunk (N > 1)")
+    ap.add_argument("--chunk", type=int, default=0, help="rays per interleaved shard chunk (N > 1); 0 = the library's choice, 8 chunks per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -181,7 +181,7 @@ def workload_config(args, scene, world):
                         f"{len(scene.aabbs)} AABB + {len(scene.obbs)} OBB + {len(scene.spheres)} spheres",
             "rays": scene.n_rays, "max_hits_per_ray": scene.max_hits_per_ray, "targets": scene.n_targets,
             "colliders": scene.n_colliders, "batch_count": scene.batch_count,
-            "sharding": "none" if world == 1 else f"rays interleaved in chunks of {args.chunk} over {world} ranks; per-source partials "
+            "sharding": "none" if world == 1 else f"rays interleaved in chunks of {args.chunk or 'N / (8 x ranks)'} over {world} ranks; per-source partials "
                                                   "all-gathered on the device inside the library (ncclAllGather), merged and finalised on every rank",
             "l2": "flushed between steps (256 MiB write)", "reverb_reduction": "exact integer",
             "path": "default: bounce-only tracer on the uniform grid, then one query kernel over all hit points using per-frame target "

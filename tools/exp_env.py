@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--set", action="append", default=[], help="NAME=v1,v2,... ('-' = unset)")
     ap.add_argument("--frames", type=int, default=3)
     ap.add_argument("--shard", default=None)
+    ap.add_argument("--chunk", type=int, default=256, help="rays per interleaved shard chunk (0 = one contiguous slice)")
     a = ap.parse_args()
     build.build()
     shard = tuple(int(x) for x in a.shard.split("/")) if a.shard else None
@@ -30,7 +31,7 @@ def main():
         native.upload(ctx, s)
         flags = native.FRAME_NO_HOST_OUTPUTS
         if shard:
-            ctx.set_ray_shard(shard[0], shard[1], 256)
+            ctx.set_ray_shard(shard[0], shard[1], a.chunk)
             flags |= native.FRAME_PARTIALS_ONLY
         for combo in itertools.product(*values) if values else [()]:
             for n, v in zip(names, combo):
@@ -43,7 +44,8 @@ def main():
                 c = ctx.run_frame(s, flags=flags, want=()).counters
                 ms.append((c["traceMs"], c["permeationMs"], c["deviceMs"]))
             best = min(ms)
-            print(" ".join(f"{n}={v}" for n, v in zip(names, combo)) + f": trace {best[0]:.3f} ms perm {best[1]:.3f} ms device {best[2]:.3f} ms", flush=True)
+            print(" ".join(f"{n}={v}" for n, v in zip(names, combo)) + f": trace {best[0]:.3f} ms (fan {c['fanBuildMs']:.3f} bounce {c['bounceMs']:.3f} "
+                  f"queries {c['queryMs']:.3f}) perm {best[1]:.3f} ms device {best[2]:.3f} ms", flush=True)
 
 
 if __name__ == "__main__":
