@@ -38,7 +38,7 @@ namespace art {
 #define ART_Q_WARPS 32
 #endif
 #ifndef ART_Q_RUN
-#define ART_Q_RUN 192
+#define ART_Q_RUN 96
 #endif
 #ifndef ART_Q_MIN_LANES
 #define ART_Q_MIN_LANES 20

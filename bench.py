@@ -378,7 +378,10 @@ def main():
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             ent = tr.get(f"{args.workload}:{scene.n_rays}:{world}")
             if ent and ent.get("csrc_sha1") == h.hexdigest():
-                traffic, ncu_util = ent.get("traffic"), ent.get("ncu")
+                ncu_util = ent.get("ncu")
+                by_kernel = ent.get("traffic") or {}
+                traffic = by_kernel.get("query_fan_kernel" if split else "trace_grid_kernel")     # the dominant kernel's, bytes per launch
+                traffic_note = f"dram bytes per launch by kernel: {by_kernel} ({ent.get('source')})"
             elif ent:
                 traffic_note = f"profiles/traffic.json was captured from other kernel sources ({ent.get('csrc_sha1', '?')[:10]} != {h.hexdigest()[:10]}): not reported"
         except Exception:
@@ -423,7 +426,7 @@ def main():
                          "kernels": {
                              "query_fan_kernel": {"ms": query_ms_avg, "tests_executed": q_tests, "executed_flops": q_flops,
                                                   "achieved": tfl(q_flops, query_ms_avg), "frac": (tfl(q_flops, query_ms_avg) or 0) / peak_tflops},
-                             "trace_grid_kernel_bounce_only": {"ms": bounce_ms_avg, "tests_executed": b_tests, "executed_flops": b_flops,
+                             "bounce_kernel": {"ms": bounce_ms_avg, "tests_executed": b_tests, "executed_flops": b_flops,
                                                                "achieved": tfl(b_flops, bounce_ms_avg), "frac": (tfl(b_flops, bounce_ms_avg) or 0) / peak_tflops},
                              "permeation (K2)": {"ms": perm_ms_avg, "executed_flops": exec_perm_flops,
                                                  "achieved": tfl(exec_perm_flops, perm_ms_avg), "frac": (tfl(exec_perm_flops, perm_ms_avg) or 0) / peak_tflops}},
