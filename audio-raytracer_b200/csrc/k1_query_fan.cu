@@ -53,7 +53,7 @@ constexpr int kQCapSO = 2 * kQRun + 128;             // sphere / OBB queue: addi
 constexpr int kQEntry = 4;                           // float4 per queued query
 constexpr int kQMuffleSmemMax = 4096;                // per-CTA muffle counters [T * Na] kept in shared memory up to this size
 
-// A queued query, 64 B:  e0 = (1/dir.xyz, limit L)   e1 = (P.xyz, |goal - P|)   e2 = (bin header x, y, slot | cursor << 16, batch row)
+// A queued query, 64 B:  e0 = (1/dir.xyz, limit L)   e1 = (P.xyz, |goal - P|)   e2 = (bin header x, y, slot | cursor << 16, -)
 //                        e3 = (material Echo, rayResultId, -, -)
 struct QEnv {
     const QueryArgs& a;
@@ -80,10 +80,11 @@ __device__ __forceinline__ uint4 q_near(const QEnv& E, int slot)
     return __ldg(&E.f.cells4[(size_t)q_fan_of(E.a, slot) * kFanCells + 6 * kFanCellsPerFace]);
 }
 // the query sees its goal: RT:133-145 (echo ray, slot 0) / RT:168-172 (muffle ray of target slot - 1)
-__device__ __forceinline__ void q_visible(const QEnv& E, int slot, float L, float echoMul, int resultId, int row)
+__device__ __forceinline__ void q_visible(const QEnv& E, int slot, float L, float echoMul, int resultId)
 {
     if (slot == 0) E.a.echo[resultId] = um_f32tof16(mulr(L, echoMul));
     else {
+        const int row = E.a.map.to_global(resultId / E.a.H) / E.a.batchSize;     // ART:161/191 batch of the ray
         const int idx = row * E.a.nTargets + (slot - 1);
         if (E.sMuffle) atomicAdd(&E.sMuffle[idx], 1u);
         else atomicAdd(&E.a.muffleCounts[idx], 1u);
@@ -141,7 +142,7 @@ __device__ __forceinline__ int q_loop_aabb(const QEnv& E, float4* listA, int nIn
             else if (k >= nAll) {
                 have = false;
                 if (anySO) toSO = true;
-                else q_visible(E, (int)(__float_as_uint(e2.z) & 0xFFFFu), e0.w, e3.x, __float_as_int(e3.y), __float_as_int(e2.w));
+                else q_visible(E, (int)(__float_as_uint(e2.z) & 0xFFFFu), e0.w, e3.x, __float_as_int(e3.y));
             }
         }
         const uint32_t sm = __ballot_sync(kFull, toSO);
@@ -234,7 +235,7 @@ __device__ __forceinline__ int q_loop_so(const QEnv& E, float4* listSO, int nIn,
             if (blocked) have = false;
             else if (k >= nTot) {
                 have = false;
-                q_visible(E, (int)(__float_as_uint(e2.z) & 0xFFFFu), L, e3.x, __float_as_int(e3.y), __float_as_int(e2.w));
+                q_visible(E, (int)(__float_as_uint(e2.z) & 0xFFFFu), L, e3.x, __float_as_int(e3.y));
             }
         }
     }
@@ -310,16 +311,12 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
         if (blk >= nBlocks) break;
         const unsigned int ri = blk * 32u + (unsigned)lane;
         const bool valid = ri < nRec;
+        // the lane keeps only the hit point in registers; the rest of its record is re-read (L1) where a query needs it
         f3 P = mk3(0, 0, 0);
-        float echoL = 0.0f, echoMul = 0.0f;
-        int resultId = 0, row = 0;
         if (valid) {
             const float4 ra = a.recA[ri];
-            const float2 rb = a.recB[ri];
-            P = mk3(ra.x, ra.y, ra.z); echoL = ra.w; echoMul = rb.x;
-            resultId = __float_as_int(rb.y);
-            ART_CHECK(a.counters, resultId >= 0 && resultId / a.H < a.map.nLocal);
-            row = a.map.to_global(resultId / a.H) / a.batchSize;         // ART:161/191 batch of the ray
+            P = mk3(ra.x, ra.y, ra.z);
+            ART_CHECK(a.counters, __float_as_int(a.recB[ri].y) >= 0 && __float_as_int(a.recB[ri].y) / a.H < a.map.nLocal);
         }
         // ---- pass 0: lane = hit point, all lanes walk the goals together
         for (int s = sBeg; s < sEnd; s++) {
@@ -335,12 +332,14 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
                 uint4 c4 = make_uint4(0u, 0u, 0u, 0u);
                 if (bin >= 0) c4 = __ldg(&f.cells4[(size_t)q_fan_of(a, s) * kFanCells + bin]);
                 len = sqrtr(dot3(v, v));
-                float L = echoL;                                                   // RT:130
+                float L;
                 bool gate = true;
                 if (s > 0) { L = len; gate = L < a.maxMuffle; }                    // RT:165, 168
+                else L = __ldg(&a.recA[ri].w);                                     // RT:130
                 if (gate) {
                     if (bin < 0 || len != len) {
-                        q_visible(E, s, L, echoMul, resultId, row);                // degenerate (hit point == goal): no test can block
+                        const float2 rb = __ldg(&a.recB[ri]);
+                        q_visible(E, s, L, rb.x, __float_as_int(rb.y));            // degenerate (hit point == goal): no test can block
                     } else {
                         const f3 nd = smul3(rcpr(len), v);                         // normalize = rsqrt(dot) * v
                         const f3 inv = mk3(rcpr(nd.x), rcpr(nd.y), rcpr(nd.z));
@@ -360,10 +359,10 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
                         if (!blocked) {
                             if (nAll > nFirst) push = 1;
                             else if (((n4.y | c4.y) & 1023u) | ((n4.y | c4.y) >> 21)) push = 2;
-                            else q_visible(E, s, L, echoMul, resultId, row);
+                            else { const float2 rb = __ldg(&a.recB[ri]); q_visible(E, s, L, rb.x, __float_as_int(rb.y)); }
                             e0 = make_float4(inv.x, inv.y, inv.z, L);
                             e2 = make_float4(__uint_as_float(c4.x), __uint_as_float(c4.y),
-                                             __uint_as_float((uint32_t)s | (push == 1 ? (uint32_t)nFirst << 16 : 0u)), __int_as_float(row));
+                                             __uint_as_float((uint32_t)s | (push == 1 ? (uint32_t)nFirst << 16 : 0u)), 0.0f);
                         }
                     }
                 }
@@ -376,7 +375,8 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
                 dst[0] = e0;
                 dst[1] = make_float4(P.x, P.y, P.z, len);
                 dst[2] = e2;
-                dst[3] = make_float4(echoMul, __int_as_float(resultId), 0.0f, 0.0f);
+                const float2 rb = __ldg(&a.recB[ri]);
+                dst[3] = make_float4(rb.x, rb.y, 0.0f, 0.0f);
             }
             nA += __popc(am);
             nSO += __popc(sm);

@@ -8,6 +8,8 @@
 // repeats the sweep and writes the indices -- so every list is grouped by type and ordered like the sweep
 // (fan_order_kernel: nearest to the goal first), and its content does not depend on scheduling (only its
 // position in the entry array does).
+#include <cstdlib>
+
 #include "device_util.cuh"
 #include "fan_dev.cuh"
 #include "launchers.h"
@@ -98,18 +100,15 @@ __global__ void __launch_bounds__(1024, 1) fan_order_kernel(const FanBuildArgs a
     for (int g = tid; g < nc; g += 1024) a.order[(size_t)fan * nc + g] = (uint32_t)(sKeys[g] & 0xFFFFFFFFull);
 }
 
-// ROWS bin rows (= warps) per CTA: a face can be cut into 32 / ROWS strips. Measured on B200 (C3, 65 fans x 4,096 colliders):
-// whole faces (390 CTAs, two waves of which the second is one third full) 396 us, strips of 8 rows (1,560 CTAs) 505 us --
-// every strip sweeps and projects all colliders itself, which costs more than the shorter last wave saves.
-#ifndef ART_FAN_ROWS
-#define ART_FAN_ROWS 32
-#endif
-constexpr int kFanRows = ART_FAN_ROWS;
-constexpr int kFanThreads = kFanRows * 32;
-constexpr int kFanParts = kFanBins / kFanRows;
-
-__global__ void __launch_bounds__(kFanThreads, 2048 / kFanThreads) fan_build_kernel(const FanBuildArgs a)
+// ROWS bin rows (= warps) per CTA: a face can be cut into 32 / ROWS strips, one CTA each (ART_FAN_ROWS). Measured on B200 and
+// NOT used by default: a CTA's time goes into matching every bin row against the rectangles of the sweep, which every strip
+// repeats for its rows plus the whole sweep itself -- C3 (65 fans x 4,096 colliders, 390 CTAs): whole faces 396 us, strips of
+// 16 rows 465 us, of 8 rows 505 us; C5 (9 fans x 16,384 colliders, only 54 CTAs for 148 SMs): 1.34 / 1.45 / 1.55 / 1.75 ms for
+// 32 / 16 / 8 / 4 rows.
+template <int ROWS>
+__global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_build_kernel(const FanBuildArgs a)
 {
+    constexpr int kFanRows = ROWS, kFanThreads = ROWS * 32, kFanParts = kFanBins / ROWS;
     static_assert(kFanCellsPerFace == 1024 && kFanBins == 32 && kFanBins % kFanRows == 0, "one thread per bin, one warp per bin row");
     __shared__ uint32_t sRect[kFanThreads];
     __shared__ uint32_t sIdT[kFanThreads];   // local collider index | type << 16
@@ -287,7 +286,15 @@ cudaError_t launch_fan_build(const FanBuildArgs& a, cudaStream_t stream)
         fan_order_kernel<<<nFans, 1024, smem, stream>>>(a, nPow2);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    fan_build_kernel<<<dim3(6 * kFanParts, nFans), kFanThreads, 0, stream>>>(a);
+    // whole faces unless ART_FAN_ROWS (experiment knob, read per launch) asks for strips
+    int rows = 32;
+    if (const char* v = getenv("ART_FAN_ROWS")) { const int r = atoi(v); if (r == 4 || r == 8 || r == 16) rows = r; }
+    switch (rows) {
+    case 32: fan_build_kernel<32><<<dim3(6, nFans), 1024, 0, stream>>>(a); break;
+    case 16: fan_build_kernel<16><<<dim3(12, nFans), 512, 0, stream>>>(a); break;
+    case 8: fan_build_kernel<8><<<dim3(24, nFans), 256, 0, stream>>>(a); break;
+    default: fan_build_kernel<4><<<dim3(48, nFans), 128, 0, stream>>>(a); break;
+    }
     return cudaGetLastError();
 }
 
