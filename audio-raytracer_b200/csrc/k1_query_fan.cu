@@ -297,10 +297,11 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
     // covers all goals of its block.
     const unsigned int nBlocks = (nRec + 31u) / 32u;
 
+    unsigned int ticket = 0;                         // the NEXT unit: its ticket travels while the current unit is processed
+    if (lane == 0) ticket = atomicAdd(a.queue, 1u);
     for (;;) {
-        unsigned int unit = 0;
-        if (lane == 0) unit = atomicAdd(a.queue, 1u);
-        unit = __shfl_sync(kFull, unit, 0);
+        const unsigned int unit = __shfl_sync(kFull, ticket, 0);
+        if (lane == 0) ticket = atomicAdd(a.queue, 1u);
         unsigned int blk = unit;
         int sBeg = 0, sEnd = slots;
         if (a.goalGroups > 1) {

@@ -130,6 +130,18 @@ __device__ __forceinline__ float clip_len_b(float tEnter, float tExit, float tIn
     return fmaxf(0.0f, fminf(tExit, tOut) - fmaxf(tEnter, tIn));
 }
 
+// body(id) for every entry of one list, in list order. The list is the same for all lanes of the warp: 32 ids per coalesced
+// load, handed round by shuffle. Every lane must call this (warp-uniform off / n).
+template <class Body>
+__device__ __forceinline__ void perm_each_entry(const uint16_t* entries, uint32_t off, int n, int lane, Body body)
+{
+    for (int base = 0; base < n; base += 32) {
+        const int mine = base + lane < n ? (int)__ldg(entries + off + base + lane) : 0;
+        const int m = min(32, n - base);
+        for (int j = 0; j < m; j++) body(__shfl_sync(kFull, mine, j));
+    }
+}
+
 template <bool SMEM>
 __global__ void __launch_bounds__(kPBinThreads, 1) perm_loss_binned_kernel(const PermArgs a, const PermBinArgs ba, const FanDesc f)
 {
@@ -215,16 +227,13 @@ __global__ void __launch_bounds__(kPBinThreads, 1) perm_loss_binned_kernel(const
                     const f3 inv = mk3(rcpr(dir.x), rcpr(dir.y), rcpr(dir.z));         // PM:270
                     const float tT = sqrt_fast(fmaf(toT.z, toT.z, fmaf(toT.y, toT.y, toT.x * toT.x)));   // line parameter of the target
                     float loss = 0.0f;
+                    // The three lists of a type are walked one after the other -- near list (whole line), bin towards the hit
+                    // point (t in [0, tT]), opposite bin (t > tT) -- with the clip interval a constant of the list. All 32
+                    // lines of the segment walk the SAME lists, so the warp fetches 32 entry ids with one coalesced load and
+                    // hands them round by shuffle (perm_each_entry) instead of every lane loading every id.
                     {   // ---- AABBs, PM:265-288 in the reference's operation order
-                        const int n01 = nA0 + nA1, n = n01 + nA2;
-                        const uint32_t o0 = h0.x + nS0, o1 = h1.x + nS1 - nA0, o2 = h2.x + nS2 - n01;
-                        int nxt = n > 0 ? (int)__ldg(f.entries + (0 < nA0 ? o0 : (0 < n01 ? o1 : o2))) : 0;
-                        for (int k = 0; k < n; k++) {
-                            const int id = nxt;
-                            const int k1 = k + 1;
-                            if (k1 < n) nxt = (int)__ldg(f.entries + ((k1 < nA0 ? o0 : (k1 < n01 ? o1 : o2)) + (uint32_t)k1));
+                        auto test = [&](int id, float tIn, float tOut) {
                             ART_CHECK(a.counters, id < a.L.na);
-                            const float tIn = k >= n01 ? tT : 0.0f, tOut = (k >= nA0 && k < n01) ? tT : inf;
                             const float4 A = gv.aabbA[id];
                             const float2 B = gv.aabbB[id];
                             float tEnter, tExit;
@@ -232,42 +241,37 @@ __global__ void __launch_bounds__(kPBinThreads, 1) perm_loss_binned_kernel(const
                                     inv.x, inv.y, inv.z, tEnter, tExit);
                             const float len = clip_len_b(tEnter, tExit, tIn, tOut);
                             if (len > 0.0f) loss = fmaf(len, densA[id], loss);
-                        }
+                        };
+                        perm_each_entry(f.entries, h0.x + nS0, nA0, lane, [&](int id) { test(id, 0.0f, inf); });
+                        perm_each_entry(f.entries, h1.x + nS1, nA1, lane, [&](int id) { test(id, 0.0f, tT); });
+                        perm_each_entry(f.entries, h2.x + nS2, nA2, lane, [&](int id) { test(id, tT, inf); });
                     }
                     {   // ---- spheres, PM:303-328 (unit direction)
-                        const int n01 = nS0 + nS1, n = n01 + nS2;
-                        const uint32_t o0 = h0.x, o1 = h1.x - nS0, o2 = h2.x - n01;
-                        for (int k = 0; k < n; k++) {
-                            const int id = (int)__ldg(f.entries + ((k < nS0 ? o0 : (k < n01 ? o1 : o2)) + (uint32_t)k));
+                        auto test = [&](int id, float tIn, float tOut) {
                             ART_CHECK(a.counters, id < a.L.ns);
-                            const float tIn = k >= n01 ? tT : 0.0f, tOut = (k >= nS0 && k < n01) ? tT : inf;
                             const float4 sp = gv.sph[id];
                             const f3 oc = sub3(Pp, mk3(sp.x, sp.y, sp.z));
                             const float cc = subr(dot3(oc, oc), sp.w);
                             float b;
-                            if (sphere_loss_fast_miss(oc, cc, dir, b)) continue;       // disc < 0 (PM:311)
+                            if (sphere_loss_fast_miss(oc, cc, dir, b)) return;         // disc < 0 (PM:311)
                             const float sq = sqrtr(subr(mulr(b, b), cc));
                             const float len = clip_len_b(subr(-b, sq), addr(-b, sq), tIn, tOut);
                             if (len > 0.0f) loss = fmaf(len, densS[id], loss);
-                        }
+                        };
+                        perm_each_entry(f.entries, h0.x, nS0, lane, [&](int id) { test(id, 0.0f, inf); });
+                        perm_each_entry(f.entries, h1.x, nS1, lane, [&](int id) { test(id, 0.0f, tT); });
+                        perm_each_entry(f.entries, h2.x, nS2, lane, [&](int id) { test(id, tT, inf); });
                     }
                     {   // ---- OBBs, PM:294-300 (stored rotation as is), cheap arithmetic about the point of closest approach
-                        const int n01 = nO0 + nO1, n = n01 + nO2;
-                        const uint32_t o0 = h0.x + nS0 + nA0, o1 = h1.x + nS1 + nA1 - nO0, o2 = h2.x + nS2 + nA2 - n01;
-                        int nxt = n > 0 ? (int)__ldg(f.entries + (0 < nO0 ? o0 : (0 < n01 ? o1 : o2))) : 0;
-                        for (int k = 0; k < n; k++) {
-                            const int id = nxt;
-                            const int k1 = k + 1;
-                            if (k1 < n) nxt = (int)__ldg(f.entries + ((k1 < nO0 ? o0 : (k1 < n01 ? o1 : o2)) + (uint32_t)k1));
+                        auto test = [&](int id, float tIn, float tOut) {
                             ART_CHECK(a.counters, id < a.L.no);
-                            const float tIn = k >= n01 ? tT : 0.0f, tOut = (k >= nO0 && k < n01) ? tT : inf;
                             const float4 c4 = gv.obbC[id];
                             const float2 h2o = gv.obbH[id];
                             const f3 pc = mk3(Pp.x - c4.x, Pp.y - c4.y, Pp.z - c4.z);
                             const float bq = fmaf(pc.z, dir.z, fmaf(pc.y, dir.y, pc.x * dir.x));
                             const float pp = fmaf(pc.z, pc.z, fmaf(pc.y, pc.y, pc.x * pc.x));
                             const float r2 = fmaf(h2o.y, h2o.y, fmaf(h2o.x, h2o.x, c4.w * c4.w));
-                            if (pp - bq * bq > r2 * 1.001f + 1e-4f) continue;         // the line passes the bounding sphere
+                            if (pp - bq * bq > r2 * 1.001f + 1e-4f) return;            // the line passes the bounding sphere
                             const float4 q4 = gv.obbQ[id];
                             const f3 pn = mk3(fmaf(dir.x, -bq, pc.x), fmaf(dir.y, -bq, pc.y), fmaf(dir.z, -bq, pc.z));
                             const f3 lo = qrot_fast(q4, pn), ld = qrot_fast(q4, dir);
@@ -279,7 +283,10 @@ __global__ void __launch_bounds__(kPBinThreads, 1) perm_loss_binned_kernel(const
                             const float tExit = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) - bq;
                             const float len = clip_len_b(tEnter, tExit, tIn, tOut);
                             if (len > 0.0f) loss = fmaf(len, densO[id], loss);
-                        }
+                        };
+                        perm_each_entry(f.entries, h0.x + nS0 + nA0, nO0, lane, [&](int id) { test(id, 0.0f, inf); });
+                        perm_each_entry(f.entries, h1.x + nS1 + nA1, nO1, lane, [&](int id) { test(id, 0.0f, tT); });
+                        perm_each_entry(f.entries, h2.x + nS2 + nA2, nO2, lane, [&](int id) { test(id, tT, inf); });
                     }
                     if (on) {
                         const float v = subr(a.nTimesS, loss);                         // PM:260
