@@ -273,6 +273,8 @@ struct ArtCtx {
     bool frameIsRerun = false;                     // the frame in flight is the second pass of a frame whose fan build overflowed
     bool frameSplit = false;                       // the frame in flight ran the bounce-only tracer + query kernel
     bool rayHostValid = false;                     // pinRays holds the whole batch (art_set_rays); false for device-generated rays
+    bool rayHostLocal = false;                     // pinRays holds only this context's shard, packed in local order
+    int rayStamp[3] = { 0, 1, 0 };                 //   ... for this (shardIndex, shardCount, chunk)
     bool dirsLocal = false;                        // the device direction array holds only this context's shard, in local order
 
     // multi-device context (ArtConfig.nDevices > 1): this object owns no CUDA state itself, only one child per device
@@ -654,12 +656,31 @@ ART_API int32_t art_set_rays(ArtCtx* ctx, const uint16_t* dirs, int32_t rayCount
         return ART_OK;
     }
     cudaSetDevice(ctx->device);
-    CK(ctx->pinRays.ensure(6 * (size_t)rayCount));
-    memcpy(ctx->pinRays.p, dirs, 6 * (size_t)rayCount);
     ctx->nGlobal = rayCount;
+    if (ctx->shardCount > 1) {
+        // a shard needs only its own directions: take the chunks it owns straight from the caller's array, in local order
+        // (one rank of 8 stages 0.8 MB of C3's 6.3 MB). The context then holds only its shard: after a change of the shard
+        // map the rays have to be set again.
+        const int chunk = effective_chunk(ctx);
+        const size_t nLoc = (size_t)local_ray_count(rayCount, ctx->shardIndex, ctx->shardCount, chunk);
+        ShardMap m;
+        m.nGlobal = rayCount; m.nLocal = (int)nLoc; m.shardIndex = ctx->shardIndex; m.shardCount = ctx->shardCount; m.chunk = chunk; m.dirsLocal = 1;
+        CK(ctx->pinRays.ensure(6 * nLoc + 16));
+        unsigned char* dst = ctx->pinRays.as<unsigned char>();
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(dirs);
+        for (size_t j0 = 0; j0 < nLoc; j0 += (size_t)chunk) {
+            const size_t cnt = std::min((size_t)chunk, nLoc - j0);
+            memcpy(dst + 6 * j0, src + 6 * (size_t)m.to_global((int)j0), 6 * cnt);
+        }
+        ctx->rayHostLocal = true; ctx->rayHostValid = false;
+        ctx->rayStamp[0] = ctx->shardIndex; ctx->rayStamp[1] = ctx->shardCount; ctx->rayStamp[2] = chunk;
+    } else {
+        CK(ctx->pinRays.ensure(6 * (size_t)rayCount));
+        memcpy(ctx->pinRays.p, dirs, 6 * (size_t)rayCount);
+        ctx->rayHostLocal = false; ctx->rayHostValid = true;
+    }
     ctx->haveRays = true;
     ctx->raysDirty = true;
-    ctx->rayHostValid = true;
     return ART_OK;
 }
 
@@ -683,7 +704,7 @@ ART_API int32_t art_generate_fibonacci_rays(ArtCtx* ctx, int32_t rayCount)
     ctx->nGlobal = rayCount;
     ctx->haveRays = true;
     ctx->raysDirty = false;
-    ctx->rayHostValid = false;
+    ctx->rayHostValid = false; ctx->rayHostLocal = false;
     ctx->dirsLocal = false;                        // the whole batch lives on the device
     return ART_OK;
 }
@@ -696,6 +717,7 @@ ART_API int32_t art_get_rays(ArtCtx* ctx, uint16_t* dirs, int32_t capacityRays)
     if (capacityRays < ctx->nGlobal) return fail(ctx, ART_E_ARG, "art_get_rays: capacity %d < %d", capacityRays, ctx->nGlobal);
     cudaSetDevice(ctx->device);
     if (ctx->rayHostValid) { memcpy(dirs, ctx->pinRays.p, 6 * (size_t)ctx->nGlobal); return ART_OK; }
+    if (ctx->rayHostLocal) return fail(ctx, ART_E_STATE, "art_get_rays: a sharded context holds only its own shard of the directions");
     CK(cudaMemcpyAsync(dirs, ctx->dirs.p, 6 * (size_t)ctx->nGlobal, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return ART_OK;
@@ -906,9 +928,15 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         ctx->gridBuilt = false;                        // built lazily by the first frame that wants it
         ctx->sceneDirty = false;
     }
+    if (ctx->rayHostLocal && (ctx->rayStamp[0] != ctx->shardIndex || ctx->rayStamp[1] != ctx->shardCount || ctx->rayStamp[2] != chunk))
+        return fail(ctx, ART_E_STATE, "the shard map changed after art_set_rays: set the rays again (a sharded context keeps only its own directions)");
     if (ctx->raysDirty) {
-        if (ctx->shardCount > 1) {
-            // a shard needs only its own directions: pack the chunks it owns (local order) behind the batch in pinned memory
+        if (ctx->rayHostLocal) {
+            CK(ctx->dirs.ensure(6 * nLoc + 16));
+            CK(cudaMemcpyAsync(ctx->dirs.p, ctx->pinRays.p, 6 * nLoc, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->dirsLocal = true;
+        } else if (ctx->shardCount > 1) {
+            // the batch was set before the shard map: pack the chunks this shard owns (local order) behind it in pinned memory
             const size_t all = (6 * (size_t)N + 63) & ~(size_t)63;
             if (ctx->pinRays.cap < all + 6 * nLoc) {
                 PinBuf bigger;
@@ -1317,6 +1345,10 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         bool binned = useGrid && useFans && !(prm->flags & ART_FRAME_GRID_STATS) && (size_t)map.nLocal * Na >= ((size_t)1 << 21);
         if (const char* v = getenv("ART_K2_BINNED")) binned = useGrid && useFans && !(prm->flags & ART_FRAME_GRID_STATS) && atoi(v) != 0;
         if (binned && ((size_t)map.nLocal * Na > ((size_t)1 << 31) || Na > 65535)) binned = false;   // 32-bit offsets inside the pair list; one grid row per target
+        if (useGrid && binned) {
+            // 4 B per (ray, target) line: when that allocation fails the per-line kernel below runs instead (same results)
+            if (ctx->permPairs.ensure((size_t)Na * nLoc * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); binned = false; }
+        }
         if (useGrid && binned) {
             PermBinArgs ba;
             ba.slices = perm_binned_slices(map.nLocal, Na, ctx->numSms);

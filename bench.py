@@ -412,8 +412,8 @@ def main():
             "kernel_ms": {"trace": trace_ms_avg, "trace_fan_build": fan_ms_avg, "trace_bounce": bounce_ms_avg, "trace_queries": query_ms_avg,
                           "permeation": float(np.mean(perm_ms)), "reduce": float(np.mean(reduce_ms)),
                           "partials_allgather": ex_ms_tot / args.steps,
-                          "note": "trace = per-frame fan build (fan_order_kernel + fan_build_kernel) + bounce tracer (trace_grid_kernel, "
-                                  "bounce-only) + query_fan_kernel; partials_allgather = ncclAllGather of the per-source blobs inside the library"},
+                          "note": "trace = per-frame fan build (fan_order_kernel + fan_build_kernel) + bounce tracer (bounce_kernel) "
+                                  "+ query_fan_kernel; partials_allgather = ncclAllGather of the per-source blobs inside the library"},
             "wall_ms_per_step_device_mode": wall_dev_max / args.steps * 1e3,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
