@@ -344,12 +344,15 @@ int effective_chunk(const ArtCtx* c)
 {
     if (c->shardCount <= 1) return c->nGlobal > 0 ? c->nGlobal : 1;
     if (c->chunkAuto) {
-        // Library-owned shard maps: 8 interleaved chunks per shard. Few, long chunks keep a shard's first-hit points (one
-        // latitude band of the Fibonacci sphere per chunk) together, so the permeation job's (source, direction bin) groups
-        // stay long enough to fill warps; 8 of them still balance the bands' different geometry over the shards (B200, C3 / 8:
-        // chunks of 256 rays 5.47 ms per rank, 16,384 rays 5.18 ms, one contiguous slice 4.7 .. 5.5 ms depending on the rank).
+        // Library-owned shard maps: interleaved chunks of N / (8 * shards) rays, at most 16,384. Long chunks keep a shard's
+        // first-hit points (one latitude band of the Fibonacci sphere per chunk) together, so the permeation job's (source,
+        // direction bin) groups stay long enough to fill warps when a shard has few rays (B200, C3 / 8: chunks of 256 rays
+        // 5.47 ms per rank, 16,384 rays 5.18 ms, one contiguous slice 4.7 .. 5.5 ms depending on the rank); with many rays per
+        // shard the groups are long anyway and more, shorter chunks balance the bands' different geometry better (C3 / 2 with
+        // 8 chunks of 65,536 rays: one rank waits 0.3 ms of 16.7 for the other).
         long long ch = ((long long)c->nGlobal + 8LL * c->shardCount - 1) / (8LL * c->shardCount);
         ch = (ch + 255) / 256 * 256;
+        if (ch > 16384) ch = 16384;
         return (int)(ch < 256 ? 256 : ch);
     }
     if (c->chunkRays > 0) return c->chunkRays;

@@ -96,7 +96,7 @@ typedef struct ArtConfig {
     int32_t  device;         /* CUDA device ordinal (used when nDevices <= 1) */
     uint32_t flags;
     /* nDevices > 1: ONE context over several GPUs of this process. The library owns one device context per entry of
-     * devices[], the ray shard map (interleaved chunks of shardChunkRays rays; 0 = 8 chunks per device), the exchange and exact merge of the
+     * devices[], the ray shard map (interleaved chunks of shardChunkRays rays; 0 = N / (8 x devices) rays, at most 16,384), the exchange and exact merge of the
      * per-source partial results and the scatter of the per-ray outputs into the caller's arrays; every entry point keeps
      * its single-device meaning and art_trace_schedule stays one call (ART:161-237). Results are bit-identical with a
      * one-device context. */
@@ -269,7 +269,7 @@ ART_API int32_t art_finalize(const void* blob, int64_t blobBytes, const ArtParam
 /* ---- multi-process sharding (one rank per GPU, e.g. under torchrun / mpirun) -----------------------------------------
  * art_comm_init joins the context to a communicator of `world` ranks (NCCL, loaded with dlopen("libnccl.so.2") on first
  * use -- single-GPU hosts need no NCCL) and makes it trace shard `rank` of the batch (interleaved chunks of chunkRays rays,
- * 0 = 8 chunks per rank). From then on a frame scheduled WITHOUT ART_FRAME_PARTIALS_ONLY all-gathers the ranks' partial blobs on the
+ * 0 = N / (8 x ranks) rays, at most 16,384). From then on a frame scheduled WITHOUT ART_FRAME_PARTIALS_ONLY all-gathers the ranks' partial blobs on the
  * device (one ncclAllGather of a few KB on the context's stream, no host round trip), merges them exactly and finalises on
  * every rank: art_complete returns the same per-source outputs everywhere. Per-ray outputs stay local (local ray indexing).
  * uniqueId: 128 bytes from art_comm_unique_id on one rank, distributed by the caller (MPI_Bcast, torch.distributed ...). */
