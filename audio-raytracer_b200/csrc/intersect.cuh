@@ -132,12 +132,6 @@ __device__ __forceinline__ float rcp_fast(float x)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ float rsqrt_fast(float x)
-{
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
 __device__ __forceinline__ float sqrt_fast(float x)
 {
     float r;

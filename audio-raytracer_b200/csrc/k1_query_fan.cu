@@ -13,15 +13,9 @@
 // Mapping. A warp takes 32 consecutive records; LANE = HIT POINT (its record stays in registers), the goals are walked in
 // lock step, so the goal position and its near-list header are warp-uniform shared-memory broadcasts and the bin header +
 // first AABB ids come with ONE 16-byte load (FanDesc::cells4):
-//   pass 0   every (hit point, goal) query is tested against the first two AABBs of its lists -- with nearest-first lists
-//            that blocks most queries -- by a CONSERVATIVE classification that needs no exact set-up: the ray is left
-//            un-normalised (parameter s in [0, 1] along goal - P, three rcp.approx), and a test only answers "certainly
-//            blocked" / "certainly not" when the reference's own FP32 evaluation cannot differ (q_classify_aabb: relative
-//            error bounds on every compared quantity); everything else counts as undecided;
-//   prepare  the queries pass 0 did not block (and the undecided ones, to be re-tested from the start) are queued with 16 B
-//            each and PREPARED exactly, 32 at a time at full width (RT:127/162 normalize: exact sqrt and divide, RT:289:
-//            three exact reciprocals) -- one third of the queries instead of all of them;
-//   AABBs    the prepared queries wait WITH their state (64 B, self-contained) in a per-warp list in global scratch
+//   pass 0   every (hit point, goal) query is prepared (exact sqrt, four exact reciprocals) and tested against the first two
+//            AABBs of its lists -- with nearest-first lists that blocks most queries;
+//   AABBs    the others are queued WITH their prepared state (64 B, self-contained) in a per-warp list in global scratch
 //            (L2 resident). Whenever enough have gathered, every lane takes one into registers and tests one AABB per step;
 //            a lane whose query is blocked takes the next one at once, so the lanes stay full whatever the list lengths.
 //            When the queue runs dry the few queries still in flight are written back (with their cursor) and wait for the
@@ -54,11 +48,9 @@ constexpr int kQThreads = kQWarps * 32;
 constexpr int kQFirstTests = 2;                      // AABBs of pass 0 at most (their ids come with the headers, FanDesc::cells4)
 constexpr int kQRun = ART_Q_RUN;                     // queued queries from which a refill loop runs
 constexpr int kQMinLanes = ART_Q_MIN_LANES;          // a loop whose queue is dry stops (and writes its queries back) below this many busy lanes
-constexpr int kQCap0 = kQRun + 32;                   // unprepared queries: < kQRun before a goal step, <= 32 more per step
-constexpr int kQCapA = 2 * kQRun + 64;               // AABB queue: < kQRun + what one prepare run adds + <= 32 written back
-constexpr int kQCapSO = 4 * kQRun + 128;             // sphere / OBB queue: additionally everything a prepare and an AABB run pass on
-constexpr int kQEntry = 4;                           // float4 per prepared query
-constexpr float kQRelErr = 1e-6f;                    // bound used for |reference value - conservative value| / |value| (derivation: q_classify_aabb)
+constexpr int kQCapA = kQRun + 64;                   // AABB queue: < kQRun before a goal step, <= 32 more per step, <= 32 written back
+constexpr int kQCapSO = 2 * kQRun + 128;             // sphere / OBB queue: additionally everything one AABB run passes on
+constexpr int kQEntry = 4;                           // float4 per queued query
 constexpr int kQMuffleSmemMax = 4096;                // per-CTA muffle counters [T * Na] kept in shared memory up to this size
 
 // A queued query, 64 B:  e0 = (1/dir.xyz, limit L)   e1 = (P.xyz, |goal - P|)   e2 = (bin header x, y, slot | cursor << 16, -)
@@ -97,90 +89,6 @@ __device__ __forceinline__ void q_visible(const QEnv& E, int slot, float L, floa
         if (E.sMuffle) atomicAdd(&E.sMuffle[idx], 1u);
         else atomicAdd(&E.a.muffleCounts[idx], 1u);
     }
-}
-
-// Conservative AABB any-hit classification in un-normalised ray space: 1 = the reference's test (RT:284-308 + the caller's
-// `dist < distToTarget`, RT:384 / RT:430) certainly reports a blocker, 0 = it certainly does not, 2 = undecided.
-//
-// The reference evaluates, per axis k, t0 = fl(A*inv), A = fl(min - P) (the same float here), inv = fl(1/nd), nd = fl(rl*v),
-// rl = fl(1/len): t0 = (A/v) * (1/rl) * (1 + th), |th| <= 3 * 2^-24. Here a = fl(A * r), r = rcp.approx(v) (relative error
-// <= 2^-23): a = (A/v) * (1 + th'), |th'| <= 3 * 2^-24. So rl * t0 and a differ by at most 6 * 2^-24 = 3.6e-7 of |a|; rl > 0
-// is the same factor for every axis and collider, and min / max are monotone, hence rl * tNear lies within kQRelErr * |sn| of
-// sn and rl * tFar within kQRelErr * |sf| of sf (kQRelErr = 1e-6). All values are finite (the caller guarantees 1e-12 <= |v_k|,
-// 1e-12 <= |v|^2 <= 1e12), so the reference meets no NaN either. A comparison is decided only if it holds with the margin
-// e = kQRelErr * max(|sn|, |sf|) + 1e-30 on both sides. The limit: rl * distToTarget lies in [limLo, limHi] (caller).
-__device__ __forceinline__ int q_classify_aabb(const GeomView& gv, int id, f3 P, f3 r, float limLo, float limHi)
-{
-    const float4 A = gv.aabbA[id];
-    const float2 B = gv.aabbB[id];
-    const float ax = mulr(subr(A.x, P.x), r.x), bx = mulr(subr(A.w, P.x), r.x);
-    const float ay = mulr(subr(A.y, P.y), r.y), by = mulr(subr(B.x, P.y), r.y);
-    const float az = mulr(subr(A.z, P.z), r.z), bz = mulr(subr(B.y, P.z), r.z);
-    const float sn = max3f(fminf(ax, bx), fminf(ay, by), fminf(az, bz));
-    const float sf = min3f(fmaxf(ax, bx), fmaxf(ay, by), fmaxf(az, bz));
-    const float e = fmaf(kQRelErr, fmaxf(fabsf(sn), fabsf(sf)), 1e-30f);
-    const bool miss = (sn - sf > 2.0f * e) || (sf < -e);                  // tNear > tFar  or  tFar < 0, certainly
-    const bool hit = (sf - sn > 2.0f * e) && (sf > e);                    // neither, certainly
-    const bool pos = sn > e, neg = sn < -e;                               // the sign of tNear decides which distance is reported (RT:306)
-    const float dist = pos ? sn : sf;
-    if (hit && (pos || neg) && dist + e < limLo) return 1;
-    if (miss || ((pos || neg) && dist - e >= limHi)) return 0;
-    return 2;
-}
-
-// Exact set-up of the queries pass 0 queued (16 B each: record index, slot | first AABB to test << 16 | flags, bin header):
-// 32 at a time, one lane per query -- RT:127 / RT:162 normalize (exact sqrt, exact divide), RT:289 the three reciprocals,
-// RT:130 / RT:165 the limit, RT:168 the gate -- then on to the AABB queue, the sphere / OBB queue, or the goal is visible.
-constexpr uint32_t kQFlagNoBin = 1u << 30;           // the direction goal -> hit point has no bin (hit point == goal, non-finite)
-template <bool STATS>
-__device__ __forceinline__ void q_prepare(const QEnv& E, const uint4* list0, int n0, float4* listA, int& nA, float4* listSO, int& nSO)
-{
-    const QueryArgs& a = E.a;
-    for (int i0 = 0; i0 < n0; i0 += 32) {
-        const int i = i0 + E.lane;
-        int push = 0;
-        float4 e0 = make_float4(0, 0, 0, 0), e1 = e0, e2 = e0, e3 = e0;
-        if (i < n0) {
-            const uint4 q = list0[i];
-            const int slot = (int)(q.y & 0xFFFFu), cursor = (int)((q.y >> 16) & 0xFFFu);
-            ART_CHECK(a.counters, slot <= a.nTargets && q.x < *a.recCount);
-            const float4 ra = __ldg(&a.recA[q.x]);
-            const float2 rb = __ldg(&a.recB[q.x]);
-            const f3 P = mk3(ra.x, ra.y, ra.z);
-            const f3 v = sub3(q_goal(E, slot), P);                             // RT:127 / RT:162
-            const float len = sqrtr(dot3(v, v));
-            float L = ra.w;                                                    // RT:130
-            bool gate = true;
-            if (slot > 0) { L = len; gate = L < a.maxMuffle; }                 // RT:165, 168
-            if (gate) {
-                if ((q.y & kQFlagNoBin) || len != len) {
-                    q_visible(E, slot, L, rb.x, __float_as_int(rb.y));         // degenerate (hit point == goal): no test can block
-                } else {
-                    const f3 nd = smul3(rcpr(len), v);                         // normalize = rsqrt(dot) * v
-                    const f3 inv = mk3(rcpr(nd.x), rcpr(nd.y), rcpr(nd.z));
-                    const uint4 n4 = q_near(E, slot);
-                    const int nAll = (int)((n4.y >> 10) & 2047u) + (int)((q.w >> 10) & 2047u);
-                    if (cursor < nAll) push = 1;
-                    else if (((n4.y | q.w) & 1023u) | ((n4.y | q.w) >> 21)) push = 2;
-                    else q_visible(E, slot, L, rb.x, __float_as_int(rb.y));
-                    e0 = make_float4(inv.x, inv.y, inv.z, L);
-                    e1 = make_float4(P.x, P.y, P.z, len);
-                    e2 = make_float4(__uint_as_float(q.z), __uint_as_float(q.w), __uint_as_float((uint32_t)slot | (push == 1 ? (uint32_t)cursor << 16 : 0u)), 0.0f);
-                    e3 = make_float4(rb.x, rb.y, 0.0f, 0.0f);
-                }
-            }
-        }
-        const uint32_t am = __ballot_sync(kFull, push == 1), sm = __ballot_sync(kFull, push == 2);
-        if (push) {
-            const int pos = push == 1 ? nA + __popc(am & E.ltMask) : nSO + __popc(sm & E.ltMask);
-            ART_CHECK(a.counters, pos < (push == 1 ? kQCapA : kQCapSO));
-            float4* dst = (push == 1 ? listA : listSO) + (size_t)kQEntry * pos;
-            dst[0] = e0; dst[1] = e1; dst[2] = e2; dst[3] = e3;
-        }
-        nA += __popc(am);
-        nSO += __popc(sm);
-    }
-    __syncwarp();
 }
 
 // The AABB lists of the queued queries, entries [cursor, nA0 + nA1) of the run "near list, then bin". Every lane holds ONE
@@ -379,10 +287,9 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
     const uint32_t ltMask = (1u << lane) - 1u;
     unsigned int st[4] = { 0, 0, 0, 0 };
     const QEnv E = { a, f, gv, goalTab, nearTab, sMuffle, lane, ltMask, st };
-    float4* listA = a.scratch + ((size_t)blockIdx.x * kQWarps + warp) * (size_t)(kQEntry * (kQCapA + kQCapSO) + kQCap0);
+    float4* listA = a.scratch + ((size_t)blockIdx.x * kQWarps + warp) * (size_t)(kQEntry * (kQCapA + kQCapSO));
     float4* listSO = listA + kQEntry * kQCapA;
-    uint4* list0 = reinterpret_cast<uint4*>(listSO + kQEntry * kQCapSO);
-    int n0 = 0, nA = 0, nSO = 0;                     // queued queries (kept across goals and record blocks)
+    int nA = 0, nSO = 0;                             // queued queries (kept across goals and record blocks)
     const unsigned int nRec = *a.recCount;           // the bounce tracer has finished (stream order)
 
     // Work unit = (block of 32 records, group of goals). With few records (a small batch against many targets) the launcher
@@ -412,87 +319,74 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
             P = mk3(ra.x, ra.y, ra.z);
             ART_CHECK(a.counters, __float_as_int(a.recB[ri].y) >= 0 && __float_as_int(a.recB[ri].y) / a.H < a.map.nLocal);
         }
-        // ---- pass 0: lane = hit point, all lanes walk the goals together; conservative tests only (q_classify_aabb)
+        // ---- pass 0: lane = hit point, all lanes walk the goals together
         for (int s = sBeg; s < sEnd; s++) {
-            bool push = false;
-            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            int push = 0;                                                // 1: AABB queue, 2: sphere / OBB queue
+            float4 e0 = make_float4(0, 0, 0, 0), e2 = e0;
+            float len = 0.0f;
             const uint4 n4 = q_near(E, s);
             if (valid) {
-                const f3 v = sub3(q_goal(E, s), P);                                // RT:127 / RT:162 (the reference's own operand)
-                // the bin header depends on the direction's bin only: its load (L2) is issued first
+                const f3 v = sub3(q_goal(E, s), P);                                // RT:127 / RT:162
+                // the bin header depends on the direction's bin only: its load (L2) is issued first and completes
+                // while the exact square root and reciprocals below are computed
                 const int bin = fan_bin(-v.x, -v.y, -v.z);                         // direction goal -> hit point
                 uint4 c4 = make_uint4(0u, 0u, 0u, 0u);
                 if (bin >= 0) c4 = __ldg(&f.cells4[(size_t)q_fan_of(a, s) * kFanCells + bin]);
-                const float d2 = fmaf(v.z, v.z, fmaf(v.y, v.y, v.x * v.x));        // |v|^2 up to 2 ulp
-                // un-normalised ray: X(s) = P + s * v, s = t / len; everything below compares rl * t = s-values
-                const f3 r = mk3(rcp_fast(v.x), rcp_fast(v.y), rcp_fast(v.z));
-                const bool sure = fminf(fminf(fabsf(v.x), fabsf(v.y)), fabsf(v.z)) >= 1e-12f && d2 >= 1e-12f && d2 <= 1e12f && bin >= 0;
-                // RT:168 gate (muffle rays): |v| against MaxMuffleHitDistance, decided only outside a 2e-6 band
-                const bool gateFail = s > 0 && sure && d2 > a.gateHi2, gateSure = s == 0 || d2 < a.gateLo2;
-                float limLo = 1.0f - 1e-6f, limHi = 1.0f + 1e-6f;                  // muffle: distToTarget = len, len * fl(1 / len) = 1 +- 2^-24
-                if (s == 0) {                                                      // echo: distToStartOrigin (RT:130) against |v|
-                    const float sl = __ldg(&a.recA[ri].w) * rsqrt_fast(d2);        // rl within 6e-7 of rsqrt.approx(|v|^2)
-                    limLo = fmaf(-2e-6f, sl, sl) - 1e-30f; limHi = fmaf(2e-6f, sl, sl) + 1e-30f;
-                }
-                const int nA0 = (n4.y >> 10) & 2047, nA1 = (c4.y >> 10) & 2047, nAll = nA0 + nA1;
-                if (STATS) st[3] += 2;
-                // the run "near list, then bin" starts with these ids: no dependent load of the entry lists here
-                const uint32_t ids = nA0 >= 2 ? n4.z : (nA0 == 1 ? (n4.z & 0xFFFFu) | (c4.z << 16) : c4.z);
-                const int nFirst = min(nAll, a.firstTests);
-                bool blocked = false, unsure = !sure || !gateSure;
-                if (sure && !gateFail) {
-#pragma unroll 1
-                    for (int t = 0; t < nFirst && !blocked; t++) {
-                        const int id = (int)((ids >> (16 * t)) & 0xFFFFu);
-                        ART_CHECK(a.counters, id < a.L.na);
-                        if (STATS) st[1]++;
-                        const int c = q_classify_aabb(gv, id, P, r, limLo, limHi);
-                        blocked = c == 1;
-                        unsure = unsure || c == 2;
-#ifdef ART_Q_VERIFY
-                        {   // cross-check against the exact evaluation (debug builds): a decided test must agree with it
-                            const float lenX = sqrtr(dot3(v, v));
-                            const f3 ndX = smul3(rcpr(lenX), v);
-                            const f3 invX = mk3(rcpr(ndX.x), rcpr(ndX.y), rcpr(ndX.z));
-                            const float LX = s == 0 ? a.recA[ri].w : lenX;
-                            const bool bx = aabb_blocks(gv, id, P, invX, LX);
-                            const bool gx = s == 0 || LX < a.maxMuffle;
-                            if ((c == 1 && gx && !bx) || (c == 0 && bx) || (gateSure && !gx)) atomicAdd(&a.counters[C_DEBUG_VIOLATIONS], 1ull);
-                        }
-#endif
-                    }
-                }
-#ifdef ART_Q_VERIFY
-                if (gateFail && sqrtr(dot3(v, v)) < a.maxMuffle) atomicAdd(&a.counters[C_DEBUG_VIOLATIONS], 1ull);
-#endif
-                if (!blocked && !gateFail) {
-                    // a decided-clear query with nothing left to test sees its goal; everything else is prepared exactly
-                    // (q_prepare) and continues at AABB `nFirst`, or -- if anything was undecided -- from the start
-                    if (!unsure && nAll <= nFirst && !(((n4.y | c4.y) & 1023u) | ((n4.y | c4.y) >> 21))) {
+                len = sqrtr(dot3(v, v));
+                float L;
+                bool gate = true;
+                if (s > 0) { L = len; gate = L < a.maxMuffle; }                    // RT:165, 168
+                else L = __ldg(&a.recA[ri].w);                                     // RT:130
+                if (gate) {
+                    if (bin < 0 || len != len) {
                         const float2 rb = __ldg(&a.recB[ri]);
-                        q_visible(E, s, s == 0 ? __ldg(&a.recA[ri].w) : 0.0f, rb.x, __float_as_int(rb.y));
+                        q_visible(E, s, L, rb.x, __float_as_int(rb.y));            // degenerate (hit point == goal): no test can block
                     } else {
-                        push = true;
-                        q = make_uint4(ri, (uint32_t)s | ((uint32_t)(unsure ? 0 : nFirst) << 16) | (bin < 0 ? kQFlagNoBin : 0u), c4.x, c4.y);
+                        const f3 nd = smul3(rcpr(len), v);                         // normalize = rsqrt(dot) * v
+                        const f3 inv = mk3(rcpr(nd.x), rcpr(nd.y), rcpr(nd.z));
+                        const int nA0 = (n4.y >> 10) & 2047, nA1 = (c4.y >> 10) & 2047, nAll = nA0 + nA1;
+                        if (STATS) st[3] += 2;
+                        // the run "near list, then bin" starts with these ids: no dependent load of the entry lists here
+                        const uint32_t ids = nA0 >= 2 ? n4.z : (nA0 == 1 ? (n4.z & 0xFFFFu) | (c4.z << 16) : c4.z);
+                        const int nFirst = min(nAll, a.firstTests);
+                        bool blocked = false;
+#pragma unroll 1
+                        for (int t = 0; t < nFirst && !blocked; t++) {
+                            const int id = (int)((ids >> (16 * t)) & 0xFFFFu);
+                            ART_CHECK(a.counters, id < a.L.na);
+                            if (STATS) st[1]++;
+                            blocked = aabb_blocks(gv, id, P, inv, L);
+                        }
+                        if (!blocked) {
+                            if (nAll > nFirst) push = 1;
+                            else if (((n4.y | c4.y) & 1023u) | ((n4.y | c4.y) >> 21)) push = 2;
+                            else { const float2 rb = __ldg(&a.recB[ri]); q_visible(E, s, L, rb.x, __float_as_int(rb.y)); }
+                            e0 = make_float4(inv.x, inv.y, inv.z, L);
+                            e2 = make_float4(__uint_as_float(c4.x), __uint_as_float(c4.y),
+                                             __uint_as_float((uint32_t)s | (push == 1 ? (uint32_t)nFirst << 16 : 0u)), 0.0f);
+                        }
                     }
                 }
             }
-            const uint32_t pm = __ballot_sync(kFull, push);
+            const uint32_t am = __ballot_sync(kFull, push == 1), sm = __ballot_sync(kFull, push == 2);
             if (push) {
-                const int pos = n0 + __popc(pm & ltMask);
-                ART_CHECK(a.counters, pos < kQCap0);
-                list0[pos] = q;
+                const int pos = push == 1 ? nA + __popc(am & ltMask) : nSO + __popc(sm & ltMask);
+                ART_CHECK(a.counters, pos < (push == 1 ? kQCapA : kQCapSO));
+                float4* dst = (push == 1 ? listA : listSO) + (size_t)kQEntry * pos;
+                dst[0] = e0;
+                dst[1] = make_float4(P.x, P.y, P.z, len);
+                dst[2] = e2;
+                const float2 rb = __ldg(&a.recB[ri]);
+                dst[3] = make_float4(rb.x, rb.y, 0.0f, 0.0f);
             }
-            n0 += __popc(pm);
-            // ---- exact set-up of the queued queries, their remaining AABBs, their sphere and OBB lists -- each whenever
-            //      enough have gathered to fill the lanes
-            if (n0 >= kQRun) { __syncwarp(); q_prepare<STATS>(E, list0, n0, listA, nA, listSO, nSO); n0 = 0; }
+            nA += __popc(am);
+            nSO += __popc(sm);
+            // ---- the queued queries' remaining AABBs / sphere and OBB lists, whenever enough have gathered to fill the lanes
             if (nA >= kQRun) { __syncwarp(); nA = q_loop_aabb<STATS>(E, listA, nA, false, listSO, nSO); }
             if (nSO >= kQRun) { __syncwarp(); nSO = q_loop_so<STATS>(E, listSO, nSO, false); }
         }
     }
     __syncwarp();
-    if (n0 > 0) q_prepare<STATS>(E, list0, n0, listA, nA, listSO, nSO);
     if (nA > 0) q_loop_aabb<STATS>(E, listA, nA, true, listSO, nSO);
     if (nSO > 0) q_loop_so<STATS>(E, listSO, nSO, true);
 
@@ -513,7 +407,7 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
 
 // ---- launcher -----------------------------------------------------------------------------------
 size_t query_fan_smem_bytes(const GeomLayout& L, bool geomInSmem) { return geomInSmem ? L.bytes : 0; }
-size_t query_fan_scratch_bytes(int numCtas) { return (size_t)numCtas * kQWarps * (kQEntry * (kQCapA + kQCapSO) + kQCap0) * sizeof(float4); }
+size_t query_fan_scratch_bytes(int numCtas) { return (size_t)numCtas * kQWarps * kQEntry * (kQCapA + kQCapSO) * sizeof(float4); }
 
 cudaError_t launch_query_fan(const QueryArgs& a0, const FanDesc& fans, int numCtas, bool geomInSmem, bool stats, int maxSmemOptin, cudaStream_t stream)
 {
@@ -531,14 +425,6 @@ cudaError_t launch_query_fan(const QueryArgs& a0, const FanDesc& fans, int numCt
         if (maxBlocks > 0 && maxBlocks < 2 * warps) g = std::min<long long>(slots, (2 * warps + maxBlocks - 1) / maxBlocks);
         a.goalsPerGroup = (int)((slots + g - 1) / g);
         a.goalGroups = (slots + a.goalsPerGroup - 1) / a.goalsPerGroup;
-    }
-    // RT:168 gate, decided conservatively in pass 0: |v|^2 against MaxMuffleHitDistance^2 outside a relative band of 4e-6
-    {
-        const double m = (double)a.maxMuffle;
-        a.gateLo2 = (float)(m * m * (1.0 - 4e-6));
-        a.gateHi2 = (float)(m * m * (1.0 + 4e-6));
-        if (!(m > 0.0)) { a.gateLo2 = 0.0f; a.gateHi2 = 0.0f; }      // (0, negative or NaN: nothing is certain, the exact compare decides)
-        if (m != m) { a.gateLo2 = -1.0f; a.gateHi2 = 3.0e38f; }
     }
     // experiment knob (read per launch): AABBs tested in pass 0 (1 or 2)
     a.firstTests = kQFirstTests;

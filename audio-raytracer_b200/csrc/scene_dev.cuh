@@ -184,7 +184,6 @@ struct QueryArgs {
     int muffleInSmem;              // per-CTA muffle counters [T*Na] in shared memory
     int firstTests;                // AABBs every query tests in pass 0 (1 or 2)
     int goalGroups, goalsPerGroup; // > 1 group: the goals of a record block are split over several warps (small batches)
-    float gateLo2, gateHi2;        // |goal - P|^2 below / above which the RT:168 gate certainly passes / fails (launch_query_fan)
 };
 
 // Uniform grid over the collider scene (acceleration structure). Built on the host at
