@@ -1181,6 +1181,14 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             fa.targets = ctx->targets.as<float>(); fa.nTargets = Na;
             fa.lx = prm->rayOrigin[0]; fa.ly = prm->rayOrigin[1]; fa.lz = prm->rayOrigin[2];
             fa.nearDist = 1e-3f * ctx->grid.d.errScale;
+            {   // covering depths (query_fan_kernel's cull); ART_Q_NO_COVER (experiment knob, read per frame) leaves them out
+                const char* nc0 = getenv("ART_Q_NO_COVER");
+                const bool cover = !(nc0 && atoi(nc0) != 0);
+                const unsigned char* gb = ctx->geom.as<unsigned char>();
+                fa.aabbA = cover ? reinterpret_cast<const float4*>(gb + L.offAabbA) : nullptr;
+                fa.aabbB = cover ? reinterpret_cast<const float2*>(gb + L.offAabbB) : nullptr;
+                fa.coverMinThickness = 1e-4f * ctx->grid.d.errScale;
+            }
             fa.cells4 = ctx->fanCells.as<uint4>();
             fa.cells = reinterpret_cast<uint2*>(fa.cells4 + nFans * kFanCells); fa.entries = ctx->fanEntries.as<uint16_t>();
             fa.firstA = reinterpret_cast<uint32_t*>(fa.cells + nFans * kFanCells);

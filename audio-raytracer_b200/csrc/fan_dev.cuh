@@ -39,8 +39,9 @@ struct FanDesc {
     int nEntries;              // capacity (bounds checks of debug builds)
     const uint32_t* firstA;    // [nFans * kFanCells]: the cell's first two AABB entries, id0 | id1 << 16 (K1's first pass tests
                                // exactly those: it reads them beside the header instead of chasing the entry list afterwards)
-    const uint4* cells4;       // [nFans * kFanCells]: (cells[i].x, cells[i].y, AABB ids 0 | 1 << 16, AABB ids 2 | 3 << 16) -- header and
-                               // first ids in ONE 16-byte load (query_fan_kernel: one divergent L2 access per query)
+    const uint4* cells4;       // [nFans * kFanCells]: (cells[i].x, cells[i].y, AABB ids 0 | 1 << 16, covering depth as float bits) -- header,
+                               // first ids and the cull threshold of the bin in ONE 16-byte entry (k4_fan_build.cu "covering depth";
+                               // the near cell's w is unused)
 };
 
 // fan_build_kernel arguments (k4_fan_build.cu)
@@ -53,6 +54,8 @@ struct FanBuildArgs {
     int nTargets;
     float lx, ly, lz;          // listener = goal of fan nTargets
     float nearDist;
+    const float4* aabbA; const float2* aabbB;   // the AABBs' own min / max (GeomView), for the covering depth; null: no covering depths
+    float coverMinThickness;   // 1e-4 * errScale: a covering depth interval must be at least this long
     uint2* cells;              // [(nTargets + 1) * kFanCells]
     uint32_t* firstA;          // [(nTargets + 1) * kFanCells], see FanDesc
     uint4* cells4;             // [(nTargets + 1) * kFanCells], see FanDesc
@@ -64,10 +67,11 @@ struct FanBuildArgs {
 
 // Cell index (within one fan) of the bin that direction v (from the goal, any length) falls in.
 // Returns -1 when v has no usable direction (zero or non-finite).
-__device__ __forceinline__ int fan_bin(float vx, float vy, float vz)
+// `w` receives the depth of v on its face (the largest |component|).
+__device__ __forceinline__ int fan_bin_w(float vx, float vy, float vz, float& w)
 {
     const float ax = fabsf(vx), ay = fabsf(vy), az = fabsf(vz);
-    int k; float w, p, q, s;
+    int k; float p, q, s;
     if (ax >= ay && ax >= az) { k = 0; w = ax; s = vx; p = vy; q = vz; }
     else if (ay >= az) { k = 1; w = ay; s = vy; p = vz; q = vx; }
     else { k = 2; w = az; s = vz; p = vx; q = vy; }
@@ -79,5 +83,6 @@ __device__ __forceinline__ int fan_bin(float vx, float vy, float vz)
     const int face = 2 * k + (s < 0.0f ? 1 : 0);
     return face * kFanCellsPerFace + ib * kFanBins + ia;
 }
+__device__ __forceinline__ int fan_bin(float vx, float vy, float vz) { float w; return fan_bin_w(vx, vy, vz, w); }
 
 }  // namespace art

@@ -10,12 +10,17 @@
 // colliders (RT:365-449), so which non-blocking colliders are skipped and in which order the others are tested cannot change
 // a result: outputs are bit-identical with k1_trace.cu and the oracle.
 //
-// Mapping. A warp takes 32 consecutive records; LANE = HIT POINT (its record stays in registers), the goals are walked in
-// lock step, so the goal position and its near-list header are warp-uniform shared-memory broadcasts and the bin header +
-// first AABB ids come with ONE 16-byte load (FanDesc::cells4):
-//   pass 0   every (hit point, goal) query is prepared (exact sqrt, four exact reciprocals) and tested against the first two
-//            AABBs of its lists -- with nearest-first lists that blocks most queries;
-//   AABBs    the others are queued WITH their prepared state (64 B, self-contained) in a per-warp list in global scratch
+// Mapping. A warp takes 32 consecutive records; LANE = HIT POINT (its position stays in registers), the goals are walked in
+// lock step, so the goal position and its near-list header are warp-uniform shared-memory broadcasts:
+//   cull     every (hit point, goal) query first asks the fan for the COVERING DEPTH of its direction bin (k4_fan_build.cu):
+//            beyond that depth some AABB fills the whole bin as seen from the goal, so the segment hit point -> goal runs
+//            through it and the reference's test reports it, by margins a hundred times its FP32 rounding -- the query is
+//            blocked (any-hit: nothing is written for it) at the price of one subtraction, the bin index, one 4-byte load and
+//            two compares. About 70 % of C3's queries end here;
+//   first    the others are queued with 8 B each (record, goal, bin) and, 32 at a time at full width, set up exactly as the
+//            reference does (RT:127/162 normalize: exact sqrt and divide, RT:289: three exact reciprocals) and tested against
+//            the first two AABBs of their lists (ids beside the bin header, FanDesc::cells4; nearest to the goal first);
+//   AABBs    the queries still unblocked wait WITH their state (64 B, self-contained) in a per-warp list in global scratch
 //            (L2 resident). Whenever enough have gathered, every lane takes one into registers and tests one AABB per step;
 //            a lane whose query is blocked takes the next one at once, so the lanes stay full whatever the list lengths.
 //            When the queue runs dry the few queries still in flight are written back (with their cursor) and wait for the
@@ -45,10 +50,11 @@ namespace art {
 #endif
 constexpr int kQWarps = ART_Q_WARPS;
 constexpr int kQThreads = kQWarps * 32;
-constexpr int kQFirstTests = 2;                      // AABBs of pass 0 at most (their ids come with the headers, FanDesc::cells4)
+constexpr int kQFirstTests = 2;                      // AABBs of the "first" step at most (their ids come with the headers, FanDesc::cells4)
+constexpr int kQCap0 = 64;                           // queries waiting for their set-up (uint2 each): < 32 before a goal step, <= 32 more per step
 constexpr int kQRun = ART_Q_RUN;                     // queued queries from which a refill loop runs
 constexpr int kQMinLanes = ART_Q_MIN_LANES;          // a loop whose queue is dry stops (and writes its queries back) below this many busy lanes
-constexpr int kQCapA = kQRun + 64;                   // AABB queue: < kQRun before a goal step, <= 32 more per step, <= 32 written back
+constexpr int kQCapA = kQRun + 64;                   // AABB queue: < kQRun before a goal step, <= 32 more per step (one q_first run), <= 32 written back
 constexpr int kQCapSO = 2 * kQRun + 128;             // sphere / OBB queue: additionally everything one AABB run passes on
 constexpr int kQEntry = 4;                           // float4 per queued query
 constexpr int kQMuffleSmemMax = 4096;                // per-CTA muffle counters [T * Na] kept in shared memory up to this size
@@ -80,8 +86,12 @@ __device__ __forceinline__ uint4 q_near(const QEnv& E, int slot)
     return __ldg(&E.f.cells4[(size_t)q_fan_of(E.a, slot) * kFanCells + 6 * kFanCellsPerFace]);
 }
 // the query sees its goal: RT:133-145 (echo ray, slot 0) / RT:168-172 (muffle ray of target slot - 1)
+constexpr int kQVerifyCulled = 0x40000000;          // -DART_Q_VERIFY builds: the cull would have dropped this query (travels in the result id)
 __device__ __forceinline__ void q_visible(const QEnv& E, int slot, float L, float echoMul, int resultId)
 {
+#ifdef ART_Q_VERIFY
+    if (resultId & kQVerifyCulled) { atomicAdd(&E.a.counters[C_DEBUG_VIOLATIONS], 1ull); resultId &= ~kQVerifyCulled; }
+#endif
     if (slot == 0) E.a.echo[resultId] = um_f32tof16(mulr(L, echoMul));
     else {
         const int row = E.a.map.to_global(resultId / E.a.H) / E.a.batchSize;     // ART:161/191 batch of the ray
@@ -89,6 +99,81 @@ __device__ __forceinline__ void q_visible(const QEnv& E, int slot, float L, floa
         if (E.sMuffle) atomicAdd(&E.sMuffle[idx], 1u);
         else atomicAdd(&E.a.muffleCounts[idx], 1u);
     }
+}
+
+// Exact set-up and first tests of n <= 32 queries the cull did not decide (8 B each: record index, slot | bin << 16 | flags),
+// one lane per query: RT:127 / RT:162 normalize (exact sqrt, exact divide), RT:289 the three reciprocals, RT:130 / RT:165 the
+// limit, RT:168 the gate, then the first two AABBs of the run "near list, then bin" -- and on to the AABB queue, the sphere /
+// OBB queue, or the goal is visible.
+constexpr uint32_t kQFlagNoBin = 1u << 30;           // the direction goal -> hit point has no bin (hit point == goal, non-finite)
+constexpr uint32_t kQFlagCulled = 1u << 29;          // -DART_Q_VERIFY builds only
+template <bool STATS>
+__device__ __forceinline__ void q_first(const QEnv& E, const uint2* src, int n, float4* listA, int& nA, float4* listSO, int& nSO)
+{
+    const QueryArgs& a = E.a;
+    int push = 0;                                                        // 1: AABB queue, 2: sphere / OBB queue
+    float4 e0 = make_float4(0, 0, 0, 0), e1 = e0, e2 = e0, e3 = e0;
+    if (E.lane < n) {
+        const uint2 q = src[E.lane];
+        const int s = (int)(q.y & 0xFFFFu);
+        ART_CHECK(a.counters, s <= a.nTargets && q.x < *a.recCount);
+        // the bin header: issued first, it arrives while the exact square root and reciprocals are computed
+        uint4 c4 = make_uint4(0u, 0u, 0u, 0u);
+        if (!(q.y & kQFlagNoBin)) c4 = __ldg(&E.f.cells4[(size_t)q_fan_of(a, s) * kFanCells + ((q.y >> 16) & 0x1FFFu)]);
+        const float4 ra = __ldg(&a.recA[q.x]);
+        float2 rb = __ldg(&a.recB[q.x]);
+#ifdef ART_Q_VERIFY
+        if (q.y & kQFlagCulled) rb.y = __int_as_float(__float_as_int(rb.y) | kQVerifyCulled);
+#endif
+        const uint4 n4 = q_near(E, s);
+        const f3 P = mk3(ra.x, ra.y, ra.z);
+        const f3 v = sub3(q_goal(E, s), P);                                // RT:127 / RT:162
+        const float len = sqrtr(dot3(v, v));
+        float L = ra.w;                                                    // RT:130
+        bool gate = true;
+        if (s > 0) { L = len; gate = L < a.maxMuffle; }                    // RT:165, 168
+        if (gate) {
+            if ((q.y & kQFlagNoBin) || len != len) {
+                q_visible(E, s, L, rb.x, __float_as_int(rb.y));            // degenerate (hit point == goal): no test can block
+            } else {
+                const f3 nd = smul3(rcpr(len), v);                         // normalize = rsqrt(dot) * v
+                const f3 inv = mk3(rcpr(nd.x), rcpr(nd.y), rcpr(nd.z));
+                const int nA0 = (n4.y >> 10) & 2047, nA1 = (c4.y >> 10) & 2047, nAll = nA0 + nA1;
+                if (STATS) E.st[3] += 2;
+                // the run "near list, then bin" starts with these ids: no dependent load of the entry lists here
+                const uint32_t ids = nA0 >= 2 ? n4.z : (nA0 == 1 ? (n4.z & 0xFFFFu) | (c4.z << 16) : c4.z);
+                const int nFirst = min(nAll, a.firstTests);
+                bool blocked = false;
+#pragma unroll 1
+                for (int t = 0; t < nFirst && !blocked; t++) {
+                    const int id = (int)((ids >> (16 * t)) & 0xFFFFu);
+                    ART_CHECK(a.counters, id < a.L.na);
+                    if (STATS) E.st[1]++;
+                    blocked = aabb_blocks(E.gv, id, P, inv, L);
+                }
+                if (!blocked) {
+                    if (nAll > nFirst) push = 1;
+                    else if (((n4.y | c4.y) & 1023u) | ((n4.y | c4.y) >> 21)) push = 2;
+                    else q_visible(E, s, L, rb.x, __float_as_int(rb.y));
+                    e0 = make_float4(inv.x, inv.y, inv.z, L);
+                    e1 = make_float4(P.x, P.y, P.z, len);
+                    e2 = make_float4(__uint_as_float(c4.x), __uint_as_float(c4.y),
+                                     __uint_as_float((uint32_t)s | (push == 1 ? (uint32_t)nFirst << 16 : 0u)), 0.0f);
+                    e3 = make_float4(rb.x, rb.y, 0.0f, 0.0f);
+                }
+            }
+        }
+    }
+    const uint32_t am = __ballot_sync(kFull, push == 1), sm = __ballot_sync(kFull, push == 2);
+    if (push) {
+        const int pos = push == 1 ? nA + __popc(am & E.ltMask) : nSO + __popc(sm & E.ltMask);
+        ART_CHECK(a.counters, pos < (push == 1 ? kQCapA : kQCapSO));
+        float4* dst = (push == 1 ? listA : listSO) + (size_t)kQEntry * pos;
+        dst[0] = e0; dst[1] = e1; dst[2] = e2; dst[3] = e3;
+    }
+    nA += __popc(am);
+    nSO += __popc(sm);
+    __syncwarp();
 }
 
 // The AABB lists of the queued queries, entries [cursor, nA0 + nA1) of the run "near list, then bin". Every lane holds ONE
@@ -287,10 +372,12 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
     const uint32_t ltMask = (1u << lane) - 1u;
     unsigned int st[4] = { 0, 0, 0, 0 };
     const QEnv E = { a, f, gv, goalTab, nearTab, sMuffle, lane, ltMask, st };
-    float4* listA = a.scratch + ((size_t)blockIdx.x * kQWarps + warp) * (size_t)(kQEntry * (kQCapA + kQCapSO));
+    float4* listA = a.scratch + ((size_t)blockIdx.x * kQWarps + warp) * (size_t)(kQEntry * (kQCapA + kQCapSO) + kQCap0 / 2);
     float4* listSO = listA + kQEntry * kQCapA;
-    int nA = 0, nSO = 0;                             // queued queries (kept across goals and record blocks)
+    uint2* list0 = reinterpret_cast<uint2*>(listSO + kQEntry * kQCapSO);
+    int n0 = 0, nA = 0, nSO = 0;                     // queued queries (kept across goals and record blocks)
     const unsigned int nRec = *a.recCount;           // the bounce tracer has finished (stream order)
+    const float* coverDepth = reinterpret_cast<const float*>(f.cells4) + 3;      // cells4[i].w
 
     // Work unit = (block of 32 records, group of goals). With few records (a small batch against many targets) the launcher
     // splits the goals of a block over several warps so that the whole GPU is busy (QueryArgs::goalGroups); otherwise a unit
@@ -319,74 +406,41 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
             P = mk3(ra.x, ra.y, ra.z);
             ART_CHECK(a.counters, __float_as_int(a.recB[ri].y) >= 0 && __float_as_int(a.recB[ri].y) / a.H < a.map.nLocal);
         }
-        // ---- pass 0: lane = hit point, all lanes walk the goals together
+        // ---- cull: lane = hit point, all lanes walk the goals together
         for (int s = sBeg; s < sEnd; s++) {
-            int push = 0;                                                // 1: AABB queue, 2: sphere / OBB queue
-            float4 e0 = make_float4(0, 0, 0, 0), e2 = e0;
-            float len = 0.0f;
-            const uint4 n4 = q_near(E, s);
+            bool push = false;
+            uint32_t qy = 0;
             if (valid) {
-                const f3 v = sub3(q_goal(E, s), P);                                // RT:127 / RT:162
-                // the bin header depends on the direction's bin only: its load (L2) is issued first and completes
-                // while the exact square root and reciprocals below are computed
-                const int bin = fan_bin(-v.x, -v.y, -v.z);                         // direction goal -> hit point
-                uint4 c4 = make_uint4(0u, 0u, 0u, 0u);
-                if (bin >= 0) c4 = __ldg(&f.cells4[(size_t)q_fan_of(a, s) * kFanCells + bin]);
-                len = sqrtr(dot3(v, v));
-                float L;
-                bool gate = true;
-                if (s > 0) { L = len; gate = L < a.maxMuffle; }                    // RT:165, 168
-                else L = __ldg(&a.recA[ri].w);                                     // RT:130
-                if (gate) {
-                    if (bin < 0 || len != len) {
-                        const float2 rb = __ldg(&a.recB[ri]);
-                        q_visible(E, s, L, rb.x, __float_as_int(rb.y));            // degenerate (hit point == goal): no test can block
-                    } else {
-                        const f3 nd = smul3(rcpr(len), v);                         // normalize = rsqrt(dot) * v
-                        const f3 inv = mk3(rcpr(nd.x), rcpr(nd.y), rcpr(nd.z));
-                        const int nA0 = (n4.y >> 10) & 2047, nA1 = (c4.y >> 10) & 2047, nAll = nA0 + nA1;
-                        if (STATS) st[3] += 2;
-                        // the run "near list, then bin" starts with these ids: no dependent load of the entry lists here
-                        const uint32_t ids = nA0 >= 2 ? n4.z : (nA0 == 1 ? (n4.z & 0xFFFFu) | (c4.z << 16) : c4.z);
-                        const int nFirst = min(nAll, a.firstTests);
-                        bool blocked = false;
-#pragma unroll 1
-                        for (int t = 0; t < nFirst && !blocked; t++) {
-                            const int id = (int)((ids >> (16 * t)) & 0xFFFFu);
-                            ART_CHECK(a.counters, id < a.L.na);
-                            if (STATS) st[1]++;
-                            blocked = aabb_blocks(gv, id, P, inv, L);
-                        }
-                        if (!blocked) {
-                            if (nAll > nFirst) push = 1;
-                            else if (((n4.y | c4.y) & 1023u) | ((n4.y | c4.y) >> 21)) push = 2;
-                            else { const float2 rb = __ldg(&a.recB[ri]); q_visible(E, s, L, rb.x, __float_as_int(rb.y)); }
-                            e0 = make_float4(inv.x, inv.y, inv.z, L);
-                            e2 = make_float4(__uint_as_float(c4.x), __uint_as_float(c4.y),
-                                             __uint_as_float((uint32_t)s | (push == 1 ? (uint32_t)nFirst << 16 : 0u)), 0.0f);
-                        }
-                    }
+                const f3 g = q_goal(E, s);
+                float w;
+                const int bin = fan_bin_w(P.x - g.x, P.y - g.y, P.z - g.z, w);     // direction goal -> hit point, its depth on the face
+                push = true;
+                qy = (uint32_t)s | kQFlagNoBin;
+                if (bin >= 0) {
+                    // beyond the covering depth of its bin an AABB certainly blocks the query (k4_fan_build.cu; w <= errScale
+                    // is the range the margins were derived for)
+                    const float cover = __ldg(coverDepth + 4 * ((size_t)q_fan_of(a, s) * kFanCells + bin));
+                    const bool culled = w > cover && w <= a.errScale;
+                    qy = (uint32_t)s | ((uint32_t)bin << 16);
+#ifdef ART_Q_VERIFY
+                    if (culled) qy |= kQFlagCulled;
+#else
+                    push = !culled;
+#endif
                 }
             }
-            const uint32_t am = __ballot_sync(kFull, push == 1), sm = __ballot_sync(kFull, push == 2);
-            if (push) {
-                const int pos = push == 1 ? nA + __popc(am & ltMask) : nSO + __popc(sm & ltMask);
-                ART_CHECK(a.counters, pos < (push == 1 ? kQCapA : kQCapSO));
-                float4* dst = (push == 1 ? listA : listSO) + (size_t)kQEntry * pos;
-                dst[0] = e0;
-                dst[1] = make_float4(P.x, P.y, P.z, len);
-                dst[2] = e2;
-                const float2 rb = __ldg(&a.recB[ri]);
-                dst[3] = make_float4(rb.x, rb.y, 0.0f, 0.0f);
-            }
-            nA += __popc(am);
-            nSO += __popc(sm);
-            // ---- the queued queries' remaining AABBs / sphere and OBB lists, whenever enough have gathered to fill the lanes
+            const uint32_t pm = __ballot_sync(kFull, push);
+            if (push) list0[n0 + __popc(pm & ltMask)] = make_uint2(ri, qy);
+            n0 += __popc(pm);
+            // ---- exact set-up + first tests of the survivors, their remaining AABBs, their sphere and OBB lists -- each
+            //      whenever enough queries have gathered to fill the lanes
+            if (n0 >= 32) { __syncwarp(); n0 -= 32; q_first<STATS>(E, list0 + n0, 32, listA, nA, listSO, nSO); }
             if (nA >= kQRun) { __syncwarp(); nA = q_loop_aabb<STATS>(E, listA, nA, false, listSO, nSO); }
             if (nSO >= kQRun) { __syncwarp(); nSO = q_loop_so<STATS>(E, listSO, nSO, false); }
         }
     }
     __syncwarp();
+    if (n0 > 0) q_first<STATS>(E, list0, n0, listA, nA, listSO, nSO);
     if (nA > 0) q_loop_aabb<STATS>(E, listA, nA, true, listSO, nSO);
     if (nSO > 0) q_loop_so<STATS>(E, listSO, nSO, true);
 
@@ -407,7 +461,7 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
 
 // ---- launcher -----------------------------------------------------------------------------------
 size_t query_fan_smem_bytes(const GeomLayout& L, bool geomInSmem) { return geomInSmem ? L.bytes : 0; }
-size_t query_fan_scratch_bytes(int numCtas) { return (size_t)numCtas * kQWarps * kQEntry * (kQCapA + kQCapSO) * sizeof(float4); }
+size_t query_fan_scratch_bytes(int numCtas) { return (size_t)numCtas * kQWarps * (kQEntry * (kQCapA + kQCapSO) + kQCap0 / 2) * sizeof(float4); }
 
 cudaError_t launch_query_fan(const QueryArgs& a0, const FanDesc& fans, int numCtas, bool geomInSmem, bool stats, int maxSmemOptin, cudaStream_t stream)
 {

@@ -58,6 +58,51 @@ __device__ __forceinline__ uint32_t fan_rect(const float lo[3], const float hi[3
     return a0 | (a1 << 8) | (b0 << 16) | (b1 << 24);
 }
 
+// ---- covering depth of a bin --------------------------------------------------------------------
+// An AABB COVERS bin (face, ia, ib) of goal G over the depth interval [w1, w2] (depth = coordinate along the face's major
+// axis, measured from G) when every point G + z * (+-1, a, b), z in [w1, w2], (a, b) in the bin's tangent rectangle widened by
+// kFanCoverTan, lies inside the box shrunk by the rounding of its subtraction from G. The segment from a hit point P in that
+// bin at depth wP > w1 to G then runs INSIDE the box between the depths w1 and min(w2, wP), so the reference's slab test
+// (RT:284-308) reports the box with a distance below the limit (RT:384 / RT:430) -- by margins that exceed its FP32 rounding
+// a hundredfold (query_fan_kernel, "cull"):
+//   * its t values are s * Lr * (1 + th), s the true segment parameter of a plane crossing, Lr = 1 / fl(1 / len) common to all of
+//     them, |th| < 6e-7; the true entry and exit parameters differ by >= min(2^-10, (w2 - w1) / wP) >= 1e-4 (w2 - w1 >= 1e-4 * D
+//     is required below, wP <= D is checked by the query), the exit parameter is >= 2^-10 (cover threshold w1 * (1 + 2^-9)), so
+//     "tNear > tFar" and "tFar < 0" are both false;
+//   * the reported distance is <= tFar <= len - zl + 6e-7 * len, zl >= 1e-3 * D >= 0.033 the depth of the box's near face (G is
+//     outside the box); the limit is len (muffle rays) or distance(RayOrigin, hit point) >= len - 1.01e-4 (echo rays: P is the
+//     hit point moved back by kEpsilon = 1e-4): dist < limit;
+//   * no 0 * Inf: a zero direction component k means P_k == G_k, and then lo_k - P_k < 0 < hi_k - P_k by the tangent margin.
+// The bin stores the smallest threshold depth over its covering AABBs (cells4.w); +Inf when there is none.
+constexpr float kFanCoverTan = 1e-3f;
+
+// cover parameters of AABB [lo, hi] (the reference's own min / max, GeomView::aabbA/B) on face (k, neg) of goal T:
+// depth range [c[0], c[1]], tangent ranges [c[2], c[3]] (axis i) and [c[4], c[5]] (axis j), all shrunk; c[0] > c[1] if unusable
+// (degenerate, or nearer to the goal than minDepth)
+__device__ __forceinline__ void fan_cover_params(const float lo[3], const float hi[3], const float T[3], int k, bool neg, float minDepth, float c[6])
+{
+    float rl[3], rh[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        const float e = 4e-6f * (fabsf(T[q]) + fabsf(lo[q]) + fabsf(hi[q])) + 1e-6f;
+        rl[q] = lo[q] - T[q] + e;
+        rh[q] = hi[q] - T[q] - e;
+    }
+    const int i = k == 2 ? 0 : k + 1, j = k == 0 ? 2 : k - 1;
+    c[0] = neg ? -rh[k] : rl[k];
+    c[1] = neg ? -rl[k] : rh[k];
+    c[2] = rl[i]; c[3] = rh[i]; c[4] = rl[j]; c[5] = rh[j];
+    // the near face must lie at least minDepth in front of the goal (the goal is outside the box, with room for kEpsilon)
+    if (!(c[0] >= minDepth) || !(c[0] <= c[1]) || !(c[2] <= c[3]) || !(c[4] <= c[5])) { c[0] = 1.0f; c[1] = 0.0f; }
+}
+// the depth interval over which `coef * z <= bound` holds, intersected into [w1, w2]
+__device__ __forceinline__ void fan_cover_clip(float coef, float bound, float& w1, float& w2)
+{
+    if (coef > 0.0f) w2 = fminf(w2, __fdividef(bound, coef));
+    else if (coef < 0.0f) w1 = fmaxf(w1, __fdividef(bound, coef));
+    else if (bound < 0.0f) w2 = -1.0f;
+}
+
 // Per goal: the colliders sorted by (type, distance of their box from the goal, index). The build sweeps them in this
 // order, so every list comes out grouped by type and nearest-first: a collider close to the goal subtends more of the
 // bin and lies between the goal and more hit points, hence an any-hit query (K1) finds its blocker in the first entries.
@@ -112,6 +157,7 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_build_kerne
     static_assert(kFanCellsPerFace == 1024 && kFanBins == 32 && kFanBins % kFanRows == 0, "one thread per bin, one warp per bin row");
     __shared__ uint32_t sRect[kFanThreads];
     __shared__ uint32_t sIdT[kFanThreads];   // local collider index | type << 16
+    __shared__ float sCov[6][kFanThreads];   // pass 1: fan_cover_params of the compacted AABB rectangles
     __shared__ uint32_t sNear[kFanMaxNear];
     __shared__ int sWarpCnt[32], sWarpNear[32], sWarpTot[32];
     __shared__ int sNearCount;
@@ -136,14 +182,17 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_build_kerne
     unsigned int wpos = 0;                   // pass 1: next entry of this bin
     unsigned int aPos = 0;                   // pass 1: where this bin's AABB entries start
     uint32_t firstIds = 0;                   // pass 1: first two AABB entries of this bin, id0 | id1 << 16
-    uint32_t nextIds = 0;                    // pass 1: AABB entries 2 and 3, id2 | id3 << 16
     uint2 myCell = make_uint2(0u, 0u);       // this bin's header (written in pass 0, repeated in cells4 after pass 1)
+    float cover = __int_as_float(0x7F800000);   // pass 1: smallest threshold depth of an AABB that covers this bin
+    const float binA0 = -1.0f + (float)ia * (2.0f / kFanBins) - kFanCoverTan, binA1 = -1.0f + (float)(ia + 1u) * (2.0f / kFanBins) + kFanCoverTan;
+    const float binB0 = -1.0f + (float)ib * (2.0f / kFanBins) - kFanCoverTan, binB1 = -1.0f + (float)(ib + 1u) * (2.0f / kFanBins) + kFanCoverTan;
     unsigned int blockTotal = 0;
     int nearTotal = 0;
     for (int pass = 0; pass < 2; pass++) {
         for (int base = 0; base < nc; base += kFanThreads) {
             uint32_t rect = kRectEmpty, idT = 0;
             bool near = false;
+            float cov[6] = { 1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f };
             if (base + tid < nc) {
                 const int g = a.order ? (int)a.order[(size_t)fan * nc + base + tid] : base + tid;
                 int type, id; short owner;
@@ -155,6 +204,12 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_build_kerne
                     const float lo[3] = { l4.x, l4.y, l4.z }, hi[3] = { h4.x, h4.y, h4.z };
                     rect = fan_rect(lo, hi, T, k, neg, a.nearDist, near);
                     idT = (uint32_t)id | ((uint32_t)type << 16);
+                    if (pass == 1 && type == 1 && rect != kRectEmpty && a.aabbA) {
+                        const float4 A = a.aabbA[id];
+                        const float2 B = a.aabbB[id];
+                        const float elo[3] = { A.x, A.y, A.z }, ehi[3] = { A.w, B.x, B.y };
+                        fan_cover_params(elo, ehi, T, k, neg, a.nearDist, cov);
+                    }
                 }
             }
             const uint32_t bal = __ballot_sync(kFull, rect != kRectEmpty);
@@ -173,6 +228,10 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_build_kerne
             if (rect != kRectEmpty) {
                 const int pos = prefix + __popc(bal & ltMask);
                 sRect[pos] = rect; sIdT[pos] = idT;
+                if (pass == 1) {
+#pragma unroll
+                    for (int q = 0; q < 6; q++) sCov[q][pos] = cov[q];
+                }
             }
             if (near && nearCta && pass == 0) {
                 const int pos = sNearCount + nprefix + __popc(nbal & ltMask);
@@ -194,9 +253,18 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_build_kerne
                         else {
                             if (wpos == aPos) firstIds = (e & 0xFFFFu) | (e << 16);          // (a single AABB is listed twice)
                             else if (wpos == aPos + 1u) firstIds = (firstIds & 0xFFFFu) | (e << 16);
-                            else if (wpos == aPos + 2u) nextIds = (e & 0xFFFFu) | (e << 16);
-                            else if (wpos == aPos + 3u) nextIds = (nextIds & 0xFFFFu) | (e << 16);
                             a.entries[wpos++] = (uint16_t)(e & 0xFFFFu);
+                            if ((e >> 16) == 1u) {
+                                float w1 = sCov[0][c0 + j], w2 = sCov[1][c0 + j];
+                                if (w1 <= w2) {
+                                    fan_cover_clip(binA1, sCov[3][c0 + j], w1, w2);      //  a * z <= xh for every a <= binA1
+                                    fan_cover_clip(-binA0, -sCov[2][c0 + j], w1, w2);    //  a * z >= xl for every a >= binA0
+                                    fan_cover_clip(binB1, sCov[5][c0 + j], w1, w2);
+                                    fan_cover_clip(-binB0, -sCov[4][c0 + j], w1, w2);
+                                    // (the clipped bounds carry the 2-ulp error of the fast division: far inside the margins)
+                                    if (w2 >= w1 * 1.00390625f && w2 - w1 >= a.coverMinThickness) cover = fminf(cover, w1 * 1.001953125f);
+                                }
+                            }
                         }
                     }
                 }
@@ -206,7 +274,7 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_build_kerne
         }
         if (pass == 1) {
             if (cA > 0) a.firstA[(size_t)fan * kFanCells + cellOfThread] = firstIds;
-            a.cells4[(size_t)fan * kFanCells + cellOfThread] = make_uint4(myCell.x, myCell.y, firstIds, nextIds);
+            a.cells4[(size_t)fan * kFanCells + cellOfThread] = make_uint4(myCell.x, myCell.y, firstIds, __float_as_uint(cover));
             break;
         }
         // ---- reserve the CTA's span: block scan of the per-bin totals
@@ -239,10 +307,10 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_build_kerne
         uint2* cells = a.cells + (size_t)fan * kFanCells;
         if (bs == 0xFFFFFFFFu) {
             cells[cellOfThread] = make_uint2(0u, 0u);
-            a.cells4[(size_t)fan * kFanCells + cellOfThread] = make_uint4(0u, 0u, 0u, 0u);
+            a.cells4[(size_t)fan * kFanCells + cellOfThread] = make_uint4(0u, 0u, 0u, 0x7F800000u);
             if (nearCta && tid == 0) {
                 cells[6 * kFanCellsPerFace] = make_uint2(0u, 0u);
-                a.cells4[(size_t)fan * kFanCells + 6 * kFanCellsPerFace] = make_uint4(0u, 0u, 0u, 0u);
+                a.cells4[(size_t)fan * kFanCells + 6 * kFanCellsPerFace] = make_uint4(0u, 0u, 0u, 0x7F800000u);
             }
             return;
         }
