@@ -51,11 +51,15 @@ namespace art {
 constexpr int kQWarps = ART_Q_WARPS;
 constexpr int kQThreads = kQWarps * 32;
 constexpr int kQFirstTests = 2;                      // AABBs of the "first" step at most (their ids come with the headers, FanDesc::cells4)
-constexpr int kQCap0 = 64;                           // queries waiting for their set-up (uint2 each): < 32 before a goal step, <= 32 more per step
+#ifndef ART_Q_GOALS
+#define ART_Q_GOALS 4
+#endif
+constexpr int kQGoals = ART_Q_GOALS;                 // goals per cull step
+constexpr int kQCap0 = 32 + 32 * kQGoals;            // queries waiting for their set-up (uint2 each): < 32 before a step, <= 32 more per goal
 constexpr int kQRun = ART_Q_RUN;                     // queued queries from which a refill loop runs
 constexpr int kQMinLanes = ART_Q_MIN_LANES;          // a loop whose queue is dry stops (and writes its queries back) below this many busy lanes
-constexpr int kQCapA = kQRun + 64;                   // AABB queue: < kQRun before a goal step, <= 32 more per step (one q_first run), <= 32 written back
-constexpr int kQCapSO = 2 * kQRun + 128;             // sphere / OBB queue: additionally everything one AABB run passes on
+constexpr int kQCapA = kQRun + 32 + 32 * kQGoals;    // AABB queue: < kQRun before a step, <= 32 more per goal of the step (q_first runs), <= 32 written back
+constexpr int kQCapSO = 2 * kQRun + 64 + 64 * kQGoals;             // sphere / OBB queue: additionally everything one AABB run passes on
 constexpr int kQEntry = 4;                           // float4 per queued query
 constexpr int kQMuffleSmemMax = 4096;                // per-CTA muffle counters [T * Na] kept in shared memory up to this size
 
@@ -406,35 +410,44 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
             P = mk3(ra.x, ra.y, ra.z);
             ART_CHECK(a.counters, __float_as_int(a.recB[ri].y) >= 0 && __float_as_int(a.recB[ri].y) / a.H < a.map.nLocal);
         }
-        // ---- cull: lane = hit point, all lanes walk the goals together
-        for (int s = sBeg; s < sEnd; s++) {
-            bool push = false;
-            uint32_t qy = 0;
-            if (valid) {
-                const f3 g = q_goal(E, s);
-                float w;
-                const int bin = fan_bin_w(P.x - g.x, P.y - g.y, P.z - g.z, w);     // direction goal -> hit point, its depth on the face
-                push = true;
-                qy = (uint32_t)s | kQFlagNoBin;
-                if (bin >= 0) {
-                    // beyond the covering depth of its bin an AABB certainly blocks the query (k4_fan_build.cu; w <= errScale
-                    // is the range the margins were derived for)
-                    const float cover = __ldg(coverDepth + 4 * ((size_t)q_fan_of(a, s) * kFanCells + bin));
-                    const bool culled = w > cover && w <= a.errScale;
-                    qy = (uint32_t)s | ((uint32_t)bin << 16);
+        // ---- cull: lane = hit point, all lanes walk the goals together -- kQGoals goals per step, so that as many
+        //      covering-depth loads (L2) are in flight per warp
+        for (int s = sBeg; s < sEnd; s += kQGoals) {
+            bool push[kQGoals];
+            uint32_t qy[kQGoals];
+#pragma unroll
+            for (int u = 0; u < kQGoals; u++) {
+                push[u] = false; qy[u] = 0u;
+                if (valid && s + u < sEnd) {
+                    const f3 g = q_goal(E, s + u);
+                    float w;
+                    const int bin = fan_bin_w(P.x - g.x, P.y - g.y, P.z - g.z, w);   // direction goal -> hit point, its depth on the face
+                    push[u] = true;
+                    qy[u] = (uint32_t)(s + u) | kQFlagNoBin;
+                    if (bin >= 0) {
+                        // beyond the covering depth of its bin an AABB certainly blocks the query (k4_fan_build.cu; w <= errScale
+                        // is the range the margins were derived for)
+                        const float cover = __ldg(coverDepth + 4 * ((size_t)q_fan_of(a, s + u) * kFanCells + bin));
+                        const bool culled = w > cover && w <= a.errScale;
+                        qy[u] = (uint32_t)(s + u) | ((uint32_t)bin << 16);
 #ifdef ART_Q_VERIFY
-                    if (culled) qy |= kQFlagCulled;
+                        if (culled) qy[u] |= kQFlagCulled;
 #else
-                    push = !culled;
+                        push[u] = !culled;
 #endif
+                    }
                 }
             }
-            const uint32_t pm = __ballot_sync(kFull, push);
-            if (push) list0[n0 + __popc(pm & ltMask)] = make_uint2(ri, qy);
-            n0 += __popc(pm);
+#pragma unroll
+            for (int u = 0; u < kQGoals; u++) {
+                const uint32_t pm = __ballot_sync(kFull, push[u]);
+                if (push[u]) list0[n0 + __popc(pm & ltMask)] = make_uint2(ri, qy[u]);
+                n0 += __popc(pm);
+            }
             // ---- exact set-up + first tests of the survivors, their remaining AABBs, their sphere and OBB lists -- each
             //      whenever enough queries have gathered to fill the lanes
-            if (n0 >= 32) { __syncwarp(); n0 -= 32; q_first<STATS>(E, list0 + n0, 32, listA, nA, listSO, nSO); }
+#pragma unroll 1
+            while (n0 >= 32) { __syncwarp(); n0 -= 32; q_first<STATS>(E, list0 + n0, 32, listA, nA, listSO, nSO); }
             if (nA >= kQRun) { __syncwarp(); nA = q_loop_aabb<STATS>(E, listA, nA, false, listSO, nSO); }
             if (nSO >= kQRun) { __syncwarp(); nSO = q_loop_so<STATS>(E, listSO, nSO, false); }
         }
