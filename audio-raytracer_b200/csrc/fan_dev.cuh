@@ -70,18 +70,18 @@ struct FanBuildArgs {
 // `w` receives the depth of v on its face (the largest |component|).
 __device__ __forceinline__ int fan_bin_w(float vx, float vy, float vz, float& w)
 {
+    // branch-free: selects instead of an if-chain, the validity check folded into the result
     const float ax = fabsf(vx), ay = fabsf(vy), az = fabsf(vz);
-    int k; float p, q, s;
-    if (ax >= ay && ax >= az) { k = 0; w = ax; s = vx; p = vy; q = vz; }
-    else if (ay >= az) { k = 1; w = ay; s = vy; p = vz; q = vx; }
-    else { k = 2; w = az; s = vz; p = vx; q = vy; }
-    if (!(w > 0.0f) || !(w < 3.0e38f)) return -1;
+    const bool fx = ax >= ay && ax >= az, fy = !fx && ay >= az;
+    w = fx ? ax : (fy ? ay : az);
+    const float s = fx ? vx : (fy ? vy : vz), p = fx ? vy : (fy ? vz : vx), q = fx ? vz : (fy ? vx : vy);
     const float r = __fdividef(1.0f, w);
-    const float a = p * r, b = q * r;                       // tangent-plane coordinates in [-1, 1]
-    const int ia = min(kFanBins - 1, max(0, (int)floorf((a + 1.0f) * (0.5f * kFanBins))));
-    const int ib = min(kFanBins - 1, max(0, (int)floorf((b + 1.0f) * (0.5f * kFanBins))));
-    const int face = 2 * k + (s < 0.0f ? 1 : 0);
-    return face * kFanCellsPerFace + ib * kFanBins + ia;
+    // tangent-plane coordinates a = p * r, b = q * r in [-1, 1]; (a + 1) * (kFanBins / 2) as one FMA (the same float: the
+    // scaling by a power of two is exact)
+    const int ia = min(kFanBins - 1, max(0, __float2int_rd(fmaf(p * r, 0.5f * kFanBins, 0.5f * kFanBins))));
+    const int ib = min(kFanBins - 1, max(0, __float2int_rd(fmaf(q * r, 0.5f * kFanBins, 0.5f * kFanBins))));
+    const int face = (fx ? 0 : (fy ? 2 : 4)) + (s < 0.0f ? 1 : 0);
+    return (w > 0.0f && w < 3.0e38f) ? face * kFanCellsPerFace + ib * kFanBins + ia : -1;
 }
 __device__ __forceinline__ int fan_bin(float vx, float vy, float vz) { float w; return fan_bin_w(vx, vy, vz, w); }
 

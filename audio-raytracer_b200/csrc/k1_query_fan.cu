@@ -285,7 +285,7 @@ __device__ __forceinline__ int q_loop_so(const QEnv& E, float4* listSO, int nIn,
                 const int slot = (int)(packed & 0xFFFFu);
                 ART_CHECK(a.counters, slot <= a.nTargets);
                 const f3 v = sub3(q_goal(E, slot), mk3(e1.x, e1.y, e1.z));   // RT:127 / RT:162
-                d = smul3(rcpr(e1.w), v);                                    // normalize = rsqrt(dot) * v, |v| from pass 0
+                d = smul3(rcpr(e1.w), v);                                    // normalize = rsqrt(dot) * v, |v| from the set-up (q_first)
                 dd = dot3(d, d);
                 const uint4 n4 = q_near(E, slot);
                 const uint32_t hBx = __float_as_uint(e2.x), hBy = __float_as_uint(e2.y);
@@ -493,7 +493,7 @@ cudaError_t launch_query_fan(const QueryArgs& a0, const FanDesc& fans, int numCt
         a.goalsPerGroup = (int)((slots + g - 1) / g);
         a.goalGroups = (slots + a.goalsPerGroup - 1) / a.goalsPerGroup;
     }
-    // experiment knob (read per launch): AABBs tested in pass 0 (1 or 2)
+    // experiment knob (read per launch): AABBs of the first tests, q_first (1 or 2)
     a.firstTests = kQFirstTests;
     if (const char* v = getenv("ART_Q_FIRST_TESTS")) { const int n = atoi(v); if (n >= 1 && n <= kQFirstTests) a.firstTests = n; }
     if (tabs && smem + tables <= (size_t)maxSmemOptin) { a.tablesInSmem = 1; smem += tables; }

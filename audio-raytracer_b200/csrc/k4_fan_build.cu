@@ -254,7 +254,12 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_build_kerne
                             if (wpos == aPos) firstIds = (e & 0xFFFFu) | (e << 16);          // (a single AABB is listed twice)
                             else if (wpos == aPos + 1u) firstIds = (firstIds & 0xFFFFu) | (e << 16);
                             a.entries[wpos++] = (uint16_t)(e & 0xFFFFu);
-                            if ((e >> 16) == 1u) {
+                            // (a bin on the border of the rectangle holds the edge of the projection at the depth where it is
+                            // widest, so it is covered at no depth -- unless the rectangle was clipped at the edge of the face:
+                            // only the other bins do the interval arithmetic)
+                            const uint32_t ra0 = rj & 255u, ra1 = (rj >> 8) & 255u, rb0 = (rj >> 16) & 255u, rb1 = rj >> 24;
+                            if ((e >> 16) == 1u && (ia > ra0 || ra0 == 0u) && (ia < ra1 || ra1 == (uint32_t)kFanBins - 1u) &&
+                                (ib > rb0 || rb0 == 0u) && (ib < rb1 || rb1 == (uint32_t)kFanBins - 1u)) {
                                 float w1 = sCov[0][c0 + j], w2 = sCov[1][c0 + j];
                                 if (w1 <= w2) {
                                     fan_cover_clip(binA1, sCov[3][c0 + j], w1, w2);      //  a * z <= xh for every a <= binA1

@@ -182,7 +182,7 @@ struct QueryArgs {
     float4* scratch;               // per-warp survivor lists (query_fan_scratch_bytes)
     int tablesInSmem;              // goal positions + near-list headers of all slots staged in shared memory
     int muffleInSmem;              // per-CTA muffle counters [T*Na] in shared memory
-    int firstTests;                // AABBs every query tests in pass 0 (1 or 2)
+    int firstTests;                // AABBs every query the cull leaves is tested against at once, q_first (1 or 2)
     int goalGroups, goalsPerGroup; // > 1 group: the goals of a record block are split over several warps (small batches)
 };
 
