@@ -225,7 +225,7 @@ struct ArtCtx {
     bool sceneLayoutChanged = true;                // counts changed: everything is uploaded
     DevBuf hitRecs, queryScratch;                  // bounce-only trace job: hit records + survivor lists of query_fan_kernel
     DevBuf permHitPts, permBinCnt, permPairs;       // binned loss lines (k2_permeation_binned.cu)
-    DevBuf fanBoxes, fanCells, fanEntries, fanCtl, fanOrder;  // target fans (fan_dev.cuh): collider bounds (per scene), lists (per frame)
+    DevBuf fanBoxes, fanCells, fanEntries, fanCtl, fanOrder, fanScratch;  // target fans (fan_dev.cuh): collider bounds (per scene), lists (per frame)
     PinBuf pinFanCtl;
     bool fansDisabled = false;                     // ART_DISABLE_FANS=1
     size_t fanEntriesPerPair = 64;                 // entry capacity = fans * colliders * this (grows after an overflow); ART_FAN_ENTRIES_PER_PAIR
@@ -481,7 +481,7 @@ static void release_ctx(ArtCtx* ctx)
     if (ctx->copyStream) cudaStreamSynchronize(ctx->copyStream);
     if (ctx->comm && nccl_api().ok()) nccl_api().CommDestroy(ctx->comm);
     ctx->comm = nullptr;
-    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->rotateLog, &ctx->gridCnt, &ctx->gridCtl, &ctx->hitRecs, &ctx->queryScratch, &ctx->permHitPts, &ctx->permBinCnt, &ctx->permPairs, &ctx->fanBoxes, &ctx->fanCells, &ctx->fanEntries, &ctx->fanCtl, &ctx->fanOrder, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
+    for (DevBuf* b : { &ctx->rawScene, &ctx->geom, &ctx->attrs, &ctx->owners, &ctx->perm, &ctx->gridCells, &ctx->gridEntries, &ctx->gridRangeO, &ctx->gridScratch, &ctx->rotateLog, &ctx->gridCnt, &ctx->gridCtl, &ctx->hitRecs, &ctx->queryScratch, &ctx->permHitPts, &ctx->permBinCnt, &ctx->permPairs, &ctx->fanBoxes, &ctx->fanCells, &ctx->fanEntries, &ctx->fanCtl, &ctx->fanOrder, &ctx->fanScratch, &ctx->dirs, &ctx->targets, &ctx->ownedCount,
                        &ctx->outAll, &ctx->firstHit, &ctx->partials, &ctx->queue, &ctx->gathered })
         b->release();
     for (PinBuf* b : { &ctx->pinScene, &ctx->pinRays, &ctx->pinTargets, &ctx->pinOwnedCount, &ctx->pinPartials, &ctx->pinAll, &ctx->pinPerm, &ctx->pinFanCtl, &ctx->pinGathered, &ctx->pinGrid, &ctx->pinGridCtl })
@@ -1199,9 +1199,11 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
                 fa.order = ctx->fanOrder.as<uint32_t>();
                 ctx->kernelLaunches++;
             }
+            CK(ctx->fanScratch.ensure(fan_build_scratch_bytes((int)nFans, (int)nc)));
+            fan_build_set_scratch(fa, ctx->fanScratch.p);
             CK(launch_fan_build(fa, fanStream));
             if (fanBeside) CK(cudaEventRecord(ctx->evFan, ctx->stream2));
-            ctx->kernelLaunches++;
+            ctx->kernelLaunches += 2;                // fan_project_kernel, fan_match_kernel
             fd.nFans = (int)nFans; fd.cells = fa.cells; fd.entries = fa.entries; fd.nEntries = (int)cap; fd.firstA = fa.firstA; fd.cells4 = fa.cells4;
             ctx->frameGridUsed |= 4u;
         }

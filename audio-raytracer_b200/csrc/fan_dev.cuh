@@ -63,6 +63,12 @@ struct FanBuildArgs {
     unsigned int capacity;     // entries available
     unsigned int* ctl;         // [0] next free entry, [1] overflow flag (zeroed by the host before the launch)
     uint32_t* order;           // [(nTargets + 1) * (ns + na + no)] per-goal sweep order (fan_order_kernel), or null
+    // scratch between the projection and the matching step (fan_build_set_scratch)
+    uint2* rects;              // [(nTargets + 1) * 6][ns + na + no]: per (goal, face) the non-empty rectangles in sweep order,
+                               // x = a0 | a1 << 8 | b0 << 16 | b1 << 24 (bins), y = local collider index | type << 16
+    uint32_t* rectCount;       // [(nTargets + 1) * 6][3]: rectangles of the face | of its spheres | of its spheres and AABBs
+    uint32_t* nearList;        // [(nTargets + 1)][kFanMaxNear]: index | type << 16 of the colliders near the goal, in sweep order
+    uint32_t* nearCount;       // [(nTargets + 1)] (may exceed kFanMaxNear: overflow)
 };
 
 // Cell index (within one fan) of the bin that direction v (from the goal, any length) falls in.

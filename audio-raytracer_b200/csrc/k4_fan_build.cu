@@ -1,13 +1,12 @@
 // k4_fan_build.cu -- per-frame construction of the target fans (fan_dev.cuh) on the device.
 //
-// One CTA per (goal, cube face), one thread per direction bin (32 x 32). The CTA sweeps the colliders in
-// canonical order (spheres | AABBs | OBBs) in chunks of 1,024: every thread projects one collider's
-// conservative box onto the face (a bin rectangle, or nothing), the non-empty rectangles are compacted IN
-// ORDER into shared memory, and every thread then scans the compacted chunk for the rectangles that contain
-// its bin. Pass 0 counts, a block scan + one atomicAdd reserves the CTA's span of the entry array, pass 1
-// repeats the sweep and writes the indices -- so every list is grouped by type and ordered like the sweep
-// (fan_order_kernel: nearest to the goal first), and its content does not depend on scheduling (only its
-// position in the entry array does).
+// Two steps (after the per-goal ordering, fan_order_kernel). fan_project_kernel, one CTA per (goal, cube face): the colliders
+// are swept in the goal's order (spheres | AABBs | OBBs, each nearest first), every thread projects one collider's
+// conservative box onto the face (a bin rectangle, or nothing) and the non-empty rectangles are compacted IN ORDER into the
+// face's rectangle list. fan_match_kernel, one CTA per (goal, face, strip of bin rows), one thread per direction bin: every
+// warp walks the face's list for the rectangles that contain its bins. Pass 0 counts, a block scan + one atomicAdd reserves
+// the CTA's span of the entry array, pass 1 walks the list again and writes the indices -- so every list is grouped by type
+// and ordered like the sweep, and its content does not depend on scheduling (only its position in the entry array does).
 #include <cstdlib>
 
 #include "device_util.cuh"
@@ -145,28 +144,18 @@ __global__ void __launch_bounds__(1024, 1) fan_order_kernel(const FanBuildArgs a
     for (int g = tid; g < nc; g += 1024) a.order[(size_t)fan * nc + g] = (uint32_t)(sKeys[g] & 0xFFFFFFFFull);
 }
 
-// ROWS bin rows (= warps) per CTA: a face can be cut into 32 / ROWS strips, one CTA each (ART_FAN_ROWS). Measured on B200 and
-// NOT used by default: a CTA's time goes into matching every bin row against the rectangles of the sweep, which every strip
-// repeats for its rows plus the whole sweep itself -- C3 (65 fans x 4,096 colliders, 390 CTAs): whole faces 396 us, strips of
-// 16 rows 465 us, of 8 rows 505 us; C5 (9 fans x 16,384 colliders, only 54 CTAs for 148 SMs): 1.34 / 1.45 / 1.55 / 1.75 ms for
-// 32 / 16 / 8 / 4 rows.
-template <int ROWS>
-__global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_build_kernel(const FanBuildArgs a)
+// ---- step 1: projection --------------------------------------------------------------------------
+// One CTA per (goal, face): the colliders are swept in the goal's order, 1,024 at a time; every thread projects one
+// collider's conservative box onto the face and the non-empty rectangles are compacted IN ORDER into the face's rectangle
+// list in global scratch (8 B each: rectangle, local collider index | type << 16). The CTA of face 0 also collects the
+// goal's near list.
+__global__ void __launch_bounds__(1024, 2) fan_project_kernel(const FanBuildArgs a)
 {
-    constexpr int kFanRows = ROWS, kFanThreads = ROWS * 32, kFanParts = kFanBins / ROWS;
-    static_assert(kFanCellsPerFace == 1024 && kFanBins == 32 && kFanBins % kFanRows == 0, "one thread per bin, one warp per bin row");
-    __shared__ uint32_t sRect[kFanThreads];
-    __shared__ uint32_t sIdT[kFanThreads];   // local collider index | type << 16
-    __shared__ float sCov[6][kFanThreads];   // pass 1: fan_cover_params of the compacted AABB rectangles
-    __shared__ uint32_t sNear[kFanMaxNear];
-    __shared__ int sWarpCnt[32], sWarpNear[32], sWarpTot[32];
-    __shared__ int sNearCount;
-    __shared__ unsigned int sBase;
-
-    const int face = blockIdx.x / kFanParts, part = blockIdx.x % kFanParts, fan = blockIdx.y;
+    constexpr int kThreads = 1024;
+    __shared__ int sWarpCnt[32], sWarpNear[32];
+    __shared__ unsigned int sTypeCnt[2];     // sphere / AABB rectangles of the face (the list is grouped by type, like the sweep)
+    const int face = blockIdx.x, fan = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t ia = (uint32_t)lane, ib = (uint32_t)(part * kFanRows + warp);
-    const int cellOfThread = face * kFanCellsPerFace + (int)ib * kFanBins + lane;
     const uint32_t ltMask = (1u << lane) - 1u;
     const int nc = a.ns + a.na + a.no;
     float T[3];
@@ -174,108 +163,163 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_build_kerne
     else { T[0] = a.lx; T[1] = a.ly; T[2] = a.lz; }
     const int k = face >> 1;
     const bool neg = face & 1;
-    const bool nearCta = face == 0 && part == 0;
-    if (tid == 0) sNearCount = 0;
+    const bool nearCta = face == 0;
+    uint2* out = a.rects + ((size_t)fan * 6 + face) * nc;
+    uint32_t* nearOut = a.nearList + (size_t)fan * kFanMaxNear;
+    int total = 0, nearTotal = 0;
+    if (tid < 2) sTypeCnt[tid] = 0u;
     __syncthreads();
+    for (int base = 0; base < nc; base += kThreads) {
+        uint32_t rect = kRectEmpty, idT = 0;
+        bool near = false;
+        int type = 2;
+        if (base + tid < nc) {
+            const int g = a.order ? (int)a.order[(size_t)fan * nc + base + tid] : base + tid;
+            int id; short owner;
+            if (g < a.ns) { type = 0; id = g; owner = a.ownS[id]; }
+            else if (g < a.ns + a.na) { type = 1; id = g - a.ns; owner = a.ownA[id]; }
+            else { type = 2; id = g - a.ns - a.na; owner = a.ownO[id]; }
+            if (!(fan < a.nTargets && (int)owner == fan)) {          // RT:413/426/439, PM:235/245/255
+                const float4 l4 = a.boxLo[g], h4 = a.boxHi[g];
+                const float lo[3] = { l4.x, l4.y, l4.z }, hi[3] = { h4.x, h4.y, h4.z };
+                rect = fan_rect(lo, hi, T, k, neg, a.nearDist, near);
+                idT = (uint32_t)id | ((uint32_t)type << 16);
+            }
+        }
+        const uint32_t bal = __ballot_sync(kFull, rect != kRectEmpty);
+        const uint32_t nbal = __ballot_sync(kFull, near && nearCta);
+        const uint32_t balS = __ballot_sync(kFull, rect != kRectEmpty && type == 0), balA = __ballot_sync(kFull, rect != kRectEmpty && type == 1);
+        if (lane == 0) {
+            sWarpCnt[warp] = __popc(bal); sWarpNear[warp] = __popc(nbal);
+            if (balS) atomicAdd(&sTypeCnt[0], (unsigned)__popc(balS));
+            if (balA) atomicAdd(&sTypeCnt[1], (unsigned)__popc(balA));
+        }
+        __syncthreads();
+        int incl = sWarpCnt[lane], nincl = sWarpNear[lane];
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, s), nv = __shfl_up_sync(kFull, nincl, s);
+            if (lane >= s) { incl += v; nincl += nv; }
+        }
+        const int M = __shfl_sync(kFull, incl, 31), nM = __shfl_sync(kFull, nincl, 31);
+        const int prefix = warp == 0 ? 0 : __shfl_sync(kFull, incl, warp - 1);
+        const int nprefix = warp == 0 ? 0 : __shfl_sync(kFull, nincl, warp - 1);
+        if (rect != kRectEmpty) out[total + prefix + __popc(bal & ltMask)] = make_uint2(rect, idT);
+        if (near && nearCta) {
+            const int pos = nearTotal + nprefix + __popc(nbal & ltMask);
+            if (pos < kFanMaxNear) nearOut[pos] = idT;
+        }
+        total += M; nearTotal += nM;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        uint32_t* rc = a.rectCount + (size_t)(fan * 6 + face) * 3;
+        rc[0] = (uint32_t)total; rc[1] = sTypeCnt[0]; rc[2] = sTypeCnt[0] + sTypeCnt[1];   // all | spheres | spheres + AABBs
+        if (nearCta) a.nearCount[fan] = (uint32_t)nearTotal;       // (may exceed kFanMaxNear: the match step flags it)
+    }
+}
+
+// ---- step 2: matching ----------------------------------------------------------------------------
+// One CTA per (goal, face, strip of ROWS bin rows), one warp per bin row, one thread per bin; the warps do not synchronise
+// while they walk the face's rectangle list: 32 rectangles per coalesced load, the warp picks the ones that overlap its row
+// and every lane checks its column against those only (in order). Pass 0 counts, a block scan + one atomicAdd reserves the
+// CTA's span of the entry array, pass 1 walks the list again and writes the indices, the first AABB ids and the covering
+// depth. (Round 2: the sweep used to be part of this kernel, with a __syncthreads per 1,024 colliders -- rows with little to
+// match waited at every barrier for the longest one, and cutting a face into strips repeated the whole sweep per strip. With
+// the projection done once per face, strips of 8 rows are finer work units, and with per-lane masks the per-entry work runs once
+// per entry of a bin instead of once per (row, rectangle) pair: C3's build 0.50 -> 0.35 ms, C4's 257 goals 1.03 -> 0.78 ms, C5's
+// 9 goals x 16,384 colliders -- formerly 54 CTAs on 148 SMs -- 1.49 -> 0.87 ms, of which the one-CTA-per-goal sort is 0.20 and
+// the longest row's walk through its face's list most of the rest. Prefetching the next 32 rectangles changed nothing.)
+template <int ROWS>
+__global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_match_kernel(const FanBuildArgs a)
+{
+    constexpr int kFanRows = ROWS, kFanThreads = ROWS * 32, kFanParts = kFanBins / ROWS;
+    static_assert(kFanCellsPerFace == 1024 && kFanBins == 32 && kFanBins % kFanRows == 0, "one thread per bin, one warp per bin row");
+    __shared__ int sWarpTot[32];
+    __shared__ unsigned int sBase;
+    __shared__ uint2 sStep[ROWS][32];        // pass 1: the 32 rectangles of the warp's current step
+
+    const int face = blockIdx.x / kFanParts, part = blockIdx.x % kFanParts, fan = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t ia = (uint32_t)lane, ib = (uint32_t)(part * kFanRows + warp);
+    const int cellOfThread = face * kFanCellsPerFace + (int)ib * kFanBins + lane;
+    const int nc = a.ns + a.na + a.no;
+    float T[3];
+    if (fan < a.nTargets) { T[0] = a.targets[3 * fan]; T[1] = a.targets[3 * fan + 1]; T[2] = a.targets[3 * fan + 2]; }
+    else { T[0] = a.lx; T[1] = a.ly; T[2] = a.lz; }
+    const int k = face >> 1;
+    const bool neg = face & 1;
+    const bool nearCta = face == 0 && part == 0;
+    const uint2* rects = a.rects + ((size_t)fan * 6 + face) * nc;
+    const uint32_t* rc = a.rectCount + (size_t)(fan * 6 + face) * 3;
+    const int M = (int)rc[0], mS = (int)rc[1], mSA = (int)rc[2];
+    const int nearTotal = nearCta ? (int)a.nearCount[fan] : 0;
+    const uint32_t* nearList = a.nearList + (size_t)fan * kFanMaxNear;
 
     int cS = 0, cA = 0, cO = 0;
     unsigned int wpos = 0;                   // pass 1: next entry of this bin
     unsigned int aPos = 0;                   // pass 1: where this bin's AABB entries start
     uint32_t firstIds = 0;                   // pass 1: first two AABB entries of this bin, id0 | id1 << 16
-    uint2 myCell = make_uint2(0u, 0u);       // this bin's header (written in pass 0, repeated in cells4 after pass 1)
+    uint2 myCell = make_uint2(0u, 0u);       // this bin's header (written after pass 0, repeated in cells4 after pass 1)
     float cover = __int_as_float(0x7F800000);   // pass 1: smallest threshold depth of an AABB that covers this bin
     const float binA0 = -1.0f + (float)ia * (2.0f / kFanBins) - kFanCoverTan, binA1 = -1.0f + (float)(ia + 1u) * (2.0f / kFanBins) + kFanCoverTan;
     const float binB0 = -1.0f + (float)ib * (2.0f / kFanBins) - kFanCoverTan, binB1 = -1.0f + (float)(ib + 1u) * (2.0f / kFanBins) + kFanCoverTan;
     unsigned int blockTotal = 0;
-    int nearTotal = 0;
     for (int pass = 0; pass < 2; pass++) {
-        for (int base = 0; base < nc; base += kFanThreads) {
-            uint32_t rect = kRectEmpty, idT = 0;
-            bool near = false;
-            float cov[6] = { 1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f };
-            if (base + tid < nc) {
-                const int g = a.order ? (int)a.order[(size_t)fan * nc + base + tid] : base + tid;
-                int type, id; short owner;
-                if (g < a.ns) { type = 0; id = g; owner = a.ownS[id]; }
-                else if (g < a.ns + a.na) { type = 1; id = g - a.ns; owner = a.ownA[id]; }
-                else { type = 2; id = g - a.ns - a.na; owner = a.ownO[id]; }
-                if (!(fan < a.nTargets && (int)owner == fan)) {          // RT:413/426/439, PM:235/245/255
-                    const float4 l4 = a.boxLo[g], h4 = a.boxHi[g];
-                    const float lo[3] = { l4.x, l4.y, l4.z }, hi[3] = { h4.x, h4.y, h4.z };
-                    rect = fan_rect(lo, hi, T, k, neg, a.nearDist, near);
-                    idT = (uint32_t)id | ((uint32_t)type << 16);
-                    if (pass == 1 && type == 1 && rect != kRectEmpty && a.aabbA) {
-                        const float4 A = a.aabbA[id];
-                        const float2 B = a.aabbB[id];
-                        const float elo[3] = { A.x, A.y, A.z }, ehi[3] = { A.w, B.x, B.y };
-                        fan_cover_params(elo, ehi, T, k, neg, a.nearDist, cov);
+        for (int c0 = 0; c0 < M; c0 += 32) {
+            const uint2 re = c0 + lane < M ? __ldg(&rects[c0 + lane]) : make_uint2(kRectEmpty, 0u);
+            const uint32_t r = re.x;
+            uint32_t rows = __ballot_sync(kFull, ib >= ((r >> 16) & 255u) && ib <= (r >> 24) && (r & 255u) <= ((r >> 8) & 255u));
+            if (!rows) continue;
+            // every lane's own mask of the step's rectangles that contain its bin: a short uniform loop over the rectangles
+            // that overlap the row, full width (the per-entry work below then runs once per ENTRY OF A BIN, not once per
+            // (row, rectangle) pair with the few lanes of the rectangle's columns)
+            uint32_t mine = 0;
+            while (rows) {
+                const int j = __ffs(rows) - 1;
+                rows &= rows - 1;
+                const uint32_t rj = __shfl_sync(kFull, r, j);
+                if (ia >= (rj & 255u) && ia <= ((rj >> 8) & 255u)) mine |= 1u << j;
+            }
+            if (pass == 0) {
+                // the list is grouped by type like the sweep: entries [0, mS) spheres, [mS, mSA) AABBs, then OBBs
+                const uint32_t belowS = mS <= c0 ? 0u : (mS - c0 >= 32 ? 0xFFFFFFFFu : (1u << (mS - c0)) - 1u);
+                const uint32_t belowSA = mSA <= c0 ? 0u : (mSA - c0 >= 32 ? 0xFFFFFFFFu : (1u << (mSA - c0)) - 1u);
+                cS += __popc(mine & belowS); cA += __popc(mine & belowSA & ~belowS); cO += __popc(mine & ~belowSA);
+                continue;
+            }
+            __syncwarp();
+            sStep[warp][lane] = re;
+            __syncwarp();
+            while (mine) {
+                const int j = __ffs(mine) - 1;
+                mine &= mine - 1;
+                const uint32_t rj = sStep[warp][j].x, e = sStep[warp][j].y;
+                if (wpos == aPos) firstIds = (e & 0xFFFFu) | (e << 16);          // (a single AABB is listed twice)
+                else if (wpos == aPos + 1u) firstIds = (firstIds & 0xFFFFu) | (e << 16);
+                a.entries[wpos++] = (uint16_t)(e & 0xFFFFu);
+                // (a bin on the border of the rectangle holds the edge of the projection at the depth where it is
+                // widest, so it is covered at no depth -- unless the rectangle was clipped at the edge of the face:
+                // only the other bins do the interval arithmetic)
+                const uint32_t ra0 = rj & 255u, ra1 = (rj >> 8) & 255u, rb0 = (rj >> 16) & 255u, rb1 = rj >> 24;
+                if ((e >> 16) == 1u && a.aabbA && (ia > ra0 || ra0 == 0u) && (ia < ra1 || ra1 == (uint32_t)kFanBins - 1u) &&
+                    (ib > rb0 || rb0 == 0u) && (ib < rb1 || rb1 == (uint32_t)kFanBins - 1u)) {
+                    const float4 A = __ldg(&a.aabbA[e & 0xFFFFu]);
+                    const float2 B = __ldg(&a.aabbB[e & 0xFFFFu]);
+                    const float elo[3] = { A.x, A.y, A.z }, ehi[3] = { A.w, B.x, B.y };
+                    float c[6];
+                    fan_cover_params(elo, ehi, T, k, neg, a.nearDist, c);
+                    float w1 = c[0], w2 = c[1];
+                    if (w1 <= w2) {
+                        fan_cover_clip(binA1, c[3], w1, w2);      //  a * z <= xh for every a <= binA1
+                        fan_cover_clip(-binA0, -c[2], w1, w2);    //  a * z >= xl for every a >= binA0
+                        fan_cover_clip(binB1, c[5], w1, w2);
+                        fan_cover_clip(-binB0, -c[4], w1, w2);
+                        // (the clipped bounds carry the 2-ulp error of the fast division: far inside the margins)
+                        if (w2 >= w1 * 1.00390625f && w2 - w1 >= a.coverMinThickness) cover = fminf(cover, w1 * 1.001953125f);
                     }
                 }
             }
-            const uint32_t bal = __ballot_sync(kFull, rect != kRectEmpty);
-            const uint32_t nbal = __ballot_sync(kFull, near && nearCta && pass == 0);
-            if (lane == 0) { sWarpCnt[warp] = __popc(bal); sWarpNear[warp] = __popc(nbal); }
-            __syncthreads();
-            int incl = lane < kFanRows ? sWarpCnt[lane] : 0, nincl = lane < kFanRows ? sWarpNear[lane] : 0;
-#pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                const int v = __shfl_up_sync(kFull, incl, s), nv = __shfl_up_sync(kFull, nincl, s);
-                if (lane >= s) { incl += v; nincl += nv; }
-            }
-            const int M = __shfl_sync(kFull, incl, 31), nM = __shfl_sync(kFull, nincl, 31);
-            const int prefix = warp == 0 ? 0 : __shfl_sync(kFull, incl, warp - 1);
-            const int nprefix = warp == 0 ? 0 : __shfl_sync(kFull, nincl, warp - 1);
-            if (rect != kRectEmpty) {
-                const int pos = prefix + __popc(bal & ltMask);
-                sRect[pos] = rect; sIdT[pos] = idT;
-                if (pass == 1) {
-#pragma unroll
-                    for (int q = 0; q < 6; q++) sCov[q][pos] = cov[q];
-                }
-            }
-            if (near && nearCta && pass == 0) {
-                const int pos = sNearCount + nprefix + __popc(nbal & ltMask);
-                if (pos < kFanMaxNear) sNear[pos] = idT;
-            }
-            __syncthreads();
-            // a warp owns one bin row: its lanes first pick, 32 rectangles at a time, the ones that overlap the row,
-            // then every lane checks its own column against those only (in order)
-            for (int c0 = 0; c0 < M; c0 += 32) {
-                const uint32_t r = c0 + lane < M ? sRect[c0 + lane] : kRectEmpty;
-                uint32_t rows = __ballot_sync(kFull, ib >= ((r >> 16) & 255u) && ib <= (r >> 24) && (r & 255u) <= ((r >> 8) & 255u));
-                while (rows) {
-                    const int j = __ffs(rows) - 1;
-                    rows &= rows - 1;
-                    const uint32_t rj = __shfl_sync(kFull, r, j);
-                    if (ia >= (rj & 255u) && ia <= ((rj >> 8) & 255u)) {
-                        const uint32_t e = sIdT[c0 + j];
-                        if (pass == 0) { const uint32_t t = e >> 16; cS += t == 0; cA += t == 1; cO += t == 2; }
-                        else {
-                            if (wpos == aPos) firstIds = (e & 0xFFFFu) | (e << 16);          // (a single AABB is listed twice)
-                            else if (wpos == aPos + 1u) firstIds = (firstIds & 0xFFFFu) | (e << 16);
-                            a.entries[wpos++] = (uint16_t)(e & 0xFFFFu);
-                            // (a bin on the border of the rectangle holds the edge of the projection at the depth where it is
-                            // widest, so it is covered at no depth -- unless the rectangle was clipped at the edge of the face:
-                            // only the other bins do the interval arithmetic)
-                            const uint32_t ra0 = rj & 255u, ra1 = (rj >> 8) & 255u, rb0 = (rj >> 16) & 255u, rb1 = rj >> 24;
-                            if ((e >> 16) == 1u && (ia > ra0 || ra0 == 0u) && (ia < ra1 || ra1 == (uint32_t)kFanBins - 1u) &&
-                                (ib > rb0 || rb0 == 0u) && (ib < rb1 || rb1 == (uint32_t)kFanBins - 1u)) {
-                                float w1 = sCov[0][c0 + j], w2 = sCov[1][c0 + j];
-                                if (w1 <= w2) {
-                                    fan_cover_clip(binA1, sCov[3][c0 + j], w1, w2);      //  a * z <= xh for every a <= binA1
-                                    fan_cover_clip(-binA0, -sCov[2][c0 + j], w1, w2);    //  a * z >= xl for every a >= binA0
-                                    fan_cover_clip(binB1, sCov[5][c0 + j], w1, w2);
-                                    fan_cover_clip(-binB0, -sCov[4][c0 + j], w1, w2);
-                                    // (the clipped bounds carry the 2-ulp error of the fast division: far inside the margins)
-                                    if (w2 >= w1 * 1.00390625f && w2 - w1 >= a.coverMinThickness) cover = fminf(cover, w1 * 1.001953125f);
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-            if (tid == 0) sNearCount += nM;
         }
         if (pass == 1) {
             if (cA > 0) a.firstA[(size_t)fan * kFanCells + cellOfThread] = firstIds;
@@ -283,8 +327,6 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_build_kerne
             break;
         }
         // ---- reserve the CTA's span: block scan of the per-bin totals
-        __syncthreads();
-        nearTotal = nearCta ? sNearCount : 0;
         const int tot = cS + cA + cO;
         bool bad = cS > kGridMaxS || cA > kGridMaxA || cO > kGridMaxO || nearTotal > kFanMaxNear;
         int incl = tot;
@@ -326,12 +368,13 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_build_kerne
         if (nearCta && tid == 0) {
             uint32_t nS = 0, nA = 0, nO = 0, ids = 0, ids2 = 0;
             for (int q = 0; q < nearTotal; q++) {
-                const uint32_t t = sNear[q] >> 16;
+                const uint32_t nq = nearList[q];
+                const uint32_t t = nq >> 16;
                 if (t == 1) {
-                    if (nA == 0) ids = (sNear[q] & 0xFFFFu) | (sNear[q] << 16);
-                    else if (nA == 1) ids = (ids & 0xFFFFu) | (sNear[q] << 16);
-                    else if (nA == 2) ids2 = (sNear[q] & 0xFFFFu) | (sNear[q] << 16);
-                    else if (nA == 3) ids2 = (ids2 & 0xFFFFu) | (sNear[q] << 16);
+                    if (nA == 0) ids = (nq & 0xFFFFu) | (nq << 16);
+                    else if (nA == 1) ids = (ids & 0xFFFFu) | (nq << 16);
+                    else if (nA == 2) ids2 = (nq & 0xFFFFu) | (nq << 16);
+                    else if (nA == 3) ids2 = (ids2 & 0xFFFFu) | (nq << 16);
                 }
                 nS += t == 0; nA += t == 1; nO += t == 2;
             }
@@ -341,11 +384,25 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_build_kerne
             a.cells4[(size_t)fan * kFanCells + 6 * kFanCellsPerFace] = make_uint4(nc2.x, nc2.y, ids, ids2);
         }
         if (nearCta)
-            for (int q = tid; q < nearTotal; q += kFanThreads) a.entries[bs + blockTotal + q] = (uint16_t)(sNear[q] & 0xFFFFu);
+            for (int q = tid; q < nearTotal; q += kFanThreads) a.entries[bs + blockTotal + q] = (uint16_t)(nearList[q] & 0xFFFFu);
     }
 }
 
-// a.order (may be null: canonical order) needs (nTargets + 1) * (ns + na + no) words
+// a.order (may be null: canonical order) needs (nTargets + 1) * (ns + na + no) words; a.rects etc.: fan_build_scratch_bytes
+size_t fan_build_scratch_bytes(int nFans, int nc)
+{
+    return (size_t)nFans * 6 * nc * sizeof(uint2) + (size_t)nFans * (18 + kFanMaxNear + 1) * sizeof(uint32_t);
+}
+// carves a.rects / rectCount / nearList / nearCount out of `scratch` (fan_build_scratch_bytes)
+void fan_build_set_scratch(FanBuildArgs& a, void* scratch)
+{
+    const size_t nFans = (size_t)a.nTargets + 1, nc = (size_t)a.ns + a.na + a.no;
+    a.rects = reinterpret_cast<uint2*>(scratch);
+    a.rectCount = reinterpret_cast<uint32_t*>(a.rects + nFans * 6 * nc);
+    a.nearList = a.rectCount + nFans * 18;
+    a.nearCount = a.nearList + nFans * kFanMaxNear;
+}
+
 cudaError_t launch_fan_build(const FanBuildArgs& a, cudaStream_t stream)
 {
     const int nFans = a.nTargets + 1;
@@ -359,14 +416,17 @@ cudaError_t launch_fan_build(const FanBuildArgs& a, cudaStream_t stream)
         fan_order_kernel<<<nFans, 1024, smem, stream>>>(a, nPow2);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    // whole faces unless ART_FAN_ROWS (experiment knob, read per launch) asks for strips
-    int rows = 32;
-    if (const char* v = getenv("ART_FAN_ROWS")) { const int r = atoi(v); if (r == 4 || r == 8 || r == 16) rows = r; }
+    fan_project_kernel<<<dim3(6, nFans), 1024, 0, stream>>>(a);
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return e2;
+    // strips of 8 bin rows unless ART_FAN_ROWS (experiment knob, read per launch) says otherwise
+    int rows = 8;
+    if (const char* v = getenv("ART_FAN_ROWS")) { const int r = atoi(v); if (r == 4 || r == 8 || r == 16 || r == 32) rows = r; }
     switch (rows) {
-    case 32: fan_build_kernel<32><<<dim3(6, nFans), 1024, 0, stream>>>(a); break;
-    case 16: fan_build_kernel<16><<<dim3(12, nFans), 512, 0, stream>>>(a); break;
-    case 8: fan_build_kernel<8><<<dim3(24, nFans), 256, 0, stream>>>(a); break;
-    default: fan_build_kernel<4><<<dim3(48, nFans), 128, 0, stream>>>(a); break;
+    case 32: fan_match_kernel<32><<<dim3(6, nFans), 1024, 0, stream>>>(a); break;
+    case 16: fan_match_kernel<16><<<dim3(12, nFans), 512, 0, stream>>>(a); break;
+    case 8: fan_match_kernel<8><<<dim3(24, nFans), 256, 0, stream>>>(a); break;
+    default: fan_match_kernel<4><<<dim3(48, nFans), 128, 0, stream>>>(a); break;
     }
     return cudaGetLastError();
 }

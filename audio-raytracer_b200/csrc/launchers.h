@@ -21,6 +21,8 @@ size_t query_fan_smem_bytes(const GeomLayout& L, bool geomInSmem);
 cudaError_t launch_query_fan(const QueryArgs& a, const FanDesc& fans, int numCtas, bool geomInSmem, bool stats, int maxSmemOptin, cudaStream_t stream);
 cudaError_t launch_grid_build(const GridBuildArgs& a, cudaStream_t stream);
 cudaError_t launch_fan_build(const FanBuildArgs& a, cudaStream_t stream);
+size_t fan_build_scratch_bytes(int nFans, int nc);
+void fan_build_set_scratch(FanBuildArgs& a, void* scratch);
 size_t perm_smem_bytes(const GeomLayout& L, bool geomInSmem);
 cudaError_t launch_permeation(const PermArgs& a, int numCtas, bool geomInSmem, int T, cudaStream_t stream);
 cudaError_t launch_perm_last(const PermArgs& a, int T, cudaStream_t stream);
