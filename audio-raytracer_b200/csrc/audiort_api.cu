@@ -1188,6 +1188,9 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
                 fa.aabbA = cover ? reinterpret_cast<const float4*>(gb + L.offAabbA) : nullptr;
                 fa.aabbB = cover ? reinterpret_cast<const float2*>(gb + L.offAabbB) : nullptr;
                 fa.coverMinThickness = 1e-4f * ctx->grid.d.errScale;
+                // covering-depth codes: c = S * log2(depth / nearDist), 253 code units up to 1.01 * errScale
+                fa.coverLogS = 253.0f / log2f(1.01f * ctx->grid.d.errScale / fa.nearDist);
+                fa.coverLogK = -log2f(fa.nearDist) * fa.coverLogS;
             }
             fa.cells4 = ctx->fanCells.as<uint4>();
             fa.cells = reinterpret_cast<uint2*>(fa.cells4 + nFans * kFanCells); fa.entries = ctx->fanEntries.as<uint16_t>();
@@ -1204,7 +1207,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             CK(launch_fan_build(fa, fanStream));
             if (fanBeside) CK(cudaEventRecord(ctx->evFan, ctx->stream2));
             ctx->kernelLaunches += 2;                // fan_project_kernel, fan_match_kernel
-            fd.nFans = (int)nFans; fd.cells = fa.cells; fd.entries = fa.entries; fd.nEntries = (int)cap; fd.firstA = fa.firstA; fd.cells4 = fa.cells4;
+            fd.nFans = (int)nFans; fd.cells = fa.cells; fd.entries = fa.entries; fd.nEntries = (int)cap; fd.firstA = fa.firstA; fd.cells4 = fa.cells4; fd.coverLogS = fa.coverLogS; fd.coverLogK = fa.coverLogK;
             ctx->frameGridUsed |= 4u;
         }
     }

@@ -29,6 +29,9 @@ namespace art {
 constexpr int kFanBins = 32;                         // B: bins per cube-face edge (one CTA thread per bin when building)
 constexpr int kFanCellsPerFace = kFanBins * kFanBins;
 constexpr int kFanCells = 6 * kFanCellsPerFace + 1;  // per goal; the last cell is the near list
+constexpr int kFanSub = 2;                           // sub-bins per bin edge (covering depths are kept per sub-bin, cells4.w)
+constexpr int kFanFine = kFanBins * kFanSub;
+constexpr float kFanCoverLogEps = 0.01f;             // slack (in code units) of the log-domain covering-depth compare, k4_fan_build.cu
 constexpr float kFanTanMargin = 4e-3f;
 constexpr int kFanMaxNear = 512;                     // near-list capacity per goal (else the frame falls back to the grid walk)
 
@@ -39,9 +42,10 @@ struct FanDesc {
     int nEntries;              // capacity (bounds checks of debug builds)
     const uint32_t* firstA;    // [nFans * kFanCells]: the cell's first two AABB entries, id0 | id1 << 16 (K1's first pass tests
                                // exactly those: it reads them beside the header instead of chasing the entry list afterwards)
-    const uint4* cells4;       // [nFans * kFanCells]: (cells[i].x, cells[i].y, AABB ids 0 | 1 << 16, covering depth as float bits) -- header,
-                               // first ids and the cull threshold of the bin in ONE 16-byte entry (k4_fan_build.cu "covering depth";
-                               // the near cell's w is unused)
+    const uint4* cells4;       // [nFans * kFanCells]: (cells[i].x, cells[i].y, AABB ids 0 | 1 << 16, covering-depth codes of the bin's
+                               // kFanSub x kFanSub sub-bins, one byte each) -- header, first ids and the cull thresholds of the bin
+                               // in ONE 16-byte entry (k4_fan_build.cu "covering depth"; the near cell's w is unused)
+    float coverLogS, coverLogK; // code of depth w = coverLogS * log2(w) + coverLogK (set by the API, the same for build and query)
 };
 
 // fan_build_kernel arguments (k4_fan_build.cu)
@@ -56,6 +60,7 @@ struct FanBuildArgs {
     float nearDist;
     const float4* aabbA; const float2* aabbB;   // the AABBs' own min / max (GeomView), for the covering depth; null: no covering depths
     float coverMinThickness;   // 1e-4 * errScale: a covering depth interval must be at least this long
+    float coverLogS, coverLogK; // see FanDesc
     uint2* cells;              // [(nTargets + 1) * kFanCells]
     uint32_t* firstA;          // [(nTargets + 1) * kFanCells], see FanDesc
     uint4* cells4;             // [(nTargets + 1) * kFanCells], see FanDesc
@@ -66,6 +71,7 @@ struct FanBuildArgs {
     // scratch between the projection and the matching step (fan_build_set_scratch)
     uint2* rects;              // [(nTargets + 1) * 6][ns + na + no]: per (goal, face) the non-empty rectangles in sweep order,
                                // x = a0 | a1 << 8 | b0 << 16 | b1 << 24 (bins), y = local collider index | type << 16
+    float* rectDepth;          // the same shape: depth of the inflated box's near face (no AABB covers a bin from nearer)
     uint32_t* rectCount;       // [(nTargets + 1) * 6][3]: rectangles of the face | of its spheres | of its spheres and AABBs
     uint32_t* nearList;        // [(nTargets + 1)][kFanMaxNear]: index | type << 16 of the colliders near the goal, in sweep order
     uint32_t* nearCount;       // [(nTargets + 1)] (may exceed kFanMaxNear: overflow)
@@ -74,21 +80,26 @@ struct FanBuildArgs {
 // Cell index (within one fan) of the bin that direction v (from the goal, any length) falls in.
 // Returns -1 when v has no usable direction (zero or non-finite).
 // `w` receives the depth of v on its face (the largest |component|).
-__device__ __forceinline__ int fan_bin_w(float vx, float vy, float vz, float& w)
+// `sub` receives the sub-bin (sb * kFanSub + sa) of v inside its bin: floor(x * kFanSub) / kFanSub == floor(x) for x >= 0 and the
+// scaling by kFanSub = 2 is exact, so the bin is the same as without sub-bins.
+__device__ __forceinline__ int fan_bin_w(float vx, float vy, float vz, float& w, int& sub)
 {
+    static_assert(kFanSub == 2, "exact only for powers of two");
     // branch-free: selects instead of an if-chain, the validity check folded into the result
     const float ax = fabsf(vx), ay = fabsf(vy), az = fabsf(vz);
     const bool fx = ax >= ay && ax >= az, fy = !fx && ay >= az;
     w = fx ? ax : (fy ? ay : az);
     const float s = fx ? vx : (fy ? vy : vz), p = fx ? vy : (fy ? vz : vx), q = fx ? vz : (fy ? vx : vy);
     const float r = __fdividef(1.0f, w);
-    // tangent-plane coordinates a = p * r, b = q * r in [-1, 1]; (a + 1) * (kFanBins / 2) as one FMA (the same float: the
+    // tangent-plane coordinates a = p * r, b = q * r in [-1, 1]; (a + 1) * (kFanFine / 2) as one FMA (the same float: the
     // scaling by a power of two is exact)
-    const int ia = min(kFanBins - 1, max(0, __float2int_rd(fmaf(p * r, 0.5f * kFanBins, 0.5f * kFanBins))));
-    const int ib = min(kFanBins - 1, max(0, __float2int_rd(fmaf(q * r, 0.5f * kFanBins, 0.5f * kFanBins))));
+    const int ia = min(kFanFine - 1, max(0, __float2int_rd(fmaf(p * r, 0.5f * kFanFine, 0.5f * kFanFine))));
+    const int ib = min(kFanFine - 1, max(0, __float2int_rd(fmaf(q * r, 0.5f * kFanFine, 0.5f * kFanFine))));
     const int face = (fx ? 0 : (fy ? 2 : 4)) + (s < 0.0f ? 1 : 0);
-    return (w > 0.0f && w < 3.0e38f) ? face * kFanCellsPerFace + ib * kFanBins + ia : -1;
+    sub = (ib % kFanSub) * kFanSub + (ia % kFanSub);
+    return (w > 0.0f && w < 3.0e38f) ? face * kFanCellsPerFace + (ib / kFanSub) * kFanBins + ia / kFanSub : -1;
 }
+__device__ __forceinline__ int fan_bin_w(float vx, float vy, float vz, float& w) { int sub; return fan_bin_w(vx, vy, vz, w, sub); }
 __device__ __forceinline__ int fan_bin(float vx, float vy, float vz) { float w; return fan_bin_w(vx, vy, vz, w); }
 
 }  // namespace art

@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
     uint2* list0 = reinterpret_cast<uint2*>(listSO + kQEntry * kQCapSO);
     int n0 = 0, nA = 0, nSO = 0;                     // queued queries (kept across goals and record blocks)
     const unsigned int nRec = *a.recCount;           // the bounce tracer has finished (stream order)
-    const float* coverDepth = reinterpret_cast<const float*>(f.cells4) + 3;      // cells4[i].w
+    const uint32_t* coverCodes = reinterpret_cast<const uint32_t*>(f.cells4) + 3;  // cells4[i].w
 
     // Work unit = (block of 32 records, group of goals). With few records (a small batch against many targets) the launcher
     // splits the goals of a block over several warps so that the whole GPU is busy (QueryArgs::goalGroups); otherwise a unit
@@ -421,14 +421,16 @@ __global__ void __launch_bounds__(kQThreads, 1) query_fan_kernel(const QueryArgs
                 if (valid && s + u < sEnd) {
                     const f3 g = q_goal(E, s + u);
                     float w;
-                    const int bin = fan_bin_w(P.x - g.x, P.y - g.y, P.z - g.z, w);   // direction goal -> hit point, its depth on the face
+                    int sub;
+                    const int bin = fan_bin_w(P.x - g.x, P.y - g.y, P.z - g.z, w, sub);   // direction goal -> hit point: bin, depth on the face, sub-bin
                     push[u] = true;
                     qy[u] = (uint32_t)(s + u) | kQFlagNoBin;
                     if (bin >= 0) {
-                        // beyond the covering depth of its bin an AABB certainly blocks the query (k4_fan_build.cu; w <= errScale
-                        // is the range the margins were derived for)
-                        const float cover = __ldg(coverDepth + 4 * ((size_t)q_fan_of(a, s + u) * kFanCells + bin));
-                        const bool culled = w > cover && w <= a.errScale;
+                        // beyond the covering depth of its sub-bin an AABB certainly blocks the query (k4_fan_build.cu; compared in
+                        // the log domain, one code byte per sub-bin; w <= errScale is the range the margins were derived for)
+                        const uint32_t codes = __ldg(coverCodes + 4 * ((size_t)q_fan_of(a, s + u) * kFanCells + bin));
+                        const uint32_t code = (codes >> (8 * sub)) & 255u;
+                        const bool culled = fmaf(__log2f(w), f.coverLogS, f.coverLogK) > (float)code + kFanCoverLogEps && code < 255u && w <= a.errScale;
                         qy[u] = (uint32_t)(s + u) | ((uint32_t)bin << 16);
 #ifdef ART_Q_VERIFY
                         if (culled) qy[u] |= kQFlagCulled;

@@ -17,10 +17,12 @@ namespace art {
 
 constexpr uint32_t kRectEmpty = 0x000000FFu;   // a0 = 255 > a1 = 0
 
-// Bin rectangle of the box [lo, hi] (already conservative, grid_host.h) seen from T on cube face (k, sgn),
-// packed a0 | a1 << 8 | b0 << 16 | b1 << 24, or kRectEmpty. near: T lies within nearDist of the box (per axis).
-__device__ __forceinline__ uint32_t fan_rect(const float lo[3], const float hi[3], const float T[3], int k, bool neg, float nearDist, bool& near)
+// Rectangle of the box [lo, hi] (already conservative, grid_host.h) seen from T on cube face (k, sgn), in SUB-BIN units
+// (kFanSub x kFanSub sub-bins per bin; bin index = sub-bin index / kFanSub -- the lists are per bin, the covering depths per
+// sub-bin), packed a0 | a1 << 8 | b0 << 16 | b1 << 24, or kRectEmpty. near: T lies within nearDist of the box (per axis).
+__device__ __forceinline__ uint32_t fan_rect(const float lo[3], const float hi[3], const float T[3], int k, bool neg, float nearDist, bool& near, float& nearDepth)
 {
+    nearDepth = 0.0f;
     float rl[3], rh[3];
     near = true;
 #pragma unroll
@@ -33,6 +35,7 @@ __device__ __forceinline__ uint32_t fan_rect(const float lo[3], const float hi[3
     if (near) return kRectEmpty;
     const int i = k == 2 ? 0 : k + 1, j = k == 0 ? 2 : k - 1;   // (k+1)%3, (k+2)%3
     const float w0 = neg ? -rh[k] : rl[k], w1 = neg ? -rl[k] : rh[k];
+    nearDepth = w0;                                             // depth of the (inflated) box's near face: no AABB covers a bin from nearer
     if (!(w1 > 0.0f)) return kRectEmpty;
     const float x0 = rl[i], x1 = rh[i], y0 = rl[j], y1 = rh[j];
     const float xmin = (x0 <= 0.0f && x1 >= 0.0f) ? 0.0f : fminf(fabsf(x0), fabsf(x1));
@@ -49,11 +52,11 @@ __device__ __forceinline__ uint32_t fan_rect(const float lo[3], const float hi[3
     const float bmin = (y0 >= 0.0f ? y0 * r1 : (pos ? y0 * rlo : -inf)) - kFanTanMargin;
     const float bmax = (y1 <= 0.0f ? y1 * r1 : (pos ? y1 * rlo : inf)) + kFanTanMargin;
     if (amin > 1.0f || amax < -1.0f || bmin > 1.0f || bmax < -1.0f) return kRectEmpty;
-    const float sc = 0.5f * kFanBins;
-    const uint32_t a0 = (uint32_t)min(kFanBins - 1, max(0, (int)floorf((fmaxf(amin, -1.0f) + 1.0f) * sc)));
-    const uint32_t a1 = (uint32_t)min(kFanBins - 1, max(0, (int)floorf((fminf(amax, 1.0f) + 1.0f) * sc)));
-    const uint32_t b0 = (uint32_t)min(kFanBins - 1, max(0, (int)floorf((fmaxf(bmin, -1.0f) + 1.0f) * sc)));
-    const uint32_t b1 = (uint32_t)min(kFanBins - 1, max(0, (int)floorf((fminf(bmax, 1.0f) + 1.0f) * sc)));
+    const float sc = 0.5f * kFanFine;
+    const uint32_t a0 = (uint32_t)min(kFanFine - 1, max(0, (int)floorf((fmaxf(amin, -1.0f) + 1.0f) * sc)));
+    const uint32_t a1 = (uint32_t)min(kFanFine - 1, max(0, (int)floorf((fminf(amax, 1.0f) + 1.0f) * sc)));
+    const uint32_t b0 = (uint32_t)min(kFanFine - 1, max(0, (int)floorf((fmaxf(bmin, -1.0f) + 1.0f) * sc)));
+    const uint32_t b1 = (uint32_t)min(kFanFine - 1, max(0, (int)floorf((fminf(bmax, 1.0f) + 1.0f) * sc)));
     return a0 | (a1 << 8) | (b0 << 16) | (b1 << 24);
 }
 
@@ -72,8 +75,18 @@ __device__ __forceinline__ uint32_t fan_rect(const float lo[3], const float hi[3
 //     outside the box); the limit is len (muffle rays) or distance(RayOrigin, hit point) >= len - 1.01e-4 (echo rays: P is the
 //     hit point moved back by kEpsilon = 1e-4): dist < limit;
 //   * no 0 * Inf: a zero direction component k means P_k == G_k, and then lo_k - P_k < 0 < hi_k - P_k by the tangent margin.
-// The bin stores the smallest threshold depth over its covering AABBs (cells4.w); +Inf when there is none.
+// Covering depths are kept per SUB-BIN (kFanSub x kFanSub per bin: the finer the cell, the more often one box fills it -- C3:
+// 75 % of the queries lie beyond the covering depth of their bin, 86 % beyond that of their sub-bin), as the smallest threshold
+// over the covering AABBs, one byte each in cells4.w: code c stands for the depth nearDist * 2^(c / coverLogS), rounded UP when
+// encoded (fan_cover_code; a larger threshold only culls less), 255 = none. The query compares in the log domain,
+// coverLogS * log2(w) + coverLogK > c + kFanCoverLogEps, with lg2.approx on both sides (abs. error < 3e-4 code units).
 constexpr float kFanCoverTan = 1e-3f;
+__device__ __forceinline__ uint32_t fan_cover_code(float depth, float logS, float logK)
+{
+    if (!(depth < 3.0e38f)) return 255u;
+    const float c = ceilf(fmaf(__log2f(depth), logS, logK) + kFanCoverLogEps);
+    return c <= 254.0f ? (uint32_t)fmaxf(c, 0.0f) : 255u;
+}
 
 // cover parameters of AABB [lo, hi] (the reference's own min / max, GeomView::aabbA/B) on face (k, neg) of goal T:
 // depth range [c[0], c[1]], tangent ranges [c[2], c[3]] (axis i) and [c[4], c[5]] (axis j), all shrunk; c[0] > c[1] if unusable
@@ -165,6 +178,7 @@ __global__ void __launch_bounds__(1024, 2) fan_project_kernel(const FanBuildArgs
     const bool neg = face & 1;
     const bool nearCta = face == 0;
     uint2* out = a.rects + ((size_t)fan * 6 + face) * nc;
+    float* depthOut = a.rectDepth + ((size_t)fan * 6 + face) * nc;
     uint32_t* nearOut = a.nearList + (size_t)fan * kFanMaxNear;
     int total = 0, nearTotal = 0;
     if (tid < 2) sTypeCnt[tid] = 0u;
@@ -172,6 +186,7 @@ __global__ void __launch_bounds__(1024, 2) fan_project_kernel(const FanBuildArgs
     for (int base = 0; base < nc; base += kThreads) {
         uint32_t rect = kRectEmpty, idT = 0;
         bool near = false;
+        float depth = 0.0f;
         int type = 2;
         if (base + tid < nc) {
             const int g = a.order ? (int)a.order[(size_t)fan * nc + base + tid] : base + tid;
@@ -182,7 +197,7 @@ __global__ void __launch_bounds__(1024, 2) fan_project_kernel(const FanBuildArgs
             if (!(fan < a.nTargets && (int)owner == fan)) {          // RT:413/426/439, PM:235/245/255
                 const float4 l4 = a.boxLo[g], h4 = a.boxHi[g];
                 const float lo[3] = { l4.x, l4.y, l4.z }, hi[3] = { h4.x, h4.y, h4.z };
-                rect = fan_rect(lo, hi, T, k, neg, a.nearDist, near);
+                rect = fan_rect(lo, hi, T, k, neg, a.nearDist, near, depth);
                 idT = (uint32_t)id | ((uint32_t)type << 16);
             }
         }
@@ -204,7 +219,11 @@ __global__ void __launch_bounds__(1024, 2) fan_project_kernel(const FanBuildArgs
         const int M = __shfl_sync(kFull, incl, 31), nM = __shfl_sync(kFull, nincl, 31);
         const int prefix = warp == 0 ? 0 : __shfl_sync(kFull, incl, warp - 1);
         const int nprefix = warp == 0 ? 0 : __shfl_sync(kFull, nincl, warp - 1);
-        if (rect != kRectEmpty) out[total + prefix + __popc(bal & ltMask)] = make_uint2(rect, idT);
+        if (rect != kRectEmpty) {
+            const int pos = total + prefix + __popc(bal & ltMask);
+            out[pos] = make_uint2(rect, idT);
+            depthOut[pos] = depth;
+        }
         if (near && nearCta) {
             const int pos = nearTotal + nprefix + __popc(nbal & ltMask);
             if (pos < kFanMaxNear) nearOut[pos] = idT;
@@ -230,14 +249,18 @@ __global__ void __launch_bounds__(1024, 2) fan_project_kernel(const FanBuildArgs
 // per entry of a bin instead of once per (row, rectangle) pair: C3's build 0.50 -> 0.35 ms, C4's 257 goals 1.03 -> 0.78 ms, C5's
 // 9 goals x 16,384 colliders -- formerly 54 CTAs on 148 SMs -- 1.49 -> 0.87 ms, of which the one-CTA-per-goal sort is 0.20 and
 // the longest row's walk through its face's list most of the rest. Prefetching the next 32 rectangles changed nothing.)
+#ifndef ART_FAN_MATCH_THREADS_PER_SM
+#define ART_FAN_MATCH_THREADS_PER_SM 1024     // 60 registers, no spills: measured faster than 2048 (32 registers, spills) on C3, C4 and C5
+#endif
 template <int ROWS>
-__global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_match_kernel(const FanBuildArgs a)
+__global__ void __launch_bounds__(ROWS * 32, ART_FAN_MATCH_THREADS_PER_SM / (ROWS * 32)) fan_match_kernel(const FanBuildArgs a)
 {
     constexpr int kFanRows = ROWS, kFanThreads = ROWS * 32, kFanParts = kFanBins / ROWS;
     static_assert(kFanCellsPerFace == 1024 && kFanBins == 32 && kFanBins % kFanRows == 0, "one thread per bin, one warp per bin row");
     __shared__ int sWarpTot[32];
     __shared__ unsigned int sBase;
     __shared__ uint2 sStep[ROWS][32];        // pass 1: the 32 rectangles of the warp's current step
+    __shared__ float sDepth[ROWS][32];       //         and the depths of their near faces
 
     const int face = blockIdx.x / kFanParts, part = blockIdx.x % kFanParts, fan = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -251,6 +274,7 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_match_kerne
     const bool neg = face & 1;
     const bool nearCta = face == 0 && part == 0;
     const uint2* rects = a.rects + ((size_t)fan * 6 + face) * nc;
+    const float* rectDepth = a.rectDepth + ((size_t)fan * 6 + face) * nc;
     const uint32_t* rc = a.rectCount + (size_t)(fan * 6 + face) * 3;
     const int M = (int)rc[0], mS = (int)rc[1], mSA = (int)rc[2];
     const int nearTotal = nearCta ? (int)a.nearCount[fan] : 0;
@@ -261,15 +285,15 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_match_kerne
     unsigned int aPos = 0;                   // pass 1: where this bin's AABB entries start
     uint32_t firstIds = 0;                   // pass 1: first two AABB entries of this bin, id0 | id1 << 16
     uint2 myCell = make_uint2(0u, 0u);       // this bin's header (written after pass 0, repeated in cells4 after pass 1)
-    float cover = __int_as_float(0x7F800000);   // pass 1: smallest threshold depth of an AABB that covers this bin
-    const float binA0 = -1.0f + (float)ia * (2.0f / kFanBins) - kFanCoverTan, binA1 = -1.0f + (float)(ia + 1u) * (2.0f / kFanBins) + kFanCoverTan;
-    const float binB0 = -1.0f + (float)ib * (2.0f / kFanBins) - kFanCoverTan, binB1 = -1.0f + (float)(ib + 1u) * (2.0f / kFanBins) + kFanCoverTan;
+    float cover[kFanSub * kFanSub];          // pass 1: smallest threshold depth of an AABB that covers sub-bin (sa, sb) of this bin
+#pragma unroll
+    for (int q = 0; q < kFanSub * kFanSub; q++) cover[q] = __int_as_float(0x7F800000);
     unsigned int blockTotal = 0;
     for (int pass = 0; pass < 2; pass++) {
         for (int c0 = 0; c0 < M; c0 += 32) {
             const uint2 re = c0 + lane < M ? __ldg(&rects[c0 + lane]) : make_uint2(kRectEmpty, 0u);
             const uint32_t r = re.x;
-            uint32_t rows = __ballot_sync(kFull, ib >= ((r >> 16) & 255u) && ib <= (r >> 24) && (r & 255u) <= ((r >> 8) & 255u));
+            uint32_t rows = __ballot_sync(kFull, ib >= ((r >> 16) & 255u) / kFanSub && ib <= (r >> 24) / kFanSub && (r & 255u) <= ((r >> 8) & 255u));
             if (!rows) continue;
             // every lane's own mask of the step's rectangles that contain its bin: a short uniform loop over the rectangles
             // that overlap the row, full width (the per-entry work below then runs once per ENTRY OF A BIN, not once per
@@ -279,7 +303,7 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_match_kerne
                 const int j = __ffs(rows) - 1;
                 rows &= rows - 1;
                 const uint32_t rj = __shfl_sync(kFull, r, j);
-                if (ia >= (rj & 255u) && ia <= ((rj >> 8) & 255u)) mine |= 1u << j;
+                if (ia >= (rj & 255u) / kFanSub && ia <= ((rj >> 8) & 255u) / kFanSub) mine |= 1u << j;
             }
             if (pass == 0) {
                 // the list is grouped by type like the sweep: entries [0, mS) spheres, [mS, mSA) AABBs, then OBBs
@@ -290,6 +314,7 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_match_kerne
             }
             __syncwarp();
             sStep[warp][lane] = re;
+            sDepth[warp][lane] = c0 + lane < M ? __ldg(&rectDepth[c0 + lane]) : 0.0f;
             __syncwarp();
             while (mine) {
                 const int j = __ffs(mine) - 1;
@@ -298,32 +323,71 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_match_kerne
                 if (wpos == aPos) firstIds = (e & 0xFFFFu) | (e << 16);          // (a single AABB is listed twice)
                 else if (wpos == aPos + 1u) firstIds = (firstIds & 0xFFFFu) | (e << 16);
                 a.entries[wpos++] = (uint16_t)(e & 0xFFFFu);
-                // (a bin on the border of the rectangle holds the edge of the projection at the depth where it is
-                // widest, so it is covered at no depth -- unless the rectangle was clipped at the edge of the face:
-                // only the other bins do the interval arithmetic)
-                const uint32_t ra0 = rj & 255u, ra1 = (rj >> 8) & 255u, rb0 = (rj >> 16) & 255u, rb1 = rj >> 24;
-                if ((e >> 16) == 1u && a.aabbA && (ia > ra0 || ra0 == 0u) && (ia < ra1 || ra1 == (uint32_t)kFanBins - 1u) &&
-                    (ib > rb0 || rb0 == 0u) && (ib < rb1 || rb1 == (uint32_t)kFanBins - 1u)) {
-                    const float4 A = __ldg(&a.aabbA[e & 0xFFFFu]);
-                    const float2 B = __ldg(&a.aabbB[e & 0xFFFFu]);
-                    const float elo[3] = { A.x, A.y, A.z }, ehi[3] = { A.w, B.x, B.y };
-                    float c[6];
-                    fan_cover_params(elo, ehi, T, k, neg, a.nearDist, c);
-                    float w1 = c[0], w2 = c[1];
-                    if (w1 <= w2) {
-                        fan_cover_clip(binA1, c[3], w1, w2);      //  a * z <= xh for every a <= binA1
-                        fan_cover_clip(-binA0, -c[2], w1, w2);    //  a * z >= xl for every a >= binA0
-                        fan_cover_clip(binB1, c[5], w1, w2);
-                        fan_cover_clip(-binB0, -c[4], w1, w2);
-                        // (the clipped bounds carry the 2-ulp error of the fast division: far inside the margins)
-                        if (w2 >= w1 * 1.00390625f && w2 - w1 >= a.coverMinThickness) cover = fminf(cover, w1 * 1.001953125f);
+                // A sub-bin on the border of the rectangle holds the edge of the projection at the depth where it is widest,
+                // so it is covered at no depth -- unless the rectangle was clipped at the edge of the face: only the other
+                // sub-bins do the interval arithmetic (none at all for most small or distant colliders).
+                // (... and a box whose near face lies beyond the covering depths the sub-bins already have cannot lower any of them:
+                // the sweep is nearest first, so that is most boxes once a bin is covered)
+                uint32_t open = 0;                                     // sub-bins this box could still lower
+                if ((e >> 16) == 1u && a.aabbA) {
+                    const float d = sDepth[warp][j] * 1.001953125f;
+#pragma unroll
+                    for (int q = 0; q < kFanSub * kFanSub; q++) open |= (d < cover[q] ? 1u : 0u) << q;
+                }
+                if (open) {
+                    const uint32_t fa0 = rj & 255u, fa1 = (rj >> 8) & 255u, fb0 = (rj >> 16) & 255u, fb1 = rj >> 24;
+                    uint32_t candA = 0, candB = 0;
+#pragma unroll
+                    for (uint32_t q = 0; q < (uint32_t)kFanSub; q++) {
+                        const uint32_t fa = ia * kFanSub + q, fb = ib * kFanSub + q;
+                        if ((fa > fa0 || (fa == fa0 && fa0 == 0u)) && (fa < fa1 || (fa == fa1 && fa1 == (uint32_t)kFanFine - 1u))) candA |= 1u << q;
+                        if ((fb > fb0 || (fb == fb0 && fb0 == 0u)) && (fb < fb1 || (fb == fb1 && fb1 == (uint32_t)kFanFine - 1u))) candB |= 1u << q;
+                    }
+                    // (candidate sub-bins as a 2 x 2 mask, bit sb * kFanSub + sa)
+                    static_assert(kFanSub == 2, "mask arithmetic below");
+                    open &= ((candB & 1u) ? candA : 0u) | ((candB & 2u) ? candA << 2 : 0u);
+                    if (!open) candA = 0;
+                    if (candA && candB) {
+                        const float4 A = __ldg(&a.aabbA[e & 0xFFFFu]);
+                        const float2 B = __ldg(&a.aabbB[e & 0xFFFFu]);
+                        const float elo[3] = { A.x, A.y, A.z }, ehi[3] = { A.w, B.x, B.y };
+                        float c[6];
+                        fan_cover_params(elo, ehi, T, k, neg, a.nearDist, c);
+                        if (c[0] <= c[1]) {
+                            // the depth interval per sub-bin column / row (the constraints separate), then their intersections
+                            float a1[kFanSub], a2[kFanSub], b1[kFanSub], b2[kFanSub];
+#pragma unroll
+                            for (int q = 0; q < kFanSub; q++) {
+                                const float aLo = -1.0f + (float)(ia * kFanSub + q) * (2.0f / kFanFine) - kFanCoverTan;
+                                const float aHi = -1.0f + (float)(ia * kFanSub + q + 1u) * (2.0f / kFanFine) + kFanCoverTan;
+                                const float bLo = -1.0f + (float)(ib * kFanSub + q) * (2.0f / kFanFine) - kFanCoverTan;
+                                const float bHi = -1.0f + (float)(ib * kFanSub + q + 1u) * (2.0f / kFanFine) + kFanCoverTan;
+                                a1[q] = c[0]; a2[q] = c[1]; b1[q] = c[0]; b2[q] = c[1];
+                                fan_cover_clip(aHi, c[3], a1[q], a2[q]);      //  a * z <= xh for every a <= aHi
+                                fan_cover_clip(-aLo, -c[2], a1[q], a2[q]);    //  a * z >= xl for every a >= aLo
+                                fan_cover_clip(bHi, c[5], b1[q], b2[q]);
+                                fan_cover_clip(-bLo, -c[4], b1[q], b2[q]);
+                            }
+                            // (the clipped bounds carry the 2-ulp error of the fast division: far inside the margins)
+#pragma unroll
+                            for (int sb = 0; sb < kFanSub; sb++)
+#pragma unroll
+                                for (int sa = 0; sa < kFanSub; sa++) {
+                                    const float w1 = fmaxf(a1[sa], b1[sb]), w2 = fminf(a2[sa], b2[sb]);
+                                    if ((open >> (sb * kFanSub + sa) & 1u) && w2 >= w1 * 1.00390625f && w2 - w1 >= a.coverMinThickness)
+                                        cover[sb * kFanSub + sa] = fminf(cover[sb * kFanSub + sa], w1 * 1.001953125f);
+                                }
+                        }
                     }
                 }
             }
         }
         if (pass == 1) {
             if (cA > 0) a.firstA[(size_t)fan * kFanCells + cellOfThread] = firstIds;
-            a.cells4[(size_t)fan * kFanCells + cellOfThread] = make_uint4(myCell.x, myCell.y, firstIds, __float_as_uint(cover));
+            uint32_t codes = 0;
+#pragma unroll
+            for (int q = 0; q < kFanSub * kFanSub; q++) codes |= fan_cover_code(cover[q], a.coverLogS, a.coverLogK) << (8 * q);
+            a.cells4[(size_t)fan * kFanCells + cellOfThread] = make_uint4(myCell.x, myCell.y, firstIds, codes);
             break;
         }
         // ---- reserve the CTA's span: block scan of the per-bin totals
@@ -354,10 +418,10 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_match_kerne
         uint2* cells = a.cells + (size_t)fan * kFanCells;
         if (bs == 0xFFFFFFFFu) {
             cells[cellOfThread] = make_uint2(0u, 0u);
-            a.cells4[(size_t)fan * kFanCells + cellOfThread] = make_uint4(0u, 0u, 0u, 0x7F800000u);
+            a.cells4[(size_t)fan * kFanCells + cellOfThread] = make_uint4(0u, 0u, 0u, 0xFFFFFFFFu);
             if (nearCta && tid == 0) {
                 cells[6 * kFanCellsPerFace] = make_uint2(0u, 0u);
-                a.cells4[(size_t)fan * kFanCells + 6 * kFanCellsPerFace] = make_uint4(0u, 0u, 0u, 0x7F800000u);
+                a.cells4[(size_t)fan * kFanCells + 6 * kFanCellsPerFace] = make_uint4(0u, 0u, 0u, 0xFFFFFFFFu);
             }
             return;
         }
@@ -391,14 +455,15 @@ __global__ void __launch_bounds__(ROWS * 32, 2048 / (ROWS * 32)) fan_match_kerne
 // a.order (may be null: canonical order) needs (nTargets + 1) * (ns + na + no) words; a.rects etc.: fan_build_scratch_bytes
 size_t fan_build_scratch_bytes(int nFans, int nc)
 {
-    return (size_t)nFans * 6 * nc * sizeof(uint2) + (size_t)nFans * (18 + kFanMaxNear + 1) * sizeof(uint32_t);
+    return (size_t)nFans * 6 * nc * (sizeof(uint2) + sizeof(float)) + (size_t)nFans * (18 + kFanMaxNear + 1) * sizeof(uint32_t);
 }
 // carves a.rects / rectCount / nearList / nearCount out of `scratch` (fan_build_scratch_bytes)
 void fan_build_set_scratch(FanBuildArgs& a, void* scratch)
 {
     const size_t nFans = (size_t)a.nTargets + 1, nc = (size_t)a.ns + a.na + a.no;
     a.rects = reinterpret_cast<uint2*>(scratch);
-    a.rectCount = reinterpret_cast<uint32_t*>(a.rects + nFans * 6 * nc);
+    a.rectDepth = reinterpret_cast<float*>(a.rects + nFans * 6 * nc);
+    a.rectCount = reinterpret_cast<uint32_t*>(a.rectDepth + nFans * 6 * nc);
     a.nearList = a.rectCount + nFans * 18;
     a.nearCount = a.nearList + nFans * kFanMaxNear;
 }

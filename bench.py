@@ -354,9 +354,11 @@ def main():
             achieved = tfl(q_flops, query_ms_avg)
             kernel_name = "query_fan_kernel (K1b: echo + muffle queries of every hit point against the target fans)"
             accounting = ("collider tests the kernel actually executed (ART_FRAME_GRID_STATS) x reference flops per test; the "
-                          "acceleration structures change WHICH tests run (about 2.6 per occlusion query instead of the reference's "
-                          "scan), so the full-scan count is reported beside it (SURVEY 8f-4). The fraction is low by design: a "
-                          "query costs an exact sqrt + four exact reciprocals and a direction-bin lookup before its first test; "
+                          "acceleration structures change WHICH tests run (about 1.2 per occlusion query instead of the reference's "
+                          "scan: three quarters of the queries are decided blocked by the covering-depth compare of their direction bin, "
+                          "without a collider test), so the full-scan count is reported beside it (SURVEY 8f-4). The fraction is low by "
+                          "design: a query costs a direction-bin lookup, and a surviving one an exact sqrt + four exact reciprocals, "
+                          "before its first test; "
                           "profiles/ holds issue-slot and lane utilisation. 'kernels' lists the bounce tracer and K2 as well.")
         elif grid_used & 1:
             achieved = tfl(exec_trace_flops, trace_ms_avg)
@@ -412,7 +414,7 @@ def main():
             "kernel_ms": {"trace": trace_ms_avg, "trace_fan_build": fan_ms_avg, "trace_bounce": bounce_ms_avg, "trace_queries": query_ms_avg,
                           "permeation": float(np.mean(perm_ms)), "reduce": float(np.mean(reduce_ms)),
                           "partials_allgather": ex_ms_tot / args.steps,
-                          "note": "trace = per-frame fan build (fan_order_kernel + fan_build_kernel) + bounce tracer (bounce_kernel) "
+                          "note": "trace = per-frame fan build (fan_order_kernel + fan_project_kernel + fan_match_kernel) + bounce tracer (bounce_kernel) "
                                   "+ query_fan_kernel; partials_allgather = ncclAllGather of the per-source blobs inside the library"},
             "wall_ms_per_step_device_mode": wall_dev_max / args.steps * 1e3,
             "clocks": clocks,
