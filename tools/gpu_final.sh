@@ -12,5 +12,5 @@ python bench.py --workload c5 --rays 524288 --steps 3 --warmup 3 --no-cpu-baseli
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/f1_bench_ref.json 2> gpurun_out/f1_bench_ref.err
 python tools/exp_env.py --workload c3 --frames 4 --shard 0/8 --chunk 16384 > gpurun_out/f1_shard.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/f1_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/f1_ncu_launch.log 2>&1
-ncu --set full --clock-control none --import-source on --kernel-name 'regex:query_fan|bounce_kernel|perm_loss_binned|fan_build|fan_order|perm_bin|permeation_grid|perm_last|echo_stats' -c 14 -f -o gpurun_out/f1_full python tools/prof_frame.py --workload c3 --frames 1 > gpurun_out/f1_full.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name 'regex:query_fan|bounce_kernel|perm_loss_binned|fan_match|fan_project|fan_order|perm_bin|permeation_grid|perm_last|echo_stats' -c 16 -f -o gpurun_out/f1_full python tools/prof_frame.py --workload c3 --frames 1 > gpurun_out/f1_full.log 2>&1
 ls -la gpurun_out
