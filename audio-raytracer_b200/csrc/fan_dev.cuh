@@ -20,7 +20,8 @@
 //     < 1e-3 rad, i.e. < 2e-3 in the tangent-plane coordinates of a cube face;
 //   * every collider is registered in all bins its box projects onto, inflated by kFanTanMargin = 4e-3, with
 //     1 % slack on the face-membership constraint, and in the near list when G is within nearDist of the box.
-// The lists are rebuilt on the device every frame (goals move): fan_build_kernel, k4_fan_build.cu.
+// The lists are rebuilt on the device every frame (goals move): fan_order_kernel, fan_project_kernel, fan_match_kernel
+// (k4_fan_build.cu).
 #pragma once
 #include "scene_dev.cuh"
 
@@ -48,7 +49,7 @@ struct FanDesc {
     float coverLogS, coverLogK; // code of depth w = coverLogS * log2(w) + coverLogK (set by the API, the same for build and query)
 };
 
-// fan_build_kernel arguments (k4_fan_build.cu)
+// arguments of the fan build kernels (k4_fan_build.cu)
 struct FanBuildArgs {
     const float4* boxLo;       // [ns + na + no] conservative bounds of every collider, canonical order S | A | O (grid_host.h)
     const float4* boxHi;
