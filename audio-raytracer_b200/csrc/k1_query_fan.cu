@@ -43,7 +43,7 @@ namespace art {
 #define ART_Q_WARPS 32
 #endif
 #ifndef ART_Q_RUN
-#define ART_Q_RUN 96
+#define ART_Q_RUN 48     // 96 is 0.7 % faster on C3 but its queues no longer stay in L2: 5.6 GB of DRAM traffic per launch instead of 1.7
 #endif
 #ifndef ART_Q_MIN_LANES
 #define ART_Q_MIN_LANES 20
