@@ -228,6 +228,7 @@ struct ArtCtx {
     DevBuf fanBoxes, fanCells, fanEntries, fanCtl, fanOrder, fanScratch;  // target fans (fan_dev.cuh): collider bounds (per scene), lists (per frame)
     PinBuf pinFanCtl;
     bool fansDisabled = false;                     // ART_DISABLE_FANS=1
+    float frameCoverLogS = 0.0f, frameCoverLogK = 0.0f;   // covering-depth code scale of the last frame's fans (art_debug_get_fan_cover)
     size_t fanEntriesPerPair = 64;                 // entry capacity = fans * colliders * this (grows after an overflow); ART_FAN_ENTRIES_PER_PAIR
     bool frameFans = false;                        // the frame in flight uses the fans
     bool frameCopiedEarly = false;                 // per-ray outputs of the frame in flight travel on copyStream behind the trace job
@@ -1208,6 +1209,7 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             if (fanBeside) CK(cudaEventRecord(ctx->evFan, ctx->stream2));
             ctx->kernelLaunches += 2;                // fan_project_kernel, fan_match_kernel
             fd.nFans = (int)nFans; fd.cells = fa.cells; fd.entries = fa.entries; fd.nEntries = (int)cap; fd.firstA = fa.firstA; fd.cells4 = fa.cells4; fd.coverLogS = fa.coverLogS; fd.coverLogK = fa.coverLogK;
+            ctx->frameCoverLogS = fa.coverLogS; ctx->frameCoverLogK = fa.coverLogK;
             ctx->frameGridUsed |= 4u;
         }
     }
@@ -1816,6 +1818,21 @@ ART_API int32_t art_debug_get_fans(ArtCtx* ctx, ArtFanInfo* info, uint32_t* cell
         if (entriesCapacity < info->nEntries) return fail(ctx, ART_E_ARG, "entries buffer too small");
         CK(cudaMemcpy(entries, ctx->fanEntries.p, (size_t)info->nEntries * sizeof(uint16_t), cudaMemcpyDeviceToHost));
     }
+    return ART_OK;
+}
+
+ART_API int32_t art_debug_get_fan_cover(ArtCtx* ctx, uint32_t* codes, int64_t capacity, float* logS, float* logK)
+{
+    if (!ctx || !codes || !logS || !logK) return ART_E_ARG;
+    if (ctx->inFlight) return fail(ctx, ART_E_PENDING, "a frame is in flight");
+    if (!ctx->children.empty()) return art_debug_get_fan_cover(ctx->children[0], codes, capacity, logS, logK);
+    if (!ctx->frameDone || !ctx->frameFans) return fail(ctx, ART_E_STATE, "the last frame did not use the target fans");
+    cudaSetDevice(ctx->device);
+    const int64_t nCells = (int64_t)(ctx->frameNa + 1) * kFanCells;
+    if (capacity < nCells) return fail(ctx, ART_E_ARG, "codes buffer too small");
+    // cells4[i].w: one strided copy out of the 16-byte cells
+    CK(cudaMemcpy2D(codes, sizeof(uint32_t), ctx->fanCells.as<unsigned char>() + 12, sizeof(uint4), sizeof(uint32_t), (size_t)nCells, cudaMemcpyDeviceToHost));
+    *logS = ctx->frameCoverLogS; *logK = ctx->frameCoverLogK;
     return ART_OK;
 }
 

@@ -29,7 +29,7 @@ EXPORTS = [
     "art_create", "art_destroy", "art_set_scene", "art_set_rays", "art_generate_fibonacci_rays", "art_get_rays",
     "art_set_ray_shard", "art_local_ray_count", "art_trace_schedule", "art_is_completed", "art_complete",
     "art_get_counters", "art_last_error", "art_partials_size", "art_get_partials", "art_partials_merge",
-    "art_finalize", "art_microbench", "art_grid_build_host", "art_debug_get_fans", "art_comm_unique_id", "art_comm_init",
+    "art_finalize", "art_microbench", "art_grid_build_host", "art_debug_get_fans", "art_debug_get_fan_cover", "art_comm_unique_id", "art_comm_init",
 ]
 
 
@@ -133,6 +133,8 @@ def load_library(path: Optional[str] = None):
     lib.art_grid_build_host.argtypes = [vp, i32, vp, i32, vp, i32, C.c_float, C.POINTER(ArtGridInfo), vp, i64, vp, i64]
     lib.art_debug_get_fans.restype = i32
     lib.art_debug_get_fans.argtypes = [vp, C.POINTER(ArtFanInfo), vp, i64, vp, i64]
+    lib.art_debug_get_fan_cover.restype = i32
+    lib.art_debug_get_fan_cover.argtypes = [vp, vp, i64, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.art_partials_size.restype = i64
     lib.art_partials_size.argtypes = [i32, i32]
     lib.art_get_partials.restype = i32
@@ -342,6 +344,14 @@ class Context:
         entries = np.zeros(max(1, info.nEntries), dtype=np.uint16)
         self._check(self._lib.art_debug_get_fans(self._ctx, C.byref(info), cells.ctypes.data, cells.size, entries.ctypes.data, entries.size))
         return info, cells.reshape(info.nFans, info.cellsPerFan, 2), entries
+
+    def get_fan_cover(self, info):
+        """(codes uint8 [nFans, cellsPerFan, 4], logS, logK): covering-depth codes per sub-bin (sb * 2 + sa) of the last frame's
+        fans; a code c < 255 stands for the depth 2 ** ((c - logK) / logS), 255 for none."""
+        codes = np.zeros(info.nCells, dtype=np.uint32)
+        s, k = C.c_float(0), C.c_float(0)
+        self._check(self._lib.art_debug_get_fan_cover(self._ctx, codes.ctypes.data, codes.size, C.byref(s), C.byref(k)))
+        return codes.view(np.uint8).reshape(info.nFans, info.cellsPerFan, 4), float(s.value), float(k.value)
 
     def microbench(self, kind: int) -> float:
         g = C.c_double(0)

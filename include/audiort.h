@@ -306,6 +306,14 @@ typedef struct ArtFanInfo {
 ART_API int32_t art_debug_get_fans(ArtCtx* ctx, ArtFanInfo* info, uint32_t* cells, int64_t cellsCapacity,
                                    uint16_t* entries, int64_t entriesCapacity);
 
+/* ... and their covering depths (csrc/k4_fan_build.cu "covering depth": beyond that depth -- measured from the goal along the
+ * cube face's major axis -- one AABB fills the whole sub-bin, so every echo / muffle query from there is blocked and the
+ * query kernel drops it untested). codes[i] holds the four sub-bins of cell i (2 x 2 per bin: sub-bin sb * 2 + sa in byte
+ * sb * 2 + sa; sa / sb = which half of the bin in ia / ib direction); a code c < 255 stands for the depth
+ * 2^((c - logK) / logS), 255 for "none". The near-list cell of a fan (the last one) carries no codes.
+ * capacity in uint32 (>= ArtFanInfo.nCells). Returns ART_E_STATE when the last frame did not use the fans. */
+ART_API int32_t art_debug_get_fan_cover(ArtCtx* ctx, uint32_t* codes, int64_t capacity, float* logS, float* logK);
+
 /* Device-side FP32 issue-rate microbenchmarks used for the roofline denominator (bench.py):
  * kind 0 = un-fused FADD/FMUL, 1 = FMNMX, 2 = FFMA. Returns achieved Gop/s (lane-ops). */
 ART_API int32_t art_microbench(ArtCtx* ctx, int32_t kind, double* gops);
