@@ -1164,10 +1164,23 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
         // a collider can subtend every bin of a fan (a wall seen from nearby), a typical one a few dozen
         const size_t perFan = std::min(nc * (size_t)kFanCells, nc * ctx->fanEntriesPerPair + ((size_t)2048 * ctx->fanEntriesPerPair));
         const size_t cap = nFans * perFan + 4096;
-        if (cap > ((size_t)1 << 30) || nFans * kFanCells > ((size_t)1 << 28)) useFans = false;   // > 2 GiB of lists: walk the grid instead
+        bool fit = !(cap > ((size_t)1 << 30) || nFans * kFanCells > ((size_t)1 << 28));   // > 2 GiB of lists: walk the grid instead
+        if (fit) {
+            // ... and so does a frame whose fan buffers cannot be allocated (tens of thousands of targets x thousands of colliders:
+            // the build scratch alone is 72 B per (target, collider) pair)
+            const bool sorted = nc <= 16384;                 // the per-goal sort runs in one CTA's shared memory
+            fit = ctx->fanCells.ensure(nFans * kFanCells * (sizeof(uint4) + sizeof(uint2) + sizeof(uint32_t))) == cudaSuccess &&   // FanDesc::cells4, cells, firstA
+                  ctx->fanEntries.ensure(cap * sizeof(uint16_t)) == cudaSuccess &&
+                  ctx->fanScratch.ensure(fan_build_scratch_bytes((int)nFans, (int)nc)) == cudaSuccess &&
+                  (!sorted || ctx->fanOrder.ensure(nFans * nc * sizeof(uint32_t)) == cudaSuccess);
+            if (const char* v = getenv("ART_FAN_ALLOC_FAIL")) { if (atoi(v) != 0) fit = false; }   // (test knob, read per frame)
+            if (!fit) {
+                cudaGetLastError();
+                for (DevBuf* b : { &ctx->fanCells, &ctx->fanEntries, &ctx->fanScratch, &ctx->fanOrder }) b->release();
+            }
+        }
+        if (!fit) useFans = false;
         else {
-            CK(ctx->fanCells.ensure(nFans * kFanCells * (sizeof(uint4) + sizeof(uint2) + sizeof(uint32_t))));   // FanDesc::cells4, cells, firstA
-            CK(ctx->fanEntries.ensure(cap * sizeof(uint16_t)));
             CK(ctx->fanCtl.ensure(16));
             CK(ctx->pinFanCtl.ensure(16));
             // (Building the fans on the second stream beside the bounce tracer was measured and dropped: the two kernels'
@@ -1199,11 +1212,9 @@ ART_API int32_t art_trace_schedule(ArtCtx* ctx, const ArtParams* prm, const ArtO
             fa.capacity = (unsigned int)cap; fa.ctl = ctx->fanCtl.as<unsigned int>();
             fa.order = nullptr;
             if (nc <= 16384) {                       // the per-goal sort runs in one CTA's shared memory
-                CK(ctx->fanOrder.ensure(nFans * nc * sizeof(uint32_t)));
                 fa.order = ctx->fanOrder.as<uint32_t>();
                 ctx->kernelLaunches++;
             }
-            CK(ctx->fanScratch.ensure(fan_build_scratch_bytes((int)nFans, (int)nc)));
             fan_build_set_scratch(fa, ctx->fanScratch.p);
             CK(launch_fan_build(fa, fanStream));
             if (fanBeside) CK(cudaEventRecord(ctx->evFan, ctx->stream2));

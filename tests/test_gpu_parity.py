@@ -545,6 +545,25 @@ def test_fan_overflow_reruns_the_frame_on_the_grid_walk(oracle, monkeypatch):
         assert seen[0] & 8 and seen[-1] == 7, seen
 
 
+def test_fan_buffers_that_cannot_be_allocated_fall_back_to_the_grid_walk(oracle, monkeypatch):
+    """a frame whose fan buffers cannot be allocated (ART_FAN_ALLOC_FAIL stands in for cudaMalloc failing at tens of thousands of
+    targets) walks the grid instead -- same results, no error -- and the next frame builds its fans again"""
+    s = scenes.make_config("c3", n_rays=512)
+    o = oracle.run_frame(s, threads=8)
+    with native.Context(0) as ctx:
+        native.upload(ctx, s)
+        seen = []
+        for fail in ("0", "1", "0"):
+            monkeypatch.setenv("ART_FAN_ALLOC_FAIL", fail)
+            g = ctx.run_frame(s, flags=native.FRAME_FORCE_GRID)
+            seen.append(g.counters["gridUsed"])
+            np.testing.assert_array_equal(g.hit_ids, o.hit_ids)
+            np.testing.assert_array_equal(g.echo, o.echo)
+            np.testing.assert_array_equal(g.muffle, o.muffle)
+            np.testing.assert_array_equal(g.permeation.view(np.uint32), o.permeation.view(np.uint32))
+        assert seen[0] & 4 and not seen[1] & 4 and seen[1] & 1 and seen[2] & 4, seen
+
+
 @pytest.mark.parametrize("name,n_rays,flags", [("c3", 6000, 0), ("c3", 6000, native.FRAME_NO_FANS), ("c2", 20000, 0)])
 def test_goal_tables_in_shared_memory_do_not_change_results(monkeypatch, name, n_rays, flags):
     """The grid kernels keep the listener + target positions of the query pool in shared memory when they fit
